@@ -1,0 +1,154 @@
+/*
+ * mpm_b200.h -- C-ABI of the B200-native MPM substep solver (libmpm_b200.so).
+ *
+ * The reference (KAISTChangmin/MPMAvatar) has no FFI boundary: its boundary is the
+ * in-process Python API of warp_mpm.  Each entry point below
+ * names the reference interface it stands behind; mpmavatar_b200/warp_mpm/ binds
+ * them with ctypes and re-exposes the reference's own class / method names.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / warp types.
+ *  - every data pointer may be a DEVICE or a (pinned or pageable) HOST pointer:
+ *    copies use cudaMemcpyDefault (UVA).  Device pointers are the fast path.
+ *  - all work is enqueued on the caller's stream (cudaStream_t passed as void*);
+ *    no entry point synchronises the host unless its comment says so.
+ *  - one handle per GPU, not thread-safe (same as the reference: single Python thread).
+ *  - return value 0 = ok, <0 = error; mpm_last_error() returns the message.
+ *  - "canonical" arrays are the reference's layouts: particle order
+ *    [elements | traditional | vertices] (train_material_params.py:387), row-major
+ *    mat33, faces as float vertex-local indices (mpm_data_structure.py:41,211-215).
+ */
+#ifndef MPM_B200_H
+#define MPM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct MpmSolver MpmSolver;
+
+/* MPMWARP.__init__/initialize (warp_mpm/mpm_solver.py:14-51) +
+ * MPMStateStruct.init/init_grid (mpm_data_structure.py:51-156) +
+ * MPMModelStruct.init_other_params (mpm_data_structure.py:686-715) */
+typedef struct {
+    int n_particles, n_elements, n_vertices; /* n_traditional = N - Ne - Nv */
+    int n_grid;
+    float grid_lim;
+    int n_mesh_v, n_mesh_f; /* body mesh sizes, 0 = no mesh */
+    int num_joint_v, num_joint_f;
+    int device;           /* CUDA device ordinal */
+    int resort_interval;  /* substeps between particle re-sorts; <=0 = default */
+} MpmConfig;
+
+/* model scalars: MPMModelStruct fields written by set_parameters_dict
+ * (mpm_solver.py:57-126) and init_other_params */
+typedef struct {
+    int material;  /* 0 jelly 1 metal 2 sand 3 foam 4 snow 5 plasticine 6 neo-hookean 7 cloth */
+    int hardening; /* model.hardening == 1 enables hardening (mpm_utils.py:249) */
+    float friction_coeff, alpha;
+    float g[3];
+    float rpic_damping, grid_v_damping_scale;
+    float xi, plastic_viscosity, softening;
+} MpmModelParams;
+
+/* canonical particle arrays; NULL members are skipped.
+ * MPMStateStruct.from_torch / reset_state / continue_from_torch / reset_density
+ * (mpm_data_structure.py:158-467), MPMWARP.set_E_nu / prepare_mu_lam
+ * (mpm_solver.py:128-227) */
+typedef struct {
+    float *x, *v;           /* [N,3] */
+    float *C;               /* [N,9] */
+    float *F, *F_trial;     /* [Nnv,9]; only the traditional rows are used */
+    float *stress;          /* [Nnv,9] (export only) */
+    float *d;               /* [Ne,9] */
+    float *R_inv;           /* [Ne,3] */
+    float *faces;           /* [Ne,3] float vertex-local indices */
+    float *vertex_force;    /* [Nv,3] (export only) */
+    float *vol, *mass;      /* [N] */
+    float *mu, *lam, *gamma, *kappa, *yield_stress; /* [N] */
+} MpmParticleArrays;
+
+/* per-call inputs of MPMWARP.p2g2p (mpm_solver.py:229-231): body mesh points /
+ * velocities and prescribed joint velocities.  NULL = not given. */
+typedef struct {
+    const float *mesh_x, *mesh_v;             /* [n_mesh_v,3] */
+    const float *joint_traditional_v;         /* [n_joint_t,3]: pins the LAST n_joint_t traditional particles */
+    int n_joint_t;
+    const float *joint_verts_v, *joint_faces_v; /* [num_joint_v,3], [num_joint_f,3] */
+} MpmFrameInputs;
+
+typedef struct {
+    int n_active_blocks;       /* allocated 4^3-node grid blocks */
+    long long n_active_nodes;  /* distinct nodes in the union of all particle stencils */
+    int n_resorts;
+    long long n_substeps;
+    int overflow;              /* 1 = block pool exhausted or a scatter hit an unallocated block */
+    int gpu_launches;          /* kernels launched by the library since creation */
+    double sim_time;
+} MpmStats;
+
+/* cumulative per-phase device time in ms (filled only while profiling is on);
+ * stands behind MPMWARP.time_profile / print_time_profile (mpm_solver.py:16,538-541) */
+typedef struct {
+    float stress_ms, p2g_ms, collider_scatter_ms, mover_scatter_ms, grid_ms, g2p_v_ms, g2p_e_ms, resort_ms;
+    long long n_substeps;
+} MpmProfile;
+
+int mpm_create(const MpmConfig *cfg, MpmSolver **out);
+void mpm_destroy(MpmSolver *s);
+const char *mpm_last_error(MpmSolver *s); /* s may be NULL: last creation error */
+
+int mpm_set_model(MpmSolver *s, const MpmModelParams *p);
+
+/* copy the non-NULL canonical arrays into the solver (async on stream); positions
+ * trigger a particle re-sort + sparse-grid rebuild at the next step */
+int mpm_import_state(MpmSolver *s, const MpmParticleArrays *a, void *stream);
+/* write the current state back to the non-NULL canonical arrays in ORIGINAL particle
+ * order (wp.to_torch(state.particle_x), train_material_params.py:628) */
+int mpm_export_state(MpmSolver *s, const MpmParticleArrays *a, void *stream);
+
+/* body-mesh topology, MPMWARP.initialize (mpm_solver.py:45-51): faces [n_mesh_f,3] int32 */
+int mpm_set_body_mesh(MpmSolver *s, const int *faces, const float *points0, void *stream);
+/* add_mesh_collider (mpm_solver.py:805-919) */
+int mpm_add_mesh_collider(MpmSolver *s, float friction);
+/* add_particle_mover (mpm_solver.py:661-802) */
+int mpm_add_particle_mover(MpmSolver *s);
+/* add_surface_collider (mpm_solver.py:564-658); surface_type 0 sticky, 1 slip, 11 cut, 2 other */
+int mpm_add_surface_collider(MpmSolver *s, const float point[3], const float normal[3], int surface_type,
+                             float friction, float start_time, float end_time);
+/* set_velocity_on_cuboid (mpm_solver.py:929-984) */
+int mpm_set_velocity_on_cuboid(MpmSolver *s, const float point[3], const float size[3], const float velocity[3],
+                               float start_time, float end_time, int reset);
+/* add_bounding_box (mpm_solver.py:986-1053) */
+int mpm_add_bounding_box(MpmSolver *s, float start_time, float end_time);
+/* enforce_grid_velocity_by_mask (mpm_solver.py:1330-1355); mask [n_grid^3] int32 */
+int mpm_enforce_grid_velocity_by_mask(MpmSolver *s, const int *mask, void *stream);
+/* pre-P2G particle operations (mpm_solver.py:1058-1328, 1360-1417).  mask [N] int32 in canonical order.
+ * kind 0: v += force/mass*dt where mask==1 (add_impulse_on_particles)
+ * kind 1: v += force*dt where mask>=1      (add_impulse_on_particles_with_mask)
+ * kind 2: v = velocity where mask==1        (enforce_particle_velocity_translation / _by_mask) */
+int mpm_add_particle_op(MpmSolver *s, int kind, const float vec[3], const int *mask, float start_time,
+                        float end_time, void *stream);
+
+/* nsub substeps of MPMWARP.p2g2p (mpm_solver.py:229-536).  Substep k uses body points
+ * mesh_x + (float)(dt*k) * mesh_v, which is what the callers compute on the host side
+ * (train_material_params.py:622-626); nsub = 1 is exactly one p2g2p call. */
+int mpm_step(MpmSolver *s, float dt, int nsub, const MpmFrameInputs *in, void *stream);
+
+/* self.time (mpm_solver.py:28,536) */
+int mpm_set_time(MpmSolver *s, double t);
+
+/* test / measurement hooks */
+/* dense [n^3] grid_m, [n^3,3] grid_v_in, [n^3,3] grid_v_out of the LAST substep (NULL skipped);
+ * requires mpm_set_debug(s, 1) before the step.  Synchronises. */
+int mpm_export_grid(MpmSolver *s, float *grid_m, float *grid_v_in, float *grid_v_out, void *stream);
+int mpm_set_debug(MpmSolver *s, int on);
+int mpm_set_profiling(MpmSolver *s, int on); /* per-phase CUDA events; disables graph replay */
+int mpm_get_profile(MpmSolver *s, MpmProfile *out);   /* synchronises */
+int mpm_get_stats(MpmSolver *s, MpmStats *out, void *stream); /* synchronises */
+int mpm_force_resort(MpmSolver *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

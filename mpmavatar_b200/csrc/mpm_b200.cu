@@ -1,0 +1,749 @@
+// libmpm_b200.so -- host side of the B200 MPM substep solver and its C-ABI (include/mpm_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <array>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mpm_b200.h"
+#include "mpm_kernels.cuh"
+
+using namespace mpm;
+
+static std::string g_create_error;
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            char buf_[512];                                                                            \
+            snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            throw std::string(buf_);                                                                   \
+        }                                                                                              \
+    } while (0)
+
+namespace {
+
+struct Canon {  // canonical (reference-layout) device mirror
+    float *x, *v, *C, *F, *Ft, *stress, *d, *Rinv, *faces, *vforce, *vol, *mass, *mu, *lam, *gamma, *kappa, *ys;
+};
+
+// ---------------------------------------------------------------- sort / import / export kernels
+__global__ void k_keys(Grid g, int n, const float* __restrict__ x, int offset, uint32_t* keys, uint32_t* vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = x + 3 * (size_t)(offset + i);
+    keys[i] = sort_key(g, p[0], p[1], p[2]);
+    vals[i] = i;
+}
+__global__ void k_invert(int n, const uint32_t* __restrict__ perm, int* __restrict__ inv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[perm[i]] = i;
+}
+__global__ void k_import_E(int Ne, const uint32_t* __restrict__ perm, Canon c, PRec* rec, EAux* aux,
+                           const int* __restrict__ invV) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Ne) return;
+    int s = perm[i];  // canonical element index == canonical particle index
+    PRec r;
+    r.xm = make_float4(c.x[3 * s], c.x[3 * s + 1], c.x[3 * s + 2], c.mass[s]);
+    r.vv = make_float4(c.v[3 * s], c.v[3 * s + 1], c.v[3 * s + 2], c.vol[s]);
+    for (int k = 0; k < 9; k++) { r.C[k] = c.C[9 * (size_t)s + k]; r.S[k] = 0.f; }
+    r.pad[0] = r.pad[1] = 0.f;
+    rec[i] = r;
+    EAux a;
+    const float* d = c.d + 9 * (size_t)s;  // row-major -> columns
+    for (int col = 0; col < 3; col++)
+        for (int row = 0; row < 3; row++) a.dc[3 * col + row] = d[3 * row + col];
+    for (int k = 0; k < 3; k++) {
+        a.Rinv[k] = c.Rinv[3 * s + k];
+        a.face[k] = invV[(int)c.faces[3 * s + k]];  // int(face[k]) as in mpm_utils.py:172
+    }
+    a.mu = c.mu[s]; a.lam = c.lam[s]; a.gamma = c.gamma[s]; a.kappa = c.kappa[s]; a.vol = c.vol[s];
+    aux[i] = a;
+}
+__global__ void k_import_T(int Nt, int Ne, const uint32_t* __restrict__ perm, Canon c, PRec* rec, TAux* aux) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Nt) return;
+    int s = Ne + perm[i];
+    PRec r;
+    r.xm = make_float4(c.x[3 * s], c.x[3 * s + 1], c.x[3 * s + 2], c.mass[s]);
+    r.vv = make_float4(c.v[3 * s], c.v[3 * s + 1], c.v[3 * s + 2], c.vol[s]);
+    for (int k = 0; k < 9; k++) { r.C[k] = c.C[9 * (size_t)s + k]; r.S[k] = 0.f; }
+    r.pad[0] = r.pad[1] = 0.f;
+    rec[i] = r;
+    TAux a;
+    for (int k = 0; k < 9; k++) { a.F[k] = c.F[9 * (size_t)s + k]; a.Ft[k] = c.Ft[9 * (size_t)s + k]; }
+    a.mu = c.mu[s]; a.lam = c.lam[s]; a.ys = c.ys[s];
+    a.pad[0] = a.pad[1] = a.pad[2] = 0.f;
+    aux[i] = a;
+}
+__global__ void k_import_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, Canon c, VRec* rec) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Nv) return;
+    int s = Nnv + perm[i];
+    VRec r;
+    r.xm = make_float4(c.x[3 * s], c.x[3 * s + 1], c.x[3 * s + 2], c.mass[s]);
+    r.vv = make_float4(c.v[3 * s], c.v[3 * s + 1], c.v[3 * s + 2], 0.f);
+    for (int k = 0; k < 9; k++) r.C[k] = c.C[9 * (size_t)s + k];
+    r.f[0] = r.f[1] = r.f[2] = 0.f;
+    rec[i] = r;
+}
+__global__ void k_export_E(int Ne, const uint32_t* __restrict__ perm, Canon c, const PRec* rec, const EAux* aux) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Ne) return;
+    int s = perm[i];
+    PRec r = rec[i];
+    c.x[3 * s] = r.xm.x; c.x[3 * s + 1] = r.xm.y; c.x[3 * s + 2] = r.xm.z;
+    c.v[3 * s] = r.vv.x; c.v[3 * s + 1] = r.vv.y; c.v[3 * s + 2] = r.vv.z;
+    for (int k = 0; k < 9; k++) { c.C[9 * (size_t)s + k] = r.C[k]; c.stress[9 * (size_t)s + k] = r.S[k]; }
+    float* d = c.d + 9 * (size_t)s;
+    for (int col = 0; col < 3; col++)
+        for (int row = 0; row < 3; row++) d[3 * row + col] = aux[i].dc[3 * col + row];
+}
+__global__ void k_export_T(int Nt, int Ne, const uint32_t* __restrict__ perm, Canon c, const PRec* rec, const TAux* aux) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Nt) return;
+    int s = Ne + perm[i];
+    PRec r = rec[i];
+    c.x[3 * s] = r.xm.x; c.x[3 * s + 1] = r.xm.y; c.x[3 * s + 2] = r.xm.z;
+    c.v[3 * s] = r.vv.x; c.v[3 * s + 1] = r.vv.y; c.v[3 * s + 2] = r.vv.z;
+    for (int k = 0; k < 9; k++) {
+        c.C[9 * (size_t)s + k] = r.C[k];
+        c.stress[9 * (size_t)s + k] = r.S[k];
+        c.F[9 * (size_t)s + k] = aux[i].F[k];
+        c.Ft[9 * (size_t)s + k] = aux[i].Ft[k];
+    }
+    c.mu[s] = aux[i].mu; c.lam[s] = aux[i].lam; c.ys[s] = aux[i].ys;  // damage / hardening mutate these
+}
+__global__ void k_export_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, Canon c, const VRec* rec,
+                           const float* __restrict__ dbg_f) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Nv) return;
+    int s = Nnv + perm[i];
+    int vl = perm[i];
+    VRec r = rec[i];
+    c.x[3 * s] = r.xm.x; c.x[3 * s + 1] = r.xm.y; c.x[3 * s + 2] = r.xm.z;
+    c.v[3 * s] = r.vv.x; c.v[3 * s + 1] = r.vv.y; c.v[3 * s + 2] = r.vv.z;
+    for (int k = 0; k < 9; k++) c.C[9 * (size_t)s + k] = r.C[k];
+    for (int k = 0; k < 3; k++) c.vforce[3 * vl + k] = dbg_f ? dbg_f[3 * i + k] : r.f[k];
+}
+template <typename Rec>
+__global__ void k_alloc_blocks(Grid g, int n, const Rec* __restrict__ rec) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 xm = rec[i].xm;
+    ensure_stencil_blocks(g, xm.x, xm.y, xm.z);
+}
+__global__ void k_fill_int(int* p, size_t n, int v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// dense debug export of the sparse grid
+__global__ void k_export_grid(Grid g, float* gm, float* gvin, float* gvout) {
+    const int n_slots = min(*g.n_slots, g.cap);
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_slots * BN) return;
+    int slot = idx >> 6, l = idx & 63, co = g.slot_coord[slot];
+    int ix = ((co & 1023) << 2) + (l >> 4), iy = (((co >> 10) & 1023) << 2) + ((l >> 2) & 3), iz = (((co >> 20) & 1023) << 2) + (l & 3);
+    if (ix >= g.n || iy >= g.n || iz >= g.n) return;
+    size_t gi = ((size_t)ix * g.n + iy) * g.n + iz;
+    if (g.dbg_acc) {
+        float4 a = g.dbg_acc[idx];
+        if (gm) gm[gi] = a.w;
+        if (gvin) { gvin[3 * gi] = a.x; gvin[3 * gi + 1] = a.y; gvin[3 * gi + 2] = a.z; }
+    }
+    if (gvout) { float4 v = g.vout[idx]; gvout[3 * gi] = v.x; gvout[3 * gi + 1] = v.y; gvout[3 * gi + 2] = v.z; }
+}
+// distinct nodes in the union of all particle stencils (SURVEY 8d "A")
+template <typename Rec>
+__global__ void k_mark_nodes(Grid g, int n, const Rec* __restrict__ rec, unsigned long long* mask) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 xm = rec[i].xm;
+    int bx = base_of(xm.x, g.inv_dx), by = base_of(xm.y, g.inv_dx), bz = base_of(xm.z, g.inv_dx);
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++)
+            for (int c = 0; c < 3; c++) {
+                int ni = node_index(g, bx + a, by + b, bz + c);
+                if (ni >= 0) atomicOr(&mask[ni >> 6], 1ull << (ni & 63));
+            }
+}
+__global__ void k_popc(const unsigned long long* mask, int n, unsigned long long* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c = (i < n) ? __popcll(mask[i]) : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+struct MpmSolver {
+    MpmConfig cfg{};
+    int N = 0, Ne = 0, Nt = 0, Nv = 0, Nnv = 0;
+    Grid g{};
+    ModelDev md{};
+    std::string err;
+    // particles
+    PRec *erec = nullptr, *trec = nullptr;
+    VRec* vrec = nullptr;
+    EAux* eaux = nullptr;
+    TAux* taux = nullptr;
+    uint32_t *permE = nullptr, *permT = nullptr, *permV = nullptr;
+    int *invE = nullptr, *invT = nullptr, *invV = nullptr;
+    uint32_t *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr;
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    Canon canon{};
+    std::vector<void*> allocs;
+    // body mesh / joints
+    int* mesh_faces = nullptr;
+    float *mesh_x = nullptr, *mesh_v = nullptr;
+    float *joint_t = nullptr, *joint_v = nullptr, *joint_f = nullptr;
+    bool has_collider = false, has_mover = false;
+    float col_friction = 0.f;
+    // BCs / ops
+    BCDesc* d_bcs = nullptr;
+    std::vector<BCDesc> h_bcs;
+    ParticleOp* d_ops = nullptr;
+    std::vector<ParticleOp> h_ops;
+    bool bcs_dirty = false, ops_dirty = false;
+    StepState* st = nullptr;
+    // state flags
+    bool have_state = false, need_sort = true, canon_stale = false;
+    int since_sort = 0, resort_interval = 128;
+    int n_resorts = 0;
+    long long n_substeps = 0;
+    int launches = 0;
+    double host_time = 0.0;
+    bool debug = false, profiling = false;
+    float* dbg_f = nullptr;
+    unsigned long long* node_mask = nullptr;
+    // profiling
+    cudaEvent_t ev[10]{};
+    MpmProfile prof{};
+    std::vector<std::array<cudaEvent_t, 9>> pending;
+
+    template <typename T>
+    T* dalloc(size_t n) {
+        void* p = nullptr;
+        CK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+        CK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+        allocs.push_back(p);
+        return (T*)p;
+    }
+};
+
+// ---------------------------------------------------------------- internals
+static void sort_class(MpmSolver* s, int n, int offset, uint32_t* perm, int* inv, cudaStream_t q) {
+    if (n == 0) return;
+    k_keys<<<cdiv(n, 256), 256, 0, q>>>(s->g, n, s->canon.x, offset, s->keys_in, s->vals_in);
+    int bits = 6;
+    for (int nb = s->g.nb; nb > 1; nb = (nb + 1) / 2) bits += 3;
+    bits = std::min(bits + 3, 32);
+    size_t tmp = s->cub_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(s->cub_tmp, tmp, s->keys_in, s->keys_out, s->vals_in, perm, n, 0, bits, q));
+    k_invert<<<cdiv(n, 256), 256, 0, q>>>(n, perm, inv);
+    s->launches += 3;
+}
+
+static void export_to_canon(MpmSolver* s, cudaStream_t q) {
+    if (!s->have_state || !s->canon_stale) return;
+    if (s->Ne) k_export_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->permE, s->canon, s->erec, s->eaux);
+    if (s->Nt) k_export_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->permT, s->canon, s->trec, s->taux);
+    if (s->Nv) k_export_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->Nnv, s->permV, s->canon, s->vrec, s->debug ? s->dbg_f : nullptr);
+    s->launches += 3;
+    s->canon_stale = false;
+}
+
+// canonical mirror -> sorted records, and rebuild of the sparse grid
+static void resort(MpmSolver* s, cudaStream_t q) {
+    export_to_canon(s, q);
+    sort_class(s, s->Ne, 0, s->permE, s->invE, q);
+    sort_class(s, s->Nt, s->Ne, s->permT, s->invT, q);
+    sort_class(s, s->Nv, s->Nnv, s->permV, s->invV, q);
+    if (s->Ne) k_import_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->permE, s->canon, s->erec, s->eaux, s->invV);
+    if (s->Nt) k_import_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->permT, s->canon, s->trec, s->taux);
+    if (s->Nv) k_import_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->Nnv, s->permV, s->canon, s->vrec);
+    // all accumulators are zero between substeps, so rebuilding the table needs no pool sweep
+    size_t nt = (size_t)s->g.nb * s->g.nb * s->g.nb;
+    k_fill_int<<<std::min(cdiv((long long)nt, 256), 1184), 256, 0, q>>>(s->g.table, nt, -1);
+    CK(cudaMemsetAsync(s->g.n_slots, 0, sizeof(int), q));
+    if (s->Ne) k_alloc_blocks<PRec><<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->erec);
+    if (s->Nt) k_alloc_blocks<PRec><<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->trec);
+    if (s->Nv) k_alloc_blocks<VRec><<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->vrec);
+    s->launches += 7;
+    s->need_sort = false;
+    s->since_sort = 0;
+    s->n_resorts++;
+    CK(cudaGetLastError());
+}
+
+static void upload_lists(MpmSolver* s, cudaStream_t q) {
+    if (s->bcs_dirty) {
+        if (!s->h_bcs.empty())
+            CK(cudaMemcpyAsync(s->d_bcs, s->h_bcs.data(), s->h_bcs.size() * sizeof(BCDesc), cudaMemcpyHostToDevice, q));
+        s->bcs_dirty = false;
+    }
+    if (s->ops_dirty) {
+        if (!s->h_ops.empty())
+            CK(cudaMemcpyAsync(s->d_ops, s->h_ops.data(), s->h_ops.size() * sizeof(ParticleOp), cudaMemcpyHostToDevice, q));
+        s->ops_dirty = false;
+    }
+}
+
+struct SubstepArgs {
+    float dt;
+    bool collider, mover, advance_mesh;
+    int njt;
+};
+
+static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
+    const int n_bc = (int)s->h_bcs.size(), n_ops = (int)s->h_ops.size();
+    cudaEvent_t* ev = nullptr;
+    std::array<cudaEvent_t, 9> evs;
+    if (s->profiling) {
+        for (auto& e : evs) CK(cudaEventCreate(&e));
+        ev = evs.data();
+        CK(cudaEventRecord(ev[0], q));
+    }
+    if (n_ops) {
+        if (s->Ne) k_particle_ops<PRec><<<cdiv(s->Ne, 256), 256, 0, q>>>(s->Ne, s->erec, s->permE, 0, s->d_ops, n_ops, s->st, a.dt);
+        if (s->Nt) k_particle_ops<PRec><<<cdiv(s->Nt, 256), 256, 0, q>>>(s->Nt, s->trec, s->permT, s->Ne, s->d_ops, n_ops, s->st, a.dt);
+        if (s->Nv) k_particle_ops<VRec><<<cdiv(s->Nv, 256), 256, 0, q>>>(s->Nv, s->vrec, s->permV, s->Nnv, s->d_ops, n_ops, s->st, a.dt);
+        s->launches += 3;
+    }
+    if (s->Ne) { k_stress_elements<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->eaux, s->erec, s->vrec, s->md.friction_coeff); s->launches++; }
+    if (s->Nt) { k_stress_traditional<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->taux, s->trec, s->md, a.dt); s->launches++; }
+    if (ev) CK(cudaEventRecord(ev[1], q));
+    if (s->Ne) { k_p2g<0><<<cdiv(s->Ne, 256), 256, 8 * 32 * sizeof(PRec), q>>>(s->g, (const float*)s->erec, s->Ne, a.dt, s->md.rpic); s->launches++; }
+    if (s->Nt) { k_p2g<1><<<cdiv(s->Nt, 256), 256, 8 * 32 * sizeof(PRec), q>>>(s->g, (const float*)s->trec, s->Nt, a.dt, s->md.rpic); s->launches++; }
+    if (s->Nv) { k_p2g<2><<<cdiv(s->Nv, 256), 256, 8 * 32 * sizeof(VRec), q>>>(s->g, (const float*)s->vrec, s->Nv, a.dt, s->md.rpic); s->launches++; }
+    if (ev) CK(cudaEventRecord(ev[2], q));
+    if (a.collider) {
+        k_collider_scatter<<<cdiv(s->cfg.n_mesh_f, 128), 128, 0, q>>>(s->g, s->cfg.n_mesh_f, s->mesh_faces, s->mesh_x, s->mesh_v, s->st, a.dt, a.advance_mesh ? 1 : 0);
+        s->launches++;
+    }
+    if (ev) CK(cudaEventRecord(ev[3], q));
+    if (a.mover) {
+        int tot = a.njt + s->cfg.num_joint_v + s->cfg.num_joint_f;
+        if (tot) {
+            k_mover_scatter<<<cdiv(tot, 128), 128, 0, q>>>(s->g, a.njt, s->cfg.num_joint_v, s->cfg.num_joint_f, s->Nt, s->joint_t, s->joint_v, s->joint_f, s->erec, s->trec, s->vrec, s->invE, s->invT, s->invV);
+            s->launches++;
+        }
+    }
+    if (ev) CK(cudaEventRecord(ev[4], q));
+    k_grid_update<<<148 * 4, 256, 0, q>>>(s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, s->d_bcs, n_bc, s->st);
+    s->launches++;
+    if (ev) CK(cudaEventRecord(ev[5], q));
+    if (s->Nv) { k_g2p_vertices<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->vrec, a.dt, s->debug ? s->dbg_f : nullptr); s->launches++; }
+    if (s->Nt) { k_g2p_traditional<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->trec, s->taux, a.dt); s->launches++; }
+    if (ev) CK(cudaEventRecord(ev[6], q));
+    if (s->Ne) { k_g2p_elements<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->erec, s->eaux, s->vrec, a.dt); s->launches++; }
+    if (ev) CK(cudaEventRecord(ev[7], q));
+    k_advance<<<1, 32, 0, q>>>(s->st, a.dt, s->d_bcs, n_bc);
+    s->launches++;
+    if (ev) {
+        CK(cudaEventRecord(ev[8], q));
+        s->pending.push_back(evs);
+    }
+}
+
+static void drain_profile(MpmSolver* s) {
+    for (auto& evs : s->pending) {
+        CK(cudaEventSynchronize(evs[8]));
+        float t[8];
+        for (int i = 0; i < 8; i++) CK(cudaEventElapsedTime(&t[i], evs[i], evs[i + 1]));
+        s->prof.stress_ms += t[0];
+        s->prof.p2g_ms += t[1];
+        s->prof.collider_scatter_ms += t[2];
+        s->prof.mover_scatter_ms += t[3];
+        s->prof.grid_ms += t[4];
+        s->prof.g2p_v_ms += t[5];
+        s->prof.g2p_e_ms += t[6];
+        s->prof.n_substeps++;
+        for (auto& e : evs) cudaEventDestroy(e);
+    }
+    s->pending.clear();
+}
+
+// ---------------------------------------------------------------- C-ABI
+#define API_BEGIN(s)              \
+    if (!(s)) return -1;          \
+    try {                         \
+        CK(cudaSetDevice((s)->cfg.device));
+#define API_END(s)                \
+    }                             \
+    catch (const std::string& e) { \
+        (s)->err = e;             \
+        return -2;                \
+    }                             \
+    return 0;
+
+extern "C" {
+
+int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
+    if (!cfg || !out) return -1;
+    MpmSolver* s = new MpmSolver();
+    try {
+        s->cfg = *cfg;
+        CK(cudaSetDevice(cfg->device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, cfg->device));
+        if (prop.major < 9) throw std::string("mpm_b200 needs sm_90+ vector atomics; built for sm_100a");
+        s->N = cfg->n_particles; s->Ne = cfg->n_elements; s->Nv = cfg->n_vertices;
+        s->Nnv = s->N - s->Nv; s->Nt = s->Nnv - s->Ne;
+        if (s->N <= 0 || s->Ne < 0 || s->Nv < 0 || s->Nt < 0 || cfg->n_grid < 8 || cfg->n_grid > 1024)
+            throw std::string("invalid particle counts or n_grid (8..1024)");
+        if (cfg->resort_interval > 0) s->resort_interval = cfg->resort_interval;
+        Grid& g = s->g;
+        g.n = cfg->n_grid;
+        g.nb = (g.n + BS - 1) / BS;
+        g.lim = cfg->grid_lim;
+        // dx, inv_dx exactly as init_other_params: python doubles rounded to f32 (mpm_data_structure.py:692-697)
+        g.dx = (float)((double)cfg->grid_lim / (double)cfg->n_grid);
+        g.inv_dx = (float)((double)cfg->n_grid / (double)cfg->grid_lim);
+        size_t nt = (size_t)g.nb * g.nb * g.nb;
+        g.cap = (int)std::min<size_t>(nt, (size_t)1 << 21);
+        g.table = s->dalloc<int>(nt);
+        g.n_slots = s->dalloc<int>(1);
+        g.slot_coord = s->dalloc<int>(g.cap);
+        g.flags = s->dalloc<int>(4);
+        size_t pn = (size_t)g.cap * BN;
+        g.acc = s->dalloc<float4>(pn);
+        g.vout = s->dalloc<float4>(pn);
+        g.colv = s->dalloc<float4>(pn);
+        g.coln = s->dalloc<float4>(pn);
+        g.mov = s->dalloc<float4>(pn);
+        g.dbg_acc = nullptr;
+        k_fill_int<<<1184, 256>>>(g.table, nt, -1);
+        s->erec = s->dalloc<PRec>(s->Ne + 32);
+        s->trec = s->dalloc<PRec>(s->Nt + 32);
+        s->vrec = s->dalloc<VRec>(s->Nv + 32);
+        s->eaux = s->dalloc<EAux>(s->Ne);
+        s->taux = s->dalloc<TAux>(s->Nt);
+        int nmax = std::max(s->Ne, std::max(s->Nt, s->Nv));
+        s->permE = s->dalloc<uint32_t>(s->Ne); s->permT = s->dalloc<uint32_t>(s->Nt); s->permV = s->dalloc<uint32_t>(s->Nv);
+        s->invE = s->dalloc<int>(s->Ne); s->invT = s->dalloc<int>(s->Nt); s->invV = s->dalloc<int>(s->Nv);
+        s->keys_in = s->dalloc<uint32_t>(nmax); s->keys_out = s->dalloc<uint32_t>(nmax); s->vals_in = s->dalloc<uint32_t>(nmax);
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, s->cub_bytes, s->keys_in, s->keys_out, s->vals_in, s->permE, nmax, 0, 32));
+        s->cub_tmp = s->dalloc<char>(s->cub_bytes);
+        Canon& c = s->canon;
+        int N = s->N, Nnv = s->Nnv;
+        c.x = s->dalloc<float>(3 * (size_t)N); c.v = s->dalloc<float>(3 * (size_t)N); c.C = s->dalloc<float>(9 * (size_t)N);
+        c.F = s->dalloc<float>(9 * (size_t)Nnv); c.Ft = s->dalloc<float>(9 * (size_t)Nnv); c.stress = s->dalloc<float>(9 * (size_t)Nnv);
+        c.d = s->dalloc<float>(9 * (size_t)s->Ne); c.Rinv = s->dalloc<float>(3 * (size_t)s->Ne); c.faces = s->dalloc<float>(3 * (size_t)s->Ne);
+        c.vforce = s->dalloc<float>(3 * (size_t)s->Nv);
+        c.vol = s->dalloc<float>(N); c.mass = s->dalloc<float>(N); c.mu = s->dalloc<float>(N); c.lam = s->dalloc<float>(N);
+        c.gamma = s->dalloc<float>(N); c.kappa = s->dalloc<float>(N); c.ys = s->dalloc<float>(N);
+        {   // F = F_trial = I by default (reset_state, mpm_data_structure.py:348-360)
+            std::vector<float> eye(9 * (size_t)std::max(Nnv, 1), 0.f);
+            for (int i = 0; i < Nnv; i++) eye[9 * (size_t)i] = eye[9 * (size_t)i + 4] = eye[9 * (size_t)i + 8] = 1.f;
+            CK(cudaMemcpy(c.F, eye.data(), 9 * (size_t)Nnv * sizeof(float), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(c.Ft, eye.data(), 9 * (size_t)Nnv * sizeof(float), cudaMemcpyHostToDevice));
+        }
+        s->mesh_faces = s->dalloc<int>(3 * (size_t)cfg->n_mesh_f);
+        s->mesh_x = s->dalloc<float>(3 * (size_t)cfg->n_mesh_v);
+        s->mesh_v = s->dalloc<float>(3 * (size_t)cfg->n_mesh_v);
+        s->joint_t = s->dalloc<float>(3 * (size_t)std::max(s->Nt, 1));
+        s->joint_v = s->dalloc<float>(3 * (size_t)std::max(cfg->num_joint_v, 1));
+        s->joint_f = s->dalloc<float>(3 * (size_t)std::max(cfg->num_joint_f, 1));
+        s->d_bcs = s->dalloc<BCDesc>(MAX_BC);
+        s->d_ops = s->dalloc<ParticleOp>(MAX_OPS);
+        s->st = s->dalloc<StepState>(1);
+        // model defaults (mpm_data_structure.py:686-715)
+        s->md.material = 0; s->md.hardening = 0; s->md.friction_coeff = 0.f; s->md.alpha = 0.f;
+        s->md.gx = s->md.gy = s->md.gz = 0.f; s->md.rpic = 0.f; s->md.damping = 1.1f;
+        s->md.xi = 0.f; s->md.plastic_viscosity = 0.f; s->md.softening = 0.1f;
+        CK(cudaFuncSetAttribute(k_p2g<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * (int)sizeof(PRec)));
+        CK(cudaFuncSetAttribute(k_p2g<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * (int)sizeof(PRec)));
+        CK(cudaFuncSetAttribute(k_p2g<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * (int)sizeof(VRec)));
+        CK(cudaDeviceSynchronize());
+        CK(cudaGetLastError());
+    } catch (const std::string& e) {
+        g_create_error = e;
+        for (void* p : s->allocs) cudaFree(p);
+        delete s;
+        return -2;
+    }
+    *out = s;
+    return 0;
+}
+
+void mpm_destroy(MpmSolver* s) {
+    if (!s) return;
+    cudaSetDevice(s->cfg.device);
+    cudaDeviceSynchronize();
+    for (void* p : s->allocs) cudaFree(p);
+    delete s;
+}
+
+const char* mpm_last_error(MpmSolver* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+
+int mpm_set_model(MpmSolver* s, const MpmModelParams* p) {
+    API_BEGIN(s)
+    s->md.material = p->material; s->md.hardening = p->hardening;
+    s->md.friction_coeff = p->friction_coeff; s->md.alpha = p->alpha;
+    s->md.gx = p->g[0]; s->md.gy = p->g[1]; s->md.gz = p->g[2];
+    s->md.rpic = p->rpic_damping; s->md.damping = p->grid_v_damping_scale;
+    s->md.xi = p->xi; s->md.plastic_viscosity = p->plastic_viscosity; s->md.softening = p->softening;
+    API_END(s)
+}
+
+int mpm_import_state(MpmSolver* s, const MpmParticleArrays* a, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    // bring the mirror up to date first so that a partial import keeps the other fields
+    export_to_canon(s, q);
+    Canon& c = s->canon;
+    size_t N = s->N, Nnv = s->Nnv, Ne = s->Ne;
+    auto cp = [&](float* dst, const float* src, size_t n) {
+        if (src && n) CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDefault, q));
+    };
+    cp(c.x, a->x, 3 * N); cp(c.v, a->v, 3 * N); cp(c.C, a->C, 9 * N);
+    cp(c.F, a->F, 9 * Nnv); cp(c.Ft, a->F_trial, 9 * Nnv);
+    cp(c.d, a->d, 9 * Ne); cp(c.Rinv, a->R_inv, 3 * Ne); cp(c.faces, a->faces, 3 * Ne);
+    cp(c.vol, a->vol, N); cp(c.mass, a->mass, N);
+    cp(c.mu, a->mu, N); cp(c.lam, a->lam, N); cp(c.gamma, a->gamma, N); cp(c.kappa, a->kappa, N);
+    cp(c.ys, a->yield_stress, N);
+    s->have_state = true;
+    s->need_sort = true;
+    API_END(s)
+}
+
+int mpm_export_state(MpmSolver* s, const MpmParticleArrays* a, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    if (s->need_sort && s->have_state && !s->canon_stale) { /* mirror already current */ }
+    export_to_canon(s, q);
+    Canon& c = s->canon;
+    size_t N = s->N, Nnv = s->Nnv, Ne = s->Ne, Nv = s->Nv;
+    auto cp = [&](float* dst, const float* src, size_t n) {
+        if (dst && n) CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDefault, q));
+    };
+    cp(a->x, c.x, 3 * N); cp(a->v, c.v, 3 * N); cp(a->C, c.C, 9 * N);
+    cp(a->F, c.F, 9 * Nnv); cp(a->F_trial, c.Ft, 9 * Nnv); cp(a->stress, c.stress, 9 * Nnv);
+    cp(a->d, c.d, 9 * Ne); cp(a->vertex_force, c.vforce, 3 * Nv);
+    cp(a->mu, c.mu, N); cp(a->lam, c.lam, N); cp(a->yield_stress, c.ys, N);
+    cp(a->mass, c.mass, N); cp(a->vol, c.vol, N);
+    API_END(s)
+}
+
+int mpm_set_body_mesh(MpmSolver* s, const int* faces, const float* points0, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    if (s->cfg.n_mesh_f == 0) throw std::string("solver was created without a body mesh");
+    CK(cudaMemcpyAsync(s->mesh_faces, faces, 3 * (size_t)s->cfg.n_mesh_f * sizeof(int), cudaMemcpyDefault, q));
+    if (points0) CK(cudaMemcpyAsync(s->mesh_x, points0, 3 * (size_t)s->cfg.n_mesh_v * sizeof(float), cudaMemcpyDefault, q));
+    API_END(s)
+}
+
+int mpm_add_mesh_collider(MpmSolver* s, float friction) {
+    API_BEGIN(s)
+    if (s->cfg.n_mesh_f == 0) throw std::string("add_mesh_collider: no body mesh");
+    if (s->has_collider) throw std::string("only one mesh collider is supported");
+    s->has_collider = true;
+    s->col_friction = friction;
+    API_END(s)
+}
+
+int mpm_add_particle_mover(MpmSolver* s) {
+    API_BEGIN(s)
+    if (s->has_mover) throw std::string("only one particle mover is supported");
+    s->has_mover = true;
+    API_END(s)
+}
+
+static int push_bc(MpmSolver* s, const BCDesc& b) {
+    if ((int)s->h_bcs.size() >= MAX_BC) { s->err = "too many grid boundary conditions"; return -2; }
+    s->h_bcs.push_back(b);
+    s->bcs_dirty = true;
+    return 0;
+}
+
+int mpm_add_surface_collider(MpmSolver* s, const float point[3], const float normal[3], int surface_type, float friction,
+                             float start_time, float end_time) {
+    if (!s) return -1;
+    BCDesc b{};
+    b.kind = 0; b.surface_type = surface_type; b.friction = friction; b.start_time = start_time; b.end_time = end_time;
+    for (int i = 0; i < 3; i++) { b.point[i] = point[i]; b.normal[i] = normal[i]; }
+    return push_bc(s, b);
+}
+int mpm_set_velocity_on_cuboid(MpmSolver* s, const float point[3], const float size[3], const float velocity[3],
+                               float start_time, float end_time, int reset) {
+    if (!s) return -1;
+    BCDesc b{};
+    b.kind = 1; b.reset = reset; b.start_time = start_time; b.end_time = end_time;
+    for (int i = 0; i < 3; i++) { b.point[i] = point[i]; b.size[i] = size[i]; b.velocity[i] = velocity[i]; }
+    return push_bc(s, b);
+}
+int mpm_add_bounding_box(MpmSolver* s, float start_time, float end_time) {
+    if (!s) return -1;
+    BCDesc b{};
+    b.kind = 2; b.start_time = start_time; b.end_time = end_time;
+    return push_bc(s, b);
+}
+int mpm_enforce_grid_velocity_by_mask(MpmSolver* s, const int* mask, void* stream) {
+    API_BEGIN(s)
+    size_t n3 = (size_t)s->g.n * s->g.n * s->g.n;
+    int* d = s->dalloc<int>(n3);
+    CK(cudaMemcpyAsync(d, mask, n3 * sizeof(int), cudaMemcpyDefault, (cudaStream_t)stream));
+    BCDesc b{};
+    b.kind = 3; b.mask = d; b.start_time = 0.f; b.end_time = 1e30f;
+    if (push_bc(s, b)) return -2;
+    API_END(s)
+}
+int mpm_add_particle_op(MpmSolver* s, int kind, const float vec[3], const int* mask, float start_time, float end_time,
+                        void* stream) {
+    API_BEGIN(s)
+    if ((int)s->h_ops.size() >= MAX_OPS) throw std::string("too many particle operations");
+    int* d = s->dalloc<int>(s->N);
+    CK(cudaMemcpyAsync(d, mask, (size_t)s->N * sizeof(int), cudaMemcpyDefault, (cudaStream_t)stream));
+    ParticleOp op{};
+    op.kind = kind; op.mask = d; op.start_time = start_time; op.end_time = end_time;
+    for (int i = 0; i < 3; i++) op.vec[i] = vec[i];
+    s->h_ops.push_back(op);
+    s->ops_dirty = true;
+    API_END(s)
+}
+
+int mpm_set_time(MpmSolver* s, double t) {
+    API_BEGIN(s)
+    StepState h{t, 0, 0};
+    CK(cudaMemcpy(s->st, &h, sizeof h, cudaMemcpyHostToDevice));
+    s->host_time = t;
+    API_END(s)
+}
+
+int mpm_step(MpmSolver* s, float dt, int nsub, const MpmFrameInputs* in, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    if (!s->have_state) throw std::string("mpm_step before mpm_import_state");
+    MpmFrameInputs none{};
+    if (!in) in = &none;
+    if (in->n_joint_t > s->Nt) throw std::string("n_joint_t exceeds the number of traditional particles");
+    upload_lists(s, q);
+    size_t mv3 = 3 * (size_t)s->cfg.n_mesh_v * sizeof(float);
+    if (in->mesh_x && mv3) CK(cudaMemcpyAsync(s->mesh_x, in->mesh_x, mv3, cudaMemcpyDefault, q));
+    if (in->mesh_v && mv3) CK(cudaMemcpyAsync(s->mesh_v, in->mesh_v, mv3, cudaMemcpyDefault, q));
+    SubstepArgs a{};
+    a.dt = dt;
+    a.collider = s->has_collider;
+    a.advance_mesh = in->mesh_x != nullptr && nsub > 1;
+    // the mover runs only when BOTH joint_verts_v and joint_faces_v are given (mpm_solver.py:421)
+    a.mover = s->has_mover && in->joint_verts_v && in->joint_faces_v;
+    a.njt = 0;
+    if (a.mover) {
+        if (s->cfg.num_joint_v) CK(cudaMemcpyAsync(s->joint_v, in->joint_verts_v, 3 * (size_t)s->cfg.num_joint_v * sizeof(float), cudaMemcpyDefault, q));
+        if (s->cfg.num_joint_f) CK(cudaMemcpyAsync(s->joint_f, in->joint_faces_v, 3 * (size_t)s->cfg.num_joint_f * sizeof(float), cudaMemcpyDefault, q));
+        if (in->joint_traditional_v && in->n_joint_t > 0) {
+            a.njt = in->n_joint_t;
+            CK(cudaMemcpyAsync(s->joint_t, in->joint_traditional_v, 3 * (size_t)a.njt * sizeof(float), cudaMemcpyDefault, q));
+        }
+    }
+    k_reset_k<<<1, 1, 0, q>>>(s->st);
+    s->launches++;
+    for (int k = 0; k < nsub; k++) {
+        if (s->need_sort || s->since_sort >= s->resort_interval) resort(s, q);
+        launch_substep(s, a, q);
+        s->since_sort++;
+        s->n_substeps++;
+        s->canon_stale = true;
+        s->host_time += (double)dt;
+    }
+    CK(cudaGetLastError());
+    API_END(s)
+}
+
+int mpm_set_debug(MpmSolver* s, int on) {
+    API_BEGIN(s)
+    s->debug = on != 0;
+    if (s->debug && !s->g.dbg_acc) {
+        s->g.dbg_acc = s->dalloc<float4>((size_t)s->g.cap * BN);
+        s->dbg_f = s->dalloc<float>(3 * (size_t)s->Nv + 3);
+    }
+    if (!s->debug) s->g.dbg_acc = nullptr;
+    API_END(s)
+}
+
+int mpm_export_grid(MpmSolver* s, float* grid_m, float* grid_v_in, float* grid_v_out, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    size_t n3 = (size_t)s->g.n * s->g.n * s->g.n;
+    float *dm = nullptr, *dvi = nullptr, *dvo = nullptr;
+    auto tmp = [&](size_t n) { void* p; CK(cudaMalloc(&p, n * sizeof(float))); CK(cudaMemsetAsync(p, 0, n * sizeof(float), q)); return (float*)p; };
+    if (grid_m) dm = tmp(n3);
+    if (grid_v_in) dvi = tmp(3 * n3);
+    if (grid_v_out) dvo = tmp(3 * n3);
+    k_export_grid<<<cdiv((long long)s->g.cap * BN, 256), 256, 0, q>>>(s->g, dm, dvi, dvo);
+    if (dm) CK(cudaMemcpyAsync(grid_m, dm, n3 * sizeof(float), cudaMemcpyDefault, q));
+    if (dvi) CK(cudaMemcpyAsync(grid_v_in, dvi, 3 * n3 * sizeof(float), cudaMemcpyDefault, q));
+    if (dvo) CK(cudaMemcpyAsync(grid_v_out, dvo, 3 * n3 * sizeof(float), cudaMemcpyDefault, q));
+    CK(cudaStreamSynchronize(q));
+    if (dm) cudaFree(dm);
+    if (dvi) cudaFree(dvi);
+    if (dvo) cudaFree(dvo);
+    API_END(s)
+}
+
+int mpm_set_profiling(MpmSolver* s, int on) {
+    API_BEGIN(s)
+    if (!on) drain_profile(s);
+    s->profiling = on != 0;
+    API_END(s)
+}
+
+int mpm_get_profile(MpmSolver* s, MpmProfile* out) {
+    API_BEGIN(s)
+    drain_profile(s);
+    *out = s->prof;
+    API_END(s)
+}
+
+int mpm_get_stats(MpmSolver* s, MpmStats* out, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    if (s->need_sort && s->have_state) resort(s, q);
+    int n_slots = 0, flags[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(&n_slots, s->g.n_slots, sizeof(int), cudaMemcpyDeviceToHost, q));
+    CK(cudaMemcpyAsync(flags, s->g.flags, sizeof flags, cudaMemcpyDeviceToHost, q));
+    CK(cudaStreamSynchronize(q));
+    n_slots = std::min(n_slots, s->g.cap);
+    unsigned long long* mask = nullptr;
+    unsigned long long* cnt = nullptr;
+    CK(cudaMalloc(&mask, ((size_t)n_slots + 1) * sizeof(unsigned long long)));
+    CK(cudaMalloc(&cnt, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(mask, 0, ((size_t)n_slots + 1) * sizeof(unsigned long long), q));
+    CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), q));
+    if (s->Ne) k_mark_nodes<PRec><<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->erec, mask);
+    if (s->Nt) k_mark_nodes<PRec><<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->trec, mask);
+    if (s->Nv) k_mark_nodes<VRec><<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->vrec, mask);
+    if (n_slots) k_popc<<<cdiv(n_slots, 256), 256, 0, q>>>(mask, n_slots, cnt);
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, cnt, sizeof h, cudaMemcpyDeviceToHost, q));
+    CK(cudaStreamSynchronize(q));
+    cudaFree(mask);
+    cudaFree(cnt);
+    out->n_active_blocks = n_slots;
+    out->n_active_nodes = (long long)h;
+    out->n_resorts = s->n_resorts;
+    out->n_substeps = s->n_substeps;
+    out->overflow = (flags[0] ? 1 : 0) | (flags[1] ? 2 : 0);
+    out->gpu_launches = s->launches;
+    out->sim_time = s->host_time;
+    API_END(s)
+}
+
+int mpm_force_resort(MpmSolver* s) {
+    API_BEGIN(s)
+    s->since_sort = s->resort_interval;
+    API_END(s)
+}
+
+}  // extern "C"

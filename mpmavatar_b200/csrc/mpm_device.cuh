@@ -1,0 +1,272 @@
+// Device-side data layout and math for the B200 MPM substep solver.
+//
+// Grid: sparse pool of 4x4x4-node blocks.  A dense block table (nb^3 ints) maps block
+// coordinates to a pool slot (-1 = not allocated); every per-node quantity is a float4
+// so that one P2G contribution is ONE 16-byte REDG.E.ADD.F32x4 (sm_90+ vector atomic):
+//   acc  {m*vx, m*vy, m*vz, m}      <- P2G                      (mpm_utils.py:548-557)
+//   vout {vx, vy, vz, -}            <- grid update, read by G2P (mpm_utils.py:561-572)
+//   colv {w*vx, w*vy, w*vz, w}, coln {w*nx, w*ny, w*nz, -}  <- body-mesh collider scatter
+//                                                              (mpm_solver.py:829-880)
+//   mov  {w*vx, w*vy, w*vz, w}      <- particle-mover scatter  (mpm_solver.py:677-788)
+// Invariant: between substeps all accumulators of allocated slots are zero (the grid
+// update re-zeroes what it consumed), so there is no zero_grid sweep.
+//
+// Particles: three classes kept in separate arrays of fixed-size AoS records, each class
+// sorted by (Morton(block), cell-in-block).  A record is what P2G consumes, so one
+// contiguous slab of records feeds a warp (bulk-copy friendly).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mpm {
+
+constexpr int BS = 4;    // block edge in nodes
+constexpr int BN = 64;   // nodes per block
+constexpr int MAX_BC = 16;
+constexpr int MAX_OPS = 64;
+
+struct __align__(16) PRec {  // element / traditional particle record, 112 B
+    float4 xm;    // x, y, z, mass
+    float4 vv;    // vx, vy, vz, vol
+    float C[9];   // APIC affine matrix, row-major
+    float S[9];   // Kirchhoff stress (elements: already times vol, mpm_utils.py:177)
+    float pad[2];
+};
+struct __align__(16) VRec {  // cloth-vertex particle record, 80 B
+    float4 xm;
+    float4 vv;
+    float C[9];
+    float f[3];   // vertex_force accumulated by the element stress kernel
+};
+struct __align__(16) EAux {  // element constitutive state, 80 B
+    float dc[9];  // direction matrix, COLUMN-major: d1 | d2 | d3
+    float Rinv[3];
+    int face[3];  // SORTED vertex slots of the three corners
+    float mu, lam, gamma, kappa, vol;
+};
+struct __align__(16) TAux {  // traditional-particle constitutive state, 96 B
+    float F[9];
+    float Ft[9];
+    float mu, lam, ys;
+    float pad[3];
+};
+static_assert(sizeof(PRec) == 112 && sizeof(VRec) == 80 && sizeof(EAux) == 80 && sizeof(TAux) == 96, "layout");
+
+struct Grid {
+    int n, nb;
+    float dx, inv_dx, lim;
+    int cap;
+    int* table;       // [nb^3]
+    int* n_slots;     // device counter
+    int* slot_coord;  // [cap] bx | by<<10 | bz<<20
+    float4 *acc, *vout, *colv, *coln, *mov;
+    float4* dbg_acc;  // copy of acc taken by the grid update when debugging (else null)
+    int* flags;       // [0] pool overflow, [1] scatter/gather hit an unallocated block
+};
+
+struct StepState {
+    double time;  // MPMWARP.time (mpm_solver.py:28,536)
+    int k;        // substep index inside the current mpm_step call
+    int pad;
+};
+
+struct BCDesc {  // one grid_postprocess entry (mpm_solver.py:564-658, 929-1053, 1330-1355)
+    int kind;    // 0 surface, 1 cuboid, 2 bounding box, 3 mask
+    int surface_type, reset, pad;
+    float point[3], normal[3], size[3], velocity[3];
+    float friction, start_time, end_time;
+    const int* mask;
+};
+
+struct ParticleOp {  // pre-P2G operations (mpm_solver.py:1058-1151, 1289-1328, 1360-1417)
+    int kind;        // 0 impulse/mass, 1 impulse, 2 set velocity
+    float vec[3];
+    float start_time, end_time;
+    const int* mask;  // canonical order [N]
+};
+
+struct ModelDev {
+    int material, hardening;
+    float friction_coeff, alpha;
+    float gx, gy, gz;
+    float rpic, damping, xi, plastic_viscosity, softening;
+};
+
+// ------------------------------------------------------------------ small math
+__device__ __forceinline__ void mat_mul(const float* a, const float* b, float* o) {
+    float t[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) t[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; i++) o[i] = t[i];
+}
+// o = a * b^T
+__device__ __forceinline__ void mat_mul_bt(const float* a, const float* b, float* o) {
+    float t[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) t[3 * i + j] = a[3 * i] * b[3 * j] + a[3 * i + 1] * b[3 * j + 1] + a[3 * i + 2] * b[3 * j + 2];
+#pragma unroll
+    for (int i = 0; i < 9; i++) o[i] = t[i];
+}
+__device__ __forceinline__ float det3(const float* m) {
+    return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+__device__ __forceinline__ float len3(float a, float b, float c) { return sqrtf(a * a + b * b + c * c); }
+
+// Jacobi rotation on the symmetric matrix (bpp,bqq,bpq; brp,brq with r the third index) and V columns p,q
+__device__ __forceinline__ void jrot(float& bpp, float& bqq, float& bpq, float& brp, float& brq, float* V, int p, int q) {
+    if (fabsf(bpq) < 1e-30f) return;
+    float theta = (bqq - bpp) / (2.0f * bpq);
+    float t = copysignf(1.0f, theta) / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
+    float c = rsqrtf(t * t + 1.0f), s = t * c;
+    bpp -= t * bpq;
+    bqq += t * bpq;
+    bpq = 0.0f;
+    float rp = brp, rq = brq;
+    brp = c * rp - s * rq;
+    brq = s * rp + c * rq;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        float vp = V[3 * r + p], vq = V[3 * r + q];
+        V[3 * r + p] = c * vp - s * vq;
+        V[3 * r + q] = s * vp + c * vq;
+    }
+}
+__device__ __forceinline__ void swap_cols(float* V, int a, int b, float& la, float& lb) {
+    // swap two columns and negate one to keep det V = +1
+    float t = la; la = lb; lb = t;
+#pragma unroll
+    for (int r = 0; r < 3; r++) { float x = V[3 * r + a]; V[3 * r + a] = V[3 * r + b]; V[3 * r + b] = -x; }
+}
+// A = U diag(S) V^T, det U = det V = +1, S[0]>=S[1]>=|S[2]| (wp.svd3 convention; stands in for
+// warp-lang's McAdams solver at mpm_utils.py:217,265,322,369,1077)
+__device__ __forceinline__ void svd3(const float* A, float* U, float* S, float* V) {
+    float b00 = A[0] * A[0] + A[3] * A[3] + A[6] * A[6];
+    float b11 = A[1] * A[1] + A[4] * A[4] + A[7] * A[7];
+    float b22 = A[2] * A[2] + A[5] * A[5] + A[8] * A[8];
+    float b01 = A[0] * A[1] + A[3] * A[4] + A[6] * A[7];
+    float b02 = A[0] * A[2] + A[3] * A[5] + A[6] * A[8];
+    float b12 = A[1] * A[2] + A[4] * A[5] + A[7] * A[8];
+    V[0] = 1; V[1] = 0; V[2] = 0; V[3] = 0; V[4] = 1; V[5] = 0; V[6] = 0; V[7] = 0; V[8] = 1;
+#pragma unroll 1
+    for (int sweep = 0; sweep < 6; sweep++) {
+        jrot(b00, b11, b01, b02, b12, V, 0, 1);
+        jrot(b00, b22, b02, b01, b12, V, 0, 2);
+        jrot(b11, b22, b12, b01, b02, V, 1, 2);
+    }
+    if (b00 < b11) swap_cols(V, 0, 1, b00, b11);
+    if (b00 < b22) swap_cols(V, 0, 2, b00, b22);
+    if (b11 < b22) swap_cols(V, 1, 2, b11, b22);
+    float av[9];  // av[3*r+c] = (A V)[r][c]
+    mat_mul(A, V, av);
+    float s0 = len3(av[0], av[3], av[6]);
+    float u0[3], u1[3], u2[3];
+    if (s0 > 1e-30f) { float i0 = 1.0f / s0; u0[0] = av[0] * i0; u0[1] = av[3] * i0; u0[2] = av[6] * i0; }
+    else { u0[0] = 1; u0[1] = 0; u0[2] = 0; }
+    float dp = u0[0] * av[1] + u0[1] * av[4] + u0[2] * av[7];
+    float w0 = av[1] - dp * u0[0], w1 = av[4] - dp * u0[1], w2 = av[7] - dp * u0[2];
+    float n1 = len3(w0, w1, w2);
+    if (n1 > 1e-6f * fmaxf(s0, 1e-30f)) { float i1 = 1.0f / n1; u1[0] = w0 * i1; u1[1] = w1 * i1; u1[2] = w2 * i1; }
+    else {
+        float a0 = fabsf(u0[0]), a1 = fabsf(u0[1]), a2 = fabsf(u0[2]);
+        float e0 = (a0 <= a1 && a0 <= a2) ? 1.f : 0.f, e1 = (e0 == 0.f && a1 <= a2) ? 1.f : 0.f, e2 = 1.f - e0 - e1;
+        float dd = e0 * u0[0] + e1 * u0[1] + e2 * u0[2];
+        w0 = e0 - dd * u0[0]; w1 = e1 - dd * u0[1]; w2 = e2 - dd * u0[2];
+        float i1 = rsqrtf(w0 * w0 + w1 * w1 + w2 * w2);
+        u1[0] = w0 * i1; u1[1] = w1 * i1; u1[2] = w2 * i1;
+    }
+    u2[0] = u0[1] * u1[2] - u0[2] * u1[1];
+    u2[1] = u0[2] * u1[0] - u0[0] * u1[2];
+    u2[2] = u0[0] * u1[1] - u0[1] * u1[0];
+    S[0] = s0;
+    S[1] = u1[0] * av[1] + u1[1] * av[4] + u1[2] * av[7];
+    S[2] = u2[0] * av[2] + u2[1] * av[5] + u2[2] * av[8];
+#pragma unroll
+    for (int r = 0; r < 3; r++) { U[3 * r] = u0[r]; U[3 * r + 1] = u1[r]; U[3 * r + 2] = u2[r]; }
+}
+// o = U diag(dg) V^T
+__device__ __forceinline__ void diag_sandwich(const float* U, const float* dg, const float* V, float* o) {
+    float ud[9];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) ud[3 * r + c] = U[3 * r + c] * dg[c];
+    mat_mul_bt(ud, V, o);
+}
+
+// ------------------------------------------------------------------ grid helpers
+__device__ __forceinline__ uint32_t part1by2(uint32_t x) {
+    x &= 0x3ff;
+    x = (x | (x << 16)) & 0x30000ff;
+    x = (x | (x << 8)) & 0x300f00f;
+    x = (x | (x << 4)) & 0x30c30c3;
+    x = (x | (x << 2)) & 0x9249249;
+    return x;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// wp.int(x*inv_dx - 0.5) (truncation toward zero), mpm_utils.py:499-502
+__device__ __forceinline__ int base_of(float x, float inv_dx) { return (int)(x * inv_dx - 0.5f); }
+
+__device__ __forceinline__ uint32_t sort_key(const Grid& g, float x, float y, float z) {
+    int bx = clampi(base_of(x, g.inv_dx), 0, g.n - 1), by = clampi(base_of(y, g.inv_dx), 0, g.n - 1),
+        bz = clampi(base_of(z, g.inv_dx), 0, g.n - 1);
+    uint32_t m = part1by2(bx >> 2) | (part1by2(by >> 2) << 1) | (part1by2(bz >> 2) << 2);
+    return (m << 6) | ((bx & 3) << 4) | ((by & 3) << 2) | (bz & 3);
+}
+__device__ __forceinline__ int table_index(const Grid& g, int bx, int by, int bz) { return (bx * g.nb + by) * g.nb + bz; }
+
+__device__ __forceinline__ int lookup_slot(const Grid& g, int bx, int by, int bz) {
+    return g.table[table_index(g, bx, by, bz)];  // plain load: G2P allocates blocks in the same kernel
+}
+// allocate the block if needed; the slot value is only needed by LATER kernels
+__device__ __forceinline__ void ensure_block(const Grid& g, int bx, int by, int bz) {
+    int* t = &g.table[table_index(g, bx, by, bz)];
+    int s = *(volatile int*)t;
+    if (s != -1) return;
+    int old = atomicCAS(t, -1, -2);
+    if (old != -1) return;
+    int slot = atomicAdd(g.n_slots, 1);
+    if (slot >= g.cap) {
+        g.flags[0] = 1;
+        atomicExch(t, -1);
+        return;
+    }
+    g.slot_coord[slot] = bx | (by << 10) | (bz << 20);
+    __threadfence();
+    atomicExch(t, slot);
+}
+// blocks covered by the 3^3 stencil starting at node (bx,by,bz)
+__device__ __forceinline__ void ensure_stencil_blocks(const Grid& g, float x, float y, float z) {
+    int b0 = clampi(base_of(x, g.inv_dx), 0, g.n - 1), b1 = clampi(base_of(y, g.inv_dx), 0, g.n - 1),
+        b2 = clampi(base_of(z, g.inv_dx), 0, g.n - 1);
+    int x0 = b0 >> 2, x1 = min(b0 + 2, g.n - 1) >> 2;
+    int y0 = b1 >> 2, y1 = min(b1 + 2, g.n - 1) >> 2;
+    int z0 = b2 >> 2, z1 = min(b2 + 2, g.n - 1) >> 2;
+    for (int a = x0; a <= x1; a++)
+        for (int b = y0; b <= y1; b++)
+            for (int c = z0; c <= z1; c++) ensure_block(g, a, b, c);
+}
+// pool index of node (ix,iy,iz) or -1
+__device__ __forceinline__ int node_index(const Grid& g, int ix, int iy, int iz) {
+    if ((unsigned)ix >= (unsigned)g.n || (unsigned)iy >= (unsigned)g.n || (unsigned)iz >= (unsigned)g.n) return -1;
+    int s = lookup_slot(g, ix >> 2, iy >> 2, iz >> 2);
+    if (s < 0) return -1;
+    return s * BN + ((ix & 3) << 4) + ((iy & 3) << 2) + (iz & 3);
+}
+
+// quadratic B-spline factor of stencil offset i at fractional position f (mpm_utils.py:506-514):
+// w = A (f - s)^2 + B, dw = 2A (f - s) with (A,s,B) = (.5,1.5,0), (-1,1,.75), (.5,.5,0)
+__device__ __forceinline__ void bspline(float f, int i, float& w, float& dw) {
+    float s = 1.5f - 0.5f * (float)i;
+    float A = (i == 1) ? -1.0f : 0.5f;
+    float B = (i == 1) ? 0.75f : 0.0f;
+    float t = f - s;
+    w = A * t * t + B;
+    dw = 2.0f * A * t;
+}
+
+}  // namespace mpm

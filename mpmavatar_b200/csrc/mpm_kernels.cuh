@@ -1,0 +1,705 @@
+// Kernels of one MPM substep (launch order = MPMWARP.p2g2p, warp_mpm/mpm_solver.py:229-536).
+#pragma once
+#include "mpm_device.cuh"
+
+namespace mpm {
+
+// ============================================================ constitutive update
+// Fused anisotropy_return_mapping + kirchoff_stress_Anisotropy (mpm_utils.py:179-209, 101-177).
+// The reference runs wp.qr3 twice on the same d1,d2; the second QR only differs in the third
+// column of R, which is exactly the return-mapped (R02,R12,R22), so one QR serves both.
+// wp.svd3 of [[F11,F12,0],[0,F22,0],[0,0,0]] is only used for U2 V2^T = polar rotation of the
+// upper-triangular 2x2, which has the closed form [[a, b],[-b, a]]/|.|, a=F11+F22, b=F12.
+__global__ void __launch_bounds__(128) k_stress_elements(int Ne, EAux* __restrict__ aux, PRec* __restrict__ rec,
+                                                         VRec* __restrict__ vrec, float friction_coeff) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Ne) return;
+    EAux a = aux[e];
+    const float* d1 = &a.dc[0];
+    const float* d2 = &a.dc[3];
+    const float* d3 = &a.dc[6];
+    // rotation QR, sign-normalised (R00>0, R11>0, det Q=+1): Gram-Schmidt with q3 = q1 x q2
+    float r00 = len3(d1[0], d1[1], d1[2]);
+    float i00 = 1.0f / r00;
+    float q1[3] = {d1[0] * i00, d1[1] * i00, d1[2] * i00};
+    float r01 = q1[0] * d2[0] + q1[1] * d2[1] + q1[2] * d2[2];
+    float u2[3] = {d2[0] - r01 * q1[0], d2[1] - r01 * q1[1], d2[2] - r01 * q1[2]};
+    float r11 = len3(u2[0], u2[1], u2[2]);
+    float i11 = 1.0f / r11;
+    float q2[3] = {u2[0] * i11, u2[1] * i11, u2[2] * i11};
+    float q3[3] = {q1[1] * q2[2] - q1[2] * q2[1], q1[2] * q2[0] - q1[0] * q2[2], q1[0] * q2[1] - q1[1] * q2[0]};
+    float r02 = q1[0] * d3[0] + q1[1] * d3[1] + q1[2] * d3[2];
+    float r12 = q2[0] * d3[0] + q2[1] * d3[1] + q2[2] * d3[2];
+    float r22 = q3[0] * d3[0] + q3[1] * d3[1] + q3[2] * d3[2];
+    // return mapping (mpm_utils.py:196-204)
+    if (r22 > 1.0f) {
+        r22 = 1.0f;
+    } else {
+        float fn = a.kappa * (1.0f - r22) * (1.0f - r22);
+        float ff = a.gamma * sqrtf(r02 * r02 + r12 * r12);
+        if (ff > friction_coeff * fn) {
+            float sc = friction_coeff * fn / ff;
+            r02 *= sc;
+            r12 *= sc;
+        }
+    }
+    float nd3[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) nd3[r] = q1[r] * r02 + q2[r] * r12 + q3[r] * r22;
+    // stress (mpm_utils.py:125-177) with R = [r00 r01 r02; 0 r11 r12; 0 0 r22]
+    float iD11 = a.Rinv[0], iD12 = a.Rinv[1], iD22 = a.Rinv[2];
+    float F11 = r00 * iD11, F12 = r00 * iD12 + r01 * iD22, F22 = r11 * iD22;
+    float pa = F11 + F22, pb = F12;
+    float pin = rsqrtf(pa * pa + pb * pb);
+    float c = pa * pin, s = pb * pin;  // Rot = [[c, s], [-s, c]]
+    float J = F11 * F22;
+    float lj = a.lam * (J - 1.0f);
+    float k00 = 2.0f * a.mu * (F11 - c) + lj * F22;
+    float k01 = 2.0f * a.mu * (F12 - s);
+    float k11 = 2.0f * a.mu * (F22 - c) + lj * F11;  // K2[1,0] is never used (mpm_utils.py:146-148)
+    float dr13 = a.gamma * r02, dr23 = a.gamma * r12;
+    float dr33 = (r22 > 1.0f) ? 0.0f : -a.kappa * (1.0f - r22) * (1.0f - r22);
+    // K3 = dr * RiDT, RiDT = [F11 0 0; F12 F22 0; r02 r12 r22]
+    float K00 = k00 * F11 + k01 * F12 + dr13 * r02;
+    float K01 = k01 * F22 + dr13 * r12;
+    float K02 = dr13 * r22;
+    float K11 = k11 * F22 + dr23 * r12;
+    float K12 = dr23 * r22;
+    float K22 = dr33 * r22;
+    // inverse of lower-triangular RiDT (mpm_utils.py:87-99)
+    float invdet = 1.0f / (F11 * F22 * r22);
+    float I00 = F22 * r22 * invdet, I10 = -F12 * r22 * invdet, I11 = F11 * r22 * invdet;
+    float I20 = (F12 * r12 - r02 * F22) * invdet, I21 = -F11 * r12 * invdet, I22 = F11 * F22 * invdet;
+    // M = K3sym * RiDT^-1
+    float M00 = K00 * I00 + K01 * I10 + K02 * I20, M01 = K01 * I11 + K02 * I21, M02 = K02 * I22;
+    float M10 = K01 * I00 + K11 * I10 + K12 * I20, M11 = K11 * I11 + K12 * I21, M12 = K12 * I22;
+    float M20 = K02 * I00 + K12 * I10 + K22 * I20, M21 = K12 * I11 + K22 * I21, M22 = K22 * I22;
+    float P1[3], P2[3], P3[3];  // columns of P = Q M
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        P1[r] = q1[r] * M00 + q2[r] * M10 + q3[r] * M20;
+        P2[r] = q1[r] * M01 + q2[r] * M11 + q3[r] * M21;
+        P3[r] = q1[r] * M02 + q2[r] * M12 + q3[r] * M22;
+    }
+    float vol = a.vol;
+    float f1[3], f2[3], f3[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        f2[r] = -vol * (iD11 * P1[r] + iD12 * P2[r]);
+        f3[r] = -vol * iD22 * P2[r];
+        f1[r] = -(f2[r] + f3[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        atomicAdd(&vrec[a.face[0]].f[r], f1[r]);
+        atomicAdd(&vrec[a.face[1]].f[r], f2[r]);
+        atomicAdd(&vrec[a.face[2]].f[r], f3[r]);
+    }
+    // stress = vol * P3 (x) d3 with the return-mapped d3
+    PRec* pr = &rec[e];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) pr->S[3 * r + cc] = vol * (P3[r] * nd3[cc]);
+    aux[e].dc[6] = nd3[0];
+    aux[e].dc[7] = nd3[1];
+    aux[e].dc[8] = nd3[2];
+}
+
+// return mappings + stress for traditional particles (mpm_utils.py:1047-1103, 212-399, 8-84)
+__global__ void __launch_bounds__(128) k_stress_traditional(int Nt, TAux* __restrict__ aux, PRec* __restrict__ rec,
+                                                            ModelDev md, float dt) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Nt) return;
+    TAux a = aux[p];
+    float F[9], U[9], V[9], sg[3];
+    float mu = a.mu, lam = a.lam, ys = a.ys;
+    int mat = md.material;
+#pragma unroll
+    for (int i = 0; i < 9; i++) F[i] = a.Ft[i];
+    if (mat == 1 || mat == 5) {  // von Mises (:212-255) / with damage (:258-311)
+        svd3(a.Ft, U, sg, V);
+        float sc[3], eps[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { sc[i] = fmaxf(sg[i], 0.01f); eps[i] = logf(sc[i]); }
+        float tr = eps[0] + eps[1] + eps[2], temp = tr / 3.0f;
+        float tau[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) tau[i] = 2.0f * mu * eps[i] + lam * tr;
+        float st = tau[0] + tau[1] + tau[2];
+        float cn = len3(tau[0] - st / 3.0f, tau[1] - st / 3.0f, tau[2] - st / 3.0f);
+        if (cn > ys && !(mat == 5 && ys <= 0.0f)) {
+            float eh[3] = {eps[0] - temp, eps[1] - temp, eps[2] - temp};
+            float ehn = len3(eh[0], eh[1], eh[2]) + 1e-6f;
+            float dg = ehn - ys / (2.0f * mu);
+            float corr[3] = {(dg / ehn) * eh[0], (dg / ehn) * eh[1], (dg / ehn) * eh[2]};
+            float se[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) se[i] = expf(eps[i] - corr[i]);
+            if (mat == 5) {
+                ys = ys - md.softening * len3(corr[0], corr[1], corr[2]);
+                if (ys <= 0.0f) { mu = 0.0f; lam = 0.0f; }
+            }
+            diag_sandwich(U, se, V, F);
+            if (md.hardening == 1) ys = ys + 2.0f * mu * md.xi * dg;
+        }
+    } else if (mat == 2) {  // sand (:362-399)
+        svd3(a.Ft, U, sg, V);
+        float eps[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) eps[i] = logf(fmaxf(fabsf(sg[i]), 1e-14f));
+        float tr = eps[0] + eps[1] + eps[2];
+        float eh[3] = {eps[0] - tr / 3.0f, eps[1] - tr / 3.0f, eps[2] - tr / 3.0f};
+        float ehn = len3(eh[0], eh[1], eh[2]);
+        float dg = ehn + (3.0f * lam + 2.0f * mu) / (2.0f * mu) * tr * md.alpha;
+        if (dg > 0.0f && tr > 0.0f) mat_mul_bt(U, V, F);
+        if (dg > 0.0f && tr <= 0.0f) {
+            float sn[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) sn[i] = expf(eps[i] - eh[i] * (dg / ehn));
+            diag_sandwich(U, sn, V, F);
+        }
+    } else if (mat == 3) {  // viscoplastic StVK (:315-359)
+        svd3(a.Ft, U, sg, V);
+        float sc[3], eps[3], b[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { sc[i] = fmaxf(sg[i], 0.01f); b[i] = sc[i] * sc[i]; eps[i] = logf(sc[i]); }
+        float tr = eps[0] + eps[1] + eps[2];
+        float st[3] = {2.0f * mu * (eps[0] - tr / 3.0f), 2.0f * mu * (eps[1] - tr / 3.0f), 2.0f * mu * (eps[2] - tr / 3.0f)};
+        float stn = len3(st[0], st[1], st[2]);
+        float y = stn - sqrtf(2.0f / 3.0f) * ys;
+        if (y > 0.0f) {
+            float mu_hat = mu * (b[0] + b[1] + b[2]) / 3.0f;
+            float snn = stn - y / (1.0f + md.plastic_viscosity / (2.0f * mu_hat * dt));
+            float se[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) se[i] = expf(1.0f / (2.0f * mu) * ((snn / stn) * st[i]) + tr / 3.0f);
+            diag_sandwich(U, se, V, F);
+        }
+    }
+    // stress from F (:1072-1103)
+    float J = det3(F);
+    svd3(F, U, sg, V);
+    float S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (mat == 0 || mat == 5) {  // fixed corotated (:8-15)
+        float Rm[9], D[9];
+        mat_mul_bt(U, V, Rm);
+#pragma unroll
+        for (int i = 0; i < 9; i++) D[i] = F[i] - Rm[i];
+        mat_mul_bt(D, F, S);
+        float pj = lam * J * (J - 1.0f);
+#pragma unroll
+        for (int i = 0; i < 9; i++) S[i] *= 2.0f * mu;
+        S[0] += pj; S[4] += pj; S[8] += pj;
+    } else if (mat == 1 || mat == 3) {  // StVK / Hencky (:50-66)
+        float sc[3], tau[3], t[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++) sc[i] = fmaxf(sg[i], 0.01f);
+        float sum = logf(sc[0]) + logf(sc[1]) + logf(sc[2]);
+#pragma unroll
+        for (int i = 0; i < 3; i++) tau[i] = 2.0f * mu * logf(sc[i]) + lam * sum;
+        diag_sandwich(U, tau, V, t);
+        mat_mul_bt(t, F, S);
+    } else if (mat == 2) {  // Drucker-Prager (:69-84)
+        float sum = logf(sg[0]) + logf(sg[1]) + logf(sg[2]);
+        float cc[3], t[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++) cc[i] = 2.0f * mu * logf(sg[i]) * (1.0f / sg[i]) + lam * sum * (1.0f / sg[i]);
+        diag_sandwich(U, cc, V, t);
+        mat_mul_bt(t, F, S);
+    }
+    PRec* pr = &rec[p];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) pr->S[3 * r + cc] = (S[3 * r + cc] + S[3 * cc + r]) / 2.0f;
+    TAux* o = &aux[p];
+#pragma unroll
+    for (int i = 0; i < 9; i++) o->F[i] = F[i];
+    o->mu = mu;
+    o->lam = lam;
+    o->ys = ys;
+}
+
+// pre-P2G particle operations on one class (mpm_solver.py:260-279)
+template <typename Rec>
+__global__ void k_particle_ops(int n, Rec* __restrict__ rec, const uint32_t* __restrict__ perm, int canon_offset,
+                               const ParticleOp* __restrict__ ops, int n_ops, const StepState* __restrict__ st, float dt) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    float time = (float)st->time;
+    int ci = canon_offset + (int)perm[p];
+    float4 vv = rec[p].vv;
+    float m = rec[p].xm.w;
+    bool ch = false;
+    for (int k = 0; k < n_ops; k++) {
+        ParticleOp op = ops[k];
+        if (!(time >= op.start_time && time < op.end_time)) continue;
+        int mk = op.mask[ci];
+        if (op.kind == 0 && mk == 1) { vv.x += op.vec[0] / m * dt; vv.y += op.vec[1] / m * dt; vv.z += op.vec[2] / m * dt; ch = true; }
+        if (op.kind == 1 && mk >= 1) { vv.x += op.vec[0] * dt; vv.y += op.vec[1] * dt; vv.z += op.vec[2] * dt; ch = true; }
+        if (op.kind == 2 && mk == 1) { vv.x = op.vec[0]; vv.y = op.vec[1]; vv.z = op.vec[2]; ch = true; }
+    }
+    if (ch) rec[p].vv = vv;
+}
+
+// ============================================================ P2G
+// p2g_apic_with_stress (mpm_utils.py:484-557), restructured for cell-sorted particles:
+// a warp takes a slab of 32 consecutive records into shared memory; lane l (< 27) owns stencil
+// node l of the CURRENT cell and accumulates the contributions of the run of particles that
+// share that cell in registers; when the cell changes the 27 lanes flush with one
+// REDG.E.ADD.F32x4 each.  No intra-warp reduction, no shared-memory atomics, and the number of
+// global atomics drops from 27*4 per particle to 27 per (cell run).
+// KIND 0: element (S already holds vol*P3(x)d3), 1: traditional (stress*vol, :496), 2: vertex.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_p2g(Grid g, const float* __restrict__ recs, int n, float dt, float rpic) {
+    constexpr int RS = (KIND == 2) ? (int)(sizeof(VRec) / 4) : (int)(sizeof(PRec) / 4);
+    extern __shared__ float4 smem4[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p0 = (blockIdx.x * 8 + warp) * 32;
+    if (p0 >= n) return;
+    const int cnt = min(32, n - p0);
+    float* sw = reinterpret_cast<float*>(smem4) + warp * 32 * RS;
+    {
+        const float4* src = reinterpret_cast<const float4*>(recs + (size_t)p0 * RS);
+        float4* dst = reinterpret_cast<float4*>(sw);
+        const int n4 = cnt * RS / 4;
+        for (int i = lane; i < n4; i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+    const int li = lane / 9, lj = (lane / 3) % 3, lk = lane % 3;
+    const bool act = lane < 27;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cbx = INT_MIN, cby = 0, cbz = 0;
+    for (int q = 0; q < cnt; q++) {
+        const float* r = sw + q * RS;
+        const float4 xm = *reinterpret_cast<const float4*>(r);
+        const float4 vv = *reinterpret_cast<const float4*>(r + 4);
+        const float gx = xm.x * g.inv_dx, gy = xm.y * g.inv_dx, gz = xm.z * g.inv_dx;
+        const int bx = (int)(gx - 0.5f), by = (int)(gy - 0.5f), bz = (int)(gz - 0.5f);
+        if (bx != cbx || by != cby || bz != cbz) {  // warp-uniform
+            if (act && (acc.w != 0.0f || acc.x != 0.0f || acc.y != 0.0f || acc.z != 0.0f)) {
+                int ni = node_index(g, cbx + li, cby + lj, cbz + lk);
+                if (ni >= 0) atomicAdd(&g.acc[ni], acc);
+                else g.flags[1] = 1;
+            }
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            cbx = bx; cby = by; cbz = bz;
+        }
+        const float fx = gx - (float)bx, fy = gy - (float)by, fz = gz - (float)bz;
+        float wx, wy, wz, dwx, dwy, dwz;
+        bspline(fx, li, wx, dwx);
+        bspline(fy, lj, wy, dwy);
+        bspline(fz, lk, wz, dwz);
+        const float w = wx * wy * wz;
+        const float dpx = ((float)li - fx) * g.dx, dpy = ((float)lj - fy) * g.dx, dpz = ((float)lk - fz) * g.dx;
+        float C[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) C[i] = r[8 + i];
+        if (rpic != 0.0f) {  // mpm_utils.py:528-542
+            float Cn[9];
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++)
+                    Cn[3 * a + b] = (1.0f - rpic) * C[3 * a + b] + rpic / 2.0f * (C[3 * a + b] - C[3 * b + a]);
+#pragma unroll
+            for (int i = 0; i < 9; i++) C[i] = (rpic < -0.001f) ? 0.0f : Cn[i];
+        }
+        float fo[3];
+        if (KIND == 2) {
+            fo[0] = w * r[17]; fo[1] = w * r[18]; fo[2] = w * r[19];
+        } else {
+            const float sc = (KIND == 1) ? vv.w : 1.0f;
+            const float d0 = dwx * wy * wz * g.inv_dx, d1 = wx * dwy * wz * g.inv_dx, d2 = wx * wy * dwz * g.inv_dx;
+#pragma unroll
+            for (int a = 0; a < 3; a++) fo[a] = -sc * (r[17 + 3 * a] * d0 + r[18 + 3 * a] * d1 + r[19 + 3 * a] * d2);
+        }
+        const float wm = w * xm.w;
+        acc.x += wm * (vv.x + (C[0] * dpx + C[1] * dpy + C[2] * dpz)) + dt * fo[0];
+        acc.y += wm * (vv.y + (C[3] * dpx + C[4] * dpy + C[5] * dpz)) + dt * fo[1];
+        acc.z += wm * (vv.z + (C[6] * dpx + C[7] * dpy + C[8] * dpz)) + dt * fo[2];
+        acc.w += wm;
+    }
+    if (act && (acc.w != 0.0f || acc.x != 0.0f || acc.y != 0.0f || acc.z != 0.0f)) {
+        int ni = node_index(g, cbx + li, cby + lj, cbz + lk);
+        if (ni >= 0) atomicAdd(&g.acc[ni], acc);
+        else g.flags[1] = 1;
+    }
+}
+
+// ============================================================ collider / mover scatter
+struct Stencil {
+    int b[3];
+    float w[3][3];
+};
+__device__ __forceinline__ void make_stencil(const Grid& g, float x, float y, float z, Stencil& s) {
+    float p[3] = {x * g.inv_dx, y * g.inv_dx, z * g.inv_dx};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        s.b[a] = (int)(p[a] - 0.5f);
+        float f = p[a] - (float)s.b[a];
+        float wa = 1.5f - f, wb = f - 1.0f, wc = f - 0.5f;
+        s.w[a][0] = wa * wa * 0.5f;
+        s.w[a][1] = 0.0f - wb * wb + 0.75f;
+        s.w[a][2] = wc * wc * 0.5f;
+    }
+}
+// bounds test of compute_mesh / add_velocity_* (mpm_solver.py:692,858)
+__device__ __forceinline__ bool scatter_ok(const Grid& g, const Stencil& s) {
+    return s.b[0] >= 0 && s.b[0] < g.n - 3 && s.b[1] >= 0 && s.b[1] < g.n - 3 && s.b[2] >= 0 && s.b[2] < g.n - 3;
+}
+
+// compute_mesh (mpm_solver.py:829-880).  Only nodes of ALLOCATED blocks are written: a node
+// outside every particle stencil is never read by G2P, so the body mesh never allocates grid.
+__global__ void __launch_bounds__(128) k_collider_scatter(Grid g, int Mf, const int* __restrict__ faces,
+                                                          const float* __restrict__ px, const float* __restrict__ pv,
+                                                          const StepState* __restrict__ st, float dt, int advance) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= Mf) return;
+    const float s = advance ? (float)((double)dt * (double)st->k) : 0.0f;
+    int id[3] = {faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]};
+    float P[3][3], fv[3] = {0, 0, 0}, fp[3] = {0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            float vel = pv[3 * id[c] + a];
+            P[c][a] = px[3 * id[c] + a] + s * vel;
+            fv[a] += vel;
+            fp[a] += P[c][a];
+        }
+#pragma unroll
+    for (int a = 0; a < 3; a++) { fv[a] = fv[a] / 3.0f; fp[a] = fp[a] / 3.0f; }
+    float e1[3] = {P[1][0] - P[0][0], P[1][1] - P[0][1], P[1][2] - P[0][2]};
+    float e2[3] = {P[2][0] - P[0][0], P[2][1] - P[0][1], P[2][2] - P[0][2]};
+    float nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
+    float nl = len3(nx, ny, nz);
+    if (nl > 0.0f) { nx /= nl; ny /= nl; nz /= nl; } else { nx = ny = nz = 0.0f; }
+    Stencil sp;
+    make_stencil(g, fp[0], fp[1], fp[2], sp);
+    if (!scatter_ok(g, sp)) return;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            for (int k = 0; k < 3; k++) {
+                int ni = node_index(g, sp.b[0] + i, sp.b[1] + j, sp.b[2] + k);
+                if (ni < 0) continue;
+                float w = sp.w[0][i] * sp.w[1][j] * sp.w[2][k];
+                atomicAdd(&g.colv[ni], make_float4(w * fv[0], w * fv[1], w * fv[2], w));
+                atomicAdd(&g.coln[ni], make_float4(w * nx, w * ny, w * nz, 0.0f));
+            }
+}
+
+// add_velocity_traditional / _verts / _faces (mpm_solver.py:677-788) in one launch:
+// threads [0,njt) pinned traditional tail, [njt, njt+njv) joint vertices, then joint faces.
+__global__ void __launch_bounds__(128) k_mover_scatter(Grid g, int njt, int njv, int njf, int Nt,
+                                                       const float* __restrict__ vt, const float* __restrict__ vvv,
+                                                       const float* __restrict__ vf, const PRec* __restrict__ erec,
+                                                       const PRec* __restrict__ trec, const VRec* __restrict__ vrec,
+                                                       const int* __restrict__ invE, const int* __restrict__ invT,
+                                                       const int* __restrict__ invV) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= njt + njv + njf) return;
+    float4 xm;
+    const float* vel;
+    if (t < njt) { xm = trec[invT[Nt - njt + t]].xm; vel = vt + 3 * t; }
+    else if (t < njt + njv) { xm = vrec[invV[t - njt]].xm; vel = vvv + 3 * (t - njt); }
+    else { xm = erec[invE[t - njt - njv]].xm; vel = vf + 3 * (t - njt - njv); }
+    Stencil sp;
+    make_stencil(g, xm.x, xm.y, xm.z, sp);
+    if (!scatter_ok(g, sp)) return;
+    float v0 = vel[0], v1 = vel[1], v2 = vel[2];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            for (int k = 0; k < 3; k++) {
+                int ni = node_index(g, sp.b[0] + i, sp.b[1] + j, sp.b[2] + k);
+                if (ni < 0) { g.flags[1] = 1; continue; }
+                float w = sp.w[0][i] * sp.w[1][j] * sp.w[2][k];
+                atomicAdd(&g.mov[ni], make_float4(w * v0, w * v1, w * v2, w));
+            }
+}
+
+// ============================================================ grid update
+// One pass over the nodes of the allocated blocks that fuses
+//   grid_normalization_and_gravity (mpm_utils.py:561-572), add_damping_via_grid (:1162-1174),
+//   mesh collider normalize_grid + collide (mpm_solver.py:882-917),
+//   particle mover normalize_grid (:790-799), and every grid_postprocess BC in order (:487-501),
+// then re-zeroes the accumulators it consumed (replaces the three dense zero_grid sweeps).
+__global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float dt, int use_collider, float col_friction,
+                                                     int use_mover, const BCDesc* __restrict__ bcs, int n_bc,
+                                                     const StepState* __restrict__ st) {
+    const int n_slots = min(*g.n_slots, g.cap);
+    const float time = (float)st->time;
+    const int total = n_slots * BN;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int slot = idx >> 6, l = idx & 63;
+        float4 a = g.acc[idx];
+        float vx = 0.f, vy = 0.f, vz = 0.f;
+        if (g.dbg_acc) g.dbg_acc[idx] = a;
+        if (a.w > 1e-15f) {
+            float inv = 1.0f / a.w;
+            vx = a.x * inv + dt * md.gx;
+            vy = a.y * inv + dt * md.gy;
+            vz = a.z * inv + dt * md.gz;
+        }
+        if (a.w != 0.0f || a.x != 0.0f || a.y != 0.0f || a.z != 0.0f) g.acc[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (md.damping < 1.0f) {
+            vx -= (1.0f - md.damping) * vx;
+            vy -= (1.0f - md.damping) * vy;
+            vz -= (1.0f - md.damping) * vz;
+        }
+        if (use_collider) {
+            float4 cv = g.colv[idx];
+            if (cv.w != 0.0f) {
+                float4 cn = g.coln[idx];
+                g.colv[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                g.coln[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cv.w > 1e-15f) {
+                    float inv = 1.0f / cv.w;
+                    float mx = cv.x * inv, my = cv.y * inv, mz = cv.z * inv;
+                    float rx = vx - mx, ry = vy - my, rz = vz - mz;
+                    float nl = len3(cn.x, cn.y, cn.z);
+                    float nx = 0.f, ny = 0.f, nz = 0.f;
+                    if (nl > 0.0f) { nx = cn.x / nl; ny = cn.y / nl; nz = cn.z / nl; }
+                    float nc = rx * nx + ry * ny + rz * nz;
+                    float mn = fminf(nc, 0.0f);
+                    float px = rx - mn * nx, py = ry - mn * ny, pz = rz - mn * nz;
+                    float pl = len3(px, py, pz);
+                    if (nc < 0.0f && pl > 1e-20f) {
+                        float sc = fmaxf(0.0f, pl + nc * col_friction) / pl;
+                        px *= sc; py *= sc; pz *= sc;
+                    }
+                    vx = px + mx; vy = py + my; vz = pz + mz;
+                }
+            }
+        }
+        {
+            // the mover accumulators are consumed (and cleared) even on steps without joint inputs
+            float4 mv = g.mov[idx];
+            if (mv.w != 0.0f || mv.x != 0.0f || mv.y != 0.0f || mv.z != 0.0f) {
+                g.mov[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (use_mover && mv.w > 1e-15f) {
+                    float inv = 1.0f / mv.w;
+                    vx = mv.x * inv; vy = mv.y * inv; vz = mv.z * inv;
+                }
+            }
+        }
+        if (n_bc > 0) {
+            const int co = g.slot_coord[slot];
+            const int ix = ((co & 1023) << 2) + (l >> 4), iy = (((co >> 10) & 1023) << 2) + ((l >> 2) & 3),
+                      iz = (((co >> 20) & 1023) << 2) + (l & 3);
+            for (int k = 0; k < n_bc; k++) {
+                const BCDesc& bc = bcs[k];
+                const bool active = time >= bc.start_time && time < bc.end_time;
+                if (bc.kind == 0) {
+                    if (active) {
+                        float ox = (float)ix * g.dx - bc.point[0], oy = (float)iy * g.dx - bc.point[1],
+                              oz = (float)iz * g.dx - bc.point[2];
+                        float dp = ox * bc.normal[0] + oy * bc.normal[1] + oz * bc.normal[2];
+                        if (dp < 0.0f) {
+                            if (bc.surface_type == 11 && !((float)iz * g.dx < 0.4f || (float)iz * g.dx > 0.53f)) {
+                                vx = vx * 0.3f; vy = 0.0f; vz = vz * 0.3f;
+                            } else {
+                                // sticky; the slip / friction branches also end in a zero store (:636-655)
+                                vx = 0.f; vy = 0.f; vz = 0.f;
+                            }
+                        }
+                    }
+                } else if (bc.kind == 1) {
+                    if (active) {
+                        float ox = (float)ix * g.dx - bc.point[0], oy = (float)iy * g.dx - bc.point[1],
+                              oz = (float)iz * g.dx - bc.point[2];
+                        if (fabsf(ox) < bc.size[0] && fabsf(oy) < bc.size[1] && fabsf(oz) < bc.size[2]) {
+                            vx = bc.velocity[0]; vy = bc.velocity[1]; vz = bc.velocity[2];
+                        }
+                    } else if (bc.reset == 1) {
+                        if (time < bc.end_time + 15.0f * dt) { vx = 0.f; vy = 0.f; vz = 0.f; }
+                    }
+                } else if (bc.kind == 2) {
+                    if (active) {
+                        const int pad = 3;
+                        if (ix < pad && vx < 0.f) vx = 0.f;
+                        if (ix >= g.n - pad && vx > 0.f) vx = 0.f;
+                        if (iy < pad && vy < 0.f) vy = 0.f;
+                        if (iy >= g.n - pad && vy > 0.f) vy = 0.f;
+                        if (iz < pad && vz < 0.f) vz = 0.f;
+                        if (iz >= g.n - pad && vz > 0.f) vz = 0.f;
+                    }
+                } else if (bc.kind == 3) {
+                    if (ix < g.n && iy < g.n && iz < g.n && bc.mask[((size_t)ix * g.n + iy) * g.n + iz] >= 1) {
+                        vx = 0.f; vy = 0.f; vz = 0.f;
+                    }
+                }
+            }
+        }
+        g.vout[idx] = make_float4(vx, vy, vz, 0.0f);
+    }
+}
+
+// end of substep: self.time += dt (mpm_solver.py:536), substep counter, moving cuboids (:975-981)
+__global__ void k_advance(StepState* st, float dt, BCDesc* bcs, int n_bc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float time = (float)st->time;
+    for (int k = 0; k < n_bc; k++)
+        if (bcs[k].kind == 1 && time >= bcs[k].start_time && time < bcs[k].end_time)
+            for (int a = 0; a < 3; a++) bcs[k].point[a] = bcs[k].point[a] + dt * bcs[k].velocity[a];
+    st->time = st->time + (double)dt;
+    st->k = st->k + 1;
+}
+__global__ void k_reset_k(StepState* st) { st->k = 0; }
+
+// ============================================================ G2P
+struct Gathered {
+    float v[3];
+    float C[9];
+    float G[9];  // grad v
+};
+// shared gather of g2p_v / g2p_e (mpm_utils.py:726-763, 798-836)
+__device__ __forceinline__ void g2p_gather(const Grid& g, float x, float y, float z, Gathered& o) {
+    const float gx = x * g.inv_dx, gy = y * g.inv_dx, gz = z * g.inv_dx;
+    const int bx = (int)(gx - 0.5f), by = (int)(gy - 0.5f), bz = (int)(gz - 0.5f);
+    const float fx = gx - (float)bx, fy = gy - (float)by, fz = gz - (float)bz;
+    float w[3][3], dw[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        bspline(fx, i, w[0][i], dw[0][i]);
+        bspline(fy, i, w[1][i], dw[1][i]);
+        bspline(fz, i, w[2][i], dw[2][i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) o.v[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; i++) { o.C[i] = 0.f; o.G[i] = 0.f; }
+    // up to 2x2x2 blocks under the stencil
+    int sl[8];
+    const int X0 = bx >> 2, Y0 = by >> 2, Z0 = bz >> 2;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int X = X0 + (c >> 2), Y = Y0 + ((c >> 1) & 1), Z = Z0 + (c & 1);
+        bool ok = bx >= 0 && by >= 0 && bz >= 0 && X < g.nb && Y < g.nb && Z < g.nb;
+        sl[c] = ok ? lookup_slot(g, X, Y, Z) : -1;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int ix = bx + i, iy = by + j, iz = bz + k;
+                const int c = (((ix >> 2) - X0) << 2) | (((iy >> 2) - Y0) << 1) | ((iz >> 2) - Z0);
+                int s = sl[0];
+#pragma unroll
+                for (int q = 1; q < 8; q++) s = (c == q) ? sl[q] : s;
+                const bool inb = ix < g.n && iy < g.n && iz < g.n;
+                float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (inb && s >= 0) gv = g.vout[s * BN + ((ix & 3) << 4) + ((iy & 3) << 2) + (iz & 3)];
+                else if (inb && bx >= 0 && by >= 0 && bz >= 0) g.flags[1] = 1;
+                const float wt = w[0][i] * w[1][j] * w[2][k];
+                const float dpx = (float)i - fx, dpy = (float)j - fy, dpz = (float)k - fz;
+                const float d0 = dw[0][i] * w[1][j] * w[2][k] * g.inv_dx, d1 = w[0][i] * dw[1][j] * w[2][k] * g.inv_dx,
+                            d2 = w[0][i] * w[1][j] * dw[2][k] * g.inv_dx;
+                const float sc = wt * g.inv_dx * 4.0f;
+                const float vv[3] = {gv.x, gv.y, gv.z};
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    o.v[r] += vv[r] * wt;
+                    o.C[3 * r + 0] += (vv[r] * dpx) * sc;
+                    o.C[3 * r + 1] += (vv[r] * dpy) * sc;
+                    o.C[3 * r + 2] += (vv[r] * dpz) * sc;
+                    o.G[3 * r + 0] += vv[r] * d0;
+                    o.G[3 * r + 1] += vv[r] * d1;
+                    o.G[3 * r + 2] += vv[r] * d2;
+                }
+            }
+}
+__device__ __forceinline__ float clampf(float x, float a, float b) { return fminf(fmaxf(x, a), b); }
+
+// g2p_v for cloth vertices (mpm_utils.py:716-786); also clears vertex_force for the next substep
+// (replaces set_vec3_to_zero, mpm_solver.py:251-256) and allocates grid blocks for the new position.
+__global__ void __launch_bounds__(128) k_g2p_vertices(Grid g, int Nv, VRec* __restrict__ rec, float dt,
+                                                      float* __restrict__ dbg_f) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Nv) return;
+    float4 xm = rec[p].xm;
+    Gathered o;
+    g2p_gather(g, xm.x, xm.y, xm.z, o);
+    const float dxc = 1.0f / g.inv_dx, a_min = dxc * 2.0f, a_max = g.lim - dxc * 2.0f;
+    xm.x = clampf(xm.x + dt * o.v[0], a_min, a_max);
+    xm.y = clampf(xm.y + dt * o.v[1], a_min, a_max);
+    xm.z = clampf(xm.z + dt * o.v[2], a_min, a_max);
+    VRec* r = &rec[p];
+    r->xm = xm;
+    r->vv = make_float4(o.v[0], o.v[1], o.v[2], 0.0f);
+#pragma unroll
+    for (int i = 0; i < 9; i++) r->C[i] = o.C[i];
+    if (dbg_f) { dbg_f[3 * p] = r->f[0]; dbg_f[3 * p + 1] = r->f[1]; dbg_f[3 * p + 2] = r->f[2]; }
+    r->f[0] = 0.f; r->f[1] = 0.f; r->f[2] = 0.f;
+    ensure_stencil_blocks(g, xm.x, xm.y, xm.z);
+}
+
+// g2p_v for traditional particles: additionally F_trial = (I + dt grad v) F (mpm_utils.py:783-786)
+__global__ void __launch_bounds__(128) k_g2p_traditional(Grid g, int Nt, PRec* __restrict__ rec, TAux* __restrict__ aux,
+                                                         float dt) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Nt) return;
+    float4 xm = rec[p].xm;
+    Gathered o;
+    g2p_gather(g, xm.x, xm.y, xm.z, o);
+    const float dxc = 1.0f / g.inv_dx, a_min = dxc * 2.0f, a_max = g.lim - dxc * 2.0f;
+    xm.x = clampf(xm.x + dt * o.v[0], a_min, a_max);
+    xm.y = clampf(xm.y + dt * o.v[1], a_min, a_max);
+    xm.z = clampf(xm.z + dt * o.v[2], a_min, a_max);
+    PRec* r = &rec[p];
+    const float vol = r->vv.w;
+    r->xm = xm;
+    r->vv = make_float4(o.v[0], o.v[1], o.v[2], vol);
+#pragma unroll
+    for (int i = 0; i < 9; i++) r->C[i] = o.C[i];
+    float M[9], F[9], Ft[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { M[i] = o.G[i] * dt; F[i] = aux[p].F[i]; }
+    M[0] += 1.0f; M[4] += 1.0f; M[8] += 1.0f;
+    mat_mul(M, F, Ft);
+#pragma unroll
+    for (int i = 0; i < 9; i++) aux[p].Ft[i] = Ft[i];
+    ensure_stencil_blocks(g, xm.x, xm.y, xm.z);
+}
+
+// g2p_e (mpm_utils.py:788-857): C and grad v at the OLD centroid, x/v = mean of the three
+// already-updated corner vertices, d = [x2-x1, x3-x1, (I + dt grad v) d3]
+__global__ void __launch_bounds__(128) k_g2p_elements(Grid g, int Ne, PRec* __restrict__ rec, EAux* __restrict__ aux,
+                                                      const VRec* __restrict__ vrec, float dt) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Ne) return;
+    float4 xm = rec[p].xm;
+    Gathered o;
+    g2p_gather(g, xm.x, xm.y, xm.z, o);
+    EAux* a = &aux[p];
+    const int f0 = a->face[0], f1 = a->face[1], f2 = a->face[2];
+    const float4 x1 = vrec[f0].xm, x2 = vrec[f1].xm, x3 = vrec[f2].xm;
+    const float4 v1 = vrec[f0].vv, v2 = vrec[f1].vv, v3 = vrec[f2].vv;
+    PRec* r = &rec[p];
+    const float vol = r->vv.w;
+    xm.x = (x1.x + x2.x + x3.x) / 3.0f;
+    xm.y = (x1.y + x2.y + x3.y) / 3.0f;
+    xm.z = (x1.z + x2.z + x3.z) / 3.0f;
+    r->xm = xm;
+    r->vv = make_float4((v1.x + v2.x + v3.x) / 3.0f, (v1.y + v2.y + v3.y) / 3.0f, (v1.z + v2.z + v3.z) / 3.0f, vol);
+#pragma unroll
+    for (int i = 0; i < 9; i++) r->C[i] = o.C[i];
+    const float d3[3] = {a->dc[6], a->dc[7], a->dc[8]};
+    float nd3[3];
+#pragma unroll
+    for (int rr = 0; rr < 3; rr++) {
+        float m0 = o.G[3 * rr] * dt + (rr == 0 ? 1.0f : 0.0f);
+        float m1 = o.G[3 * rr + 1] * dt + (rr == 1 ? 1.0f : 0.0f);
+        float m2 = o.G[3 * rr + 2] * dt + (rr == 2 ? 1.0f : 0.0f);
+        nd3[rr] = m0 * d3[0] + m1 * d3[1] + m2 * d3[2];
+    }
+    a->dc[0] = x2.x - x1.x; a->dc[1] = x2.y - x1.y; a->dc[2] = x2.z - x1.z;
+    a->dc[3] = x3.x - x1.x; a->dc[4] = x3.y - x1.y; a->dc[5] = x3.z - x1.z;
+    a->dc[6] = nd3[0]; a->dc[7] = nd3[1]; a->dc[8] = nd3[2];
+    ensure_stencil_blocks(g, xm.x, xm.y, xm.z);
+}
+
+}  // namespace mpm

@@ -242,7 +242,7 @@ def scene_c5(Nu=1152, Nr=580, n_grid=512, seed=3) -> Scene:
 
 
 def scene_small_cloth_body(Nu=48, Nr=26, n_grid=48, seed=5) -> Scene:
-    """Small C3-shaped case (cloth + body + joints) the oracle finishes in seconds."""
+    """Small C3-shaped case (cloth + body + joints) a CPU check finishes in seconds."""
     return _cloth_scene(f"small_cloth_body_{Nu}x{Nr}_{n_grid}", seed, Nu, Nr, n_grid, with_body=True)
 
 

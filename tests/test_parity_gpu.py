@@ -1,0 +1,200 @@
+"""GPU parity: the CUDA path (through the reference-facing API and the C-ABI) against the CPU
+oracle on identical seeded inputs.  Tolerance (BASELINE.json north_star): 1e-4 relative on
+positions / velocities after N substeps; 1e-3 of max|.| on C, d, F_trial, stress."""
+import numpy as np
+import pytest
+import torch
+
+from mpmavatar_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+TOL_XV = 1e-4
+TOL_AUX = 1e-3
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def run_oracle(sc, nsub, precision="f32", threads=8, joint_t=None):
+    from oracle.oracle import OracleSim
+    o = OracleSim.from_scene(sc, precision, threads=threads)
+    fi = sc.frame_inputs(0)
+    for k in range(nsub):
+        mx = None if fi["mesh_x"] is None else fi["mesh_x"] + np.float32(sc.dt * k) * fi["mesh_v"]
+        o.p2g2p(sc.dt, mx, fi["mesh_v"], joint_t, fi["joint_verts_v"], fi["joint_faces_v"])
+    return o
+
+
+def run_cuda(sc, nsub, per_call=True, debug=False, joint_t=None, resort_interval=0):
+    from mpmavatar_b200.scene_setup import build_from_scene, frame_tensors
+    solver, model, state = build_from_scene(sc, resort_interval=resort_interval)
+    if debug:
+        solver.set_debug(True)
+    ft = frame_tensors(sc, 0)
+    jt = None if joint_t is None else torch.as_tensor(joint_t, dtype=torch.float32, device="cuda")
+    if per_call:  # exactly the caller's loop (train_material_params.py:622-626)
+        for k in range(nsub):
+            mx = None if ft["mesh_x"] is None else ft["mesh_x"] + sc.dt * k * ft["mesh_v"]
+            solver.p2g2p(model, state, sc.dt, mesh_x=mx, mesh_v=ft["mesh_v"], joint_traditional_v=jt,
+                         joint_verts_v=ft["joint_verts_v"], joint_faces_v=ft["joint_faces_v"])
+    else:
+        solver.step(model, state, sc.dt, nsub, ft["mesh_x"], ft["mesh_v"], jt, ft["joint_verts_v"], ft["joint_faces_v"])
+    st = solver.stats()
+    assert st["overflow"] == 0, st
+    return solver, model, state
+
+
+def compare(o, state, sc, tol_xv=TOL_XV, tol_aux=TOL_AUX):
+    x = state.particle_x.cpu().numpy()
+    v = state.particle_v.cpu().numpy()
+    assert np.isfinite(x).all() and np.isfinite(v).all()
+    assert rel(x, o.x) < tol_xv, ("x", rel(x, o.x))
+    assert rel(v, o.v) < tol_xv, ("v", rel(v, o.v))
+    assert rel(state.particle_C.cpu().numpy(), o.C) < tol_aux, ("C", rel(state.particle_C.cpu().numpy(), o.C))
+    if sc.n_elements:
+        assert rel(state.particle_d.cpu().numpy(), o.d) < tol_aux
+        assert rel(state.particle_stress.cpu().numpy()[: sc.n_elements], o.stress[: sc.n_elements]) < tol_aux
+    if sc.n_traditional:
+        sl = slice(sc.n_elements, sc.n_elements + sc.n_traditional)
+        assert rel(state.particle_F_trial.cpu().numpy()[sl], o.F_trial[sl]) < tol_aux
+        assert rel(state.particle_F.cpu().numpy()[sl], o.F[sl]) < tol_aux
+        assert rel(state.particle_stress.cpu().numpy()[sl], o.stress[sl]) < tol_aux
+
+
+def test_c1_jelly_one_substep_with_grid():
+    sc = S.scene_c1()
+    o = run_oracle(sc, 1)
+    solver, model, state = run_cuda(sc, 1, debug=True)
+    compare(o, state, sc)
+    gm, gvi, gvo = state.export_grid()
+    gm, gvi, gvo = gm.cpu().numpy().reshape(-1), gvi.cpu().numpy().reshape(-1, 3), gvo.cpu().numpy().reshape(-1, 3)
+    assert abs(gm.sum() - o.mass.sum()) < 1e-5 * o.mass.sum()
+    assert rel(gm, o.grid_m) < 1e-5
+    assert rel(gvi, o.grid_v_in) < 1e-4
+    has = o.grid_m > 1e-15
+    assert rel(gvo[has], o.grid_v_out[has]) < 1e-4
+
+
+@pytest.mark.parametrize("material", ["jelly", "metal", "sand", "foam", "plasticine", "snow"])
+def test_traditional_materials(material):
+    sc = S.scene_c1(n=3000, n_grid=32, seed=11, material=material)
+    o = run_oracle(sc, 5)
+    _, _, state = run_cuda(sc, 5)
+    compare(o, state, sc)
+
+
+@pytest.mark.parametrize("nsub", [1, 10, 100])
+def test_small_cloth_body_joints(nsub):
+    sc = S.scene_small_cloth_body()
+    o = run_oracle(sc, nsub)
+    _, _, state = run_cuda(sc, nsub)
+    compare(o, state, sc)
+
+
+def test_vertex_force_and_first_substep_details():
+    sc = S.scene_small_cloth_body()
+    # pre-stretch the cloth so that stress and vertex forces are non-trivial
+    sc.x = sc.x.copy()
+    Ne = sc.n_elements
+    verts = sc.x[Ne:] * np.array([1.0, 1.03, 1.0], np.float32) + np.array([0, -0.03, 0], np.float32)
+    sc.x[Ne:] = verts
+    sc.x[:Ne] = verts[sc.faces].mean(1)
+    d1 = verts[sc.faces[:, 1]] - verts[sc.faces[:, 0]]
+    d2 = verts[sc.faces[:, 2]] - verts[sc.faces[:, 0]]
+    sc.d = np.stack([d1, d2, sc.d[:, :, 2]], -1).astype(np.float32)
+    o = run_oracle(sc, 1)
+    solver, model, state = run_cuda(sc, 1, debug=True)
+    compare(o, state, sc)
+    vf = state.vertex_force.cpu().numpy()
+    assert np.abs(o.vertex_force).max() > 0
+    assert rel(vf, o.vertex_force) < 1e-3
+
+
+def test_multi_substep_call_equals_caller_loop():
+    sc = S.scene_small_cloth_body()
+    _, _, a = run_cuda(sc, 20, per_call=True)
+    _, _, b = run_cuda(sc, 20, per_call=False)
+    assert rel(b.particle_x.cpu().numpy(), a.particle_x.cpu().numpy()) < 1e-6
+    assert rel(b.particle_v.cpu().numpy(), a.particle_v.cpu().numpy()) < 1e-4
+
+
+def test_resort_interval_does_not_change_results():
+    sc = S.scene_small_cloth_body()
+    _, _, a = run_cuda(sc, 30, per_call=False, resort_interval=1000)
+    s2, _, b = run_cuda(sc, 30, per_call=False, resort_interval=4)
+    assert s2.stats()["n_resorts"] >= 7
+    assert rel(b.particle_x.cpu().numpy(), a.particle_x.cpu().numpy()) < 1e-6
+    assert rel(b.particle_v.cpu().numpy(), a.particle_v.cpu().numpy()) < 1e-4
+
+
+def test_demo_like_sand_plane_pinned_tail():
+    sc = S.scene_demo_like()
+    jt = np.zeros((sc.num_joint_t, 3), np.float32)
+    o = run_oracle(sc, 10, joint_t=jt)
+    _, _, state = run_cuda(sc, 10, joint_t=jt)
+    compare(o, state, sc)
+
+
+def test_c2_cloth_100k():
+    sc = S.scene_c2()
+    o = run_oracle(sc, 10)
+    _, _, state = run_cuda(sc, 10)
+    compare(o, state, sc)
+
+
+def test_fp64_envelope_small_cloth():
+    """The CUDA fp32 path must sit as close to the fp64 oracle as the fp32 oracle does (x3)."""
+    sc = S.scene_small_cloth_body()
+    o32 = run_oracle(sc, 50, "f32")
+    o64 = run_oracle(sc, 50, "f64")
+    _, _, state = run_cuda(sc, 50)
+    x = state.particle_x.cpu().numpy()
+    e_ref = np.abs(o32.x - o64.x).max()
+    e_cuda = np.abs(x - o64.x).max()
+    assert e_cuda < max(3 * e_ref, 1e-6), (e_cuda, e_ref)
+
+
+def test_c3_full_size_properties():
+    """BASELINE.json's headline size: size-independent properties instead of the dense oracle."""
+    sc = S.scene_c3()
+    solver, model, state = run_cuda(sc, 1, per_call=False, debug=True)
+    gm, gvi, gvo = state.export_grid()
+    total_mass = float(state.particle_mass.double().sum())
+    assert abs(float(gm.double().sum()) - total_mass) < 1e-4 * total_mass  # mass conservation
+    x0 = torch.as_tensor(sc.x, device="cuda")
+    v = state.particle_v
+    # free cloth starts at rest: after one substep every unconstrained particle has v ~ dt*g
+    free = torch.ones(sc.n_particles, dtype=torch.bool, device="cuda")
+    assert torch.isfinite(state.particle_x).all()
+    assert float((state.particle_x - x0).abs().max()) < 1e-3
+    assert float(v[free][:, 1].median()) == pytest.approx(-9.8 * sc.dt, rel=1e-2)
+    st = solver.stats()
+    assert st["overflow"] == 0 and st["n_active_nodes"] > 0
+    solver.set_debug(False)
+    ft = __import__("mpmavatar_b200.scene_setup", fromlist=["frame_tensors"]).frame_tensors(sc, 0)
+    solver.step(model, state, sc.dt, 200, ft["mesh_x"], ft["mesh_v"], None, ft["joint_verts_v"], ft["joint_faces_v"])
+    assert torch.isfinite(state.particle_x).all() and torch.isfinite(state.particle_v).all()
+    assert solver.stats()["overflow"] == 0
+
+
+def test_kats_on_gpu_free_fall_and_clamp():
+    sc = S.scene_c1(n=500, n_grid=16, seed=5, material="snow")  # no stress branch -> zero stress
+    sc.v[:] = np.array([0.3, -0.2, 0.1], np.float32)
+    sc.F_trial = None
+    _, _, state = run_cuda(sc, 1)
+    v = state.particle_v.cpu().numpy()
+    assert np.abs(v - (sc.v + sc.dt * np.array(sc.g, np.float32))).max() < 1e-5
+    assert np.abs(state.particle_C.cpu().numpy()).max() < 1e-3
+    dx = 2.0 / 16
+    sc2 = S.scene_c1(n=2, n_grid=16, seed=5, material="snow")
+    sc2.F_trial = None
+    sc2.x = np.array([[2 * dx + 1e-6, 1, 1], [1, 2 - 2 * dx - 1e-6, 1]], np.float32)
+    sc2.v = np.array([[-5, 0, 0], [0, 5, 0]], np.float32)
+    sc2.dt = 1e-2
+    _, _, st2 = run_cuda(sc2, 1)
+    x = st2.particle_x.cpu().numpy()
+    assert x[0, 0] == np.float32(2 * dx) and x[1, 1] == np.float32(2.0) - np.float32(2 * dx)
