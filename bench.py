@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- MPM substeps/s at 500k particles / 256^3 grid (BASELINE.json metric).
+
+A "step" is one simulated frame of the reference's operating point: 400 substeps at
+dt = 1e-4 s (arguments/__init__.py:97, train_material_params.py:578-580) on the synthetic C3
+scene (499 968 cloth particles, 256^3 grid, capsule body collider, joint rings).
+
+  value     whole-job substeps/s with all inputs resident in HBM (CUDA events, max over ranks)
+  e2e       the same through the C-ABI with HOST (pinned) buffers: per step the body-mesh /
+            joint inputs go host->device and the particle positions come back device->host
+  roofline  P2G+G2P algorithmic bytes (SURVEY 8d byte model, A counted exactly) / measured
+            P2G+G2P time (per-phase CUDA events in a separate profiling pass) vs measured HBM peak
+  cpu_baseline  the CPU oracle (line-faithful port of the reference kernels, OpenMP) on a
+            bounded sample of the same workload, rank 0 / N=1 only
+
+--impl reference times the reference algorithm's CPU port (oracle/) on all host threads.
+With torchrun (N>1) every rank runs an independent rollout of the same scene (the reference's
+finite-difference probes are independent simulations, train_material_params.py:583); there is
+no data-path collective, scaling is weak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SUBSTEPS_PER_STEP = 400
+METRIC = "mpm_substeps_per_sec_500k_particles_256grid"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(sc, A):
+    """304*Ne + 248*Nt + 148*Nv + 28*A bytes per substep for P2G+G2P."""
+    return 304 * sc.n_elements + 248 * sc.n_traditional + 148 * sc.n_vertices + 28 * A
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference kernels on all host threads."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import oracle as orc
+    from mpmavatar_b200 import synthetic as S
+    orc.build()
+    sc = S.scene_c3()
+    threads = orc.max_threads()
+    o = orc.OracleSim.from_scene(sc, "f32", threads=threads)
+    fi = sc.frame_inputs(0)
+    sample = 2  # substeps per "step": a bounded sample of the 400-substep frame
+    k = 0
+
+    def one_step():
+        nonlocal k
+        for _ in range(sample):
+            mx = fi["mesh_x"] + np.float32(sc.dt * k) * fi["mesh_v"]
+            o.p2g2p(sc.dt, mx, fi["mesh_v"], None, fi["joint_verts_v"], fi["joint_faces_v"])
+            k += 1
+    for _ in range(args.warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    val = args.steps * sample / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "substeps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C3: 499968 cloth particles (332928 elements + 167040 vertices), 256^3 grid, "
+                                   "capsule body collider (10466 verts / 20928 faces) + 1152 joint vertices/faces, "
+                                   "dt=1e-4", "substeps_per_step": sample, "dense_grid": True},
+            "cpu_baseline": {"value": val, "unit": "substeps/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample} substeps per step x {args.steps} steps of the C3 workload, "
+                                       f"dense 256^3 grid, OpenMP {threads} threads (reference Warp runtime is not "
+                                       f"installable offline; oracle/ is its line-faithful C port)"},
+            "e2e": {"value": val, "unit": "substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(sc):
+    import numpy as np
+    from oracle import oracle as orc
+    orc.build()
+    threads = orc.max_threads()
+    o = orc.OracleSim.from_scene(sc, "f32", threads=threads)
+    fi = sc.frame_inputs(0)
+
+    def sub(k):
+        mx = fi["mesh_x"] + np.float32(sc.dt * k) * fi["mesh_v"]
+        o.p2g2p(sc.dt, mx, fi["mesh_v"], None, fi["joint_verts_v"], fi["joint_faces_v"])
+    sub(0)
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 200):
+        sub(n + 1)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "substeps/s", "cores": threads, "kind": "port",
+            "sample": f"{n} substeps of the C3 workload after 1 warm-up, dense 256^3 grid, OpenMP {threads} threads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="c3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mpmavatar_b200 import synthetic as S
+    from mpmavatar_b200.scene_setup import build_from_scene
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sc = getattr(S, "scene_" + args.scene)()
+    S_PER = SUBSTEPS_PER_STEP
+    solver, model, state = build_from_scene(sc, device=dev)
+    frames = [sc.frame_inputs(i) for i in range(args.warmup + args.steps + 2)]
+    keys = ("mesh_x", "mesh_v", "joint_verts_v", "joint_faces_v")
+    dev_frames = [{k: torch.as_tensor(f[k], device=dev) for k in keys} for f in frames]
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step_dev(i):
+        f = dev_frames[i]
+        solver.step(model, state, sc.dt, S_PER, f["mesh_x"], f["mesh_v"], None, f["joint_verts_v"], f["joint_faces_v"])
+
+    # ---------------- value: inputs resident in HBM
+    fi = 0
+    for _ in range(args.warmup):
+        step_dev(fi); fi += 1
+    st0 = solver.stats()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush_buf.fill_(k)  # L2 flush between timed steps (not timed)
+        evs[k][0].record()
+        step_dev(fi); fi += 1
+        evs[k][1].record()
+    barrier()
+    clk = clocks.stop()
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    st1 = solver.stats()
+    launches = st1["gpu_launches"] - st0["gpu_launches"]
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * args.steps * S_PER / (ms_total * 1e-3)
+    finite = bool(torch.isfinite(state.particle_x).all())
+
+    # ---------------- e2e: host buffers through the C-ABI, H2D + D2H inside the timed region
+    import ctypes as C
+    from mpmavatar_b200 import _lib
+    pin = [{k: torch.as_tensor(f[k]).pin_memory() for k in keys} for f in frames]
+    host_x = torch.empty(sc.n_particles, 3, dtype=torch.float32).pin_memory()
+    h2d = sum(pin[0][k].numel() * 4 for k in keys)
+    d2h = host_x.numel() * 4
+    lib, h = solver._libh, solver._h
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def step_host(i):
+        f = pin[i]
+        fin = _lib.MpmFrameInputs()
+        fin.mesh_x, fin.mesh_v = f["mesh_x"].data_ptr(), f["mesh_v"].data_ptr()
+        fin.joint_verts_v, fin.joint_faces_v = f["joint_verts_v"].data_ptr(), f["joint_faces_v"].data_ptr()
+        assert lib.mpm_step(h, C.c_float(sc.dt), S_PER, C.byref(fin), stream) == 0
+        out = _lib.MpmParticleArrays()
+        out.x = host_x.data_ptr()
+        assert lib.mpm_export_state(h, C.byref(out), stream) == 0
+
+    from mpmavatar_b200.scene_setup import reset_rollout
+    reset_rollout(sc, solver, model, state, dev)
+    solver._bind(model, state)
+    for i in range(min(args.warmup, 2)):
+        step_host(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        step_host(2 + k)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps * S_PER / (float(t.item()) * 1e-3)
+    state._stale = True
+    finite = finite and bool(torch.isfinite(host_x).all())
+
+    # ---------------- roofline: per-phase events in a separate profiling pass
+    stats = solver.stats()
+    A = int(stats["n_active_nodes"])
+    solver.enable_profiling(True)
+    f = dev_frames[-1]
+    fin = _lib.MpmFrameInputs()
+    fin.mesh_x, fin.mesh_v = f["mesh_x"].data_ptr(), f["mesh_v"].data_ptr()
+    fin.joint_verts_v, fin.joint_faces_v = f["joint_verts_v"].data_ptr(), f["joint_faces_v"].data_ptr()
+    assert lib.mpm_step(h, C.c_float(sc.dt), 200, C.byref(fin), stream) == 0
+    prof = solver.get_profile()
+    solver.enable_profiling(False)
+    n = max(prof["n_substeps"], 1)
+    per = {k: prof[k] / n for k in prof if k.endswith("_ms")}
+    t_pg = (per["p2g_ms"] + per["g2p_v_ms"] + per["g2p_e_ms"]) * 1e-3
+    peak, peak_src = measured_peaks()
+    bytes_pg = algorithmic_bytes(sc, A)
+    achieved = bytes_pg / t_pg / 1e9
+    roofline = {"bound": "hbm", "kernel": "p2g + g2p (k_p2g<0,1,2>, k_g2p_vertices, k_g2p_traditional, k_g2p_elements)",
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "algorithmic_bytes_per_substep": bytes_pg, "active_nodes": A,
+                "phase_us_per_substep": {k[:-3]: round(v * 1e3, 2) for k, v in per.items()}}
+
+    line = {"metric": METRIC, "value": value, "unit": "substeps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C3: {sc.n_particles} cloth particles ({sc.n_elements} elements + {sc.n_vertices} "
+                                   f"vertices), {sc.n_grid}^3 grid, capsule body collider ({sc.body_verts.shape[0]} verts / "
+                                   f"{sc.body_faces.shape[0]} faces) + {sc.num_joint_v} joint vertices/faces, dt=1e-4",
+                       "substeps_per_step": S_PER, "l2": "256 MiB L2 flush between timed steps",
+                       "parallelism": "1 rollout per GPU (independent finite-difference probes), no collective"},
+            "clocks": clk, "e2e": {"value": e2e_value, "unit": "substeps/s", "h2d_bytes_per_step": h2d,
+                                   "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline, "finite": finite,
+            "active_blocks": int(stats["n_active_blocks"]), "resorts": int(stats["n_resorts"])}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample(sc)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
