@@ -54,7 +54,12 @@ def compare(o, state, sc, tol_xv=TOL_XV, tol_aux=TOL_AUX):
     assert np.isfinite(x).all() and np.isfinite(v).all()
     assert rel(x, o.x) < tol_xv, ("x", rel(x, o.x))
     assert rel(v, o.v) < tol_xv, ("v", rel(v, o.v))
-    assert rel(state.particle_C.cpu().numpy(), o.C) < tol_aux, ("C", rel(state.particle_C.cpu().numpy(), o.C))
+    # C = 4/dx * sum w v (x_i - x_p): an allowed velocity error eps_v maps to 4*inv_dx*eps_v in C, which is
+    # the floor when the true affine field is ~0 (cloth at rest: C is pure round-off)
+    Cc = state.particle_C.cpu().numpy()
+    inv_dx = sc.n_grid / sc.grid_lim
+    c_tol = tol_aux * np.abs(o.C).max() + tol_xv * np.abs(o.v).max() * 4.0 * inv_dx
+    assert np.abs(Cc - o.C).max() < c_tol, ("C", np.abs(Cc - o.C).max(), c_tol)
     if sc.n_elements:
         assert rel(state.particle_d.cpu().numpy(), o.d) < tol_aux
         # cloth at rest has stress ~ round-off of mu*vol: compare against that scale, not against noise
