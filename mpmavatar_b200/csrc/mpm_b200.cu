@@ -89,9 +89,9 @@ __global__ void k_import_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, C
     int s = Nnv + perm[i];
     VRec r;
     r.xm = make_float4(c.x[3 * s], c.x[3 * s + 1], c.x[3 * s + 2], c.mass[s]);
-    r.vv = make_float4(c.v[3 * s], c.v[3 * s + 1], c.v[3 * s + 2], 0.f);
+    r.f = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 3; k++) r.v[k] = c.v[3 * s + k];
     for (int k = 0; k < 9; k++) r.C[k] = c.C[9 * (size_t)s + k];
-    r.f[0] = r.f[1] = r.f[2] = 0.f;
     rec[i] = r;
 }
 __global__ void k_export_E(int Ne, const uint32_t* __restrict__ perm, Canon c, const PRec* rec, const EAux* aux) {
@@ -129,9 +129,10 @@ __global__ void k_export_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, C
     int vl = perm[i];
     VRec r = rec[i];
     c.x[3 * s] = r.xm.x; c.x[3 * s + 1] = r.xm.y; c.x[3 * s + 2] = r.xm.z;
-    c.v[3 * s] = r.vv.x; c.v[3 * s + 1] = r.vv.y; c.v[3 * s + 2] = r.vv.z;
+    for (int k = 0; k < 3; k++) c.v[3 * s + k] = r.v[k];
     for (int k = 0; k < 9; k++) c.C[9 * (size_t)s + k] = r.C[k];
-    for (int k = 0; k < 3; k++) c.vforce[3 * vl + k] = dbg_f ? dbg_f[3 * i + k] : r.f[k];
+    const float fr[3] = {r.f.x, r.f.y, r.f.z};
+    for (int k = 0; k < 3; k++) c.vforce[3 * vl + k] = dbg_f ? dbg_f[3 * i + k] : fr[k];
 }
 template <typename Rec>
 __global__ void k_alloc_blocks(Grid g, int n, const Rec* __restrict__ rec) {
@@ -225,6 +226,12 @@ struct MpmSolver {
     bool debug = false, profiling = false;
     float* dbg_f = nullptr;
     unsigned long long* node_mask = nullptr;
+    // device block count mirrored (asynchronously) into pinned host memory after each re-sort
+    int* h_nslots = nullptr;
+    int slots_seen = 0;
+    void* graph_cache_ptr = nullptr;
+    bool use_graphs = true;
+    cudaStream_t cap_stream = nullptr;
     // profiling
     cudaEvent_t ev[10]{};
     MpmProfile prof{};
@@ -278,6 +285,7 @@ static void resort(MpmSolver* s, cudaStream_t q) {
     if (s->Ne) k_alloc_blocks<PRec><<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->erec);
     if (s->Nt) k_alloc_blocks<PRec><<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->trec);
     if (s->Nv) k_alloc_blocks<VRec><<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->vrec);
+    CK(cudaMemcpyAsync(s->h_nslots, s->g.n_slots, sizeof(int), cudaMemcpyDeviceToHost, q));
     s->launches += 7;
     s->need_sort = false;
     s->since_sort = 0;
@@ -302,6 +310,7 @@ struct SubstepArgs {
     float dt;
     bool collider, mover, advance_mesh;
     int njt;
+    int grid_blocks;
 };
 
 static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
@@ -322,9 +331,10 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
     if (s->Ne) { k_stress_elements<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->eaux, s->erec, s->vrec, s->md.friction_coeff); s->launches++; }
     if (s->Nt) { k_stress_traditional<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->taux, s->trec, s->md, a.dt); s->launches++; }
     if (ev) CK(cudaEventRecord(ev[1], q));
-    if (s->Ne) { k_p2g<0><<<cdiv(s->Ne, 256), 256, 8 * 32 * sizeof(PRec), q>>>(s->g, (const float*)s->erec, s->Ne, a.dt, s->md.rpic); s->launches++; }
-    if (s->Nt) { k_p2g<1><<<cdiv(s->Nt, 256), 256, 8 * 32 * sizeof(PRec), q>>>(s->g, (const float*)s->trec, s->Nt, a.dt, s->md.rpic); s->launches++; }
-    if (s->Nv) { k_p2g<2><<<cdiv(s->Nv, 256), 256, 8 * 32 * sizeof(VRec), q>>>(s->g, (const float*)s->vrec, s->Nv, a.dt, s->md.rpic); s->launches++; }
+    const int ppb = 32 * P2G_WARPS;
+    if (s->Ne) { k_p2g<0><<<cdiv(s->Ne, ppb), ppb, P2G_SMEM, q>>>(s->g, (const float*)s->erec, s->Ne, a.dt, s->md.rpic); s->launches++; }
+    if (s->Nt) { k_p2g<1><<<cdiv(s->Nt, ppb), ppb, P2G_SMEM, q>>>(s->g, (const float*)s->trec, s->Nt, a.dt, s->md.rpic); s->launches++; }
+    if (s->Nv) { k_p2g<2><<<cdiv(s->Nv, ppb), ppb, P2G_SMEM, q>>>(s->g, (const float*)s->vrec, s->Nv, a.dt, s->md.rpic); s->launches++; }
     if (ev) CK(cudaEventRecord(ev[2], q));
     if (a.collider) {
         k_collider_scatter<<<cdiv(s->cfg.n_mesh_f, 128), 128, 0, q>>>(s->g, s->cfg.n_mesh_f, s->mesh_faces, s->mesh_x, s->mesh_v, s->st, a.dt, a.advance_mesh ? 1 : 0);
@@ -339,21 +349,40 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
         }
     }
     if (ev) CK(cudaEventRecord(ev[4], q));
-    k_grid_update<<<148 * 4, 256, 0, q>>>(s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, s->d_bcs, n_bc, s->st);
+    // one thread per node of the allocated blocks; the block count lives on the device, so the grid is
+    // sized from the last value copied back (a hint: the kernel grid-strides over the true count)
+    k_grid_update<<<a.grid_blocks, 256, 0, q>>>(s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, s->d_bcs, n_bc, s->st);
     s->launches++;
     if (ev) CK(cudaEventRecord(ev[5], q));
-    if (s->Nv) { k_g2p_vertices<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->vrec, a.dt, s->debug ? s->dbg_f : nullptr); s->launches++; }
-    if (s->Nt) { k_g2p_traditional<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->trec, s->taux, a.dt); s->launches++; }
+    Advance none{nullptr, nullptr, 0}, adv{s->st, s->d_bcs, n_bc};
+    const int last = s->Ne ? 2 : (s->Nt ? 1 : 0);  // the last kernel of the substep advances time
+    if (s->Nv) { k_g2p_vertices<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->vrec, a.dt, s->debug ? s->dbg_f : nullptr, last == 0 ? adv : none); s->launches++; }
+    if (s->Nt) { k_g2p_traditional<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->trec, s->taux, a.dt, last == 1 ? adv : none); s->launches++; }
     if (ev) CK(cudaEventRecord(ev[6], q));
-    if (s->Ne) { k_g2p_elements<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->erec, s->eaux, s->vrec, a.dt); s->launches++; }
-    if (ev) CK(cudaEventRecord(ev[7], q));
-    k_advance<<<1, 32, 0, q>>>(s->st, a.dt, s->d_bcs, n_bc);
-    s->launches++;
+    if (s->Ne) { k_g2p_elements<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->erec, s->eaux, s->vrec, a.dt, last == 2 ? adv : none); s->launches++; }
     if (ev) {
+        CK(cudaEventRecord(ev[7], q));
         CK(cudaEventRecord(ev[8], q));
         s->pending.push_back(evs);
     }
 }
+
+// ---------------------------------------------------------------- CUDA graphs
+// A captured run of GRAPH_U substeps is replayed instead of ~8 launches per substep; every
+// per-substep quantity (time, substep index, block count) lives in device memory, so one
+// instantiated graph serves every call with the same launch geometry.
+constexpr int GRAPH_U = 16;
+struct GraphKey {
+    float dt;
+    int collider, mover, advance_mesh, njt, grid_blocks, n_bc, n_ops, debug;
+    bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;
+    int launches_per_replay;
+};
+static std::vector<GraphEntry>& graph_cache(MpmSolver* s);
 
 static void drain_profile(MpmSolver* s) {
     for (auto& evs : s->pending) {
@@ -371,6 +400,68 @@ static void drain_profile(MpmSolver* s) {
         for (auto& e : evs) cudaEventDestroy(e);
     }
     s->pending.clear();
+}
+
+static std::vector<GraphEntry>& graph_cache(MpmSolver* s) {
+    if (!s->graph_cache_ptr) s->graph_cache_ptr = new std::vector<GraphEntry>();
+    return *static_cast<std::vector<GraphEntry>*>(s->graph_cache_ptr);
+}
+static void destroy_graphs(MpmSolver* s) {
+    if (!s->graph_cache_ptr) return;
+    auto& v = graph_cache(s);
+    for (auto& e : v) cudaGraphExecDestroy(e.exec);
+    delete &v;
+    s->graph_cache_ptr = nullptr;
+}
+static int grid_blocks_hint(MpmSolver* s) {
+    int seen = std::max(s->slots_seen, *s->h_nslots);
+    s->slots_seen = seen;
+    // round up to a power of two so that the launch geometry (and the graph key) changes rarely
+    int want = std::max(64, seen + seen / 4 + 32);
+    int p2 = 64;
+    while (p2 < want) p2 <<= 1;
+    p2 = std::min(p2, s->g.cap);
+    return std::min(cdiv((long long)p2 * BN, 256), 65535 * 8);
+}
+static void run_substeps(MpmSolver* s, SubstepArgs a, int count, cudaStream_t q) {
+    a.grid_blocks = grid_blocks_hint(s);
+    const bool graphs = s->use_graphs && !s->profiling;
+    while (count > 0) {
+        if (graphs && count >= GRAPH_U) {
+            GraphKey key{};
+            key.dt = a.dt; key.collider = a.collider; key.mover = a.mover; key.advance_mesh = a.advance_mesh;
+            key.njt = a.njt; key.grid_blocks = a.grid_blocks; key.n_bc = (int)s->h_bcs.size();
+            key.n_ops = (int)s->h_ops.size(); key.debug = s->debug;
+            auto& cache = graph_cache(s);
+            GraphEntry* hit = nullptr;
+            for (auto& e : cache) if (e.key == key) hit = &e;
+            if (!hit) {
+                cudaGraph_t graph;
+                int before = s->launches;
+                // capture on a private stream (the caller's stream may be the legacy default stream,
+                // which cannot be captured); the instantiated graph is launched on the caller's stream
+                if (!s->cap_stream) CK(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+                CK(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
+                for (int i = 0; i < GRAPH_U; i++) launch_substep(s, a, s->cap_stream);
+                CK(cudaStreamEndCapture(s->cap_stream, &graph));
+                GraphEntry e;
+                e.key = key;
+                e.launches_per_replay = s->launches - before;
+                s->launches = before;
+                CK(cudaGraphInstantiate(&e.exec, graph, 0));
+                cudaGraphDestroy(graph);
+                if (cache.size() > 32) { for (auto& c : cache) cudaGraphExecDestroy(c.exec); cache.clear(); }
+                cache.push_back(e);
+                hit = &cache.back();
+            }
+            CK(cudaGraphLaunch(hit->exec, q));
+            s->launches += hit->launches_per_replay;
+            count -= GRAPH_U;
+        } else {
+            launch_substep(s, a, q);
+            count -= 1;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- C-ABI
@@ -399,8 +490,8 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         if (prop.major < 9) throw std::string("mpm_b200 needs sm_90+ vector atomics; built for sm_100a");
         s->N = cfg->n_particles; s->Ne = cfg->n_elements; s->Nv = cfg->n_vertices;
         s->Nnv = s->N - s->Nv; s->Nt = s->Nnv - s->Ne;
-        if (s->N <= 0 || s->Ne < 0 || s->Nv < 0 || s->Nt < 0 || cfg->n_grid < 8 || cfg->n_grid > 1024)
-            throw std::string("invalid particle counts or n_grid (8..1024)");
+        if (s->N <= 0 || s->Ne < 0 || s->Nv < 0 || s->Nt < 0 || cfg->n_grid < 8 || cfg->n_grid > 1020)
+            throw std::string("invalid particle counts or n_grid (8..1020)");
         if (cfg->resort_interval > 0) s->resort_interval = cfg->resort_interval;
         Grid& g = s->g;
         g.n = cfg->n_grid;
@@ -457,13 +548,15 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         s->d_bcs = s->dalloc<BCDesc>(MAX_BC);
         s->d_ops = s->dalloc<ParticleOp>(MAX_OPS);
         s->st = s->dalloc<StepState>(1);
+        CK(cudaHostAlloc((void**)&s->h_nslots, sizeof(int), cudaHostAllocDefault));
+        *s->h_nslots = 0;
         // model defaults (mpm_data_structure.py:686-715)
         s->md.material = 0; s->md.hardening = 0; s->md.friction_coeff = 0.f; s->md.alpha = 0.f;
         s->md.gx = s->md.gy = s->md.gz = 0.f; s->md.rpic = 0.f; s->md.damping = 1.1f;
         s->md.xi = 0.f; s->md.plastic_viscosity = 0.f; s->md.softening = 0.1f;
-        CK(cudaFuncSetAttribute(k_p2g<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * (int)sizeof(PRec)));
-        CK(cudaFuncSetAttribute(k_p2g<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * (int)sizeof(PRec)));
-        CK(cudaFuncSetAttribute(k_p2g<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * (int)sizeof(VRec)));
+        CK(cudaFuncSetAttribute(k_p2g<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
+        CK(cudaFuncSetAttribute(k_p2g<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
+        CK(cudaFuncSetAttribute(k_p2g<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
         CK(cudaDeviceSynchronize());
         CK(cudaGetLastError());
     } catch (const std::string& e) {
@@ -480,6 +573,9 @@ void mpm_destroy(MpmSolver* s) {
     if (!s) return;
     cudaSetDevice(s->cfg.device);
     cudaDeviceSynchronize();
+    destroy_graphs(s);
+    if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
+    if (s->h_nslots) cudaFreeHost(s->h_nslots);
     for (void* p : s->allocs) cudaFree(p);
     delete s;
 }
@@ -649,13 +745,16 @@ int mpm_step(MpmSolver* s, float dt, int nsub, const MpmFrameInputs* in, void* s
     }
     k_reset_k<<<1, 1, 0, q>>>(s->st);
     s->launches++;
-    for (int k = 0; k < nsub; k++) {
+    int left = nsub;
+    while (left > 0) {
         if (s->need_sort || s->since_sort >= s->resort_interval) resort(s, q);
-        launch_substep(s, a, q);
-        s->since_sort++;
-        s->n_substeps++;
+        int chunk = std::min(left, s->resort_interval - s->since_sort);
+        run_substeps(s, a, chunk, q);
+        s->since_sort += chunk;
+        s->n_substeps += chunk;
         s->canon_stale = true;
-        s->host_time += (double)dt;
+        for (int k = 0; k < chunk; k++) s->host_time += (double)dt;
+        left -= chunk;
     }
     CK(cudaGetLastError());
     API_END(s)

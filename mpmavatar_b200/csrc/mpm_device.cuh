@@ -33,10 +33,10 @@ struct __align__(16) PRec {  // element / traditional particle record, 112 B
     float pad[2];
 };
 struct __align__(16) VRec {  // cloth-vertex particle record, 80 B
-    float4 xm;
-    float4 vv;
+    float4 xm;    // x, y, z, mass
+    float4 f;     // vertex_force accumulated by the element stress kernel (one REDG.128 per corner), w unused
+    float v[3];
     float C[9];
-    float f[3];   // vertex_force accumulated by the element stress kernel
 };
 struct __align__(16) EAux {  // element constitutive state, 80 B
     float dc[9];  // direction matrix, COLUMN-major: d1 | d2 | d3
@@ -91,6 +91,11 @@ struct ModelDev {
     float gx, gy, gz;
     float rpic, damping, xi, plastic_viscosity, softening;
 };
+
+__device__ __forceinline__ float4 rec_v(const PRec& r) { return r.vv; }
+__device__ __forceinline__ float4 rec_v(const VRec& r) { return make_float4(r.v[0], r.v[1], r.v[2], 0.f); }
+__device__ __forceinline__ void rec_set_v(PRec& r, float4 v) { r.vv = v; }
+__device__ __forceinline__ void rec_set_v(VRec& r, float4 v) { r.v[0] = v.x; r.v[1] = v.y; r.v[2] = v.z; }
 
 // ------------------------------------------------------------------ small math
 __device__ __forceinline__ void mat_mul(const float* a, const float* b, float* o) {

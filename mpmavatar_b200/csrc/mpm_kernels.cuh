@@ -89,12 +89,10 @@ __global__ void __launch_bounds__(128) k_stress_elements(int Ne, EAux* __restric
         f3[r] = -vol * iD22 * P2[r];
         f1[r] = -(f2[r] + f3[r]);
     }
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-        atomicAdd(&vrec[a.face[0]].f[r], f1[r]);
-        atomicAdd(&vrec[a.face[1]].f[r], f2[r]);
-        atomicAdd(&vrec[a.face[2]].f[r], f3[r]);
-    }
+    // one 16-byte vector atomic per corner (REDG.E.ADD.F32x4) instead of three scalar ones
+    atomicAdd(&vrec[a.face[0]].f, make_float4(f1[0], f1[1], f1[2], 0.f));
+    atomicAdd(&vrec[a.face[1]].f, make_float4(f2[0], f2[1], f2[2], 0.f));
+    atomicAdd(&vrec[a.face[2]].f, make_float4(f3[0], f3[1], f3[2], 0.f));
     // stress = vol * P3 (x) d3 with the return-mapped d3
     PRec* pr = &rec[e];
 #pragma unroll
@@ -229,7 +227,7 @@ __global__ void k_particle_ops(int n, Rec* __restrict__ rec, const uint32_t* __r
     if (p >= n) return;
     float time = (float)st->time;
     int ci = canon_offset + (int)perm[p];
-    float4 vv = rec[p].vv;
+    float4 vv = rec_v(rec[p]);
     float m = rec[p].xm.w;
     bool ch = false;
     for (int k = 0; k < n_ops; k++) {
@@ -240,62 +238,96 @@ __global__ void k_particle_ops(int n, Rec* __restrict__ rec, const uint32_t* __r
         if (op.kind == 1 && mk >= 1) { vv.x += op.vec[0] * dt; vv.y += op.vec[1] * dt; vv.z += op.vec[2] * dt; ch = true; }
         if (op.kind == 2 && mk == 1) { vv.x = op.vec[0]; vv.y = op.vec[1]; vv.z = op.vec[2]; ch = true; }
     }
-    if (ch) rec[p].vv = vv;
+    if (ch) rec_set_v(rec[p], vv);
 }
 
 // ============================================================ P2G
-// p2g_apic_with_stress (mpm_utils.py:484-557), restructured for cell-sorted particles:
-// a warp takes a slab of 32 consecutive records into shared memory; lane l (< 27) owns stencil
-// node l of the CURRENT cell and accumulates the contributions of the run of particles that
-// share that cell in registers; when the cell changes the 27 lanes flush with one
-// REDG.E.ADD.F32x4 each.  No intra-warp reduction, no shared-memory atomics, and the number of
-// global atomics drops from 27*4 per particle to 27 per (cell run).
+// PTX helpers: 1-D bulk async copy (TMA unit, SASS UBLKCP) completing on an mbarrier.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+
+// p2g_apic_with_stress (mpm_utils.py:484-557), restructured for cell-sorted particles.
+//  stage 0  one cp.async.bulk per warp brings its slab of 32 consecutive AoS records into smem.
+//  stage 1  lane = particle: each lane turns its record into a separable "pack".  With
+//           dpos = (ijk - f) dx the contribution to stencil node (i,j,k) is
+//             w m (v + C dpos) + dt force = A w + ux[i] wy wz + wx uy[j] wz + wx wy uz[k]
+//           with A = m (v - dx C f) (+ dt f_vertex), u_a[i] = m dx C[:,a] i w_a[i] - dt vol/dx S[:,a] dw_a[i],
+//           so a pack is three float4 per axis {w, u_0, u_1, u_2} plus {A_0, A_1, A_2, m}.
+//  stage 2  lane = stencil node (27 of 32 lanes): walk the 32 packs; particles of one cell form a
+//           run, whose 27 node sums are accumulated in registers and flushed with ONE
+//           REDG.E.ADD.F32x4 per node when the cell changes.  No intra-warp reduction, no
+//           shared-memory atomics; global atomics drop from 27*4 per particle to 27 per cell run.
 // KIND 0: element (S already holds vol*P3(x)d3), 1: traditional (stress*vol, :496), 2: vertex.
+constexpr int P2G_PK = 40;                       // floats per pack
+constexpr int P2G_WARP_BYTES = 32 * P2G_PK * 4 + 32 * 4;  // packs + cell ids
+constexpr int P2G_WARPS = 8;
+constexpr int P2G_SMEM = 128 + P2G_WARPS * P2G_WARP_BYTES;
+
 template <int KIND>
-__global__ void __launch_bounds__(256) k_p2g(Grid g, const float* __restrict__ recs, int n, float dt, float rpic) {
+__global__ void __launch_bounds__(32 * P2G_WARPS) k_p2g(Grid g, const float* __restrict__ recs, int n, float dt, float rpic) {
     constexpr int RS = (KIND == 2) ? (int)(sizeof(VRec) / 4) : (int)(sizeof(PRec) / 4);
-    extern __shared__ float4 smem4[];
+    extern __shared__ __align__(128) unsigned char p2g_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p0 = (blockIdx.x * 8 + warp) * 32;
+    const int p0 = (blockIdx.x * P2G_WARPS + warp) * 32;
     if (p0 >= n) return;
     const int cnt = min(32, n - p0);
-    float* sw = reinterpret_cast<float*>(smem4) + warp * 32 * RS;
-    {
-        const float4* src = reinterpret_cast<const float4*>(recs + (size_t)p0 * RS);
-        float4* dst = reinterpret_cast<float4*>(sw);
-        const int n4 = cnt * RS / 4;
-        for (int i = lane; i < n4; i += 32) dst[i] = src[i];
-    }
+    uint64_t* bar = reinterpret_cast<uint64_t*>(p2g_smem) + warp;
+    float* buf = reinterpret_cast<float*>(p2g_smem + 128 + warp * P2G_WARP_BYTES);
+    int* cell = reinterpret_cast<int*>(buf + 32 * P2G_PK);
+    // ---- stage 0
+    if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
-    const int li = lane / 9, lj = (lane / 3) % 3, lk = lane % 3;
-    const bool act = lane < 27;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int cbx = INT_MIN, cby = 0, cbz = 0;
-    for (int q = 0; q < cnt; q++) {
-        const float* r = sw + q * RS;
-        const float4 xm = *reinterpret_cast<const float4*>(r);
-        const float4 vv = *reinterpret_cast<const float4*>(r + 4);
-        const float gx = xm.x * g.inv_dx, gy = xm.y * g.inv_dx, gz = xm.z * g.inv_dx;
-        const int bx = (int)(gx - 0.5f), by = (int)(gy - 0.5f), bz = (int)(gz - 0.5f);
-        if (bx != cbx || by != cby || bz != cbz) {  // warp-uniform
-            if (act && (acc.w != 0.0f || acc.x != 0.0f || acc.y != 0.0f || acc.z != 0.0f)) {
-                int ni = node_index(g, cbx + li, cby + lj, cbz + lk);
-                if (ni >= 0) atomicAdd(&g.acc[ni], acc);
-                else g.flags[1] = 1;
-            }
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            cbx = bx; cby = by; cbz = bz;
-        }
-        const float fx = gx - (float)bx, fy = gy - (float)by, fz = gz - (float)bz;
-        float wx, wy, wz, dwx, dwy, dwz;
-        bspline(fx, li, wx, dwx);
-        bspline(fy, lj, wy, dwy);
-        bspline(fz, lk, wz, dwz);
-        const float w = wx * wy * wz;
-        const float dpx = ((float)li - fx) * g.dx, dpy = ((float)lj - fy) * g.dx, dpz = ((float)lk - fz) * g.dx;
-        float C[9];
+    if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)(cnt * RS * 4));
+        bulk_g2s(buf, recs + (size_t)p0 * RS, (uint32_t)(cnt * RS * 4), bar);
+    }
+    while (!mbar_try_wait(bar, 0)) {}
+    // ---- stage 1
+    float r[RS];
+    if (lane < cnt) {
+        const float4* src = reinterpret_cast<const float4*>(buf + lane * RS);
 #pragma unroll
-        for (int i = 0; i < 9; i++) C[i] = r[8 + i];
+        for (int i = 0; i < RS / 4; i++) {
+            float4 t = src[i];
+            r[4 * i] = t.x; r[4 * i + 1] = t.y; r[4 * i + 2] = t.z; r[4 * i + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < RS; i++) r[i] = 0.f;
+    }
+    __syncwarp();  // packs overwrite the raw slab
+    {
+        const float m = r[3];
+        float v[3], C[9], Sp[9];
+        if (KIND == 2) {
+            v[0] = r[8]; v[1] = r[9]; v[2] = r[10];
+#pragma unroll
+            for (int i = 0; i < 9; i++) { C[i] = r[11 + i]; Sp[i] = 0.f; }
+        } else {
+            v[0] = r[4]; v[1] = r[5]; v[2] = r[6];
+            const float sc = -dt * g.inv_dx * ((KIND == 1) ? r[7] : 1.0f);
+#pragma unroll
+            for (int i = 0; i < 9; i++) { C[i] = r[8 + i]; Sp[i] = sc * r[17 + i]; }
+        }
         if (rpic != 0.0f) {  // mpm_utils.py:528-542
             float Cn[9];
 #pragma unroll
@@ -306,26 +338,60 @@ __global__ void __launch_bounds__(256) k_p2g(Grid g, const float* __restrict__ r
 #pragma unroll
             for (int i = 0; i < 9; i++) C[i] = (rpic < -0.001f) ? 0.0f : Cn[i];
         }
-        float fo[3];
-        if (KIND == 2) {
-            fo[0] = w * r[17]; fo[1] = w * r[18]; fo[2] = w * r[19];
-        } else {
-            const float sc = (KIND == 1) ? vv.w : 1.0f;
-            const float d0 = dwx * wy * wz * g.inv_dx, d1 = wx * dwy * wz * g.inv_dx, d2 = wx * wy * dwz * g.inv_dx;
+        const float gp[3] = {r[0] * g.inv_dx, r[1] * g.inv_dx, r[2] * g.inv_dx};
+        int b[3];
+        float f[3];
 #pragma unroll
-            for (int a = 0; a < 3; a++) fo[a] = -sc * (r[17 + 3 * a] * d0 + r[18 + 3 * a] * d1 + r[19 + 3 * a] * d2);
+        for (int a = 0; a < 3; a++) { b[a] = (int)(gp[a] - 0.5f); f[a] = gp[a] - (float)b[a]; }
+        float4* out = reinterpret_cast<float4*>(buf + lane * P2G_PK);
+        const float mdx = m * g.dx;
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                float w, dw;
+                bspline(f[a], i, w, dw);
+                const float iw = (float)i * w * mdx;
+                out[3 * a + i] = make_float4(w, C[a] * iw + Sp[a] * dw, C[3 + a] * iw + Sp[3 + a] * dw,
+                                             C[6 + a] * iw + Sp[6 + a] * dw);
+            }
+        float A[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) A[c] = m * (v[c] - g.dx * (C[3 * c] * f[0] + C[3 * c + 1] * f[1] + C[3 * c + 2] * f[2]));
+        if (KIND == 2) { A[0] += dt * r[4]; A[1] += dt * r[5]; A[2] += dt * r[6]; }
+        out[9] = make_float4(A[0], A[1], A[2], m);
+        cell[lane] = (clampi(b[0] + 2, 0, 1023)) | (clampi(b[1] + 2, 0, 1023) << 10) | (clampi(b[2] + 2, 0, 1023) << 20);
+    }
+    __syncwarp();
+    // ---- stage 2
+    const bool act = lane < 27;
+    const int li = act ? lane / 9 : 0, lj = act ? (lane / 3) % 3 : 0, lk = act ? lane % 3 : 0;
+    const float4* P = reinterpret_cast<const float4*>(buf);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cur = cell[0];
+    auto flush = [&](int c) {
+        if (act && (acc.w != 0.0f || acc.x != 0.0f || acc.y != 0.0f || acc.z != 0.0f)) {
+            int ni = node_index(g, (c & 1023) - 2 + li, ((c >> 10) & 1023) - 2 + lj, ((c >> 20) & 1023) - 2 + lk);
+            if (ni >= 0) atomicAdd(&g.acc[ni], acc);
+            else g.flags[1] = 1;
         }
-        const float wm = w * xm.w;
-        acc.x += wm * (vv.x + (C[0] * dpx + C[1] * dpy + C[2] * dpz)) + dt * fo[0];
-        acc.y += wm * (vv.y + (C[3] * dpx + C[4] * dpy + C[5] * dpz)) + dt * fo[1];
-        acc.z += wm * (vv.z + (C[6] * dpx + C[7] * dpy + C[8] * dpz)) + dt * fo[2];
-        acc.w += wm;
+    };
+#pragma unroll 4
+    for (int q = 0; q < cnt; q++) {
+        const int c = cell[q];
+        if (c != cur) {  // warp-uniform
+            flush(cur);
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            cur = c;
+        }
+        const float4 X = P[q * 10 + li], Y = P[q * 10 + 3 + lj], Z = P[q * 10 + 6 + lk], H = P[q * 10 + 9];
+        const float wyz = Y.x * Z.x, wxz = X.x * Z.x, wxy = X.x * Y.x, w = X.x * wyz;
+        acc.x += H.x * w + X.y * wyz + Y.y * wxz + Z.y * wxy;
+        acc.y += H.y * w + X.z * wyz + Y.z * wxz + Z.z * wxy;
+        acc.z += H.z * w + X.w * wyz + Y.w * wxz + Z.w * wxy;
+        acc.w += H.w * w;
     }
-    if (act && (acc.w != 0.0f || acc.x != 0.0f || acc.y != 0.0f || acc.z != 0.0f)) {
-        int ni = node_index(g, cbx + li, cby + lj, cbz + lk);
-        if (ni >= 0) atomicAdd(&g.acc[ni], acc);
-        else g.flags[1] = 1;
-    }
+    flush(cur);
 }
 
 // ============================================================ collider / mover scatter
@@ -349,9 +415,34 @@ __device__ __forceinline__ void make_stencil(const Grid& g, float x, float y, fl
 __device__ __forceinline__ bool scatter_ok(const Grid& g, const Stencil& s) {
     return s.b[0] >= 0 && s.b[0] < g.n - 3 && s.b[1] >= 0 && s.b[1] < g.n - 3 && s.b[2] >= 0 && s.b[2] < g.n - 3;
 }
+// the (up to) 2x2x2 pool slots under a 3^3 stencil whose base node is (bx,by,bz) >= 0:
+// eight independent table loads issued together instead of 27 dependent ones
+__device__ __forceinline__ void load_slots8(const Grid& g, int bx, int by, int bz, int* sl) {
+    const int X0 = bx >> 2, Y0 = by >> 2, Z0 = bz >> 2;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int X = X0 + (c >> 2), Y = Y0 + ((c >> 1) & 1), Z = Z0 + (c & 1);
+        bool ok = bx >= 0 && by >= 0 && bz >= 0 && X < g.nb && Y < g.nb && Z < g.nb;
+        sl[c] = ok ? lookup_slot(g, X, Y, Z) : -1;
+    }
+}
+__device__ __forceinline__ int sel8(const int* sl, int c) {
+    int s = sl[0];
+#pragma unroll
+    for (int q = 1; q < 8; q++) s = (c == q) ? sl[q] : s;
+    return s;
+}
+// pool index of stencil node (i,j,k) given the 8 slots, -1 if its block is not allocated
+__device__ __forceinline__ int stencil_node(const int* sl, int bx, int by, int bz, int i, int j, int k) {
+    const int ix = bx + i, iy = by + j, iz = bz + k;
+    const int c = (((ix >> 2) - (bx >> 2)) << 2) | (((iy >> 2) - (by >> 2)) << 1) | ((iz >> 2) - (bz >> 2));
+    const int s = sel8(sl, c);
+    return s < 0 ? -1 : s * BN + ((ix & 3) << 4) + ((iy & 3) << 2) + (iz & 3);
+}
 
 // compute_mesh (mpm_solver.py:829-880).  Only nodes of ALLOCATED blocks are written: a node
-// outside every particle stencil is never read by G2P, so the body mesh never allocates grid.
+// outside every particle stencil is never read by G2P, so the body mesh never allocates grid
+// (and faces far from the cloth cost eight table reads and nothing else).
 __global__ void __launch_bounds__(128) k_collider_scatter(Grid g, int Mf, const int* __restrict__ faces,
                                                           const float* __restrict__ px, const float* __restrict__ pv,
                                                           const StepState* __restrict__ st, float dt, int advance) {
@@ -371,18 +462,27 @@ __global__ void __launch_bounds__(128) k_collider_scatter(Grid g, int Mf, const 
         }
 #pragma unroll
     for (int a = 0; a < 3; a++) { fv[a] = fv[a] / 3.0f; fp[a] = fp[a] / 3.0f; }
+    Stencil sp;
+    make_stencil(g, fp[0], fp[1], fp[2], sp);
+    if (!scatter_ok(g, sp)) return;
+    int sl[8];
+    load_slots8(g, sp.b[0], sp.b[1], sp.b[2], sl);
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < 8; c++) any = any || sl[c] >= 0;
+    if (!any) return;
     float e1[3] = {P[1][0] - P[0][0], P[1][1] - P[0][1], P[1][2] - P[0][2]};
     float e2[3] = {P[2][0] - P[0][0], P[2][1] - P[0][1], P[2][2] - P[0][2]};
     float nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
     float nl = len3(nx, ny, nz);
     if (nl > 0.0f) { nx /= nl; ny /= nl; nz /= nl; } else { nx = ny = nz = 0.0f; }
-    Stencil sp;
-    make_stencil(g, fp[0], fp[1], fp[2], sp);
-    if (!scatter_ok(g, sp)) return;
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++)
+#pragma unroll
             for (int k = 0; k < 3; k++) {
-                int ni = node_index(g, sp.b[0] + i, sp.b[1] + j, sp.b[2] + k);
+                int ni = stencil_node(sl, sp.b[0], sp.b[1], sp.b[2], i, j, k);
                 if (ni < 0) continue;
                 float w = sp.w[0][i] * sp.w[1][j] * sp.w[2][k];
                 atomicAdd(&g.colv[ni], make_float4(w * fv[0], w * fv[1], w * fv[2], w));
@@ -408,11 +508,16 @@ __global__ void __launch_bounds__(128) k_mover_scatter(Grid g, int njt, int njv,
     Stencil sp;
     make_stencil(g, xm.x, xm.y, xm.z, sp);
     if (!scatter_ok(g, sp)) return;
+    int sl[8];
+    load_slots8(g, sp.b[0], sp.b[1], sp.b[2], sl);
     float v0 = vel[0], v1 = vel[1], v2 = vel[2];
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++)
+#pragma unroll
             for (int k = 0; k < 3; k++) {
-                int ni = node_index(g, sp.b[0] + i, sp.b[1] + j, sp.b[2] + k);
+                int ni = stencil_node(sl, sp.b[0], sp.b[1], sp.b[2], i, j, k);
                 if (ni < 0) { g.flags[1] = 1; continue; }
                 float w = sp.w[0][i] * sp.w[1][j] * sp.w[2][k];
                 atomicAdd(&g.mov[ni], make_float4(w * v0, w * v1, w * v2, w));
@@ -433,7 +538,11 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
     const int total = n_slots * BN;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int slot = idx >> 6, l = idx & 63;
-        float4 a = g.acc[idx];
+        // all four accumulator loads are issued before any use (memory-level parallelism)
+        const float4 a = g.acc[idx];
+        const float4 mv = g.mov[idx];
+        float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), cn = cv;
+        if (use_collider) { cv = g.colv[idx]; cn = g.coln[idx]; }
         float vx = 0.f, vy = 0.f, vz = 0.f;
         if (g.dbg_acc) g.dbg_acc[idx] = a;
         if (a.w > 1e-15f) {
@@ -442,46 +551,40 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
             vy = a.y * inv + dt * md.gy;
             vz = a.z * inv + dt * md.gz;
         }
-        if (a.w != 0.0f || a.x != 0.0f || a.y != 0.0f || a.z != 0.0f) g.acc[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.w != 0.0f || a.x != 0.0f || a.y != 0.0f || a.z != 0.0f) g.acc[idx] = zero4;
         if (md.damping < 1.0f) {
             vx -= (1.0f - md.damping) * vx;
             vy -= (1.0f - md.damping) * vy;
             vz -= (1.0f - md.damping) * vz;
         }
-        if (use_collider) {
-            float4 cv = g.colv[idx];
-            if (cv.w != 0.0f) {
-                float4 cn = g.coln[idx];
-                g.colv[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-                g.coln[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (cv.w > 1e-15f) {
-                    float inv = 1.0f / cv.w;
-                    float mx = cv.x * inv, my = cv.y * inv, mz = cv.z * inv;
-                    float rx = vx - mx, ry = vy - my, rz = vz - mz;
-                    float nl = len3(cn.x, cn.y, cn.z);
-                    float nx = 0.f, ny = 0.f, nz = 0.f;
-                    if (nl > 0.0f) { nx = cn.x / nl; ny = cn.y / nl; nz = cn.z / nl; }
-                    float nc = rx * nx + ry * ny + rz * nz;
-                    float mn = fminf(nc, 0.0f);
-                    float px = rx - mn * nx, py = ry - mn * ny, pz = rz - mn * nz;
-                    float pl = len3(px, py, pz);
-                    if (nc < 0.0f && pl > 1e-20f) {
-                        float sc = fmaxf(0.0f, pl + nc * col_friction) / pl;
-                        px *= sc; py *= sc; pz *= sc;
-                    }
-                    vx = px + mx; vy = py + my; vz = pz + mz;
+        if (use_collider && cv.w != 0.0f) {
+            g.colv[idx] = zero4;
+            g.coln[idx] = zero4;
+            if (cv.w > 1e-15f) {
+                float inv = 1.0f / cv.w;
+                float mx = cv.x * inv, my = cv.y * inv, mz = cv.z * inv;
+                float rx = vx - mx, ry = vy - my, rz = vz - mz;
+                float nl = len3(cn.x, cn.y, cn.z);
+                float nx = 0.f, ny = 0.f, nz = 0.f;
+                if (nl > 0.0f) { nx = cn.x / nl; ny = cn.y / nl; nz = cn.z / nl; }
+                float nc = rx * nx + ry * ny + rz * nz;
+                float mn = fminf(nc, 0.0f);
+                float px = rx - mn * nx, py = ry - mn * ny, pz = rz - mn * nz;
+                float pl = len3(px, py, pz);
+                if (nc < 0.0f && pl > 1e-20f) {
+                    float sc = fmaxf(0.0f, pl + nc * col_friction) / pl;
+                    px *= sc; py *= sc; pz *= sc;
                 }
+                vx = px + mx; vy = py + my; vz = pz + mz;
             }
         }
-        {
-            // the mover accumulators are consumed (and cleared) even on steps without joint inputs
-            float4 mv = g.mov[idx];
-            if (mv.w != 0.0f || mv.x != 0.0f || mv.y != 0.0f || mv.z != 0.0f) {
-                g.mov[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (use_mover && mv.w > 1e-15f) {
-                    float inv = 1.0f / mv.w;
-                    vx = mv.x * inv; vy = mv.y * inv; vz = mv.z * inv;
-                }
+        // the mover accumulators are consumed (and cleared) even on steps without joint inputs
+        if (mv.w != 0.0f || mv.x != 0.0f || mv.y != 0.0f || mv.z != 0.0f) {
+            g.mov[idx] = zero4;
+            if (use_mover && mv.w > 1e-15f) {
+                float inv = 1.0f / mv.w;
+                vx = mv.x * inv; vy = mv.y * inv; vz = mv.z * inv;
             }
         }
         if (n_bc > 0) {
@@ -536,16 +639,6 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
     }
 }
 
-// end of substep: self.time += dt (mpm_solver.py:536), substep counter, moving cuboids (:975-981)
-__global__ void k_advance(StepState* st, float dt, BCDesc* bcs, int n_bc) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float time = (float)st->time;
-    for (int k = 0; k < n_bc; k++)
-        if (bcs[k].kind == 1 && time >= bcs[k].start_time && time < bcs[k].end_time)
-            for (int a = 0; a < 3; a++) bcs[k].point[a] = bcs[k].point[a] + dt * bcs[k].velocity[a];
-    st->time = st->time + (double)dt;
-    st->k = st->k + 1;
-}
 __global__ void k_reset_k(StepState* st) { st->k = 0; }
 
 // ============================================================ G2P
@@ -554,71 +647,103 @@ struct Gathered {
     float C[9];
     float G[9];  // grad v
 };
-// shared gather of g2p_v / g2p_e (mpm_utils.py:726-763, 798-836)
+// Shared gather of g2p_v / g2p_e (mpm_utils.py:726-763, 798-836) by sum factorisation: the 27-node
+// sums v = sum w v_n, C = 4/dx sum w v_n (x) (ijk - f), grad v = sum v_n (x) grad w are separable, so
+// contract over k, then j, then i (441 FMA) instead of 27 x 33 flops.  Per axis a:
+//   w_a[i]  weight,  c_a[i] = w_a[i] (i - f_a) 4/dx  (APIC),  d_a[i] = dw_a[i] / dx  (gradient)
 __device__ __forceinline__ void g2p_gather(const Grid& g, float x, float y, float z, Gathered& o) {
-    const float gx = x * g.inv_dx, gy = y * g.inv_dx, gz = z * g.inv_dx;
-    const int bx = (int)(gx - 0.5f), by = (int)(gy - 0.5f), bz = (int)(gz - 0.5f);
-    const float fx = gx - (float)bx, fy = gy - (float)by, fz = gz - (float)bz;
-    float w[3][3], dw[3][3];
+    const float gp[3] = {x * g.inv_dx, y * g.inv_dx, z * g.inv_dx};
+    int b[3];
+    float w[3][3], cw[3][3], dw[3][3];
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-        bspline(fx, i, w[0][i], dw[0][i]);
-        bspline(fy, i, w[1][i], dw[1][i]);
-        bspline(fz, i, w[2][i], dw[2][i]);
+    for (int a = 0; a < 3; a++) {
+        b[a] = (int)(gp[a] - 0.5f);
+        const float f = gp[a] - (float)b[a];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            float ww, dd;
+            bspline(f, i, ww, dd);
+            w[a][i] = ww;
+            cw[a][i] = ww * ((float)i - f) * (g.inv_dx * 4.0f);
+            dw[a][i] = dd * g.inv_dx;
+        }
     }
+    int sl[8];
+    load_slots8(g, b[0], b[1], b[2], sl);
 #pragma unroll
     for (int i = 0; i < 3; i++) o.v[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < 9; i++) { o.C[i] = 0.f; o.G[i] = 0.f; }
-    // up to 2x2x2 blocks under the stencil
-    int sl[8];
-    const int X0 = bx >> 2, Y0 = by >> 2, Z0 = bz >> 2;
+    const int X0 = b[0] >> 2, Y0 = b[1] >> 2, Z0 = b[2] >> 2;
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-        int X = X0 + (c >> 2), Y = Y0 + ((c >> 1) & 1), Z = Z0 + (c & 1);
-        bool ok = bx >= 0 && by >= 0 && bz >= 0 && X < g.nb && Y < g.nb && Z < g.nb;
-        sl[c] = ok ? lookup_slot(g, X, Y, Z) : -1;
-    }
+    for (int i = 0; i < 3; i++) {
+        float A0[3] = {0, 0, 0}, A1[3] = {0, 0, 0}, A2[3] = {0, 0, 0}, B0[3] = {0, 0, 0}, C0[3] = {0, 0, 0};
+        const int ix = b[0] + i, ox = (ix >> 2) - X0;
 #pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++)
+        for (int j = 0; j < 3; j++) {
+            const int iy = b[1] + j, oy = (iy >> 2) - Y0;
+            const int xy = (ox << 2) | (oy << 1);
+            // the z-run of three nodes spans at most two blocks
+            const int sA = (xy == 0) ? sl[0] : (xy == 2) ? sl[2] : (xy == 4) ? sl[4] : sl[6];
+            const int sB = (xy == 0) ? sl[1] : (xy == 2) ? sl[3] : (xy == 4) ? sl[5] : sl[7];
+            const int off = ((ix & 3) << 4) + ((iy & 3) << 2);
+            float a[3] = {0, 0, 0}, bb[3] = {0, 0, 0}, c[3] = {0, 0, 0};
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                const int ix = bx + i, iy = by + j, iz = bz + k;
-                const int c = (((ix >> 2) - X0) << 2) | (((iy >> 2) - Y0) << 1) | ((iz >> 2) - Z0);
-                int s = sl[0];
-#pragma unroll
-                for (int q = 1; q < 8; q++) s = (c == q) ? sl[q] : s;
-                const bool inb = ix < g.n && iy < g.n && iz < g.n;
+                const int iz = b[2] + k;
+                const int sk = ((iz >> 2) == Z0) ? sA : sB;
                 float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (inb && s >= 0) gv = g.vout[s * BN + ((ix & 3) << 4) + ((iy & 3) << 2) + (iz & 3)];
-                else if (inb && bx >= 0 && by >= 0 && bz >= 0) g.flags[1] = 1;
-                const float wt = w[0][i] * w[1][j] * w[2][k];
-                const float dpx = (float)i - fx, dpy = (float)j - fy, dpz = (float)k - fz;
-                const float d0 = dw[0][i] * w[1][j] * w[2][k] * g.inv_dx, d1 = w[0][i] * dw[1][j] * w[2][k] * g.inv_dx,
-                            d2 = w[0][i] * w[1][j] * dw[2][k] * g.inv_dx;
-                const float sc = wt * g.inv_dx * 4.0f;
-                const float vv[3] = {gv.x, gv.y, gv.z};
-#pragma unroll
-                for (int r = 0; r < 3; r++) {
-                    o.v[r] += vv[r] * wt;
-                    o.C[3 * r + 0] += (vv[r] * dpx) * sc;
-                    o.C[3 * r + 1] += (vv[r] * dpy) * sc;
-                    o.C[3 * r + 2] += (vv[r] * dpz) * sc;
-                    o.G[3 * r + 0] += vv[r] * d0;
-                    o.G[3 * r + 1] += vv[r] * d1;
-                    o.G[3 * r + 2] += vv[r] * d2;
-                }
+                if (sk >= 0) gv = g.vout[sk * BN + off + (iz & 3)];
+                else if (b[0] >= 0 && b[1] >= 0 && b[2] >= 0 && ix < g.n && iy < g.n && iz < g.n) g.flags[1] = 1;
+                a[0] += w[2][k] * gv.x; a[1] += w[2][k] * gv.y; a[2] += w[2][k] * gv.z;
+                bb[0] += cw[2][k] * gv.x; bb[1] += cw[2][k] * gv.y; bb[2] += cw[2][k] * gv.z;
+                c[0] += dw[2][k] * gv.x; c[1] += dw[2][k] * gv.y; c[2] += dw[2][k] * gv.z;
             }
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                A0[r] += w[1][j] * a[r];
+                A1[r] += cw[1][j] * a[r];
+                A2[r] += dw[1][j] * a[r];
+                B0[r] += w[1][j] * bb[r];
+                C0[r] += w[1][j] * c[r];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            o.v[r] += w[0][i] * A0[r];
+            o.C[3 * r + 0] += cw[0][i] * A0[r];
+            o.C[3 * r + 1] += w[0][i] * A1[r];
+            o.C[3 * r + 2] += w[0][i] * B0[r];
+            o.G[3 * r + 0] += dw[0][i] * A0[r];
+            o.G[3 * r + 1] += w[0][i] * A2[r];
+            o.G[3 * r + 2] += w[0][i] * C0[r];
+        }
+    }
 }
 __device__ __forceinline__ float clampf(float x, float a, float b) { return fminf(fmaxf(x, a), b); }
 
+// end of substep: self.time += dt (mpm_solver.py:536), substep counter, moving cuboids (:975-981);
+// run by one thread of the LAST kernel of the substep
+__device__ __forceinline__ void advance_step(StepState* st, float dt, BCDesc* bcs, int n_bc) {
+    float time = (float)st->time;
+    for (int k = 0; k < n_bc; k++)
+        if (bcs[k].kind == 1 && time >= bcs[k].start_time && time < bcs[k].end_time)
+            for (int a = 0; a < 3; a++) bcs[k].point[a] = bcs[k].point[a] + dt * bcs[k].velocity[a];
+    st->time = st->time + (double)dt;
+    st->k = st->k + 1;
+}
+struct Advance {
+    StepState* st;  // null: this kernel is not the last one of the substep
+    BCDesc* bcs;
+    int n_bc;
+};
+
 // g2p_v for cloth vertices (mpm_utils.py:716-786); also clears vertex_force for the next substep
 // (replaces set_vec3_to_zero, mpm_solver.py:251-256) and allocates grid blocks for the new position.
-__global__ void __launch_bounds__(128) k_g2p_vertices(Grid g, int Nv, VRec* __restrict__ rec, float dt,
-                                                      float* __restrict__ dbg_f) {
+__global__ void __launch_bounds__(128, 4) k_g2p_vertices(Grid g, int Nv, VRec* __restrict__ rec, float dt,
+                                                      float* __restrict__ dbg_f, Advance adv) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (adv.st && p == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
     if (p >= Nv) return;
     float4 xm = rec[p].xm;
     Gathered o;
@@ -627,20 +752,21 @@ __global__ void __launch_bounds__(128) k_g2p_vertices(Grid g, int Nv, VRec* __re
     xm.x = clampf(xm.x + dt * o.v[0], a_min, a_max);
     xm.y = clampf(xm.y + dt * o.v[1], a_min, a_max);
     xm.z = clampf(xm.z + dt * o.v[2], a_min, a_max);
-    VRec* r = &rec[p];
-    r->xm = xm;
-    r->vv = make_float4(o.v[0], o.v[1], o.v[2], 0.0f);
-#pragma unroll
-    for (int i = 0; i < 9; i++) r->C[i] = o.C[i];
-    if (dbg_f) { dbg_f[3 * p] = r->f[0]; dbg_f[3 * p + 1] = r->f[1]; dbg_f[3 * p + 2] = r->f[2]; }
-    r->f[0] = 0.f; r->f[1] = 0.f; r->f[2] = 0.f;
+    float4* r4 = reinterpret_cast<float4*>(&rec[p]);
+    if (dbg_f) { float4 f = r4[1]; dbg_f[3 * p] = f.x; dbg_f[3 * p + 1] = f.y; dbg_f[3 * p + 2] = f.z; }
+    r4[0] = xm;
+    r4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    r4[2] = make_float4(o.v[0], o.v[1], o.v[2], o.C[0]);
+    r4[3] = make_float4(o.C[1], o.C[2], o.C[3], o.C[4]);
+    r4[4] = make_float4(o.C[5], o.C[6], o.C[7], o.C[8]);
     ensure_stencil_blocks(g, xm.x, xm.y, xm.z);
 }
 
 // g2p_v for traditional particles: additionally F_trial = (I + dt grad v) F (mpm_utils.py:783-786)
-__global__ void __launch_bounds__(128) k_g2p_traditional(Grid g, int Nt, PRec* __restrict__ rec, TAux* __restrict__ aux,
-                                                         float dt) {
+__global__ void __launch_bounds__(128, 4) k_g2p_traditional(Grid g, int Nt, PRec* __restrict__ rec, TAux* __restrict__ aux,
+                                                         float dt, Advance adv) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (adv.st && p == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
     if (p >= Nt) return;
     float4 xm = rec[p].xm;
     Gathered o;
@@ -667,17 +793,21 @@ __global__ void __launch_bounds__(128) k_g2p_traditional(Grid g, int Nt, PRec* _
 
 // g2p_e (mpm_utils.py:788-857): C and grad v at the OLD centroid, x/v = mean of the three
 // already-updated corner vertices, d = [x2-x1, x3-x1, (I + dt grad v) d3]
-__global__ void __launch_bounds__(128) k_g2p_elements(Grid g, int Ne, PRec* __restrict__ rec, EAux* __restrict__ aux,
-                                                      const VRec* __restrict__ vrec, float dt) {
+__global__ void __launch_bounds__(128, 4) k_g2p_elements(Grid g, int Ne, PRec* __restrict__ rec, EAux* __restrict__ aux,
+                                                      const VRec* __restrict__ vrec, float dt, Advance adv) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (adv.st && p == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
     if (p >= Ne) return;
     float4 xm = rec[p].xm;
-    Gathered o;
-    g2p_gather(g, xm.x, xm.y, xm.z, o);
     EAux* a = &aux[p];
     const int f0 = a->face[0], f1 = a->face[1], f2 = a->face[2];
+    // corner gathers first: they do not depend on the grid gather
     const float4 x1 = vrec[f0].xm, x2 = vrec[f1].xm, x3 = vrec[f2].xm;
-    const float4 v1 = vrec[f0].vv, v2 = vrec[f1].vv, v3 = vrec[f2].vv;
+    const float4 v1 = reinterpret_cast<const float4*>(&vrec[f0])[2], v2 = reinterpret_cast<const float4*>(&vrec[f1])[2],
+                 v3 = reinterpret_cast<const float4*>(&vrec[f2])[2];
+    const float d3[3] = {a->dc[6], a->dc[7], a->dc[8]};
+    Gathered o;
+    g2p_gather(g, xm.x, xm.y, xm.z, o);
     PRec* r = &rec[p];
     const float vol = r->vv.w;
     xm.x = (x1.x + x2.x + x3.x) / 3.0f;
@@ -687,7 +817,6 @@ __global__ void __launch_bounds__(128) k_g2p_elements(Grid g, int Ne, PRec* __re
     r->vv = make_float4((v1.x + v2.x + v3.x) / 3.0f, (v1.y + v2.y + v3.y) / 3.0f, (v1.z + v2.z + v3.z) / 3.0f, vol);
 #pragma unroll
     for (int i = 0; i < 9; i++) r->C[i] = o.C[i];
-    const float d3[3] = {a->dc[6], a->dc[7], a->dc[8]};
     float nd3[3];
 #pragma unroll
     for (int rr = 0; rr < 3; rr++) {
