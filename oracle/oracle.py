@@ -187,9 +187,9 @@ class OracleSim:
 
     def set_body_mesh(self, verts, faces, friction=0.0):
         r = self.np_real
-        self.mesh_points = np.ascontiguousarray(verts, dtype=r)
+        self.mesh_points = np.array(verts, dtype=r, order="C", copy=True)  # p2g2p overwrites these in place
         self.mesh_velocities = np.zeros_like(self.mesh_points)
-        self.mesh_faces = np.ascontiguousarray(faces, dtype=np.int32)
+        self.mesh_faces = np.array(faces, dtype=np.int32, order="C", copy=True)
         n3 = self.n_grid ** 3
         self.col_weight = np.zeros(n3, r)
         self.col_v_in = np.zeros((n3, 3), r)

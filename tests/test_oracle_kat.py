@@ -259,3 +259,28 @@ def test_openmp_matches_sequential():
         for k in range(3):
             o.p2g2p(sc.dt, fi["mesh_x"], fi["mesh_v"], None, fi["joint_verts_v"], fi["joint_faces_v"])
     assert np.abs(a.x - b.x).max() < 1e-6
+
+
+def test_reference_variability_envelope_and_no_input_aliasing():
+    """Size of the reference algorithm's own variability (inputs moved by one ulp, fp32 vs fp64) after
+    10 substeps with contact: a few 1e-5 relative in velocity, i.e. the 1e-4 parity tolerance of
+    BASELINE.json is meaningful at N=10.  Also guards the harness: the oracle must not write into
+    the Scene's arrays (p2g2p overwrites the body-mesh points in place)."""
+    import copy
+    sc = S.scene_small_cloth_body()
+    body0 = sc.body_verts.copy()
+    sp = copy.copy(sc)
+    sp.x = (sc.x + np.random.default_rng(1).uniform(-1e-7, 1e-7, sc.x.shape)).astype(np.float32)
+    sims = [OracleSim.from_scene(sc, "f32", threads=1), OracleSim.from_scene(sp, "f32", threads=1),
+            OracleSim.from_scene(sc, "f64", threads=1)]
+    for k in range(10):
+        fi = sc.frame_inputs(0)
+        mx = fi["mesh_x"] + np.float32(sc.dt * k) * fi["mesh_v"]
+        for o in sims:
+            o.p2g2p(sc.dt, mx, fi["mesh_v"], None, fi["joint_verts_v"], fi["joint_faces_v"])
+    assert np.array_equal(sc.body_verts, body0)
+    a, b, c = sims
+    vm = np.abs(c.v).max()
+    assert np.abs(a.v - b.v).max() / vm < 1e-4
+    assert np.abs(a.v - c.v).max() / vm < 1e-4
+    assert np.abs(a.x - c.x).max() < 1e-6
