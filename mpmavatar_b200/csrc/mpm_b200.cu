@@ -45,101 +45,95 @@ __global__ void k_invert(int n, const uint32_t* __restrict__ perm, int* __restri
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) inv[perm[i]] = i;
 }
-__global__ void k_import_E(int Ne, const uint32_t* __restrict__ perm, Canon c, PRec* rec, EAux* aux,
-                           const int* __restrict__ invV) {
+struct Recs {  // sorted sub-record arrays (see mpm_device.cuh)
+    float *EP, *ES, *ED, *EK, *TP, *TS, *TF, *VP;
+    float4* VF;
+};
+__global__ void k_import_E(int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R, const int* __restrict__ invV) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Ne) return;
     int s = perm[i];  // canonical element index == canonical particle index
-    PRec r;
-    r.xm = make_float4(c.x[3 * s], c.x[3 * s + 1], c.x[3 * s + 2], c.mass[s]);
-    r.vv = make_float4(c.v[3 * s], c.v[3 * s + 1], c.v[3 * s + 2], c.vol[s]);
-    for (int k = 0; k < 9; k++) { r.C[k] = c.C[9 * (size_t)s + k]; r.S[k] = 0.f; }
-    r.pad[0] = r.pad[1] = 0.f;
-    rec[i] = r;
-    EAux a;
-    const float* d = c.d + 9 * (size_t)s;  // row-major -> columns
+    float* p = R.EP + (size_t)i * KP_F;
+    for (int k = 0; k < 3; k++) { p[P_X + k] = c.x[3 * s + k]; p[P_V + k] = c.v[3 * s + k]; }
+    p[P_M] = c.mass[s];
+    p[P_VOL] = c.vol[s];
+    for (int k = 0; k < 9; k++) { p[P_C + k] = c.C[9 * (size_t)s + k]; R.ES[(size_t)i * S_F + k] = 0.f; }
+    float* d = R.ED + (size_t)i * ED_F;
+    const float* ds = c.d + 9 * (size_t)s;  // row-major -> columns
     for (int col = 0; col < 3; col++)
-        for (int row = 0; row < 3; row++) a.dc[3 * col + row] = d[3 * row + col];
-    for (int k = 0; k < 3; k++) {
-        a.Rinv[k] = c.Rinv[3 * s + k];
-        a.face[k] = invV[(int)c.faces[3 * s + k]];  // int(face[k]) as in mpm_utils.py:172
-    }
-    a.mu = c.mu[s]; a.lam = c.lam[s]; a.gamma = c.gamma[s]; a.kappa = c.kappa[s]; a.vol = c.vol[s];
-    aux[i] = a;
+        for (int row = 0; row < 3; row++) d[D_DC + 3 * col + row] = ds[3 * row + col];
+    for (int k = 0; k < 3; k++) d[D_FACE + k] = __int_as_float(invV[(int)c.faces[3 * s + k]]);  // int(face[k]), mpm_utils.py:172
+    float* e = R.EK + (size_t)i * EK_F;
+    for (int k = 0; k < 3; k++) e[K_RINV + k] = c.Rinv[3 * s + k];
+    e[K_MU] = c.mu[s]; e[K_LAM] = c.lam[s]; e[K_GAMMA] = c.gamma[s]; e[K_KAPPA] = c.kappa[s]; e[K_VOL] = c.vol[s];
 }
-__global__ void k_import_T(int Nt, int Ne, const uint32_t* __restrict__ perm, Canon c, PRec* rec, TAux* aux) {
+__global__ void k_import_T(int Nt, int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Nt) return;
     int s = Ne + perm[i];
-    PRec r;
-    r.xm = make_float4(c.x[3 * s], c.x[3 * s + 1], c.x[3 * s + 2], c.mass[s]);
-    r.vv = make_float4(c.v[3 * s], c.v[3 * s + 1], c.v[3 * s + 2], c.vol[s]);
-    for (int k = 0; k < 9; k++) { r.C[k] = c.C[9 * (size_t)s + k]; r.S[k] = 0.f; }
-    r.pad[0] = r.pad[1] = 0.f;
-    rec[i] = r;
-    TAux a;
-    for (int k = 0; k < 9; k++) { a.F[k] = c.F[9 * (size_t)s + k]; a.Ft[k] = c.Ft[9 * (size_t)s + k]; }
-    a.mu = c.mu[s]; a.lam = c.lam[s]; a.ys = c.ys[s];
-    a.pad[0] = a.pad[1] = a.pad[2] = 0.f;
-    aux[i] = a;
+    float* p = R.TP + (size_t)i * KP_F;
+    for (int k = 0; k < 3; k++) { p[P_X + k] = c.x[3 * s + k]; p[P_V + k] = c.v[3 * s + k]; }
+    p[P_M] = c.mass[s];
+    p[P_VOL] = c.vol[s];
+    for (int k = 0; k < 9; k++) { p[P_C + k] = c.C[9 * (size_t)s + k]; R.TS[(size_t)i * S_F + k] = 0.f; }
+    float* t = R.TF + (size_t)i * TF_F;
+    for (int k = 0; k < 9; k++) { t[T_F + k] = c.F[9 * (size_t)s + k]; t[T_FT + k] = c.Ft[9 * (size_t)s + k]; }
+    t[T_MU] = c.mu[s]; t[T_LAM] = c.lam[s]; t[T_YS] = c.ys[s];
 }
-__global__ void k_import_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, Canon c, VRec* rec) {
+__global__ void k_import_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, Canon c, Recs R) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Nv) return;
     int s = Nnv + perm[i];
-    VRec r;
-    r.xm = make_float4(c.x[3 * s], c.x[3 * s + 1], c.x[3 * s + 2], c.mass[s]);
-    r.f = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < 3; k++) r.v[k] = c.v[3 * s + k];
-    for (int k = 0; k < 9; k++) r.C[k] = c.C[9 * (size_t)s + k];
-    rec[i] = r;
+    float* p = R.VP + (size_t)i * VP_F;
+    for (int k = 0; k < 3; k++) { p[V_X + k] = c.x[3 * s + k]; p[V_V + k] = c.v[3 * s + k]; }
+    p[V_M] = c.mass[s];
+    for (int k = 0; k < 9; k++) p[V_C + k] = c.C[9 * (size_t)s + k];
+    R.VF[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
-__global__ void k_export_E(int Ne, const uint32_t* __restrict__ perm, Canon c, const PRec* rec, const EAux* aux) {
+__global__ void k_export_E(int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Ne) return;
     int s = perm[i];
-    PRec r = rec[i];
-    c.x[3 * s] = r.xm.x; c.x[3 * s + 1] = r.xm.y; c.x[3 * s + 2] = r.xm.z;
-    c.v[3 * s] = r.vv.x; c.v[3 * s + 1] = r.vv.y; c.v[3 * s + 2] = r.vv.z;
-    for (int k = 0; k < 9; k++) { c.C[9 * (size_t)s + k] = r.C[k]; c.stress[9 * (size_t)s + k] = r.S[k]; }
-    float* d = c.d + 9 * (size_t)s;
+    const float* p = R.EP + (size_t)i * KP_F;
+    for (int k = 0; k < 3; k++) { c.x[3 * s + k] = p[P_X + k]; c.v[3 * s + k] = p[P_V + k]; }
+    for (int k = 0; k < 9; k++) { c.C[9 * (size_t)s + k] = p[P_C + k]; c.stress[9 * (size_t)s + k] = R.ES[(size_t)i * S_F + k]; }
+    const float* d = R.ED + (size_t)i * ED_F;
+    float* dd = c.d + 9 * (size_t)s;
     for (int col = 0; col < 3; col++)
-        for (int row = 0; row < 3; row++) d[3 * row + col] = aux[i].dc[3 * col + row];
+        for (int row = 0; row < 3; row++) dd[3 * row + col] = d[D_DC + 3 * col + row];
 }
-__global__ void k_export_T(int Nt, int Ne, const uint32_t* __restrict__ perm, Canon c, const PRec* rec, const TAux* aux) {
+__global__ void k_export_T(int Nt, int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Nt) return;
     int s = Ne + perm[i];
-    PRec r = rec[i];
-    c.x[3 * s] = r.xm.x; c.x[3 * s + 1] = r.xm.y; c.x[3 * s + 2] = r.xm.z;
-    c.v[3 * s] = r.vv.x; c.v[3 * s + 1] = r.vv.y; c.v[3 * s + 2] = r.vv.z;
+    const float* p = R.TP + (size_t)i * KP_F;
+    const float* t = R.TF + (size_t)i * TF_F;
+    for (int k = 0; k < 3; k++) { c.x[3 * s + k] = p[P_X + k]; c.v[3 * s + k] = p[P_V + k]; }
     for (int k = 0; k < 9; k++) {
-        c.C[9 * (size_t)s + k] = r.C[k];
-        c.stress[9 * (size_t)s + k] = r.S[k];
-        c.F[9 * (size_t)s + k] = aux[i].F[k];
-        c.Ft[9 * (size_t)s + k] = aux[i].Ft[k];
+        c.C[9 * (size_t)s + k] = p[P_C + k];
+        c.stress[9 * (size_t)s + k] = R.TS[(size_t)i * S_F + k];
+        c.F[9 * (size_t)s + k] = t[T_F + k];
+        c.Ft[9 * (size_t)s + k] = t[T_FT + k];
     }
-    c.mu[s] = aux[i].mu; c.lam[s] = aux[i].lam; c.ys[s] = aux[i].ys;  // damage / hardening mutate these
+    c.mu[s] = t[T_MU]; c.lam[s] = t[T_LAM]; c.ys[s] = t[T_YS];  // damage / hardening mutate these
 }
-__global__ void k_export_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, Canon c, const VRec* rec,
-                           const float* __restrict__ dbg_f) {
+__global__ void k_export_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, Canon c, Recs R, const float* __restrict__ dbg_f) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Nv) return;
     int s = Nnv + perm[i];
     int vl = perm[i];
-    VRec r = rec[i];
-    c.x[3 * s] = r.xm.x; c.x[3 * s + 1] = r.xm.y; c.x[3 * s + 2] = r.xm.z;
-    for (int k = 0; k < 3; k++) c.v[3 * s + k] = r.v[k];
-    for (int k = 0; k < 9; k++) c.C[9 * (size_t)s + k] = r.C[k];
-    const float fr[3] = {r.f.x, r.f.y, r.f.z};
+    const float* p = R.VP + (size_t)i * VP_F;
+    for (int k = 0; k < 3; k++) { c.x[3 * s + k] = p[V_X + k]; c.v[3 * s + k] = p[V_V + k]; }
+    for (int k = 0; k < 9; k++) c.C[9 * (size_t)s + k] = p[V_C + k];
+    const float4 f = R.VF[i];
+    const float fr[3] = {f.x, f.y, f.z};
     for (int k = 0; k < 3; k++) c.vforce[3 * vl + k] = dbg_f ? dbg_f[3 * i + k] : fr[k];
 }
-template <typename Rec>
-__global__ void k_alloc_blocks(Grid g, int n, const Rec* __restrict__ rec) {
+__global__ void k_alloc_blocks(Grid g, int n, const float* __restrict__ rec, int F) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 xm = rec[i].xm;
-    ensure_stencil_blocks(g, xm.x, xm.y, xm.z);
+    const float* x = rec + (size_t)i * F;
+    ensure_stencil_blocks(g, x[0], x[1], x[2]);
 }
 __global__ void k_fill_int(int* p, size_t n, int v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
@@ -161,12 +155,11 @@ __global__ void k_export_grid(Grid g, float* gm, float* gvin, float* gvout) {
     if (gvout) { float4 v = g.vout[idx]; gvout[3 * gi] = v.x; gvout[3 * gi + 1] = v.y; gvout[3 * gi + 2] = v.z; }
 }
 // distinct nodes in the union of all particle stencils (SURVEY 8d "A")
-template <typename Rec>
-__global__ void k_mark_nodes(Grid g, int n, const Rec* __restrict__ rec, unsigned long long* mask) {
+__global__ void k_mark_nodes(Grid g, int n, const float* __restrict__ rec, int F, unsigned long long* mask) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 xm = rec[i].xm;
-    int bx = base_of(xm.x, g.inv_dx), by = base_of(xm.y, g.inv_dx), bz = base_of(xm.z, g.inv_dx);
+    const float* x = rec + (size_t)i * F;
+    int bx = base_of(x[0], g.inv_dx), by = base_of(x[1], g.inv_dx), bz = base_of(x[2], g.inv_dx);
     for (int a = 0; a < 3; a++)
         for (int b = 0; b < 3; b++)
             for (int c = 0; c < 3; c++) {
@@ -192,10 +185,7 @@ struct MpmSolver {
     ModelDev md{};
     std::string err;
     // particles
-    PRec *erec = nullptr, *trec = nullptr;
-    VRec* vrec = nullptr;
-    EAux* eaux = nullptr;
-    TAux* taux = nullptr;
+    Recs R{};
     uint32_t *permE = nullptr, *permT = nullptr, *permV = nullptr;
     int *invE = nullptr, *invT = nullptr, *invV = nullptr;
     uint32_t *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr;
@@ -262,9 +252,9 @@ static void sort_class(MpmSolver* s, int n, int offset, uint32_t* perm, int* inv
 
 static void export_to_canon(MpmSolver* s, cudaStream_t q) {
     if (!s->have_state || !s->canon_stale) return;
-    if (s->Ne) k_export_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->permE, s->canon, s->erec, s->eaux);
-    if (s->Nt) k_export_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->permT, s->canon, s->trec, s->taux);
-    if (s->Nv) k_export_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->Nnv, s->permV, s->canon, s->vrec, s->debug ? s->dbg_f : nullptr);
+    if (s->Ne) k_export_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->permE, s->canon, s->R);
+    if (s->Nt) k_export_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->permT, s->canon, s->R);
+    if (s->Nv) k_export_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->Nnv, s->permV, s->canon, s->R, s->debug ? s->dbg_f : nullptr);
     s->launches += 3;
     s->canon_stale = false;
 }
@@ -275,16 +265,16 @@ static void resort(MpmSolver* s, cudaStream_t q) {
     sort_class(s, s->Ne, 0, s->permE, s->invE, q);
     sort_class(s, s->Nt, s->Ne, s->permT, s->invT, q);
     sort_class(s, s->Nv, s->Nnv, s->permV, s->invV, q);
-    if (s->Ne) k_import_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->permE, s->canon, s->erec, s->eaux, s->invV);
-    if (s->Nt) k_import_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->permT, s->canon, s->trec, s->taux);
-    if (s->Nv) k_import_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->Nnv, s->permV, s->canon, s->vrec);
+    if (s->Ne) k_import_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->permE, s->canon, s->R, s->invV);
+    if (s->Nt) k_import_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->permT, s->canon, s->R);
+    if (s->Nv) k_import_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->Nnv, s->permV, s->canon, s->R);
     // all accumulators are zero between substeps, so rebuilding the table needs no pool sweep
     size_t nt = (size_t)s->g.nb * s->g.nb * s->g.nb;
     k_fill_int<<<std::min(cdiv((long long)nt, 256), 1184), 256, 0, q>>>(s->g.table, nt, -1);
     CK(cudaMemsetAsync(s->g.n_slots, 0, sizeof(int), q));
-    if (s->Ne) k_alloc_blocks<PRec><<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->erec);
-    if (s->Nt) k_alloc_blocks<PRec><<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->trec);
-    if (s->Nv) k_alloc_blocks<VRec><<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->vrec);
+    if (s->Ne) k_alloc_blocks<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.EP, KP_F);
+    if (s->Nt) k_alloc_blocks<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F);
+    if (s->Nv) k_alloc_blocks<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F);
     CK(cudaMemcpyAsync(s->h_nslots, s->g.n_slots, sizeof(int), cudaMemcpyDeviceToHost, q));
     s->launches += 7;
     s->need_sort = false;
@@ -322,19 +312,27 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
         ev = evs.data();
         CK(cudaEventRecord(ev[0], q));
     }
+    const Recs& R = s->R;
     if (n_ops) {
-        if (s->Ne) k_particle_ops<PRec><<<cdiv(s->Ne, 256), 256, 0, q>>>(s->Ne, s->erec, s->permE, 0, s->d_ops, n_ops, s->st, a.dt);
-        if (s->Nt) k_particle_ops<PRec><<<cdiv(s->Nt, 256), 256, 0, q>>>(s->Nt, s->trec, s->permT, s->Ne, s->d_ops, n_ops, s->st, a.dt);
-        if (s->Nv) k_particle_ops<VRec><<<cdiv(s->Nv, 256), 256, 0, q>>>(s->Nv, s->vrec, s->permV, s->Nnv, s->d_ops, n_ops, s->st, a.dt);
+        if (s->Ne) k_particle_ops<<<cdiv(s->Ne, 256), 256, 0, q>>>(s->Ne, R.EP, KP_F, s->permE, 0, s->d_ops, n_ops, s->st, a.dt);
+        if (s->Nt) k_particle_ops<<<cdiv(s->Nt, 256), 256, 0, q>>>(s->Nt, R.TP, KP_F, s->permT, s->Ne, s->d_ops, n_ops, s->st, a.dt);
+        if (s->Nv) k_particle_ops<<<cdiv(s->Nv, 256), 256, 0, q>>>(s->Nv, R.VP, VP_F, s->permV, s->Nnv, s->d_ops, n_ops, s->st, a.dt);
         s->launches += 3;
     }
-    if (s->Ne) { k_stress_elements<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->eaux, s->erec, s->vrec, s->md.friction_coeff); s->launches++; }
-    if (s->Nt) { k_stress_traditional<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->taux, s->trec, s->md, a.dt); s->launches++; }
+    auto sm = [](int nw, int wb) { return (size_t)(128 + nw * wb); };
+    if (s->Ne) {
+        k_stress_elements<<<cdiv(s->Ne, 32 * STRESS_E_NW), 32 * STRESS_E_NW, sm(STRESS_E_NW, STRESS_E_WB), q>>>(s->Ne, R.ED, R.EK, R.ES, R.VF, s->md.friction_coeff);
+        s->launches++;
+    }
+    if (s->Nt) {
+        k_stress_traditional<<<cdiv(s->Nt, 32 * STRESS_T_NW), 32 * STRESS_T_NW, sm(STRESS_T_NW, STRESS_T_WB), q>>>(s->Nt, R.TF, R.TS, s->md, a.dt);
+        s->launches++;
+    }
     if (ev) CK(cudaEventRecord(ev[1], q));
-    const int ppb = 32 * P2G_WARPS;
-    if (s->Ne) { k_p2g<0><<<cdiv(s->Ne, ppb), ppb, P2G_SMEM, q>>>(s->g, (const float*)s->erec, s->Ne, a.dt, s->md.rpic); s->launches++; }
-    if (s->Nt) { k_p2g<1><<<cdiv(s->Nt, ppb), ppb, P2G_SMEM, q>>>(s->g, (const float*)s->trec, s->Nt, a.dt, s->md.rpic); s->launches++; }
-    if (s->Nv) { k_p2g<2><<<cdiv(s->Nv, ppb), ppb, P2G_SMEM, q>>>(s->g, (const float*)s->vrec, s->Nv, a.dt, s->md.rpic); s->launches++; }
+    const int ppb = 32 * P2G_NW;
+    if (s->Ne) { k_p2g<0><<<cdiv(s->Ne, ppb), ppb, P2G_SMEM, q>>>(s->g, R.EP, R.ES, s->Ne, a.dt, s->md.rpic); s->launches++; }
+    if (s->Nt) { k_p2g<1><<<cdiv(s->Nt, ppb), ppb, P2G_SMEM, q>>>(s->g, R.TP, R.TS, s->Nt, a.dt, s->md.rpic); s->launches++; }
+    if (s->Nv) { k_p2g<2><<<cdiv(s->Nv, ppb), ppb, P2G_SMEM, q>>>(s->g, R.VP, (const float*)R.VF, s->Nv, a.dt, s->md.rpic); s->launches++; }
     if (ev) CK(cudaEventRecord(ev[2], q));
     if (a.collider) {
         k_collider_scatter<<<cdiv(s->cfg.n_mesh_f, 128), 128, 0, q>>>(s->g, s->cfg.n_mesh_f, s->mesh_faces, s->mesh_x, s->mesh_v, s->st, a.dt, a.advance_mesh ? 1 : 0);
@@ -344,7 +342,7 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
     if (a.mover) {
         int tot = a.njt + s->cfg.num_joint_v + s->cfg.num_joint_f;
         if (tot) {
-            k_mover_scatter<<<cdiv(tot, 128), 128, 0, q>>>(s->g, a.njt, s->cfg.num_joint_v, s->cfg.num_joint_f, s->Nt, s->joint_t, s->joint_v, s->joint_f, s->erec, s->trec, s->vrec, s->invE, s->invT, s->invV);
+            k_mover_scatter<<<cdiv(tot, 128), 128, 0, q>>>(s->g, a.njt, s->cfg.num_joint_v, s->cfg.num_joint_f, s->Nt, s->joint_t, s->joint_v, s->joint_f, R.EP, R.TP, R.VP, s->invE, s->invT, s->invV);
             s->launches++;
         }
     }
@@ -356,10 +354,11 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
     if (ev) CK(cudaEventRecord(ev[5], q));
     Advance none{nullptr, nullptr, 0}, adv{s->st, s->d_bcs, n_bc};
     const int last = s->Ne ? 2 : (s->Nt ? 1 : 0);  // the last kernel of the substep advances time
-    if (s->Nv) { k_g2p_vertices<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->vrec, a.dt, s->debug ? s->dbg_f : nullptr, last == 0 ? adv : none); s->launches++; }
-    if (s->Nt) { k_g2p_traditional<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->trec, s->taux, a.dt, last == 1 ? adv : none); s->launches++; }
+    const int gpb = 32 * G2P_NW;
+    if (s->Nv) { k_g2p_vertices<<<cdiv(s->Nv, gpb), gpb, sm(G2P_NW, G2P_V_WB), q>>>(s->g, s->Nv, R.VP, R.VF, a.dt, s->debug ? s->dbg_f : nullptr, last == 0 ? adv : none); s->launches++; }
+    if (s->Nt) { k_g2p_traditional<<<cdiv(s->Nt, gpb), gpb, sm(G2P_NW, G2P_T_WB), q>>>(s->g, s->Nt, R.TP, R.TF, a.dt, last == 1 ? adv : none); s->launches++; }
     if (ev) CK(cudaEventRecord(ev[6], q));
-    if (s->Ne) { k_g2p_elements<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->erec, s->eaux, s->vrec, a.dt, last == 2 ? adv : none); s->launches++; }
+    if (s->Ne) { k_g2p_elements<<<cdiv(s->Ne, gpb), gpb, sm(G2P_NW, G2P_E_WB), q>>>(s->g, s->Ne, R.EP, R.ED, R.VP, a.dt, last == 2 ? adv : none); s->launches++; }
     if (ev) {
         CK(cudaEventRecord(ev[7], q));
         CK(cudaEventRecord(ev[8], q));
@@ -514,11 +513,13 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         g.mov = s->dalloc<float4>(pn);
         g.dbg_acc = nullptr;
         k_fill_int<<<1184, 256>>>(g.table, nt, -1);
-        s->erec = s->dalloc<PRec>(s->Ne + 32);
-        s->trec = s->dalloc<PRec>(s->Nt + 32);
-        s->vrec = s->dalloc<VRec>(s->Nv + 32);
-        s->eaux = s->dalloc<EAux>(s->Ne);
-        s->taux = s->dalloc<TAux>(s->Nt);
+        {   // sorted sub-records, each with 32 records of slack for the 16-byte bulk-copy granule
+            size_t ne = (size_t)s->Ne + 32, nt = (size_t)s->Nt + 32, nv = (size_t)s->Nv + 32;
+            s->R.EP = s->dalloc<float>(ne * KP_F); s->R.ES = s->dalloc<float>(ne * S_F);
+            s->R.ED = s->dalloc<float>(ne * ED_F); s->R.EK = s->dalloc<float>(ne * EK_F);
+            s->R.TP = s->dalloc<float>(nt * KP_F); s->R.TS = s->dalloc<float>(nt * S_F); s->R.TF = s->dalloc<float>(nt * TF_F);
+            s->R.VP = s->dalloc<float>(nv * VP_F); s->R.VF = s->dalloc<float4>(nv);
+        }
         int nmax = std::max(s->Ne, std::max(s->Nt, s->Nv));
         s->permE = s->dalloc<uint32_t>(s->Ne); s->permT = s->dalloc<uint32_t>(s->Nt); s->permV = s->dalloc<uint32_t>(s->Nv);
         s->invE = s->dalloc<int>(s->Ne); s->invT = s->dalloc<int>(s->Nt); s->invV = s->dalloc<int>(s->Nv);
@@ -820,9 +821,9 @@ int mpm_get_stats(MpmSolver* s, MpmStats* out, void* stream) {
     CK(cudaMalloc(&cnt, sizeof(unsigned long long)));
     CK(cudaMemsetAsync(mask, 0, ((size_t)n_slots + 1) * sizeof(unsigned long long), q));
     CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), q));
-    if (s->Ne) k_mark_nodes<PRec><<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->erec, mask);
-    if (s->Nt) k_mark_nodes<PRec><<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->trec, mask);
-    if (s->Nv) k_mark_nodes<VRec><<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->vrec, mask);
+    if (s->Ne) k_mark_nodes<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.EP, KP_F, mask);
+    if (s->Nt) k_mark_nodes<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F, mask);
+    if (s->Nv) k_mark_nodes<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, mask);
     if (n_slots) k_popc<<<cdiv(n_slots, 256), 256, 0, q>>>(mask, n_slots, cnt);
     unsigned long long h = 0;
     CK(cudaMemcpyAsync(&h, cnt, sizeof h, cudaMemcpyDeviceToHost, q));

@@ -1,19 +1,29 @@
-// Device-side data layout and math for the B200 MPM substep solver.
+// Device-side data layout and helpers of the B200 MPM substep solver.
 //
-// Grid: sparse pool of 4x4x4-node blocks.  A dense block table (nb^3 ints) maps block
-// coordinates to a pool slot (-1 = not allocated); every per-node quantity is a float4
-// so that one P2G contribution is ONE 16-byte REDG.E.ADD.F32x4 (sm_90+ vector atomic):
+// GRID: sparse pool of 4x4x4-node blocks.  A dense block table (nb^3 ints) maps block
+// coordinates to a pool slot (-1 = not allocated); every per-node quantity is a float4 so that
+// one P2G contribution is ONE 16-byte REDG.E.ADD.F32x4 (sm_90+ vector atomic):
 //   acc  {m*vx, m*vy, m*vz, m}      <- P2G                      (mpm_utils.py:548-557)
 //   vout {vx, vy, vz, -}            <- grid update, read by G2P (mpm_utils.py:561-572)
 //   colv {w*vx, w*vy, w*vz, w}, coln {w*nx, w*ny, w*nz, -}  <- body-mesh collider scatter
 //                                                              (mpm_solver.py:829-880)
 //   mov  {w*vx, w*vy, w*vz, w}      <- particle-mover scatter  (mpm_solver.py:677-788)
-// Invariant: between substeps all accumulators of allocated slots are zero (the grid
-// update re-zeroes what it consumed), so there is no zero_grid sweep.
+// Invariant: between substeps all accumulators of allocated slots are zero (the grid update
+// re-zeroes what it consumed), so there is no zero_grid sweep.
 //
-// Particles: three classes kept in separate arrays of fixed-size AoS records, each class
-// sorted by (Morton(block), cell-in-block).  A record is what P2G consumes, so one
-// contiguous slab of records feeds a warp (bulk-copy friendly).
+// PARTICLES: three classes (elements, traditional, vertices), each sorted by
+// (Morton(block), cell-in-block).  Per class the state is split into small AoS sub-records
+// GROUPED BY THE KERNEL THAT WRITES THEM, so that every kernel reads and writes whole records:
+//   EP/TP  kinematics  {x,y,z,m, vx,vy,vz,vol, C[9]}      17 floats  written by G2P
+//   ES/TS  stress      {S[9]}                              9 floats  written by the stress kernel
+//   ED     directions  {d1,d2,d3 (column-major), face[3]} 12 floats  written by stress (d3) and G2P
+//   EK     constants   {Rinv[3], mu, lam, gamma, kappa, vol} 8 floats read-only
+//   TF     trad state  {F[9], Ft[9], mu, lam, ys}         21 floats  written by stress (F,..) and G2P (Ft)
+//   VP     kinematics  {x,y,z,m, vx,vy,vz, C[9]}          16 floats  written by G2P
+//   VF     force       float4 {fx,fy,fz,-}                           REDG.128 by stress, zeroed by G2P
+// A warp owns 32 consecutive records: the slab of each sub-record is one contiguous chunk that
+// is moved with a single cp.async.bulk (TMA, SASS UBLKCP) into / out of shared memory, where
+// lane = particle accesses are bank-conflict free (odd word strides).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,32 +35,20 @@ constexpr int BN = 64;   // nodes per block
 constexpr int MAX_BC = 16;
 constexpr int MAX_OPS = 64;
 
-struct __align__(16) PRec {  // element / traditional particle record, 112 B
-    float4 xm;    // x, y, z, mass
-    float4 vv;    // vx, vy, vz, vol
-    float C[9];   // APIC affine matrix, row-major
-    float S[9];   // Kirchhoff stress (elements: already times vol, mpm_utils.py:177)
-    float pad[2];
-};
-struct __align__(16) VRec {  // cloth-vertex particle record, 80 B
-    float4 xm;    // x, y, z, mass
-    float4 f;     // vertex_force accumulated by the element stress kernel (one REDG.128 per corner), w unused
-    float v[3];
-    float C[9];
-};
-struct __align__(16) EAux {  // element constitutive state, 80 B
-    float dc[9];  // direction matrix, COLUMN-major: d1 | d2 | d3
-    float Rinv[3];
-    int face[3];  // SORTED vertex slots of the three corners
-    float mu, lam, gamma, kappa, vol;
-};
-struct __align__(16) TAux {  // traditional-particle constitutive state, 96 B
-    float F[9];
-    float Ft[9];
-    float mu, lam, ys;
-    float pad[3];
-};
-static_assert(sizeof(PRec) == 112 && sizeof(VRec) == 80 && sizeof(EAux) == 80 && sizeof(TAux) == 96, "layout");
+// sub-record sizes in floats
+constexpr int KP_F = 17;  // EP / TP
+constexpr int S_F = 9;    // ES / TS
+constexpr int ED_F = 12;
+constexpr int EK_F = 8;
+constexpr int TF_F = 21;
+constexpr int VP_F = 16;
+constexpr int VF_F = 4;
+// field offsets
+constexpr int P_X = 0, P_M = 3, P_V = 4, P_VOL = 7, P_C = 8;  // EP / TP
+constexpr int V_X = 0, V_M = 3, V_V = 4, V_C = 7;              // VP
+constexpr int D_DC = 0, D_FACE = 9;                            // ED
+constexpr int K_RINV = 0, K_MU = 3, K_LAM = 4, K_GAMMA = 5, K_KAPPA = 6, K_VOL = 7;
+constexpr int T_F = 0, T_FT = 9, T_MU = 18, T_LAM = 19, T_YS = 20;
 
 struct Grid {
     int n, nb;
@@ -92,11 +90,6 @@ struct ModelDev {
     float rpic, damping, xi, plastic_viscosity, softening;
 };
 
-__device__ __forceinline__ float4 rec_v(const PRec& r) { return r.vv; }
-__device__ __forceinline__ float4 rec_v(const VRec& r) { return make_float4(r.v[0], r.v[1], r.v[2], 0.f); }
-__device__ __forceinline__ void rec_set_v(PRec& r, float4 v) { r.vv = v; }
-__device__ __forceinline__ void rec_set_v(VRec& r, float4 v) { r.v[0] = v.x; r.v[1] = v.y; r.v[2] = v.z; }
-
 // ------------------------------------------------------------------ small math
 __device__ __forceinline__ void mat_mul(const float* a, const float* b, float* o) {
     float t[9];
@@ -121,6 +114,13 @@ __device__ __forceinline__ float det3(const float* m) {
     return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
 }
 __device__ __forceinline__ float len3(float a, float b, float c) { return sqrtf(a * a + b * b + c * c); }
+// un-contracted (no FMA) dot / length: the cloth return mapping branches on R22 > 1 exactly at the
+// rest state (mpm_utils.py:196), so the QR that feeds it is evaluated in plain IEEE fp32
+// operation order to keep the branch reproducible against a non-FMA evaluation
+__device__ __forceinline__ float dot3_rn(const float* a, const float* b) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
+}
+__device__ __forceinline__ float len3_rn(const float* a) { return __fsqrt_rn(dot3_rn(a, a)); }
 
 // Jacobi rotation on the symmetric matrix (bpp,bqq,bpq; brp,brq with r the third index) and V columns p,q
 __device__ __forceinline__ void jrot(float& bpp, float& bqq, float& bpq, float& brp, float& brq, float* V, int p, int q) {
@@ -244,7 +244,7 @@ __device__ __forceinline__ void ensure_block(const Grid& g, int bx, int by, int 
     __threadfence();
     atomicExch(t, slot);
 }
-// blocks covered by the 3^3 stencil starting at node (bx,by,bz)
+// blocks covered by the 3^3 stencil of a particle at (x,y,z)
 __device__ __forceinline__ void ensure_stencil_blocks(const Grid& g, float x, float y, float z) {
     int b0 = clampi(base_of(x, g.inv_dx), 0, g.n - 1), b1 = clampi(base_of(y, g.inv_dx), 0, g.n - 1),
         b2 = clampi(base_of(z, g.inv_dx), 0, g.n - 1);
@@ -262,6 +262,30 @@ __device__ __forceinline__ int node_index(const Grid& g, int ix, int iy, int iz)
     if (s < 0) return -1;
     return s * BN + ((ix & 3) << 4) + ((iy & 3) << 2) + (iz & 3);
 }
+// the (up to) 2x2x2 pool slots under a 3^3 stencil whose base node is (bx,by,bz) >= 0:
+// eight independent table loads issued together instead of 27 dependent ones
+__device__ __forceinline__ void load_slots8(const Grid& g, int bx, int by, int bz, int* sl) {
+    const int X0 = bx >> 2, Y0 = by >> 2, Z0 = bz >> 2;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int X = X0 + (c >> 2), Y = Y0 + ((c >> 1) & 1), Z = Z0 + (c & 1);
+        bool ok = bx >= 0 && by >= 0 && bz >= 0 && X < g.nb && Y < g.nb && Z < g.nb;
+        sl[c] = ok ? lookup_slot(g, X, Y, Z) : -1;
+    }
+}
+__device__ __forceinline__ int sel8(const int* sl, int c) {
+    int s = sl[0];
+#pragma unroll
+    for (int q = 1; q < 8; q++) s = (c == q) ? sl[q] : s;
+    return s;
+}
+// pool index of stencil node (i,j,k) given the 8 slots, -1 if its block is not allocated
+__device__ __forceinline__ int stencil_node(const int* sl, int bx, int by, int bz, int i, int j, int k) {
+    const int ix = bx + i, iy = by + j, iz = bz + k;
+    const int c = (((ix >> 2) - (bx >> 2)) << 2) | (((iy >> 2) - (by >> 2)) << 1) | ((iz >> 2) - (bz >> 2));
+    const int s = sel8(sl, c);
+    return s < 0 ? -1 : s * BN + ((ix & 3) << 4) + ((iy & 3) << 2) + (iz & 3);
+}
 
 // quadratic B-spline factor of stencil offset i at fractional position f (mpm_utils.py:506-514):
 // w = A (f - s)^2 + B, dw = 2A (f - s) with (A,s,B) = (.5,1.5,0), (-1,1,.75), (.5,.5,0)
@@ -273,5 +297,42 @@ __device__ __forceinline__ void bspline(float f, int i, float& w, float& dw) {
     w = A * t * t + B;
     dw = 2.0f * A * t;
 }
+
+// ------------------------------------------------------------------ TMA slab staging
+// 1-D bulk async copies (cp.async.bulk, SASS UBLKCP) between global memory and a warp's
+// shared-memory slab, completing on a per-warp mbarrier (loads) or a bulk group (stores).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// generic-proxy smem writes -> visible to the async proxy (TMA store)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// bytes of a slab of cnt records of F floats, rounded up to the 16-byte bulk-copy granule
+// (arrays carry 32 records of slack, so over-reading / over-writing the tail is harmless)
+__device__ __forceinline__ uint32_t slab_bytes(int cnt, int F) { return (uint32_t)((cnt * F * 4 + 15) & ~15); }
 
 }  // namespace mpm

@@ -1,8 +1,54 @@
 // Kernels of one MPM substep (launch order = MPMWARP.p2g2p, warp_mpm/mpm_solver.py:229-536).
+//
+// Every particle kernel is "slab staged": a warp owns 32 consecutive (cell-sorted) particles, pulls
+// the sub-records it needs into shared memory with one cp.async.bulk each (TMA), works lane = particle
+// (or lane = stencil node in P2G) out of shared memory, and pushes whole updated sub-records back with
+// one bulk store each.  Global traffic is therefore exactly the records, fully coalesced, and the LSU
+// only sees the irregular accesses (grid nodes, corner vertices).  Warps never synchronise with
+// each other: one mbarrier per warp, no __syncthreads.
 #pragma once
 #include "mpm_device.cuh"
 
 namespace mpm {
+
+// ---- per-warp slab context -------------------------------------------------------------------
+struct Warp {
+    int lane, p0, cnt;
+    uint64_t* bar;
+    unsigned char* buf;  // this warp's shared-memory region
+};
+// NW warps per CTA, WB bytes of shared memory per warp (after a 128-byte barrier header)
+template <int NW, int WB>
+__device__ __forceinline__ bool warp_begin(Warp& w, int n, unsigned char* smem) {
+    const int warp = threadIdx.x >> 5;
+    w.lane = threadIdx.x & 31;
+    w.p0 = (blockIdx.x * NW + warp) * 32;
+    if (w.p0 >= n) return false;
+    w.cnt = min(32, n - w.p0);
+    w.bar = reinterpret_cast<uint64_t*>(smem) + warp;
+    w.buf = smem + 128 + warp * WB;
+    if (w.lane == 0) mbar_init(w.bar, 1);
+    __syncwarp();
+    return true;
+}
+__device__ __forceinline__ void slab_load2(const Warp& w, void* s0, const float* g0, int F0, void* s1, const float* g1, int F1) {
+    if (w.lane == 0) {
+        const uint32_t b0 = slab_bytes(w.cnt, F0), b1 = g1 ? slab_bytes(w.cnt, F1) : 0u;
+        mbar_expect_tx(w.bar, b0 + b1);
+        bulk_g2s(s0, g0 + (size_t)w.p0 * F0, b0, w.bar);
+        if (g1) bulk_g2s(s1, g1 + (size_t)w.p0 * F1, b1, w.bar);
+    }
+    while (!mbar_try_wait(w.bar, 0)) {}
+}
+__device__ __forceinline__ void slab_store2(const Warp& w, const void* s0, float* g0, int F0, const void* s1, float* g1, int F1) {
+    fence_async_smem();
+    __syncwarp();
+    if (w.lane == 0) {
+        bulk_s2g(g0 + (size_t)w.p0 * F0, s0, slab_bytes(w.cnt, F0));
+        if (g1) bulk_s2g(g1 + (size_t)w.p0 * F1, s1, slab_bytes(w.cnt, F1));
+        bulk_commit_wait();
+    }
+}
 
 // ============================================================ constitutive update
 // Fused anisotropy_return_mapping + kirchoff_stress_Anisotropy (mpm_utils.py:179-209, 101-177).
@@ -10,263 +56,259 @@ namespace mpm {
 // column of R, which is exactly the return-mapped (R02,R12,R22), so one QR serves both.
 // wp.svd3 of [[F11,F12,0],[0,F22,0],[0,0,0]] is only used for U2 V2^T = polar rotation of the
 // upper-triangular 2x2, which has the closed form [[a, b],[-b, a]]/|.|, a=F11+F22, b=F12.
-__global__ void __launch_bounds__(128) k_stress_elements(int Ne, EAux* __restrict__ aux, PRec* __restrict__ rec,
-                                                         VRec* __restrict__ vrec, float friction_coeff) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= Ne) return;
-    EAux a = aux[e];
-    const float* d1 = &a.dc[0];
-    const float* d2 = &a.dc[3];
-    const float* d3 = &a.dc[6];
-    // rotation QR, sign-normalised (R00>0, R11>0, det Q=+1): Gram-Schmidt with q3 = q1 x q2
-    float r00 = len3(d1[0], d1[1], d1[2]);
-    float i00 = 1.0f / r00;
-    float q1[3] = {d1[0] * i00, d1[1] * i00, d1[2] * i00};
-    float r01 = q1[0] * d2[0] + q1[1] * d2[1] + q1[2] * d2[2];
-    float u2[3] = {d2[0] - r01 * q1[0], d2[1] - r01 * q1[1], d2[2] - r01 * q1[2]};
-    float r11 = len3(u2[0], u2[1], u2[2]);
-    float i11 = 1.0f / r11;
-    float q2[3] = {u2[0] * i11, u2[1] * i11, u2[2] * i11};
-    float q3[3] = {q1[1] * q2[2] - q1[2] * q2[1], q1[2] * q2[0] - q1[0] * q2[2], q1[0] * q2[1] - q1[1] * q2[0]};
-    float r02 = q1[0] * d3[0] + q1[1] * d3[1] + q1[2] * d3[2];
-    float r12 = q2[0] * d3[0] + q2[1] * d3[1] + q2[2] * d3[2];
-    float r22 = q3[0] * d3[0] + q3[1] * d3[1] + q3[2] * d3[2];
-    // return mapping (mpm_utils.py:196-204)
-    if (r22 > 1.0f) {
-        r22 = 1.0f;
-    } else {
-        float fn = a.kappa * (1.0f - r22) * (1.0f - r22);
-        float ff = a.gamma * sqrtf(r02 * r02 + r12 * r12);
-        if (ff > friction_coeff * fn) {
-            float sc = friction_coeff * fn / ff;
-            r02 *= sc;
-            r12 *= sc;
+constexpr int STRESS_E_WB = (ED_F + EK_F + S_F) * 32 * 4;  // ED in/out | EK in | ES out
+constexpr int STRESS_E_NW = 4;
+__global__ void __launch_bounds__(32 * STRESS_E_NW) k_stress_elements(int Ne, float* __restrict__ ED, const float* __restrict__ EK,
+                                                                      float* __restrict__ ES, float4* __restrict__ VF,
+                                                                      float friction_coeff) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Warp w;
+    if (!warp_begin<STRESS_E_NW, STRESS_E_WB>(w, Ne, smem)) return;
+    float* sD = reinterpret_cast<float*>(w.buf);
+    float* sK = sD + 32 * ED_F;
+    float* sS = sK + 32 * EK_F;
+    slab_load2(w, sD, ED, ED_F, sK, EK, EK_F);
+    if (w.lane < w.cnt) {
+        const float4* d4 = reinterpret_cast<const float4*>(sD + w.lane * ED_F);
+        const float4 q0 = d4[0], q1v = d4[1], q2v = d4[2];
+        const float d1[3] = {q0.x, q0.y, q0.z}, d2[3] = {q0.w, q1v.x, q1v.y}, d3[3] = {q1v.z, q1v.w, q2v.x};
+        const int face0 = __float_as_int(q2v.y), face1 = __float_as_int(q2v.z), face2 = __float_as_int(q2v.w);
+        const float4 k0 = reinterpret_cast<const float4*>(sK + w.lane * EK_F)[0], k1 = reinterpret_cast<const float4*>(sK + w.lane * EK_F)[1];
+        const float iD11 = k0.x, iD12 = k0.y, iD22 = k0.z, mu = k0.w, lam = k1.x, gamma = k1.y, kappa = k1.z, vol = k1.w;
+        // rotation QR, sign-normalised (R00>0, R11>0, det Q=+1): Gram-Schmidt with q3 = q1 x q2, in
+        // un-contracted IEEE arithmetic (see dot3_rn)
+        const float r00 = len3_rn(d1);
+        const float q1[3] = {__fdiv_rn(d1[0], r00), __fdiv_rn(d1[1], r00), __fdiv_rn(d1[2], r00)};
+        const float r01 = dot3_rn(q1, d2);
+        const float u2[3] = {__fsub_rn(d2[0], __fmul_rn(r01, q1[0])), __fsub_rn(d2[1], __fmul_rn(r01, q1[1])),
+                             __fsub_rn(d2[2], __fmul_rn(r01, q1[2]))};
+        const float r11 = len3_rn(u2);
+        const float q2[3] = {__fdiv_rn(u2[0], r11), __fdiv_rn(u2[1], r11), __fdiv_rn(u2[2], r11)};
+        const float q3[3] = {__fsub_rn(__fmul_rn(q1[1], q2[2]), __fmul_rn(q1[2], q2[1])),
+                             __fsub_rn(__fmul_rn(q1[2], q2[0]), __fmul_rn(q1[0], q2[2])),
+                             __fsub_rn(__fmul_rn(q1[0], q2[1]), __fmul_rn(q1[1], q2[0]))};
+        float r02 = dot3_rn(q1, d3), r12 = dot3_rn(q2, d3), r22 = dot3_rn(q3, d3);
+        // return mapping (mpm_utils.py:196-204)
+        if (r22 > 1.0f) {
+            r22 = 1.0f;
+        } else {
+            float fn = kappa * (1.0f - r22) * (1.0f - r22);
+            float ff = gamma * sqrtf(r02 * r02 + r12 * r12);
+            if (ff > friction_coeff * fn) {
+                float sc = friction_coeff * fn / ff;
+                r02 *= sc;
+                r12 *= sc;
+            }
         }
+        float nd3[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) nd3[r] = q1[r] * r02 + q2[r] * r12 + q3[r] * r22;
+        // stress (mpm_utils.py:125-177) with R = [r00 r01 r02; 0 r11 r12; 0 0 r22]
+        const float F11 = r00 * iD11, F12 = r00 * iD12 + r01 * iD22, F22 = r11 * iD22;
+        const float pa = F11 + F22, pb = F12;
+        const float pin = rsqrtf(pa * pa + pb * pb);
+        const float c = pa * pin, s = pb * pin;  // Rot = [[c, s], [-s, c]]
+        const float J = F11 * F22;
+        const float lj = lam * (J - 1.0f);
+        const float k00 = 2.0f * mu * (F11 - c) + lj * F22;
+        const float k01 = 2.0f * mu * (F12 - s);
+        const float k11 = 2.0f * mu * (F22 - c) + lj * F11;  // K2[1,0] is never used (mpm_utils.py:146-148)
+        const float dr13 = gamma * r02, dr23 = gamma * r12;
+        const float dr33 = (r22 > 1.0f) ? 0.0f : -kappa * (1.0f - r22) * (1.0f - r22);
+        // K3 = dr * RiDT, RiDT = [F11 0 0; F12 F22 0; r02 r12 r22]
+        const float K00 = k00 * F11 + k01 * F12 + dr13 * r02;
+        const float K01 = k01 * F22 + dr13 * r12;
+        const float K02 = dr13 * r22;
+        const float K11 = k11 * F22 + dr23 * r12;
+        const float K12 = dr23 * r22;
+        const float K22 = dr33 * r22;
+        // inverse of lower-triangular RiDT (mpm_utils.py:87-99)
+        const float invdet = 1.0f / (F11 * F22 * r22);
+        const float I00 = F22 * r22 * invdet, I10 = -F12 * r22 * invdet, I11 = F11 * r22 * invdet;
+        const float I20 = (F12 * r12 - r02 * F22) * invdet, I21 = -F11 * r12 * invdet, I22 = F11 * F22 * invdet;
+        // M = K3sym * RiDT^-1
+        const float M00 = K00 * I00 + K01 * I10 + K02 * I20, M01 = K01 * I11 + K02 * I21, M02 = K02 * I22;
+        const float M10 = K01 * I00 + K11 * I10 + K12 * I20, M11 = K11 * I11 + K12 * I21, M12 = K12 * I22;
+        const float M20 = K02 * I00 + K12 * I10 + K22 * I20, M21 = K12 * I11 + K22 * I21, M22 = K22 * I22;
+        float P1[3], P2[3], P3[3];  // columns of P = Q M
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            P1[r] = q1[r] * M00 + q2[r] * M10 + q3[r] * M20;
+            P2[r] = q1[r] * M01 + q2[r] * M11 + q3[r] * M21;
+            P3[r] = q1[r] * M02 + q2[r] * M12 + q3[r] * M22;
+        }
+        float f1[3], f2[3], f3[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            f2[r] = -vol * (iD11 * P1[r] + iD12 * P2[r]);
+            f3[r] = -vol * iD22 * P2[r];
+            f1[r] = -(f2[r] + f3[r]);
+        }
+        // vertex_force scatter (mpm_utils.py:172-175): one 16-byte vector atomic per corner
+        atomicAdd(&VF[face0], make_float4(f1[0], f1[1], f1[2], 0.f));
+        atomicAdd(&VF[face1], make_float4(f2[0], f2[1], f2[2], 0.f));
+        atomicAdd(&VF[face2], make_float4(f3[0], f3[1], f3[2], 0.f));
+        // stress = vol * P3 (x) d3 with the return-mapped d3 (mpm_utils.py:177)
+        float* so = sS + w.lane * S_F;
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++) so[3 * r + cc] = vol * (P3[r] * nd3[cc]);
+        float* dd = sD + w.lane * ED_F;
+        dd[6] = nd3[0]; dd[7] = nd3[1]; dd[8] = nd3[2];
     }
-    float nd3[3];
-#pragma unroll
-    for (int r = 0; r < 3; r++) nd3[r] = q1[r] * r02 + q2[r] * r12 + q3[r] * r22;
-    // stress (mpm_utils.py:125-177) with R = [r00 r01 r02; 0 r11 r12; 0 0 r22]
-    float iD11 = a.Rinv[0], iD12 = a.Rinv[1], iD22 = a.Rinv[2];
-    float F11 = r00 * iD11, F12 = r00 * iD12 + r01 * iD22, F22 = r11 * iD22;
-    float pa = F11 + F22, pb = F12;
-    float pin = rsqrtf(pa * pa + pb * pb);
-    float c = pa * pin, s = pb * pin;  // Rot = [[c, s], [-s, c]]
-    float J = F11 * F22;
-    float lj = a.lam * (J - 1.0f);
-    float k00 = 2.0f * a.mu * (F11 - c) + lj * F22;
-    float k01 = 2.0f * a.mu * (F12 - s);
-    float k11 = 2.0f * a.mu * (F22 - c) + lj * F11;  // K2[1,0] is never used (mpm_utils.py:146-148)
-    float dr13 = a.gamma * r02, dr23 = a.gamma * r12;
-    float dr33 = (r22 > 1.0f) ? 0.0f : -a.kappa * (1.0f - r22) * (1.0f - r22);
-    // K3 = dr * RiDT, RiDT = [F11 0 0; F12 F22 0; r02 r12 r22]
-    float K00 = k00 * F11 + k01 * F12 + dr13 * r02;
-    float K01 = k01 * F22 + dr13 * r12;
-    float K02 = dr13 * r22;
-    float K11 = k11 * F22 + dr23 * r12;
-    float K12 = dr23 * r22;
-    float K22 = dr33 * r22;
-    // inverse of lower-triangular RiDT (mpm_utils.py:87-99)
-    float invdet = 1.0f / (F11 * F22 * r22);
-    float I00 = F22 * r22 * invdet, I10 = -F12 * r22 * invdet, I11 = F11 * r22 * invdet;
-    float I20 = (F12 * r12 - r02 * F22) * invdet, I21 = -F11 * r12 * invdet, I22 = F11 * F22 * invdet;
-    // M = K3sym * RiDT^-1
-    float M00 = K00 * I00 + K01 * I10 + K02 * I20, M01 = K01 * I11 + K02 * I21, M02 = K02 * I22;
-    float M10 = K01 * I00 + K11 * I10 + K12 * I20, M11 = K11 * I11 + K12 * I21, M12 = K12 * I22;
-    float M20 = K02 * I00 + K12 * I10 + K22 * I20, M21 = K12 * I11 + K22 * I21, M22 = K22 * I22;
-    float P1[3], P2[3], P3[3];  // columns of P = Q M
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-        P1[r] = q1[r] * M00 + q2[r] * M10 + q3[r] * M20;
-        P2[r] = q1[r] * M01 + q2[r] * M11 + q3[r] * M21;
-        P3[r] = q1[r] * M02 + q2[r] * M12 + q3[r] * M22;
-    }
-    float vol = a.vol;
-    float f1[3], f2[3], f3[3];
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-        f2[r] = -vol * (iD11 * P1[r] + iD12 * P2[r]);
-        f3[r] = -vol * iD22 * P2[r];
-        f1[r] = -(f2[r] + f3[r]);
-    }
-    // one 16-byte vector atomic per corner (REDG.E.ADD.F32x4) instead of three scalar ones
-    atomicAdd(&vrec[a.face[0]].f, make_float4(f1[0], f1[1], f1[2], 0.f));
-    atomicAdd(&vrec[a.face[1]].f, make_float4(f2[0], f2[1], f2[2], 0.f));
-    atomicAdd(&vrec[a.face[2]].f, make_float4(f3[0], f3[1], f3[2], 0.f));
-    // stress = vol * P3 (x) d3 with the return-mapped d3
-    PRec* pr = &rec[e];
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int cc = 0; cc < 3; cc++) pr->S[3 * r + cc] = vol * (P3[r] * nd3[cc]);
-    aux[e].dc[6] = nd3[0];
-    aux[e].dc[7] = nd3[1];
-    aux[e].dc[8] = nd3[2];
+    slab_store2(w, sD, ED, ED_F, sS, ES, S_F);
 }
 
 // return mappings + stress for traditional particles (mpm_utils.py:1047-1103, 212-399, 8-84)
-__global__ void __launch_bounds__(128) k_stress_traditional(int Nt, TAux* __restrict__ aux, PRec* __restrict__ rec,
-                                                            ModelDev md, float dt) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= Nt) return;
-    TAux a = aux[p];
-    float F[9], U[9], V[9], sg[3];
-    float mu = a.mu, lam = a.lam, ys = a.ys;
-    int mat = md.material;
+constexpr int STRESS_T_WB = (TF_F + S_F) * 32 * 4;
+constexpr int STRESS_T_NW = 4;
+__global__ void __launch_bounds__(32 * STRESS_T_NW) k_stress_traditional(int Nt, float* __restrict__ TF, float* __restrict__ TS,
+                                                                         ModelDev md, float dt) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Warp w;
+    if (!warp_begin<STRESS_T_NW, STRESS_T_WB>(w, Nt, smem)) return;
+    float* sT = reinterpret_cast<float*>(w.buf);
+    float* sS = sT + 32 * TF_F;
+    slab_load2(w, sT, TF, TF_F, nullptr, nullptr, 0);
+    if (w.lane < w.cnt) {
+        float* a = sT + w.lane * TF_F;
+        float F[9], Ft[9], U[9], V[9], sg[3];
+        float mu = a[T_MU], lam = a[T_LAM], ys = a[T_YS];
+        const int mat = md.material;
 #pragma unroll
-    for (int i = 0; i < 9; i++) F[i] = a.Ft[i];
-    if (mat == 1 || mat == 5) {  // von Mises (:212-255) / with damage (:258-311)
-        svd3(a.Ft, U, sg, V);
-        float sc[3], eps[3];
+        for (int i = 0; i < 9; i++) { Ft[i] = a[T_FT + i]; F[i] = Ft[i]; }
+        if (mat == 1 || mat == 5) {  // von Mises (:212-255) / with damage (:258-311)
+            svd3(Ft, U, sg, V);
+            float sc[3], eps[3];
 #pragma unroll
-        for (int i = 0; i < 3; i++) { sc[i] = fmaxf(sg[i], 0.01f); eps[i] = logf(sc[i]); }
-        float tr = eps[0] + eps[1] + eps[2], temp = tr / 3.0f;
-        float tau[3];
+            for (int i = 0; i < 3; i++) { sc[i] = fmaxf(sg[i], 0.01f); eps[i] = logf(sc[i]); }
+            float tr = eps[0] + eps[1] + eps[2], temp = tr / 3.0f;
+            float tau[3];
 #pragma unroll
-        for (int i = 0; i < 3; i++) tau[i] = 2.0f * mu * eps[i] + lam * tr;
-        float st = tau[0] + tau[1] + tau[2];
-        float cn = len3(tau[0] - st / 3.0f, tau[1] - st / 3.0f, tau[2] - st / 3.0f);
-        if (cn > ys && !(mat == 5 && ys <= 0.0f)) {
-            float eh[3] = {eps[0] - temp, eps[1] - temp, eps[2] - temp};
-            float ehn = len3(eh[0], eh[1], eh[2]) + 1e-6f;
-            float dg = ehn - ys / (2.0f * mu);
-            float corr[3] = {(dg / ehn) * eh[0], (dg / ehn) * eh[1], (dg / ehn) * eh[2]};
-            float se[3];
+            for (int i = 0; i < 3; i++) tau[i] = 2.0f * mu * eps[i] + lam * tr;
+            float st = tau[0] + tau[1] + tau[2];
+            float cn = len3(tau[0] - st / 3.0f, tau[1] - st / 3.0f, tau[2] - st / 3.0f);
+            if (cn > ys && !(mat == 5 && ys <= 0.0f)) {
+                float eh[3] = {eps[0] - temp, eps[1] - temp, eps[2] - temp};
+                float ehn = len3(eh[0], eh[1], eh[2]) + 1e-6f;
+                float dg = ehn - ys / (2.0f * mu);
+                float corr[3] = {(dg / ehn) * eh[0], (dg / ehn) * eh[1], (dg / ehn) * eh[2]};
+                float se[3];
 #pragma unroll
-            for (int i = 0; i < 3; i++) se[i] = expf(eps[i] - corr[i]);
-            if (mat == 5) {
-                ys = ys - md.softening * len3(corr[0], corr[1], corr[2]);
-                if (ys <= 0.0f) { mu = 0.0f; lam = 0.0f; }
+                for (int i = 0; i < 3; i++) se[i] = expf(eps[i] - corr[i]);
+                if (mat == 5) {
+                    ys = ys - md.softening * len3(corr[0], corr[1], corr[2]);
+                    if (ys <= 0.0f) { mu = 0.0f; lam = 0.0f; }
+                }
+                diag_sandwich(U, se, V, F);
+                if (md.hardening == 1) ys = ys + 2.0f * mu * md.xi * dg;
             }
-            diag_sandwich(U, se, V, F);
-            if (md.hardening == 1) ys = ys + 2.0f * mu * md.xi * dg;
+        } else if (mat == 2) {  // sand (:362-399)
+            svd3(Ft, U, sg, V);
+            float eps[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) eps[i] = logf(fmaxf(fabsf(sg[i]), 1e-14f));
+            float tr = eps[0] + eps[1] + eps[2];
+            float eh[3] = {eps[0] - tr / 3.0f, eps[1] - tr / 3.0f, eps[2] - tr / 3.0f};
+            float ehn = len3(eh[0], eh[1], eh[2]);
+            float dg = ehn + (3.0f * lam + 2.0f * mu) / (2.0f * mu) * tr * md.alpha;
+            if (dg > 0.0f && tr > 0.0f) mat_mul_bt(U, V, F);
+            if (dg > 0.0f && tr <= 0.0f) {
+                float sn[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) sn[i] = expf(eps[i] - eh[i] * (dg / ehn));
+                diag_sandwich(U, sn, V, F);
+            }
+        } else if (mat == 3) {  // viscoplastic StVK (:315-359)
+            svd3(Ft, U, sg, V);
+            float sc[3], eps[3], b[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) { sc[i] = fmaxf(sg[i], 0.01f); b[i] = sc[i] * sc[i]; eps[i] = logf(sc[i]); }
+            float tr = eps[0] + eps[1] + eps[2];
+            float st[3] = {2.0f * mu * (eps[0] - tr / 3.0f), 2.0f * mu * (eps[1] - tr / 3.0f), 2.0f * mu * (eps[2] - tr / 3.0f)};
+            float stn = len3(st[0], st[1], st[2]);
+            float y = stn - sqrtf(2.0f / 3.0f) * ys;
+            if (y > 0.0f) {
+                float mu_hat = mu * (b[0] + b[1] + b[2]) / 3.0f;
+                float snn = stn - y / (1.0f + md.plastic_viscosity / (2.0f * mu_hat * dt));
+                float se[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) se[i] = expf(1.0f / (2.0f * mu) * ((snn / stn) * st[i]) + tr / 3.0f);
+                diag_sandwich(U, se, V, F);
+            }
         }
-    } else if (mat == 2) {  // sand (:362-399)
-        svd3(a.Ft, U, sg, V);
-        float eps[3];
+        // stress from F (:1072-1103)
+        float J = det3(F);
+        svd3(F, U, sg, V);
+        float S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (mat == 0 || mat == 5) {  // fixed corotated (:8-15)
+            float Rm[9], D[9];
+            mat_mul_bt(U, V, Rm);
 #pragma unroll
-        for (int i = 0; i < 3; i++) eps[i] = logf(fmaxf(fabsf(sg[i]), 1e-14f));
-        float tr = eps[0] + eps[1] + eps[2];
-        float eh[3] = {eps[0] - tr / 3.0f, eps[1] - tr / 3.0f, eps[2] - tr / 3.0f};
-        float ehn = len3(eh[0], eh[1], eh[2]);
-        float dg = ehn + (3.0f * lam + 2.0f * mu) / (2.0f * mu) * tr * md.alpha;
-        if (dg > 0.0f && tr > 0.0f) mat_mul_bt(U, V, F);
-        if (dg > 0.0f && tr <= 0.0f) {
-            float sn[3];
+            for (int i = 0; i < 9; i++) D[i] = F[i] - Rm[i];
+            mat_mul_bt(D, F, S);
+            float pj = lam * J * (J - 1.0f);
 #pragma unroll
-            for (int i = 0; i < 3; i++) sn[i] = expf(eps[i] - eh[i] * (dg / ehn));
-            diag_sandwich(U, sn, V, F);
+            for (int i = 0; i < 9; i++) S[i] *= 2.0f * mu;
+            S[0] += pj; S[4] += pj; S[8] += pj;
+        } else if (mat == 1 || mat == 3) {  // StVK / Hencky (:50-66)
+            float sc[3], tau[3], t[9];
+#pragma unroll
+            for (int i = 0; i < 3; i++) sc[i] = fmaxf(sg[i], 0.01f);
+            float sum = logf(sc[0]) + logf(sc[1]) + logf(sc[2]);
+#pragma unroll
+            for (int i = 0; i < 3; i++) tau[i] = 2.0f * mu * logf(sc[i]) + lam * sum;
+            diag_sandwich(U, tau, V, t);
+            mat_mul_bt(t, F, S);
+        } else if (mat == 2) {  // Drucker-Prager (:69-84)
+            float sum = logf(sg[0]) + logf(sg[1]) + logf(sg[2]);
+            float cc[3], t[9];
+#pragma unroll
+            for (int i = 0; i < 3; i++) cc[i] = 2.0f * mu * logf(sg[i]) * (1.0f / sg[i]) + lam * sum * (1.0f / sg[i]);
+            diag_sandwich(U, cc, V, t);
+            mat_mul_bt(t, F, S);
         }
-    } else if (mat == 3) {  // viscoplastic StVK (:315-359)
-        svd3(a.Ft, U, sg, V);
-        float sc[3], eps[3], b[3];
+        float* so = sS + w.lane * S_F;
 #pragma unroll
-        for (int i = 0; i < 3; i++) { sc[i] = fmaxf(sg[i], 0.01f); b[i] = sc[i] * sc[i]; eps[i] = logf(sc[i]); }
-        float tr = eps[0] + eps[1] + eps[2];
-        float st[3] = {2.0f * mu * (eps[0] - tr / 3.0f), 2.0f * mu * (eps[1] - tr / 3.0f), 2.0f * mu * (eps[2] - tr / 3.0f)};
-        float stn = len3(st[0], st[1], st[2]);
-        float y = stn - sqrtf(2.0f / 3.0f) * ys;
-        if (y > 0.0f) {
-            float mu_hat = mu * (b[0] + b[1] + b[2]) / 3.0f;
-            float snn = stn - y / (1.0f + md.plastic_viscosity / (2.0f * mu_hat * dt));
-            float se[3];
+        for (int r = 0; r < 3; r++)
 #pragma unroll
-            for (int i = 0; i < 3; i++) se[i] = expf(1.0f / (2.0f * mu) * ((snn / stn) * st[i]) + tr / 3.0f);
-            diag_sandwich(U, se, V, F);
-        }
+            for (int cc = 0; cc < 3; cc++) so[3 * r + cc] = (S[3 * r + cc] + S[3 * cc + r]) / 2.0f;
+#pragma unroll
+        for (int i = 0; i < 9; i++) a[T_F + i] = F[i];
+        a[T_MU] = mu;
+        a[T_LAM] = lam;
+        a[T_YS] = ys;
     }
-    // stress from F (:1072-1103)
-    float J = det3(F);
-    svd3(F, U, sg, V);
-    float S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (mat == 0 || mat == 5) {  // fixed corotated (:8-15)
-        float Rm[9], D[9];
-        mat_mul_bt(U, V, Rm);
-#pragma unroll
-        for (int i = 0; i < 9; i++) D[i] = F[i] - Rm[i];
-        mat_mul_bt(D, F, S);
-        float pj = lam * J * (J - 1.0f);
-#pragma unroll
-        for (int i = 0; i < 9; i++) S[i] *= 2.0f * mu;
-        S[0] += pj; S[4] += pj; S[8] += pj;
-    } else if (mat == 1 || mat == 3) {  // StVK / Hencky (:50-66)
-        float sc[3], tau[3], t[9];
-#pragma unroll
-        for (int i = 0; i < 3; i++) sc[i] = fmaxf(sg[i], 0.01f);
-        float sum = logf(sc[0]) + logf(sc[1]) + logf(sc[2]);
-#pragma unroll
-        for (int i = 0; i < 3; i++) tau[i] = 2.0f * mu * logf(sc[i]) + lam * sum;
-        diag_sandwich(U, tau, V, t);
-        mat_mul_bt(t, F, S);
-    } else if (mat == 2) {  // Drucker-Prager (:69-84)
-        float sum = logf(sg[0]) + logf(sg[1]) + logf(sg[2]);
-        float cc[3], t[9];
-#pragma unroll
-        for (int i = 0; i < 3; i++) cc[i] = 2.0f * mu * logf(sg[i]) * (1.0f / sg[i]) + lam * sum * (1.0f / sg[i]);
-        diag_sandwich(U, cc, V, t);
-        mat_mul_bt(t, F, S);
-    }
-    PRec* pr = &rec[p];
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int cc = 0; cc < 3; cc++) pr->S[3 * r + cc] = (S[3 * r + cc] + S[3 * cc + r]) / 2.0f;
-    TAux* o = &aux[p];
-#pragma unroll
-    for (int i = 0; i < 9; i++) o->F[i] = F[i];
-    o->mu = mu;
-    o->lam = lam;
-    o->ys = ys;
+    slab_store2(w, sT, TF, TF_F, sS, TS, S_F);
 }
 
-// pre-P2G particle operations on one class (mpm_solver.py:260-279)
-template <typename Rec>
-__global__ void k_particle_ops(int n, Rec* __restrict__ rec, const uint32_t* __restrict__ perm, int canon_offset,
+// pre-P2G particle operations on one class (mpm_solver.py:260-279); v and mass sit at the same
+// offsets in EP/TP and VP records
+__global__ void k_particle_ops(int n, float* __restrict__ rec, int F, const uint32_t* __restrict__ perm, int canon_offset,
                                const ParticleOp* __restrict__ ops, int n_ops, const StepState* __restrict__ st, float dt) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     float time = (float)st->time;
     int ci = canon_offset + (int)perm[p];
-    float4 vv = rec_v(rec[p]);
-    float m = rec[p].xm.w;
+    float* r = rec + (size_t)p * F;
+    float vx = r[P_V], vy = r[P_V + 1], vz = r[P_V + 2];
+    float m = r[P_M];
     bool ch = false;
     for (int k = 0; k < n_ops; k++) {
         ParticleOp op = ops[k];
         if (!(time >= op.start_time && time < op.end_time)) continue;
         int mk = op.mask[ci];
-        if (op.kind == 0 && mk == 1) { vv.x += op.vec[0] / m * dt; vv.y += op.vec[1] / m * dt; vv.z += op.vec[2] / m * dt; ch = true; }
-        if (op.kind == 1 && mk >= 1) { vv.x += op.vec[0] * dt; vv.y += op.vec[1] * dt; vv.z += op.vec[2] * dt; ch = true; }
-        if (op.kind == 2 && mk == 1) { vv.x = op.vec[0]; vv.y = op.vec[1]; vv.z = op.vec[2]; ch = true; }
+        if (op.kind == 0 && mk == 1) { vx += op.vec[0] / m * dt; vy += op.vec[1] / m * dt; vz += op.vec[2] / m * dt; ch = true; }
+        if (op.kind == 1 && mk >= 1) { vx += op.vec[0] * dt; vy += op.vec[1] * dt; vz += op.vec[2] * dt; ch = true; }
+        if (op.kind == 2 && mk == 1) { vx = op.vec[0]; vy = op.vec[1]; vz = op.vec[2]; ch = true; }
     }
-    if (ch) rec_set_v(rec[p], vv);
+    if (ch) { r[P_V] = vx; r[P_V + 1] = vy; r[P_V + 2] = vz; }
 }
 
 // ============================================================ P2G
-// PTX helpers: 1-D bulk async copy (TMA unit, SASS UBLKCP) completing on an mbarrier.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-    return ok != 0;
-}
-
 // p2g_apic_with_stress (mpm_utils.py:484-557), restructured for cell-sorted particles.
-//  stage 0  one cp.async.bulk per warp brings its slab of 32 consecutive AoS records into smem.
+//  stage 0  cp.async.bulk brings the warp's kinematics slab and stress (or vertex-force) slab into smem.
 //  stage 1  lane = particle: each lane turns its record into a separable "pack".  With
 //           dpos = (ijk - f) dx the contribution to stencil node (i,j,k) is
 //             w m (v + C dpos) + dt force = A w + ux[i] wy wz + wx uy[j] wz + wx wy uz[k]
@@ -277,57 +319,52 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 //           REDG.E.ADD.F32x4 per node when the cell changes.  No intra-warp reduction, no
 //           shared-memory atomics; global atomics drop from 27*4 per particle to 27 per cell run.
 // KIND 0: element (S already holds vol*P3(x)d3), 1: traditional (stress*vol, :496), 2: vertex.
-constexpr int P2G_PK = 40;                       // floats per pack
-constexpr int P2G_WARP_BYTES = 32 * P2G_PK * 4 + 32 * 4;  // packs + cell ids
-constexpr int P2G_WARPS = 8;
-constexpr int P2G_SMEM = 128 + P2G_WARPS * P2G_WARP_BYTES;
+constexpr int P2G_PK = 40;                                // floats per pack
+constexpr int P2G_WB = 32 * P2G_PK * 4 + 32 * 4;          // packs (overlaying the raw slabs) + cell ids
+constexpr int P2G_NW = 8;
+constexpr int P2G_SMEM = 128 + P2G_NW * P2G_WB;
 
 template <int KIND>
-__global__ void __launch_bounds__(32 * P2G_WARPS) k_p2g(Grid g, const float* __restrict__ recs, int n, float dt, float rpic) {
-    constexpr int RS = (KIND == 2) ? (int)(sizeof(VRec) / 4) : (int)(sizeof(PRec) / 4);
-    extern __shared__ __align__(128) unsigned char p2g_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p0 = (blockIdx.x * P2G_WARPS + warp) * 32;
-    if (p0 >= n) return;
-    const int cnt = min(32, n - p0);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(p2g_smem) + warp;
-    float* buf = reinterpret_cast<float*>(p2g_smem + 128 + warp * P2G_WARP_BYTES);
+__global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, const float* __restrict__ KP, const float* __restrict__ SF, int n,
+                                                      float dt, float rpic) {
+    constexpr int F0 = (KIND == 2) ? VP_F : KP_F;  // kinematics record
+    constexpr int F1 = (KIND == 2) ? VF_F : S_F;   // vertex force / stress record
+    extern __shared__ __align__(128) unsigned char smem[];
+    Warp w;
+    if (!warp_begin<P2G_NW, P2G_WB>(w, n, smem)) return;
+    float* buf = reinterpret_cast<float*>(w.buf);
+    float* raw1 = buf + 32 * F0;
     int* cell = reinterpret_cast<int*>(buf + 32 * P2G_PK);
-    // ---- stage 0
-    if (lane == 0) mbar_init(bar, 1);
-    __syncwarp();
-    if (lane == 0) {
-        mbar_expect_tx(bar, (uint32_t)(cnt * RS * 4));
-        bulk_g2s(buf, recs + (size_t)p0 * RS, (uint32_t)(cnt * RS * 4), bar);
-    }
-    while (!mbar_try_wait(bar, 0)) {}
+    slab_load2(w, buf, KP, F0, raw1, SF, F1);
     // ---- stage 1
-    float r[RS];
-    if (lane < cnt) {
-        const float4* src = reinterpret_cast<const float4*>(buf + lane * RS);
+    float x[3], m, v[3], C[9], Sp[9], fv[3] = {0.f, 0.f, 0.f};
+    if (w.lane < w.cnt) {
+        const float* r = buf + w.lane * F0;
+        const float* s = raw1 + w.lane * F1;
+        if (KIND == 2) {
+            const float4* r4 = reinterpret_cast<const float4*>(r);
+            const float4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; m = a.w;
+            v[0] = b.x; v[1] = b.y; v[2] = b.z;
+            C[0] = b.w; C[1] = c.x; C[2] = c.y; C[3] = c.z; C[4] = c.w; C[5] = d.x; C[6] = d.y; C[7] = d.z; C[8] = d.w;
+            const float4 f4 = *reinterpret_cast<const float4*>(s);
+            fv[0] = f4.x; fv[1] = f4.y; fv[2] = f4.z;
 #pragma unroll
-        for (int i = 0; i < RS / 4; i++) {
-            float4 t = src[i];
-            r[4 * i] = t.x; r[4 * i + 1] = t.y; r[4 * i + 2] = t.z; r[4 * i + 3] = t.w;
+            for (int i = 0; i < 9; i++) Sp[i] = 0.f;
+        } else {
+            x[0] = r[0]; x[1] = r[1]; x[2] = r[2]; m = r[P_M];
+            v[0] = r[P_V]; v[1] = r[P_V + 1]; v[2] = r[P_V + 2];
+            const float sc = -dt * g.inv_dx * ((KIND == 1) ? r[P_VOL] : 1.0f);
+#pragma unroll
+            for (int i = 0; i < 9; i++) { C[i] = r[P_C + i]; Sp[i] = sc * s[i]; }
         }
     } else {
+        x[0] = x[1] = x[2] = 0.f; m = 0.f; v[0] = v[1] = v[2] = 0.f;
 #pragma unroll
-        for (int i = 0; i < RS; i++) r[i] = 0.f;
+        for (int i = 0; i < 9; i++) { C[i] = 0.f; Sp[i] = 0.f; }
     }
-    __syncwarp();  // packs overwrite the raw slab
+    __syncwarp();  // packs overwrite the raw slabs
     {
-        const float m = r[3];
-        float v[3], C[9], Sp[9];
-        if (KIND == 2) {
-            v[0] = r[8]; v[1] = r[9]; v[2] = r[10];
-#pragma unroll
-            for (int i = 0; i < 9; i++) { C[i] = r[11 + i]; Sp[i] = 0.f; }
-        } else {
-            v[0] = r[4]; v[1] = r[5]; v[2] = r[6];
-            const float sc = -dt * g.inv_dx * ((KIND == 1) ? r[7] : 1.0f);
-#pragma unroll
-            for (int i = 0; i < 9; i++) { C[i] = r[8 + i]; Sp[i] = sc * r[17 + i]; }
-        }
         if (rpic != 0.0f) {  // mpm_utils.py:528-542
             float Cn[9];
 #pragma unroll
@@ -338,34 +375,37 @@ __global__ void __launch_bounds__(32 * P2G_WARPS) k_p2g(Grid g, const float* __r
 #pragma unroll
             for (int i = 0; i < 9; i++) C[i] = (rpic < -0.001f) ? 0.0f : Cn[i];
         }
-        const float gp[3] = {r[0] * g.inv_dx, r[1] * g.inv_dx, r[2] * g.inv_dx};
         int b[3];
         float f[3];
 #pragma unroll
-        for (int a = 0; a < 3; a++) { b[a] = (int)(gp[a] - 0.5f); f[a] = gp[a] - (float)b[a]; }
-        float4* out = reinterpret_cast<float4*>(buf + lane * P2G_PK);
+        for (int a = 0; a < 3; a++) {
+            const float gp = x[a] * g.inv_dx;
+            b[a] = (int)(gp - 0.5f);
+            f[a] = gp - (float)b[a];
+        }
+        float4* out = reinterpret_cast<float4*>(buf + w.lane * P2G_PK);
         const float mdx = m * g.dx;
 #pragma unroll
         for (int a = 0; a < 3; a++)
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-                float w, dw;
-                bspline(f[a], i, w, dw);
-                const float iw = (float)i * w * mdx;
-                out[3 * a + i] = make_float4(w, C[a] * iw + Sp[a] * dw, C[3 + a] * iw + Sp[3 + a] * dw,
+                float ww, dw;
+                bspline(f[a], i, ww, dw);
+                const float iw = (float)i * ww * mdx;
+                out[3 * a + i] = make_float4(ww, C[a] * iw + Sp[a] * dw, C[3 + a] * iw + Sp[3 + a] * dw,
                                              C[6 + a] * iw + Sp[6 + a] * dw);
             }
         float A[3];
 #pragma unroll
-        for (int c = 0; c < 3; c++) A[c] = m * (v[c] - g.dx * (C[3 * c] * f[0] + C[3 * c + 1] * f[1] + C[3 * c + 2] * f[2]));
-        if (KIND == 2) { A[0] += dt * r[4]; A[1] += dt * r[5]; A[2] += dt * r[6]; }
+        for (int c = 0; c < 3; c++)
+            A[c] = m * (v[c] - g.dx * (C[3 * c] * f[0] + C[3 * c + 1] * f[1] + C[3 * c + 2] * f[2])) + dt * fv[c];
         out[9] = make_float4(A[0], A[1], A[2], m);
-        cell[lane] = (clampi(b[0] + 2, 0, 1023)) | (clampi(b[1] + 2, 0, 1023) << 10) | (clampi(b[2] + 2, 0, 1023) << 20);
+        cell[w.lane] = (clampi(b[0] + 2, 0, 1023)) | (clampi(b[1] + 2, 0, 1023) << 10) | (clampi(b[2] + 2, 0, 1023) << 20);
     }
     __syncwarp();
     // ---- stage 2
-    const bool act = lane < 27;
-    const int li = act ? lane / 9 : 0, lj = act ? (lane / 3) % 3 : 0, lk = act ? lane % 3 : 0;
+    const bool act = w.lane < 27;
+    const int li = act ? w.lane / 9 : 0, lj = act ? (w.lane / 3) % 3 : 0, lk = act ? w.lane % 3 : 0;
     const float4* P = reinterpret_cast<const float4*>(buf);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int cur = cell[0];
@@ -377,7 +417,7 @@ __global__ void __launch_bounds__(32 * P2G_WARPS) k_p2g(Grid g, const float* __r
         }
     };
 #pragma unroll 4
-    for (int q = 0; q < cnt; q++) {
+    for (int q = 0; q < w.cnt; q++) {
         const int c = cell[q];
         if (c != cur) {  // warp-uniform
             flush(cur);
@@ -385,11 +425,11 @@ __global__ void __launch_bounds__(32 * P2G_WARPS) k_p2g(Grid g, const float* __r
             cur = c;
         }
         const float4 X = P[q * 10 + li], Y = P[q * 10 + 3 + lj], Z = P[q * 10 + 6 + lk], H = P[q * 10 + 9];
-        const float wyz = Y.x * Z.x, wxz = X.x * Z.x, wxy = X.x * Y.x, w = X.x * wyz;
-        acc.x += H.x * w + X.y * wyz + Y.y * wxz + Z.y * wxy;
-        acc.y += H.y * w + X.z * wyz + Y.z * wxz + Z.z * wxy;
-        acc.z += H.z * w + X.w * wyz + Y.w * wxz + Z.w * wxy;
-        acc.w += H.w * w;
+        const float wyz = Y.x * Z.x, wxz = X.x * Z.x, wxy = X.x * Y.x, ww = X.x * wyz;
+        acc.x += H.x * ww + X.y * wyz + Y.y * wxz + Z.y * wxy;
+        acc.y += H.y * ww + X.z * wyz + Y.z * wxz + Z.z * wxy;
+        acc.z += H.z * ww + X.w * wyz + Y.w * wxz + Z.w * wxy;
+        acc.w += H.w * ww;
     }
     flush(cur);
 }
@@ -414,30 +454,6 @@ __device__ __forceinline__ void make_stencil(const Grid& g, float x, float y, fl
 // bounds test of compute_mesh / add_velocity_* (mpm_solver.py:692,858)
 __device__ __forceinline__ bool scatter_ok(const Grid& g, const Stencil& s) {
     return s.b[0] >= 0 && s.b[0] < g.n - 3 && s.b[1] >= 0 && s.b[1] < g.n - 3 && s.b[2] >= 0 && s.b[2] < g.n - 3;
-}
-// the (up to) 2x2x2 pool slots under a 3^3 stencil whose base node is (bx,by,bz) >= 0:
-// eight independent table loads issued together instead of 27 dependent ones
-__device__ __forceinline__ void load_slots8(const Grid& g, int bx, int by, int bz, int* sl) {
-    const int X0 = bx >> 2, Y0 = by >> 2, Z0 = bz >> 2;
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-        int X = X0 + (c >> 2), Y = Y0 + ((c >> 1) & 1), Z = Z0 + (c & 1);
-        bool ok = bx >= 0 && by >= 0 && bz >= 0 && X < g.nb && Y < g.nb && Z < g.nb;
-        sl[c] = ok ? lookup_slot(g, X, Y, Z) : -1;
-    }
-}
-__device__ __forceinline__ int sel8(const int* sl, int c) {
-    int s = sl[0];
-#pragma unroll
-    for (int q = 1; q < 8; q++) s = (c == q) ? sl[q] : s;
-    return s;
-}
-// pool index of stencil node (i,j,k) given the 8 slots, -1 if its block is not allocated
-__device__ __forceinline__ int stencil_node(const int* sl, int bx, int by, int bz, int i, int j, int k) {
-    const int ix = bx + i, iy = by + j, iz = bz + k;
-    const int c = (((ix >> 2) - (bx >> 2)) << 2) | (((iy >> 2) - (by >> 2)) << 1) | ((iz >> 2) - (bz >> 2));
-    const int s = sel8(sl, c);
-    return s < 0 ? -1 : s * BN + ((ix & 3) << 4) + ((iy & 3) << 2) + (iz & 3);
 }
 
 // compute_mesh (mpm_solver.py:829-880).  Only nodes of ALLOCATED blocks are written: a node
@@ -484,9 +500,9 @@ __global__ void __launch_bounds__(128) k_collider_scatter(Grid g, int Mf, const 
             for (int k = 0; k < 3; k++) {
                 int ni = stencil_node(sl, sp.b[0], sp.b[1], sp.b[2], i, j, k);
                 if (ni < 0) continue;
-                float w = sp.w[0][i] * sp.w[1][j] * sp.w[2][k];
-                atomicAdd(&g.colv[ni], make_float4(w * fv[0], w * fv[1], w * fv[2], w));
-                atomicAdd(&g.coln[ni], make_float4(w * nx, w * ny, w * nz, 0.0f));
+                float ww = sp.w[0][i] * sp.w[1][j] * sp.w[2][k];
+                atomicAdd(&g.colv[ni], make_float4(ww * fv[0], ww * fv[1], ww * fv[2], ww));
+                atomicAdd(&g.coln[ni], make_float4(ww * nx, ww * ny, ww * nz, 0.0f));
             }
 }
 
@@ -494,19 +510,19 @@ __global__ void __launch_bounds__(128) k_collider_scatter(Grid g, int Mf, const 
 // threads [0,njt) pinned traditional tail, [njt, njt+njv) joint vertices, then joint faces.
 __global__ void __launch_bounds__(128) k_mover_scatter(Grid g, int njt, int njv, int njf, int Nt,
                                                        const float* __restrict__ vt, const float* __restrict__ vvv,
-                                                       const float* __restrict__ vf, const PRec* __restrict__ erec,
-                                                       const PRec* __restrict__ trec, const VRec* __restrict__ vrec,
+                                                       const float* __restrict__ vf, const float* __restrict__ EP,
+                                                       const float* __restrict__ TP, const float* __restrict__ VP,
                                                        const int* __restrict__ invE, const int* __restrict__ invT,
                                                        const int* __restrict__ invV) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= njt + njv + njf) return;
-    float4 xm;
+    const float* xr;
     const float* vel;
-    if (t < njt) { xm = trec[invT[Nt - njt + t]].xm; vel = vt + 3 * t; }
-    else if (t < njt + njv) { xm = vrec[invV[t - njt]].xm; vel = vvv + 3 * (t - njt); }
-    else { xm = erec[invE[t - njt - njv]].xm; vel = vf + 3 * (t - njt - njv); }
+    if (t < njt) { xr = TP + (size_t)invT[Nt - njt + t] * KP_F; vel = vt + 3 * t; }
+    else if (t < njt + njv) { xr = VP + (size_t)invV[t - njt] * VP_F; vel = vvv + 3 * (t - njt); }
+    else { xr = EP + (size_t)invE[t - njt - njv] * KP_F; vel = vf + 3 * (t - njt - njv); }
     Stencil sp;
-    make_stencil(g, xm.x, xm.y, xm.z, sp);
+    make_stencil(g, xr[0], xr[1], xr[2], sp);
     if (!scatter_ok(g, sp)) return;
     int sl[8];
     load_slots8(g, sp.b[0], sp.b[1], sp.b[2], sl);
@@ -519,8 +535,8 @@ __global__ void __launch_bounds__(128) k_mover_scatter(Grid g, int njt, int njv,
             for (int k = 0; k < 3; k++) {
                 int ni = stencil_node(sl, sp.b[0], sp.b[1], sp.b[2], i, j, k);
                 if (ni < 0) { g.flags[1] = 1; continue; }
-                float w = sp.w[0][i] * sp.w[1][j] * sp.w[2][k];
-                atomicAdd(&g.mov[ni], make_float4(w * v0, w * v1, w * v2, w));
+                float ww = sp.w[0][i] * sp.w[1][j] * sp.w[2][k];
+                atomicAdd(&g.mov[ni], make_float4(ww * v0, ww * v1, ww * v2, ww));
             }
 }
 
@@ -638,7 +654,6 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
         g.vout[idx] = make_float4(vx, vy, vz, 0.0f);
     }
 }
-
 __global__ void k_reset_k(StepState* st) { st->k = 0; }
 
 // ============================================================ G2P
@@ -738,97 +753,123 @@ struct Advance {
     int n_bc;
 };
 
+constexpr int G2P_NW = 4;
 // g2p_v for cloth vertices (mpm_utils.py:716-786); also clears vertex_force for the next substep
 // (replaces set_vec3_to_zero, mpm_solver.py:251-256) and allocates grid blocks for the new position.
-__global__ void __launch_bounds__(128, 4) k_g2p_vertices(Grid g, int Nv, VRec* __restrict__ rec, float dt,
-                                                      float* __restrict__ dbg_f, Advance adv) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (adv.st && p == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
-    if (p >= Nv) return;
-    float4 xm = rec[p].xm;
-    Gathered o;
-    g2p_gather(g, xm.x, xm.y, xm.z, o);
-    const float dxc = 1.0f / g.inv_dx, a_min = dxc * 2.0f, a_max = g.lim - dxc * 2.0f;
-    xm.x = clampf(xm.x + dt * o.v[0], a_min, a_max);
-    xm.y = clampf(xm.y + dt * o.v[1], a_min, a_max);
-    xm.z = clampf(xm.z + dt * o.v[2], a_min, a_max);
-    float4* r4 = reinterpret_cast<float4*>(&rec[p]);
-    if (dbg_f) { float4 f = r4[1]; dbg_f[3 * p] = f.x; dbg_f[3 * p + 1] = f.y; dbg_f[3 * p + 2] = f.z; }
-    r4[0] = xm;
-    r4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    r4[2] = make_float4(o.v[0], o.v[1], o.v[2], o.C[0]);
-    r4[3] = make_float4(o.C[1], o.C[2], o.C[3], o.C[4]);
-    r4[4] = make_float4(o.C[5], o.C[6], o.C[7], o.C[8]);
-    ensure_stencil_blocks(g, xm.x, xm.y, xm.z);
+constexpr int G2P_V_WB = VP_F * 32 * 4;
+__global__ void __launch_bounds__(32 * G2P_NW, 4) k_g2p_vertices(Grid g, int Nv, float* __restrict__ VP, float4* __restrict__ VF,
+                                                                  float dt, float* __restrict__ dbg_f, Advance adv) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
+    Warp w;
+    if (!warp_begin<G2P_NW, G2P_V_WB>(w, Nv, smem)) return;
+    float* sP = reinterpret_cast<float*>(w.buf);
+    slab_load2(w, sP, VP, VP_F, nullptr, nullptr, 0);
+    if (w.lane < w.cnt) {
+        float4* r4 = reinterpret_cast<float4*>(sP + w.lane * VP_F);
+        float4 xm = r4[0];
+        Gathered o;
+        g2p_gather(g, xm.x, xm.y, xm.z, o);
+        const float dxc = 1.0f / g.inv_dx, a_min = dxc * 2.0f, a_max = g.lim - dxc * 2.0f;
+        xm.x = clampf(xm.x + dt * o.v[0], a_min, a_max);
+        xm.y = clampf(xm.y + dt * o.v[1], a_min, a_max);
+        xm.z = clampf(xm.z + dt * o.v[2], a_min, a_max);
+        r4[0] = xm;
+        r4[1] = make_float4(o.v[0], o.v[1], o.v[2], o.C[0]);
+        r4[2] = make_float4(o.C[1], o.C[2], o.C[3], o.C[4]);
+        r4[3] = make_float4(o.C[5], o.C[6], o.C[7], o.C[8]);
+        const int p = w.p0 + w.lane;
+        if (dbg_f) { float4 f = VF[p]; dbg_f[3 * p] = f.x; dbg_f[3 * p + 1] = f.y; dbg_f[3 * p + 2] = f.z; }
+        VF[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ensure_stencil_blocks(g, xm.x, xm.y, xm.z);
+    }
+    slab_store2(w, sP, VP, VP_F, nullptr, nullptr, 0);
 }
 
 // g2p_v for traditional particles: additionally F_trial = (I + dt grad v) F (mpm_utils.py:783-786)
-__global__ void __launch_bounds__(128, 4) k_g2p_traditional(Grid g, int Nt, PRec* __restrict__ rec, TAux* __restrict__ aux,
-                                                         float dt, Advance adv) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (adv.st && p == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
-    if (p >= Nt) return;
-    float4 xm = rec[p].xm;
-    Gathered o;
-    g2p_gather(g, xm.x, xm.y, xm.z, o);
-    const float dxc = 1.0f / g.inv_dx, a_min = dxc * 2.0f, a_max = g.lim - dxc * 2.0f;
-    xm.x = clampf(xm.x + dt * o.v[0], a_min, a_max);
-    xm.y = clampf(xm.y + dt * o.v[1], a_min, a_max);
-    xm.z = clampf(xm.z + dt * o.v[2], a_min, a_max);
-    PRec* r = &rec[p];
-    const float vol = r->vv.w;
-    r->xm = xm;
-    r->vv = make_float4(o.v[0], o.v[1], o.v[2], vol);
+constexpr int G2P_T_WB = (KP_F + TF_F) * 32 * 4;
+__global__ void __launch_bounds__(32 * G2P_NW, 4) k_g2p_traditional(Grid g, int Nt, float* __restrict__ TP, float* __restrict__ TF,
+                                                                     float dt, Advance adv) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
+    Warp w;
+    if (!warp_begin<G2P_NW, G2P_T_WB>(w, Nt, smem)) return;
+    float* sP = reinterpret_cast<float*>(w.buf);
+    float* sT = sP + 32 * KP_F;
+    slab_load2(w, sP, TP, KP_F, sT, TF, TF_F);
+    if (w.lane < w.cnt) {
+        float* r = sP + w.lane * KP_F;
+        float* t = sT + w.lane * TF_F;
+        float x = r[0], y = r[1], z = r[2];
+        Gathered o;
+        g2p_gather(g, x, y, z, o);
+        const float dxc = 1.0f / g.inv_dx, a_min = dxc * 2.0f, a_max = g.lim - dxc * 2.0f;
+        x = clampf(x + dt * o.v[0], a_min, a_max);
+        y = clampf(y + dt * o.v[1], a_min, a_max);
+        z = clampf(z + dt * o.v[2], a_min, a_max);
+        r[0] = x; r[1] = y; r[2] = z;
+        r[P_V] = o.v[0]; r[P_V + 1] = o.v[1]; r[P_V + 2] = o.v[2];
 #pragma unroll
-    for (int i = 0; i < 9; i++) r->C[i] = o.C[i];
-    float M[9], F[9], Ft[9];
+        for (int i = 0; i < 9; i++) r[P_C + i] = o.C[i];
+        float M[9], F[9], Ft[9];
 #pragma unroll
-    for (int i = 0; i < 9; i++) { M[i] = o.G[i] * dt; F[i] = aux[p].F[i]; }
-    M[0] += 1.0f; M[4] += 1.0f; M[8] += 1.0f;
-    mat_mul(M, F, Ft);
+        for (int i = 0; i < 9; i++) { M[i] = o.G[i] * dt; F[i] = t[T_F + i]; }
+        M[0] += 1.0f; M[4] += 1.0f; M[8] += 1.0f;
+        mat_mul(M, F, Ft);
 #pragma unroll
-    for (int i = 0; i < 9; i++) aux[p].Ft[i] = Ft[i];
-    ensure_stencil_blocks(g, xm.x, xm.y, xm.z);
+        for (int i = 0; i < 9; i++) t[T_FT + i] = Ft[i];
+        ensure_stencil_blocks(g, x, y, z);
+    }
+    slab_store2(w, sP, TP, KP_F, sT, TF, TF_F);
 }
 
 // g2p_e (mpm_utils.py:788-857): C and grad v at the OLD centroid, x/v = mean of the three
 // already-updated corner vertices, d = [x2-x1, x3-x1, (I + dt grad v) d3]
-__global__ void __launch_bounds__(128, 4) k_g2p_elements(Grid g, int Ne, PRec* __restrict__ rec, EAux* __restrict__ aux,
-                                                      const VRec* __restrict__ vrec, float dt, Advance adv) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (adv.st && p == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
-    if (p >= Ne) return;
-    float4 xm = rec[p].xm;
-    EAux* a = &aux[p];
-    const int f0 = a->face[0], f1 = a->face[1], f2 = a->face[2];
-    // corner gathers first: they do not depend on the grid gather
-    const float4 x1 = vrec[f0].xm, x2 = vrec[f1].xm, x3 = vrec[f2].xm;
-    const float4 v1 = reinterpret_cast<const float4*>(&vrec[f0])[2], v2 = reinterpret_cast<const float4*>(&vrec[f1])[2],
-                 v3 = reinterpret_cast<const float4*>(&vrec[f2])[2];
-    const float d3[3] = {a->dc[6], a->dc[7], a->dc[8]};
-    Gathered o;
-    g2p_gather(g, xm.x, xm.y, xm.z, o);
-    PRec* r = &rec[p];
-    const float vol = r->vv.w;
-    xm.x = (x1.x + x2.x + x3.x) / 3.0f;
-    xm.y = (x1.y + x2.y + x3.y) / 3.0f;
-    xm.z = (x1.z + x2.z + x3.z) / 3.0f;
-    r->xm = xm;
-    r->vv = make_float4((v1.x + v2.x + v3.x) / 3.0f, (v1.y + v2.y + v3.y) / 3.0f, (v1.z + v2.z + v3.z) / 3.0f, vol);
+constexpr int G2P_E_WB = (KP_F + ED_F) * 32 * 4;
+__global__ void __launch_bounds__(32 * G2P_NW, 4) k_g2p_elements(Grid g, int Ne, float* __restrict__ EP, float* __restrict__ ED,
+                                                                  const float* __restrict__ VP, float dt, Advance adv) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
+    Warp w;
+    if (!warp_begin<G2P_NW, G2P_E_WB>(w, Ne, smem)) return;
+    float* sP = reinterpret_cast<float*>(w.buf);
+    float* sD = sP + 32 * KP_F;
+    slab_load2(w, sP, EP, KP_F, sD, ED, ED_F);
+    if (w.lane < w.cnt) {
+        float* r = sP + w.lane * KP_F;
+        float4* d4 = reinterpret_cast<float4*>(sD + w.lane * ED_F);
+        const float4 q1v = d4[1], q2v = d4[2];
+        const float d3[3] = {q1v.z, q1v.w, q2v.x};
+        const int f0 = __float_as_int(q2v.y), f1 = __float_as_int(q2v.z), f2 = __float_as_int(q2v.w);
+        // corner gathers first (one 32-byte sector per corner: {x,y,z,m | vx,vy,vz,C0}); they do not
+        // depend on the grid gather
+        const float4* c0 = reinterpret_cast<const float4*>(VP + (size_t)f0 * VP_F);
+        const float4* c1 = reinterpret_cast<const float4*>(VP + (size_t)f1 * VP_F);
+        const float4* c2 = reinterpret_cast<const float4*>(VP + (size_t)f2 * VP_F);
+        const float4 x1 = c0[0], v1 = c0[1], x2 = c1[0], v2 = c1[1], x3 = c2[0], v3 = c2[1];
+        Gathered o;
+        g2p_gather(g, r[0], r[1], r[2], o);
+        const float nx = (x1.x + x2.x + x3.x) / 3.0f, ny = (x1.y + x2.y + x3.y) / 3.0f, nz = (x1.z + x2.z + x3.z) / 3.0f;
+        r[0] = nx; r[1] = ny; r[2] = nz;
+        r[P_V] = (v1.x + v2.x + v3.x) / 3.0f;
+        r[P_V + 1] = (v1.y + v2.y + v3.y) / 3.0f;
+        r[P_V + 2] = (v1.z + v2.z + v3.z) / 3.0f;
 #pragma unroll
-    for (int i = 0; i < 9; i++) r->C[i] = o.C[i];
-    float nd3[3];
+        for (int i = 0; i < 9; i++) r[P_C + i] = o.C[i];
+        float nd3[3];
 #pragma unroll
-    for (int rr = 0; rr < 3; rr++) {
-        float m0 = o.G[3 * rr] * dt + (rr == 0 ? 1.0f : 0.0f);
-        float m1 = o.G[3 * rr + 1] * dt + (rr == 1 ? 1.0f : 0.0f);
-        float m2 = o.G[3 * rr + 2] * dt + (rr == 2 ? 1.0f : 0.0f);
-        nd3[rr] = m0 * d3[0] + m1 * d3[1] + m2 * d3[2];
+        for (int rr = 0; rr < 3; rr++) {
+            float m0 = o.G[3 * rr] * dt + (rr == 0 ? 1.0f : 0.0f);
+            float m1 = o.G[3 * rr + 1] * dt + (rr == 1 ? 1.0f : 0.0f);
+            float m2 = o.G[3 * rr + 2] * dt + (rr == 2 ? 1.0f : 0.0f);
+            nd3[rr] = m0 * d3[0] + m1 * d3[1] + m2 * d3[2];
+        }
+        d4[0] = make_float4(x2.x - x1.x, x2.y - x1.y, x2.z - x1.z, x3.x - x1.x);
+        d4[1] = make_float4(x3.y - x1.y, x3.z - x1.z, nd3[0], nd3[1]);
+        d4[2] = make_float4(nd3[2], q2v.y, q2v.z, q2v.w);
+        ensure_stencil_blocks(g, nx, ny, nz);
     }
-    a->dc[0] = x2.x - x1.x; a->dc[1] = x2.y - x1.y; a->dc[2] = x2.z - x1.z;
-    a->dc[3] = x3.x - x1.x; a->dc[4] = x3.y - x1.y; a->dc[5] = x3.z - x1.z;
-    a->dc[6] = nd3[0]; a->dc[7] = nd3[1]; a->dc[8] = nd3[2];
-    ensure_stencil_blocks(g, xm.x, xm.y, xm.z);
+    slab_store2(w, sP, EP, KP_F, sD, ED, ED_F);
 }
 
 }  // namespace mpm
