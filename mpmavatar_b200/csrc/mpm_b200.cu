@@ -222,6 +222,8 @@ struct MpmSolver {
     void* graph_cache_ptr = nullptr;
     bool use_graphs = true;
     cudaStream_t cap_stream = nullptr;
+    cudaStream_t side = nullptr;       // body-collider / mover scatter run concurrently with stress + P2G
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // profiling
     cudaEvent_t ev[10]{};
     MpmProfile prof{};
@@ -313,6 +315,13 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
         CK(cudaEventRecord(ev[0], q));
     }
     const Recs& R = s->R;
+    // the two scatter kernels only need the block table and the particle positions, both fixed since
+    // the end of the previous substep: fork them onto a side stream (a parallel branch of the graph)
+    const bool fork = !s->profiling && (a.collider || a.mover);
+    if (fork) {
+        CK(cudaEventRecord(s->ev_fork, q));
+        CK(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+    }
     if (n_ops) {
         if (s->Ne) k_particle_ops<<<cdiv(s->Ne, 256), 256, 0, q>>>(s->Ne, R.EP, KP_F, s->permE, 0, s->d_ops, n_ops, s->st, a.dt);
         if (s->Nt) k_particle_ops<<<cdiv(s->Nt, 256), 256, 0, q>>>(s->Nt, R.TP, KP_F, s->permT, s->Ne, s->d_ops, n_ops, s->st, a.dt);
@@ -329,24 +338,31 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
         s->launches++;
     }
     if (ev) CK(cudaEventRecord(ev[1], q));
-    const int ppb = 32 * P2G_NW;
+    const int ppb = 32 * P2G_NW;  // particles per P2G block
     if (s->Ne) { k_p2g<0><<<cdiv(s->Ne, ppb), ppb, P2G_SMEM, q>>>(s->g, R.EP, R.ES, s->Ne, a.dt, s->md.rpic); s->launches++; }
     if (s->Nt) { k_p2g<1><<<cdiv(s->Nt, ppb), ppb, P2G_SMEM, q>>>(s->g, R.TP, R.TS, s->Nt, a.dt, s->md.rpic); s->launches++; }
     if (s->Nv) { k_p2g<2><<<cdiv(s->Nv, ppb), ppb, P2G_SMEM, q>>>(s->g, R.VP, (const float*)R.VF, s->Nv, a.dt, s->md.rpic); s->launches++; }
     if (ev) CK(cudaEventRecord(ev[2], q));
-    if (a.collider) {
-        k_collider_scatter<<<cdiv(s->cfg.n_mesh_f, 128), 128, 0, q>>>(s->g, s->cfg.n_mesh_f, s->mesh_faces, s->mesh_x, s->mesh_v, s->st, a.dt, a.advance_mesh ? 1 : 0);
-        s->launches++;
-    }
-    if (ev) CK(cudaEventRecord(ev[3], q));
-    if (a.mover) {
-        int tot = a.njt + s->cfg.num_joint_v + s->cfg.num_joint_f;
-        if (tot) {
-            k_mover_scatter<<<cdiv(tot, 128), 128, 0, q>>>(s->g, a.njt, s->cfg.num_joint_v, s->cfg.num_joint_f, s->Nt, s->joint_t, s->joint_v, s->joint_f, R.EP, R.TP, R.VP, s->invE, s->invT, s->invV);
+    {
+        cudaStream_t qs = fork ? s->side : q;
+        if (a.collider) {
+            k_collider_scatter<<<cdiv(s->cfg.n_mesh_f, 128), 128, 0, qs>>>(s->g, s->cfg.n_mesh_f, s->mesh_faces, s->mesh_x, s->mesh_v, s->st, a.dt, a.advance_mesh ? 1 : 0);
             s->launches++;
         }
+        if (ev) CK(cudaEventRecord(ev[3], q));
+        if (a.mover) {
+            int tot = a.njt + s->cfg.num_joint_v + s->cfg.num_joint_f;
+            if (tot) {
+                k_mover_scatter<<<cdiv(tot, 128), 128, 0, qs>>>(s->g, a.njt, s->cfg.num_joint_v, s->cfg.num_joint_f, s->Nt, s->joint_t, s->joint_v, s->joint_f, R.EP, R.TP, R.VP, s->invE, s->invT, s->invV);
+                s->launches++;
+            }
+        }
+        if (ev) CK(cudaEventRecord(ev[4], q));
+        if (fork) {
+            CK(cudaEventRecord(s->ev_join, s->side));
+            CK(cudaStreamWaitEvent(q, s->ev_join, 0));
+        }
     }
-    if (ev) CK(cudaEventRecord(ev[4], q));
     // one thread per node of the allocated blocks; the block count lives on the device, so the grid is
     // sized from the last value copied back (a hint: the kernel grid-strides over the true count)
     k_grid_update<<<a.grid_blocks, 256, 0, q>>>(s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, s->d_bcs, n_bc, s->st);
@@ -551,6 +567,9 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         s->st = s->dalloc<StepState>(1);
         CK(cudaHostAlloc((void**)&s->h_nslots, sizeof(int), cudaHostAllocDefault));
         *s->h_nslots = 0;
+        CK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
         // model defaults (mpm_data_structure.py:686-715)
         s->md.material = 0; s->md.hardening = 0; s->md.friction_coeff = 0.f; s->md.alpha = 0.f;
         s->md.gx = s->md.gy = s->md.gz = 0.f; s->md.rpic = 0.f; s->md.damping = 1.1f;
@@ -576,6 +595,9 @@ void mpm_destroy(MpmSolver* s) {
     cudaDeviceSynchronize();
     destroy_graphs(s);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
+    if (s->side) cudaStreamDestroy(s->side);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->h_nslots) cudaFreeHost(s->h_nslots);
     for (void* p : s->allocs) cudaFree(p);
     delete s;

@@ -309,19 +309,16 @@ __global__ void k_particle_ops(int n, float* __restrict__ rec, int F, const uint
 // ============================================================ P2G
 // p2g_apic_with_stress (mpm_utils.py:484-557), restructured for cell-sorted particles.
 //  stage 0  cp.async.bulk brings the warp's kinematics slab and stress (or vertex-force) slab into smem.
-//  stage 1  lane = particle: each lane turns its record into a separable "pack".  With
-//           dpos = (ijk - f) dx the contribution to stencil node (i,j,k) is
-//             w m (v + C dpos) + dt force = A w + ux[i] wy wz + wx uy[j] wz + wx wy uz[k]
-//           with A = m (v - dx C f) (+ dt f_vertex), u_a[i] = m dx C[:,a] i w_a[i] - dt vol/dx S[:,a] dw_a[i],
-//           so a pack is three float4 per axis {w, u_0, u_1, u_2} plus {A_0, A_1, A_2, m}.
-//  stage 2  lane = stencil node (27 of 32 lanes): walk the 32 packs; particles of one cell form a
-//           run, whose 27 node sums are accumulated in registers and flushed with ONE
-//           REDG.E.ADD.F32x4 per node when the cell changes.  No intra-warp reduction, no
-//           shared-memory atomics; global atomics drop from 27*4 per particle to 27 per cell run.
+//  stage 1  lane = particle (all 32 lanes busy, nothing computed twice): each lane evaluates the 27
+//           stencil contributions {dt*f + w m (v + C dpos), w m} of ITS particle and stores them as 27
+//           float4 in shared memory; a ballot marks where the cell id changes along the slab.
+//  stage 2  lane = stencil node (27 of 32 lanes): particles of one cell form a run; its 27 node sums
+//           are plain float4 adds down a shared-memory column, flushed with ONE REDG.E.ADD.F32x4 per
+//           node per run.  No intra-warp reduction, no shared-memory atomics; global atomics drop
+//           from 27*4 per particle to 27 per cell run.
 // KIND 0: element (S already holds vol*P3(x)d3), 1: traditional (stress*vol, :496), 2: vertex.
-constexpr int P2G_PK = 40;                                // floats per pack
-constexpr int P2G_WB = 32 * P2G_PK * 4 + 32 * 4;          // packs (overlaying the raw slabs) + cell ids
-constexpr int P2G_NW = 8;
+constexpr int P2G_NW = 4;
+constexpr int P2G_WB = (32 * 27 + 8) * 16 + 128;  // 27 float4 per particle (+ slack for lanes 27..31) + cell ids
 constexpr int P2G_SMEM = 128 + P2G_NW * P2G_WB;
 
 template <int KIND>
@@ -334,7 +331,6 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, const float* __rest
     if (!warp_begin<P2G_NW, P2G_WB>(w, n, smem)) return;
     float* buf = reinterpret_cast<float*>(w.buf);
     float* raw1 = buf + 32 * F0;
-    int* cell = reinterpret_cast<int*>(buf + 32 * P2G_PK);
     slab_load2(w, buf, KP, F0, raw1, SF, F1);
     // ---- stage 1
     float x[3], m, v[3], C[9], Sp[9], fv[3] = {0.f, 0.f, 0.f};
@@ -363,7 +359,8 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, const float* __rest
 #pragma unroll
         for (int i = 0; i < 9; i++) { C[i] = 0.f; Sp[i] = 0.f; }
     }
-    __syncwarp();  // packs overwrite the raw slabs
+    __syncwarp();  // the contributions overwrite the raw slabs
+    int mycell;
     {
         if (rpic != 0.0f) {  // mpm_utils.py:528-542
             float Cn[9];
@@ -376,62 +373,78 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, const float* __rest
             for (int i = 0; i < 9; i++) C[i] = (rpic < -0.001f) ? 0.0f : Cn[i];
         }
         int b[3];
-        float f[3];
+        float f[3], wgt[3][3], dwg[3][3];
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             const float gp = x[a] * g.inv_dx;
             b[a] = (int)(gp - 0.5f);
             f[a] = gp - (float)b[a];
+#pragma unroll
+            for (int i = 0; i < 3; i++) bspline(f[a], i, wgt[a][i], dwg[a][i]);
         }
-        float4* out = reinterpret_cast<float4*>(buf + w.lane * P2G_PK);
+        // w m (v + C dpos) + dt w f_vertex = w (A + B_x i + B_y j + B_z k), dpos = (ijk - f) dx
         const float mdx = m * g.dx;
+        float A[3], B[9];
 #pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                float ww, dw;
-                bspline(f[a], i, ww, dw);
-                const float iw = (float)i * ww * mdx;
-                out[3 * a + i] = make_float4(ww, C[a] * iw + Sp[a] * dw, C[3 + a] * iw + Sp[3 + a] * dw,
-                                             C[6 + a] * iw + Sp[6 + a] * dw);
-            }
-        float A[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
+        for (int c = 0; c < 3; c++) {
             A[c] = m * (v[c] - g.dx * (C[3 * c] * f[0] + C[3 * c + 1] * f[1] + C[3 * c + 2] * f[2])) + dt * fv[c];
-        out[9] = make_float4(A[0], A[1], A[2], m);
-        cell[w.lane] = (clampi(b[0] + 2, 0, 1023)) | (clampi(b[1] + 2, 0, 1023) << 10) | (clampi(b[2] + 2, 0, 1023) << 20);
+#pragma unroll
+            for (int a = 0; a < 3; a++) B[3 * c + a] = mdx * C[3 * c + a];
+        }
+        float4* out = reinterpret_cast<float4*>(buf) + w.lane * 27;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const float Ai[3] = {A[0] + B[0] * (float)i, A[1] + B[3] * (float)i, A[2] + B[6] * (float)i};
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const float wxy = wgt[0][i] * wgt[1][j];
+                const float gxy0 = dwg[0][i] * wgt[1][j], gxy1 = wgt[0][i] * dwg[1][j];
+                const float Aij[3] = {Ai[0] + B[1] * (float)j, Ai[1] + B[4] * (float)j, Ai[2] + B[7] * (float)j};
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const float ww = wxy * wgt[2][k];
+                    float4 o;
+                    o.x = ww * (Aij[0] + B[2] * (float)k);
+                    o.y = ww * (Aij[1] + B[5] * (float)k);
+                    o.z = ww * (Aij[2] + B[8] * (float)k);
+                    o.w = ww * m;
+                    if (KIND != 2) {  // dt * (-stress grad w), stress pre-scaled in Sp
+                        const float g0 = gxy0 * wgt[2][k], g1 = gxy1 * wgt[2][k], g2 = wxy * dwg[2][k];
+                        o.x += Sp[0] * g0 + Sp[1] * g1 + Sp[2] * g2;
+                        o.y += Sp[3] * g0 + Sp[4] * g1 + Sp[5] * g2;
+                        o.z += Sp[6] * g0 + Sp[7] * g1 + Sp[8] * g2;
+                    }
+                    out[(i * 3 + j) * 3 + k] = o;
+                }
+            }
+        }
+        mycell = (clampi(b[0] + 2, 0, 1023)) | (clampi(b[1] + 2, 0, 1023) << 10) | (clampi(b[2] + 2, 0, 1023) << 20);
+        if (w.lane >= w.cnt) mycell = -1 - w.lane;
     }
+    const int prev = __shfl_up_sync(0xffffffffu, mycell, 1);
+    unsigned starts = __ballot_sync(0xffffffffu, w.lane < w.cnt && (w.lane == 0 || mycell != prev));
     __syncwarp();
     // ---- stage 2
     const bool act = w.lane < 27;
     const int li = act ? w.lane / 9 : 0, lj = act ? (w.lane / 3) % 3 : 0, lk = act ? w.lane % 3 : 0;
-    const float4* P = reinterpret_cast<const float4*>(buf);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int cur = cell[0];
-    auto flush = [&](int c) {
+    const float4* P = reinterpret_cast<const float4*>(buf) + w.lane;
+    while (starts) {
+        const int s0 = __ffs(starts) - 1;
+        starts &= starts - 1;
+        const int e0 = starts ? (__ffs(starts) - 1) : w.cnt;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int q = s0; q < e0; q++) {
+            const float4 t = P[q * 27];
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        const int c = __shfl_sync(0xffffffffu, mycell, s0);
         if (act && (acc.w != 0.0f || acc.x != 0.0f || acc.y != 0.0f || acc.z != 0.0f)) {
             int ni = node_index(g, (c & 1023) - 2 + li, ((c >> 10) & 1023) - 2 + lj, ((c >> 20) & 1023) - 2 + lk);
             if (ni >= 0) atomicAdd(&g.acc[ni], acc);
             else g.flags[1] = 1;
         }
-    };
-#pragma unroll 4
-    for (int q = 0; q < w.cnt; q++) {
-        const int c = cell[q];
-        if (c != cur) {  // warp-uniform
-            flush(cur);
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            cur = c;
-        }
-        const float4 X = P[q * 10 + li], Y = P[q * 10 + 3 + lj], Z = P[q * 10 + 6 + lk], H = P[q * 10 + 9];
-        const float wyz = Y.x * Z.x, wxz = X.x * Z.x, wxy = X.x * Y.x, ww = X.x * wyz;
-        acc.x += H.x * ww + X.y * wyz + Y.y * wxz + Z.y * wxy;
-        acc.y += H.y * ww + X.z * wyz + Y.z * wxz + Z.z * wxy;
-        acc.z += H.z * ww + X.w * wyz + Y.w * wxz + Z.w * wxy;
-        acc.w += H.w * ww;
     }
-    flush(cur);
 }
 
 // ============================================================ collider / mover scatter
