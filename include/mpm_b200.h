@@ -147,6 +147,8 @@ int mpm_set_profiling(MpmSolver *s, int on); /* per-phase CUDA events; disables 
 int mpm_get_profile(MpmSolver *s, MpmProfile *out);   /* synchronises */
 int mpm_get_stats(MpmSolver *s, MpmStats *out, void *stream); /* synchronises */
 int mpm_force_resort(MpmSolver *s);
+/* latency analysis (builds with -DMPM_CLK only fill it): 8 kernels x 8 per-warp phase cycle sums; synchronises */
+int mpm_debug_phase_clocks(MpmSolver *s, unsigned long long *out64, int reset);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,7 @@ SYMBOLS = {
     "mpm_get_profile": (C.c_int, [_P, C.POINTER(MpmProfile)]),
     "mpm_get_stats": (C.c_int, [_P, C.POINTER(MpmStats), _P]),
     "mpm_force_resort": (C.c_int, [_P]),
+    "mpm_debug_phase_clocks": (C.c_int, [_P, _P, C.c_int]),
 }
 
 
@@ -89,7 +90,7 @@ def load(build_if_missing: bool = True):
             except Exception as e:  # no nvcc on the box and no prebuilt library
                 if not os.path.exists(_build.LIB):
                     raise RuntimeError(f"libmpm_b200.so is missing and could not be built: {e}") from e
-        lib = C.CDLL(_build.LIB)
+        lib = C.CDLL(os.environ.get("MPM_B200_LIB", _build.LIB))  # MPM_B200_LIB: analysis builds (tools/)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)  # AttributeError if the header and the library disagree
             fn.restype = res

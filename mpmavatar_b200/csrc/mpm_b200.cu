@@ -46,10 +46,13 @@ __global__ void k_invert(int n, const uint32_t* __restrict__ perm, int* __restri
     if (i < n) inv[perm[i]] = i;
 }
 struct Recs {  // sorted sub-record arrays (see mpm_device.cuh)
-    float *EP, *ES, *ED, *EK, *TP, *TS, *TF, *VP;
+    float *EP, *EK, *TP, *TS, *TF, *VP;
+    float* E12[2];  // ping-pong {d1,d2}
+    float4* D3[2];  // ping-pong d3
+    int* EF;
     float4* VF;
 };
-__global__ void k_import_E(int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R, const int* __restrict__ invV) {
+__global__ void k_import_E(int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R, int cur, const int* __restrict__ invV) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Ne) return;
     int s = perm[i];  // canonical element index == canonical particle index
@@ -57,15 +60,15 @@ __global__ void k_import_E(int Ne, const uint32_t* __restrict__ perm, Canon c, R
     for (int k = 0; k < 3; k++) { p[P_X + k] = c.x[3 * s + k]; p[P_V + k] = c.v[3 * s + k]; }
     p[P_M] = c.mass[s];
     p[P_VOL] = c.vol[s];
-    for (int k = 0; k < 9; k++) { p[P_C + k] = c.C[9 * (size_t)s + k]; R.ES[(size_t)i * S_F + k] = 0.f; }
-    float* d = R.ED + (size_t)i * ED_F;
-    const float* ds = c.d + 9 * (size_t)s;  // row-major -> columns
-    for (int col = 0; col < 3; col++)
-        for (int row = 0; row < 3; row++) d[D_DC + 3 * col + row] = ds[3 * row + col];
-    for (int k = 0; k < 3; k++) d[D_FACE + k] = __int_as_float(invV[(int)c.faces[3 * s + k]]);  // int(face[k]), mpm_utils.py:172
-    float* e = R.EK + (size_t)i * EK_F;
-    for (int k = 0; k < 3; k++) e[K_RINV + k] = c.Rinv[3 * s + k];
-    e[K_MU] = c.mu[s]; e[K_LAM] = c.lam[s]; e[K_GAMMA] = c.gamma[s]; e[K_KAPPA] = c.kappa[s]; e[K_VOL] = c.vol[s];
+    for (int k = 0; k < 9; k++) p[P_C + k] = c.C[9 * (size_t)s + k];
+    const float* ds = c.d + 9 * (size_t)s;  // row-major 3x3 whose COLUMNS are d1,d2,d3
+    float* e = R.E12[cur] + (size_t)i * E12_F;
+    for (int row = 0; row < 3; row++) { e[row] = ds[3 * row]; e[3 + row] = ds[3 * row + 1]; }
+    R.D3[cur][i] = make_float4(ds[2], ds[5], ds[8], 0.f);
+    for (int k = 0; k < 3; k++) R.EF[(size_t)i * EF_F + k] = invV[(int)c.faces[3 * s + k]];  // int(face[k]), mpm_utils.py:172
+    float* ek = R.EK + (size_t)i * EK_F;
+    for (int k = 0; k < 3; k++) ek[K_RINV + k] = c.Rinv[3 * s + k];
+    ek[K_MU] = c.mu[s]; ek[K_LAM] = c.lam[s]; ek[K_GAMMA] = c.gamma[s]; ek[K_KAPPA] = c.kappa[s]; ek[K_VOL] = c.vol[s];
 }
 __global__ void k_import_T(int Nt, int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,17 +93,32 @@ __global__ void k_import_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, C
     for (int k = 0; k < 9; k++) p[V_C + k] = c.C[9 * (size_t)s + k];
     R.VF[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
-__global__ void k_export_E(int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R) {
+// d from direction buffer `cur`; the element stress of the LAST substep is re-evaluated from buffer
+// `cur^1`, which still holds the d1,d2 and the return-mapped d3 that substep's stress was computed from
+// (kirchoff_stress_Anisotropy is evaluated on exactly that d in the reference, mpm_utils.py:1043-1046)
+__global__ void k_export_E(int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R, int cur, int have_prev, float friction_coeff) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Ne) return;
     int s = perm[i];
     const float* p = R.EP + (size_t)i * KP_F;
     for (int k = 0; k < 3; k++) { c.x[3 * s + k] = p[P_X + k]; c.v[3 * s + k] = p[P_V + k]; }
-    for (int k = 0; k < 9; k++) { c.C[9 * (size_t)s + k] = p[P_C + k]; c.stress[9 * (size_t)s + k] = R.ES[(size_t)i * S_F + k]; }
-    const float* d = R.ED + (size_t)i * ED_F;
+    for (int k = 0; k < 9; k++) c.C[9 * (size_t)s + k] = p[P_C + k];
+    const float* e = R.E12[cur] + (size_t)i * E12_F;
+    const float4 d3 = R.D3[cur][i];
     float* dd = c.d + 9 * (size_t)s;
-    for (int col = 0; col < 3; col++)
-        for (int row = 0; row < 3; row++) dd[3 * row + col] = d[D_DC + 3 * col + row];
+    for (int row = 0; row < 3; row++) { dd[3 * row] = e[row]; dd[3 * row + 1] = e[3 + row]; }
+    dd[2] = d3.x; dd[5] = d3.y; dd[8] = d3.z;
+    if (have_prev) {
+        const float* q = R.E12[cur ^ 1] + (size_t)i * E12_F;
+        const float4 q3 = R.D3[cur ^ 1][i];
+        const float* ek = R.EK + (size_t)i * EK_F;
+        const float d1[3] = {q[0], q[1], q[2]}, d2[3] = {q[3], q[4], q[5]}, d3p[3] = {q3.x, q3.y, q3.z};
+        const ElemConst kc{ek[K_RINV], ek[K_RINV + 1], ek[K_RINV + 2], ek[K_MU], ek[K_LAM], ek[K_GAMMA], ek[K_KAPPA], ek[K_VOL]};
+        ElemStress es;
+        element_stress(d1, d2, d3p, kc, friction_coeff, es);
+        for (int rr = 0; rr < 3; rr++)
+            for (int cc = 0; cc < 3; cc++) c.stress[9 * (size_t)s + 3 * rr + cc] = kc.vol * (es.P3[rr] * es.nd3[cc]);
+    }
 }
 __global__ void k_export_T(int Nt, int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,6 +165,7 @@ __global__ void k_export_grid(Grid g, float* gm, float* gvin, float* gvout) {
     int ix = ((co & 1023) << 2) + (l >> 4), iy = (((co >> 10) & 1023) << 2) + ((l >> 2) & 3), iz = (((co >> 20) & 1023) << 2) + (l & 3);
     if (ix >= g.n || iy >= g.n || iz >= g.n) return;
     size_t gi = ((size_t)ix * g.n + iy) * g.n + iz;
+    idx = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023) * BN + l;
     if (g.dbg_acc) {
         float4 a = g.dbg_acc[idx];
         if (gm) gm[gi] = a.w;
@@ -209,6 +228,8 @@ struct MpmSolver {
     // state flags
     bool have_state = false, need_sort = true, canon_stale = false;
     int since_sort = 0, resort_interval = 128;
+    int cur = 0;             // direction buffer (E12/D3) holding the current d
+    bool have_prev = false;  // buffer cur^1 holds the d of the last stress evaluation
     int n_resorts = 0;
     long long n_substeps = 0;
     int launches = 0;
@@ -254,7 +275,7 @@ static void sort_class(MpmSolver* s, int n, int offset, uint32_t* perm, int* inv
 
 static void export_to_canon(MpmSolver* s, cudaStream_t q) {
     if (!s->have_state || !s->canon_stale) return;
-    if (s->Ne) k_export_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->permE, s->canon, s->R);
+    if (s->Ne) k_export_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->permE, s->canon, s->R, s->cur, s->have_prev ? 1 : 0, s->md.friction_coeff);
     if (s->Nt) k_export_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->permT, s->canon, s->R);
     if (s->Nv) k_export_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->Nnv, s->permV, s->canon, s->R, s->debug ? s->dbg_f : nullptr);
     s->launches += 3;
@@ -267,7 +288,8 @@ static void resort(MpmSolver* s, cudaStream_t q) {
     sort_class(s, s->Ne, 0, s->permE, s->invE, q);
     sort_class(s, s->Nt, s->Ne, s->permT, s->invT, q);
     sort_class(s, s->Nv, s->Nnv, s->permV, s->invV, q);
-    if (s->Ne) k_import_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->permE, s->canon, s->R, s->invV);
+    if (s->Ne) k_import_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->permE, s->canon, s->R, s->cur, s->invV);
+    s->have_prev = false;
     if (s->Nt) k_import_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->permT, s->canon, s->R);
     if (s->Nv) k_import_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->Nnv, s->permV, s->canon, s->R);
     // all accumulators are zero between substeps, so rebuilding the table needs no pool sweep
@@ -302,8 +324,10 @@ struct SubstepArgs {
     float dt;
     bool collider, mover, advance_mesh;
     int njt;
-    int grid_blocks;
 };
+
+// the grid update grid-strides over the allocated blocks (count on the device): 8 CTAs of 256 threads per SM
+constexpr int GRID_UPDATE_CTAS = 148 * 8;
 
 static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
     const int n_bc = (int)s->h_bcs.size(), n_ops = (int)s->h_ops.size();
@@ -329,19 +353,28 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
         s->launches += 3;
     }
     auto sm = [](int nw, int wb) { return (size_t)(128 + nw * wb); };
-    if (s->Ne) {
-        k_stress_elements<<<cdiv(s->Ne, 32 * STRESS_E_NW), 32 * STRESS_E_NW, sm(STRESS_E_NW, STRESS_E_WB), q>>>(s->Ne, R.ED, R.EK, R.ES, R.VF, s->md.friction_coeff);
-        s->launches++;
-    }
+    const int cur = s->cur;
     if (s->Nt) {
         k_stress_traditional<<<cdiv(s->Nt, 32 * STRESS_T_NW), 32 * STRESS_T_NW, sm(STRESS_T_NW, STRESS_T_WB), q>>>(s->Nt, R.TF, R.TS, s->md, a.dt);
         s->launches++;
     }
     if (ev) CK(cudaEventRecord(ev[1], q));
     const int ppb = 32 * P2G_NW;  // particles per P2G block
-    if (s->Ne) { k_p2g<0><<<cdiv(s->Ne, ppb), ppb, P2G_SMEM, q>>>(s->g, R.EP, R.ES, s->Ne, a.dt, s->md.rpic); s->launches++; }
-    if (s->Nt) { k_p2g<1><<<cdiv(s->Nt, ppb), ppb, P2G_SMEM, q>>>(s->g, R.TP, R.TS, s->Nt, a.dt, s->md.rpic); s->launches++; }
-    if (s->Nv) { k_p2g<2><<<cdiv(s->Nv, ppb), ppb, P2G_SMEM, q>>>(s->g, R.VP, (const float*)R.VF, s->Nv, a.dt, s->md.rpic); s->launches++; }
+    if (s->Ne) {  // cloth stress fused in front of the element scatter; VF must be complete before the vertex scatter
+        P2GIn in{R.EP, nullptr, R.E12[cur], R.D3[cur], R.EF, R.EK, R.VF, s->md.friction_coeff};
+        k_p2g<0><<<cdiv(s->Ne, ppb), ppb, P2G_SMEM, q>>>(s->g, in, s->Ne, a.dt, s->md.rpic);
+        s->launches++;
+    }
+    if (s->Nt) {
+        P2GIn in{R.TP, R.TS, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
+        k_p2g<1><<<cdiv(s->Nt, ppb), ppb, P2G_SMEM, q>>>(s->g, in, s->Nt, a.dt, s->md.rpic);
+        s->launches++;
+    }
+    if (s->Nv) {
+        P2GIn in{R.VP, (const float*)R.VF, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
+        k_p2g<2><<<cdiv(s->Nv, ppb), ppb, P2G_SMEM, q>>>(s->g, in, s->Nv, a.dt, s->md.rpic);
+        s->launches++;
+    }
     if (ev) CK(cudaEventRecord(ev[2], q));
     {
         cudaStream_t qs = fork ? s->side : q;
@@ -365,7 +398,7 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
     }
     // one thread per node of the allocated blocks; the block count lives on the device, so the grid is
     // sized from the last value copied back (a hint: the kernel grid-strides over the true count)
-    k_grid_update<<<a.grid_blocks, 256, 0, q>>>(s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, s->d_bcs, n_bc, s->st);
+    k_grid_update<<<GRID_UPDATE_CTAS, 256, 0, q>>>(s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, s->d_bcs, n_bc, s->st);
     s->launches++;
     if (ev) CK(cudaEventRecord(ev[5], q));
     Advance none{nullptr, nullptr, 0}, adv{s->st, s->d_bcs, n_bc};
@@ -374,7 +407,12 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
     if (s->Nv) { k_g2p_vertices<<<cdiv(s->Nv, gpb), gpb, sm(G2P_NW, G2P_V_WB), q>>>(s->g, s->Nv, R.VP, R.VF, a.dt, s->debug ? s->dbg_f : nullptr, last == 0 ? adv : none); s->launches++; }
     if (s->Nt) { k_g2p_traditional<<<cdiv(s->Nt, gpb), gpb, sm(G2P_NW, G2P_T_WB), q>>>(s->g, s->Nt, R.TP, R.TF, a.dt, last == 1 ? adv : none); s->launches++; }
     if (ev) CK(cudaEventRecord(ev[6], q));
-    if (s->Ne) { k_g2p_elements<<<cdiv(s->Ne, gpb), gpb, sm(G2P_NW, G2P_E_WB), q>>>(s->g, s->Ne, R.EP, R.ED, R.VP, a.dt, last == 2 ? adv : none); s->launches++; }
+    if (s->Ne) {
+        k_g2p_elements<<<cdiv(s->Ne, gpb), gpb, sm(G2P_NW, G2P_E_WB), q>>>(s->g, s->Ne, R.EP, R.EF, R.D3[cur], R.E12[cur ^ 1], R.D3[cur ^ 1], R.VP, a.dt, last == 2 ? adv : none);
+        s->launches++;
+        s->cur ^= 1;
+        s->have_prev = true;
+    }
     if (ev) {
         CK(cudaEventRecord(ev[7], q));
         CK(cudaEventRecord(ev[8], q));
@@ -386,10 +424,10 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
 // A captured run of GRAPH_U substeps is replayed instead of ~8 launches per substep; every
 // per-substep quantity (time, substep index, block count) lives in device memory, so one
 // instantiated graph serves every call with the same launch geometry.
-constexpr int GRAPH_U = 16;
+constexpr int GRAPH_U = 16;  // even: the direction ping-pong index is the same before and after a replay
 struct GraphKey {
     float dt;
-    int collider, mover, advance_mesh, njt, grid_blocks, n_bc, n_ops, debug;
+    int collider, mover, advance_mesh, njt, cur, n_bc, n_ops, debug;
     bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 struct GraphEntry {
@@ -428,24 +466,13 @@ static void destroy_graphs(MpmSolver* s) {
     delete &v;
     s->graph_cache_ptr = nullptr;
 }
-static int grid_blocks_hint(MpmSolver* s) {
-    int seen = std::max(s->slots_seen, *s->h_nslots);
-    s->slots_seen = seen;
-    // round up to a power of two so that the launch geometry (and the graph key) changes rarely
-    int want = std::max(64, seen + seen / 4 + 32);
-    int p2 = 64;
-    while (p2 < want) p2 <<= 1;
-    p2 = std::min(p2, s->g.cap);
-    return std::min(cdiv((long long)p2 * BN, 256), 65535 * 8);
-}
 static void run_substeps(MpmSolver* s, SubstepArgs a, int count, cudaStream_t q) {
-    a.grid_blocks = grid_blocks_hint(s);
     const bool graphs = s->use_graphs && !s->profiling;
     while (count > 0) {
         if (graphs && count >= GRAPH_U) {
             GraphKey key{};
             key.dt = a.dt; key.collider = a.collider; key.mover = a.mover; key.advance_mesh = a.advance_mesh;
-            key.njt = a.njt; key.grid_blocks = a.grid_blocks; key.n_bc = (int)s->h_bcs.size();
+            key.njt = a.njt; key.cur = s->cur; key.n_bc = (int)s->h_bcs.size();
             key.n_ops = (int)s->h_ops.size(); key.debug = s->debug;
             auto& cache = graph_cache(s);
             GraphEntry* hit = nullptr;
@@ -470,6 +497,7 @@ static void run_substeps(MpmSolver* s, SubstepArgs a, int count, cudaStream_t q)
                 hit = &cache.back();
             }
             CK(cudaGraphLaunch(hit->exec, q));
+            if (s->Ne) s->have_prev = true;
             s->launches += hit->launches_per_replay;
             count -= GRAPH_U;
         } else {
@@ -516,7 +544,8 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         g.dx = (float)((double)cfg->grid_lim / (double)cfg->n_grid);
         g.inv_dx = (float)((double)cfg->n_grid / (double)cfg->grid_lim);
         size_t nt = (size_t)g.nb * g.nb * g.nb;
-        g.cap = (int)std::min<size_t>(nt, (size_t)1 << 21);
+        g.cap = (int)nt;  // directly addressed: one pool entry per block of the grid
+        if (nt * BN * sizeof(float4) * 5 > ((size_t)64 << 30)) throw std::string("n_grid too large for the directly addressed grid (5 node arrays > 64 GB)");
         g.table = s->dalloc<int>(nt);
         g.n_slots = s->dalloc<int>(1);
         g.slot_coord = s->dalloc<int>(g.cap);
@@ -528,11 +557,13 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         g.coln = s->dalloc<float4>(pn);
         g.mov = s->dalloc<float4>(pn);
         g.dbg_acc = nullptr;
+        g.clk = s->dalloc<unsigned long long>(64 * 64);
         k_fill_int<<<1184, 256>>>(g.table, nt, -1);
         {   // sorted sub-records, each with 32 records of slack for the 16-byte bulk-copy granule
             size_t ne = (size_t)s->Ne + 32, nt = (size_t)s->Nt + 32, nv = (size_t)s->Nv + 32;
-            s->R.EP = s->dalloc<float>(ne * KP_F); s->R.ES = s->dalloc<float>(ne * S_F);
-            s->R.ED = s->dalloc<float>(ne * ED_F); s->R.EK = s->dalloc<float>(ne * EK_F);
+            s->R.EP = s->dalloc<float>(ne * KP_F); s->R.EK = s->dalloc<float>(ne * EK_F);
+            s->R.EF = s->dalloc<int>(ne * EF_F);
+            for (int b = 0; b < 2; b++) { s->R.E12[b] = s->dalloc<float>(ne * E12_F); s->R.D3[b] = s->dalloc<float4>(ne); }
             s->R.TP = s->dalloc<float>(nt * KP_F); s->R.TS = s->dalloc<float>(nt * S_F); s->R.TF = s->dalloc<float>(nt * TF_F);
             s->R.VP = s->dalloc<float>(nv * VP_F); s->R.VF = s->dalloc<float4>(nv);
         }
@@ -839,14 +870,15 @@ int mpm_get_stats(MpmSolver* s, MpmStats* out, void* stream) {
     n_slots = std::min(n_slots, s->g.cap);
     unsigned long long* mask = nullptr;
     unsigned long long* cnt = nullptr;
-    CK(cudaMalloc(&mask, ((size_t)n_slots + 1) * sizeof(unsigned long long)));
+    const size_t nmask = (size_t)s->g.cap + 1;  // one 64-bit word per block
+    CK(cudaMalloc(&mask, nmask * sizeof(unsigned long long)));
     CK(cudaMalloc(&cnt, sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(mask, 0, ((size_t)n_slots + 1) * sizeof(unsigned long long), q));
+    CK(cudaMemsetAsync(mask, 0, nmask * sizeof(unsigned long long), q));
     CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), q));
     if (s->Ne) k_mark_nodes<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.EP, KP_F, mask);
     if (s->Nt) k_mark_nodes<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F, mask);
     if (s->Nv) k_mark_nodes<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, mask);
-    if (n_slots) k_popc<<<cdiv(n_slots, 256), 256, 0, q>>>(mask, n_slots, cnt);
+    k_popc<<<cdiv((long long)nmask, 256), 256, 0, q>>>(mask, (int)nmask, cnt);
     unsigned long long h = 0;
     CK(cudaMemcpyAsync(&h, cnt, sizeof h, cudaMemcpyDeviceToHost, q));
     CK(cudaStreamSynchronize(q));
@@ -859,6 +891,21 @@ int mpm_get_stats(MpmSolver* s, MpmStats* out, void* stream) {
     out->overflow = (flags[0] ? 1 : 0) | (flags[1] ? 2 : 0);
     out->gpu_launches = s->launches;
     out->sim_time = s->host_time;
+    API_END(s)
+}
+
+int mpm_debug_phase_clocks(MpmSolver* s, unsigned long long* out64, int reset) {
+    API_BEGIN(s)
+    CK(cudaDeviceSynchronize());
+    if (out64) {
+        std::vector<unsigned long long> h(64 * 64);
+        CK(cudaMemcpy(h.data(), s->g.clk, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 64; i++) {
+            out64[i] = 0;
+            for (int c = 0; c < 64; c++) out64[i] += h[c * 64 + i];
+        }
+    }
+    if (reset) CK(cudaMemset(s->g.clk, 0, 64 * 64 * sizeof(unsigned long long)));
     API_END(s)
 }
 

@@ -1,29 +1,41 @@
 // Device-side data layout and helpers of the B200 MPM substep solver.
 //
-// GRID: sparse pool of 4x4x4-node blocks.  A dense block table (nb^3 ints) maps block
-// coordinates to a pool slot (-1 = not allocated); every per-node quantity is a float4 so that
-// one P2G contribution is ONE 16-byte REDG.E.ADD.F32x4 (sm_90+ vector atomic):
+// GRID: 4x4x4-node blocks, DIRECTLY ADDRESSED, SPARSELY VISITED.  Node (ix,iy,iz) lives at
+// ((bx*nb+by)*nb+bz)*64 + local in every per-node array -- pure arithmetic, no lookup on the P2G / G2P
+// path (256^3: 268 MB per array, 512^3: 2.1 GB; 180 GB of HBM makes dense ADDRESSING affordable) -- while
+// only the ACTIVE blocks (those under some particle stencil) are ever touched: a block table (nb^3
+// ints, -1 = inactive, else position in the active list slot_coord[]) is maintained by the kernels that
+// move particles, and the grid update walks that list.  Nothing ever sweeps the dense arrays.
+// Every per-node quantity is a float4 so that one P2G contribution is ONE 16-byte REDG.E.ADD.F32x4
+// (sm_90+ vector atomic):
 //   acc  {m*vx, m*vy, m*vz, m}      <- P2G                      (mpm_utils.py:548-557)
 //   vout {vx, vy, vz, -}            <- grid update, read by G2P (mpm_utils.py:561-572)
 //   colv {w*vx, w*vy, w*vz, w}, coln {w*nx, w*ny, w*nz, -}  <- body-mesh collider scatter
 //                                                              (mpm_solver.py:829-880)
 //   mov  {w*vx, w*vy, w*vz, w}      <- particle-mover scatter  (mpm_solver.py:677-788)
-// Invariant: between substeps all accumulators of allocated slots are zero (the grid update
-// re-zeroes what it consumed), so there is no zero_grid sweep.
+// Invariants: (1) every block under the stencil of any particle is in the active list; (2) between
+// substeps all accumulators are zero (the grid update re-zeroes what it consumed), so there is no
+// zero_grid sweep.
 //
 // PARTICLES: three classes (elements, traditional, vertices), each sorted by
 // (Morton(block), cell-in-block).  Per class the state is split into small AoS sub-records
 // GROUPED BY THE KERNEL THAT WRITES THEM, so that every kernel reads and writes whole records:
 //   EP/TP  kinematics  {x,y,z,m, vx,vy,vz,vol, C[9]}      17 floats  written by G2P
-//   ES/TS  stress      {S[9]}                              9 floats  written by the stress kernel
-//   ED     directions  {d1,d2,d3 (column-major), face[3]} 12 floats  written by stress (d3) and G2P
+//   E12    directions  {d1[3], d2[3]}                      6 floats  written by G2P        (ping-pong)
+//   D3     direction   float4 {d3[3], -}                             return-mapped in place by the fused
+//                                                                    stress+P2G kernel, advanced by G2P (ping-pong)
+//   EF     corners     int[3] sorted vertex slots          3 ints    read-only
 //   EK     constants   {Rinv[3], mu, lam, gamma, kappa, vol} 8 floats read-only
+//   TS     stress      {S[9]}                              9 floats  written by the traditional stress kernel
 //   TF     trad state  {F[9], Ft[9], mu, lam, ys}         21 floats  written by stress (F,..) and G2P (Ft)
 //   VP     kinematics  {x,y,z,m, vx,vy,vz, C[9]}          16 floats  written by G2P
 //   VF     force       float4 {fx,fy,fz,-}                           REDG.128 by stress, zeroed by G2P
+// E12 / D3 are double buffered: G2P reads buffer `cur` and writes buffer `cur^1`, so the directions the
+// last stress evaluation saw stay available and the element stress (state.particle_stress) is
+// re-evaluated on export instead of being stored every substep.
 // A warp owns 32 consecutive records: the slab of each sub-record is one contiguous chunk that
 // is moved with a single cp.async.bulk (TMA, SASS UBLKCP) into / out of shared memory, where
-// lane = particle accesses are bank-conflict free (odd word strides).
+// lane = particle accesses are bank-conflict free.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,8 +49,9 @@ constexpr int MAX_OPS = 64;
 
 // sub-record sizes in floats
 constexpr int KP_F = 17;  // EP / TP
-constexpr int S_F = 9;    // ES / TS
-constexpr int ED_F = 12;
+constexpr int S_F = 9;    // TS
+constexpr int E12_F = 6;
+constexpr int EF_F = 3;
 constexpr int EK_F = 8;
 constexpr int TF_F = 21;
 constexpr int VP_F = 16;
@@ -46,7 +59,6 @@ constexpr int VF_F = 4;
 // field offsets
 constexpr int P_X = 0, P_M = 3, P_V = 4, P_VOL = 7, P_C = 8;  // EP / TP
 constexpr int V_X = 0, V_M = 3, V_V = 4, V_C = 7;              // VP
-constexpr int D_DC = 0, D_FACE = 9;                            // ED
 constexpr int K_RINV = 0, K_MU = 3, K_LAM = 4, K_GAMMA = 5, K_KAPPA = 6, K_VOL = 7;
 constexpr int T_F = 0, T_FT = 9, T_MU = 18, T_LAM = 19, T_YS = 20;
 
@@ -54,13 +66,40 @@ struct Grid {
     int n, nb;
     float dx, inv_dx, lim;
     int cap;
-    int* table;       // [nb^3]
-    int* n_slots;     // device counter
-    int* slot_coord;  // [cap] bx | by<<10 | bz<<20
+    int* table;       // [nb^3] -1 = inactive, else index into slot_coord
+    int* n_slots;     // device counter: number of active blocks
+    int* slot_coord;  // [cap] active list: bx | by<<10 | bz<<20
     float4 *acc, *vout, *colv, *coln, *mov;
     float4* dbg_acc;  // copy of acc taken by the grid update when debugging (else null)
     int* flags;       // [0] pool overflow, [1] scatter/gather hit an unallocated block
+    unsigned long long* clk;  // phase-clock accumulators (only read by -DMPM_CLK builds, tools/phase_clocks.py)
 };
+
+// Per-warp phase clocks for latency analysis: PHASE_BEGIN at kernel entry, PHASE(k, i) after phase i of
+// kernel k adds the elapsed SM cycles to a per-thread accumulator, PHASE_END(k) flushes lane 0's sums to
+// clk[copy*64 + k*8 + i] (and counts warps in slot 7).
+#ifdef MPM_CLK
+#define PHASE_BEGIN() long long clk_prev_ = clock64(); unsigned clk_acc_[7] = {0, 0, 0, 0, 0, 0, 0}
+#define PHASE(gr, k, i)                               \
+    do {                                              \
+        long long t_ = clock64();                     \
+        clk_acc_[i] += (unsigned)(t_ - clk_prev_);    \
+        clk_prev_ = t_;                               \
+    } while (0)
+// one flush per warp, spread over 64 copies of the table to keep the probe's own atomics cheap
+#define PHASE_END(gr, k)                                                                                   \
+    do {                                                                                                   \
+        if ((threadIdx.x & 31) == 0) {                                                                     \
+            unsigned long long* c_ = (gr).clk + (blockIdx.x & 63) * 64 + (k) * 8;                          \
+            for (int i_ = 0; i_ < 7; i_++) if (clk_acc_[i_]) atomicAdd(&c_[i_], (unsigned long long)clk_acc_[i_]); \
+            atomicAdd(&c_[7], 1ull);                                                                       \
+        }                                                                                                  \
+    } while (0)
+#else
+#define PHASE_BEGIN() do {} while (0)
+#define PHASE(gr, k, i) do {} while (0)
+#define PHASE_END(gr, k) do {} while (0)
+#endif
 
 struct StepState {
     double time;  // MPMWARP.time (mpm_solver.py:28,536)
@@ -224,10 +263,11 @@ __device__ __forceinline__ uint32_t sort_key(const Grid& g, float x, float y, fl
 }
 __device__ __forceinline__ int table_index(const Grid& g, int bx, int by, int bz) { return (bx * g.nb + by) * g.nb + bz; }
 
+// >= 0 iff the block is in the active list (plain load: G2P activates blocks in the same kernel)
 __device__ __forceinline__ int lookup_slot(const Grid& g, int bx, int by, int bz) {
-    return g.table[table_index(g, bx, by, bz)];  // plain load: G2P allocates blocks in the same kernel
+    return g.table[table_index(g, bx, by, bz)];
 }
-// allocate the block if needed; the slot value is only needed by LATER kernels
+// put the block on the active list if it is not there yet
 __device__ __forceinline__ void ensure_block(const Grid& g, int bx, int by, int bz) {
     int* t = &g.table[table_index(g, bx, by, bz)];
     int s = *(volatile int*)t;
@@ -255,15 +295,14 @@ __device__ __forceinline__ void ensure_stencil_blocks(const Grid& g, float x, fl
         for (int b = y0; b <= y1; b++)
             for (int c = z0; c <= z1; c++) ensure_block(g, a, b, c);
 }
-// pool index of node (ix,iy,iz) or -1
+// index of node (ix,iy,iz) in the per-node arrays, -1 outside the grid
 __device__ __forceinline__ int node_index(const Grid& g, int ix, int iy, int iz) {
     if ((unsigned)ix >= (unsigned)g.n || (unsigned)iy >= (unsigned)g.n || (unsigned)iz >= (unsigned)g.n) return -1;
-    int s = lookup_slot(g, ix >> 2, iy >> 2, iz >> 2);
-    if (s < 0) return -1;
-    return s * BN + ((ix & 3) << 4) + ((iy & 3) << 2) + (iz & 3);
+    return table_index(g, ix >> 2, iy >> 2, iz >> 2) * BN + ((ix & 3) << 4) + ((iy & 3) << 2) + (iz & 3);
 }
-// the (up to) 2x2x2 pool slots under a 3^3 stencil whose base node is (bx,by,bz) >= 0:
-// eight independent table loads issued together instead of 27 dependent ones
+// activity of the (up to) 2x2x2 blocks under a 3^3 stencil whose base node is (bx,by,bz) >= 0:
+// eight independent table loads issued together (used by the body / joint scatters, which must not
+// touch inactive blocks)
 __device__ __forceinline__ void load_slots8(const Grid& g, int bx, int by, int bz, int* sl) {
     const int X0 = bx >> 2, Y0 = by >> 2, Z0 = bz >> 2;
 #pragma unroll
@@ -279,12 +318,11 @@ __device__ __forceinline__ int sel8(const int* sl, int c) {
     for (int q = 1; q < 8; q++) s = (c == q) ? sl[q] : s;
     return s;
 }
-// pool index of stencil node (i,j,k) given the 8 slots, -1 if its block is not allocated
-__device__ __forceinline__ int stencil_node(const int* sl, int bx, int by, int bz, int i, int j, int k) {
+// index of stencil node (i,j,k) given the 8 activity words, -1 if its block is not active
+__device__ __forceinline__ int stencil_node(const Grid& g, const int* sl, int bx, int by, int bz, int i, int j, int k) {
     const int ix = bx + i, iy = by + j, iz = bz + k;
     const int c = (((ix >> 2) - (bx >> 2)) << 2) | (((iy >> 2) - (by >> 2)) << 1) | ((iz >> 2) - (bz >> 2));
-    const int s = sel8(sl, c);
-    return s < 0 ? -1 : s * BN + ((ix & 3) << 4) + ((iy & 3) << 2) + (iz & 3);
+    return sel8(sl, c) < 0 ? -1 : node_index(g, ix, iy, iz);
 }
 
 // quadratic B-spline factor of stencil offset i at fractional position f (mpm_utils.py:506-514):
@@ -296,6 +334,43 @@ __device__ __forceinline__ void bspline(float f, int i, float& w, float& dw) {
     float t = f - s;
     w = A * t * t + B;
     dw = 2.0f * A * t;
+}
+
+// ------------------------------------------------------------------ packed fp32 (FFMA2 / FMUL2 / FADD2)
+// sm_100 issues two IEEE fp32 operations per instruction on an aligned register pair, with a scalar
+// operand broadcast to both halves for free; the 27-node inner loops are written on float2 so that
+// the issue slots per node halve.
+__device__ __forceinline__ float2 fma2(float s, float2 a, float2 c) { return __ffma2_rn(make_float2(s, s), a, c); }
+__device__ __forceinline__ float2 fma2(float2 s, float a, float2 c) { return __ffma2_rn(s, make_float2(a, a), c); }
+__device__ __forceinline__ float2 mul2(float s, float2 a) { return __fmul2_rn(make_float2(s, s), a); }
+__device__ __forceinline__ float2 mul2(float2 s, float a) { return __fmul2_rn(s, make_float2(a, a)); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+struct V4 {
+    float2 lo, hi;  // (x, y), (z, w)
+};
+__device__ __forceinline__ V4 v4(float x, float y, float z, float w) { return V4{make_float2(x, y), make_float2(z, w)}; }
+__device__ __forceinline__ V4 mul4(float s, V4 a) { return V4{mul2(s, a.lo), mul2(s, a.hi)}; }
+__device__ __forceinline__ V4 fma4(float s, V4 a, V4 c) { return V4{fma2(s, a.lo, c.lo), fma2(s, a.hi, c.hi)}; }
+__device__ __forceinline__ V4 add4(V4 a, V4 b) { return V4{add2(a.lo, b.lo), add2(a.hi, b.hi)}; }
+
+// ------------------------------------------------------------------ cell runs of a sorted slab
+// Particles are sorted by cell, so the 32 particles of a warp form a few runs that share one 27-node
+// stencil.  `cell` packs the clamped stencil base; lanes >= cnt must pass distinct negative values.
+struct Runs {
+    unsigned starts;  // bit l set: lane l is the first particle of a run
+    int nr;           // number of runs
+    int mine;         // run index of this lane
+};
+__device__ __forceinline__ Runs find_runs(int lane, int cnt, int cell) {
+    const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+    Runs r;
+    r.starts = __ballot_sync(0xffffffffu, lane < cnt && (lane == 0 || cell != prev));
+    r.nr = __popc(r.starts);
+    r.mine = __popc(r.starts & (0xffffffffu >> (31 - lane))) - 1;
+    return r;
+}
+__device__ __forceinline__ int pack_cell(int bx, int by, int bz) {
+    return clampi(bx + 2, 0, 1023) | (clampi(by + 2, 0, 1023) << 10) | (clampi(bz + 2, 0, 1023) << 20);
 }
 
 // ------------------------------------------------------------------ TMA slab staging

@@ -31,133 +31,116 @@ __device__ __forceinline__ bool warp_begin(Warp& w, int n, unsigned char* smem) 
     __syncwarp();
     return true;
 }
-__device__ __forceinline__ void slab_load2(const Warp& w, void* s0, const float* g0, int F0, void* s1, const float* g1, int F1) {
+struct Slab {
+    void* s;        // shared-memory destination / source
+    const void* g;  // base of the global sub-record array
+    int F;          // 4-byte words per record
+};
+// one cp.async.bulk per sub-record slab, all completing on the warp's mbarrier
+template <int N>
+__device__ __forceinline__ void slab_load(const Warp& w, const Slab (&sl)[N]) {
     if (w.lane == 0) {
-        const uint32_t b0 = slab_bytes(w.cnt, F0), b1 = g1 ? slab_bytes(w.cnt, F1) : 0u;
-        mbar_expect_tx(w.bar, b0 + b1);
-        bulk_g2s(s0, g0 + (size_t)w.p0 * F0, b0, w.bar);
-        if (g1) bulk_g2s(s1, g1 + (size_t)w.p0 * F1, b1, w.bar);
+        uint32_t tot = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) tot += slab_bytes(w.cnt, sl[i].F);
+        mbar_expect_tx(w.bar, tot);
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            bulk_g2s(sl[i].s, static_cast<const float*>(sl[i].g) + (size_t)w.p0 * sl[i].F, slab_bytes(w.cnt, sl[i].F), w.bar);
     }
     while (!mbar_try_wait(w.bar, 0)) {}
 }
-__device__ __forceinline__ void slab_store2(const Warp& w, const void* s0, float* g0, int F0, const void* s1, float* g1, int F1) {
+template <int N>
+__device__ __forceinline__ void slab_store(const Warp& w, const Slab (&sl)[N]) {
     fence_async_smem();
     __syncwarp();
     if (w.lane == 0) {
-        bulk_s2g(g0 + (size_t)w.p0 * F0, s0, slab_bytes(w.cnt, F0));
-        if (g1) bulk_s2g(g1 + (size_t)w.p0 * F1, s1, slab_bytes(w.cnt, F1));
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            bulk_s2g(const_cast<float*>(static_cast<const float*>(sl[i].g)) + (size_t)w.p0 * sl[i].F, sl[i].s, slab_bytes(w.cnt, sl[i].F));
         bulk_commit_wait();
     }
 }
 
-// ============================================================ constitutive update
+// ============================================================ constitutive update (cloth elements)
 // Fused anisotropy_return_mapping + kirchoff_stress_Anisotropy (mpm_utils.py:179-209, 101-177).
 // The reference runs wp.qr3 twice on the same d1,d2; the second QR only differs in the third
 // column of R, which is exactly the return-mapped (R02,R12,R22), so one QR serves both.
 // wp.svd3 of [[F11,F12,0],[0,F22,0],[0,0,0]] is only used for U2 V2^T = polar rotation of the
 // upper-triangular 2x2, which has the closed form [[a, b],[-b, a]]/|.|, a=F11+F22, b=F12.
-constexpr int STRESS_E_WB = (ED_F + EK_F + S_F) * 32 * 4;  // ED in/out | EK in | ES out
-constexpr int STRESS_E_NW = 4;
-__global__ void __launch_bounds__(32 * STRESS_E_NW) k_stress_elements(int Ne, float* __restrict__ ED, const float* __restrict__ EK,
-                                                                      float* __restrict__ ES, float4* __restrict__ VF,
-                                                                      float friction_coeff) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    Warp w;
-    if (!warp_begin<STRESS_E_NW, STRESS_E_WB>(w, Ne, smem)) return;
-    float* sD = reinterpret_cast<float*>(w.buf);
-    float* sK = sD + 32 * ED_F;
-    float* sS = sK + 32 * EK_F;
-    slab_load2(w, sD, ED, ED_F, sK, EK, EK_F);
-    if (w.lane < w.cnt) {
-        const float4* d4 = reinterpret_cast<const float4*>(sD + w.lane * ED_F);
-        const float4 q0 = d4[0], q1v = d4[1], q2v = d4[2];
-        const float d1[3] = {q0.x, q0.y, q0.z}, d2[3] = {q0.w, q1v.x, q1v.y}, d3[3] = {q1v.z, q1v.w, q2v.x};
-        const int face0 = __float_as_int(q2v.y), face1 = __float_as_int(q2v.z), face2 = __float_as_int(q2v.w);
-        const float4 k0 = reinterpret_cast<const float4*>(sK + w.lane * EK_F)[0], k1 = reinterpret_cast<const float4*>(sK + w.lane * EK_F)[1];
-        const float iD11 = k0.x, iD12 = k0.y, iD22 = k0.z, mu = k0.w, lam = k1.x, gamma = k1.y, kappa = k1.z, vol = k1.w;
-        // rotation QR, sign-normalised (R00>0, R11>0, det Q=+1): Gram-Schmidt with q3 = q1 x q2, in
-        // un-contracted IEEE arithmetic (see dot3_rn)
-        const float r00 = len3_rn(d1);
-        const float q1[3] = {__fdiv_rn(d1[0], r00), __fdiv_rn(d1[1], r00), __fdiv_rn(d1[2], r00)};
-        const float r01 = dot3_rn(q1, d2);
-        const float u2[3] = {__fsub_rn(d2[0], __fmul_rn(r01, q1[0])), __fsub_rn(d2[1], __fmul_rn(r01, q1[1])),
-                             __fsub_rn(d2[2], __fmul_rn(r01, q1[2]))};
-        const float r11 = len3_rn(u2);
-        const float q2[3] = {__fdiv_rn(u2[0], r11), __fdiv_rn(u2[1], r11), __fdiv_rn(u2[2], r11)};
-        const float q3[3] = {__fsub_rn(__fmul_rn(q1[1], q2[2]), __fmul_rn(q1[2], q2[1])),
-                             __fsub_rn(__fmul_rn(q1[2], q2[0]), __fmul_rn(q1[0], q2[2])),
-                             __fsub_rn(__fmul_rn(q1[0], q2[1]), __fmul_rn(q1[1], q2[0]))};
-        float r02 = dot3_rn(q1, d3), r12 = dot3_rn(q2, d3), r22 = dot3_rn(q3, d3);
-        // return mapping (mpm_utils.py:196-204)
-        if (r22 > 1.0f) {
-            r22 = 1.0f;
-        } else {
-            float fn = kappa * (1.0f - r22) * (1.0f - r22);
-            float ff = gamma * sqrtf(r02 * r02 + r12 * r12);
-            if (ff > friction_coeff * fn) {
-                float sc = friction_coeff * fn / ff;
-                r02 *= sc;
-                r12 *= sc;
-            }
+struct ElemConst {
+    float iD11, iD12, iD22, mu, lam, gamma, kappa, vol;
+};
+struct ElemStress {
+    float nd3[3];                // return-mapped d3 (mpm_utils.py:205-208)
+    float f1[3], f2[3], f3[3];   // corner forces (mpm_utils.py:163-175)
+    float P3[3];                 // stress = vol * P3 (x) nd3 (mpm_utils.py:177)
+};
+__device__ __forceinline__ void element_stress(const float* d1, const float* d2, const float* d3, const ElemConst& k,
+                                               float friction_coeff, ElemStress& o) {
+    // rotation QR, sign-normalised (R00>0, R11>0, det Q=+1): Gram-Schmidt with q3 = q1 x q2, in
+    // un-contracted IEEE arithmetic (see dot3_rn)
+    const float r00 = len3_rn(d1);
+    const float q1[3] = {__fdiv_rn(d1[0], r00), __fdiv_rn(d1[1], r00), __fdiv_rn(d1[2], r00)};
+    const float r01 = dot3_rn(q1, d2);
+    const float u2[3] = {__fsub_rn(d2[0], __fmul_rn(r01, q1[0])), __fsub_rn(d2[1], __fmul_rn(r01, q1[1])),
+                         __fsub_rn(d2[2], __fmul_rn(r01, q1[2]))};
+    const float r11 = len3_rn(u2);
+    const float q2[3] = {__fdiv_rn(u2[0], r11), __fdiv_rn(u2[1], r11), __fdiv_rn(u2[2], r11)};
+    const float q3[3] = {__fsub_rn(__fmul_rn(q1[1], q2[2]), __fmul_rn(q1[2], q2[1])),
+                         __fsub_rn(__fmul_rn(q1[2], q2[0]), __fmul_rn(q1[0], q2[2])),
+                         __fsub_rn(__fmul_rn(q1[0], q2[1]), __fmul_rn(q1[1], q2[0]))};
+    float r02 = dot3_rn(q1, d3), r12 = dot3_rn(q2, d3), r22 = dot3_rn(q3, d3);
+    // return mapping (mpm_utils.py:196-204)
+    if (r22 > 1.0f) {
+        r22 = 1.0f;
+    } else {
+        float fn = k.kappa * (1.0f - r22) * (1.0f - r22);
+        float ff = k.gamma * sqrtf(r02 * r02 + r12 * r12);
+        if (ff > friction_coeff * fn) {
+            float sc = friction_coeff * fn / ff;
+            r02 *= sc;
+            r12 *= sc;
         }
-        float nd3[3];
-#pragma unroll
-        for (int r = 0; r < 3; r++) nd3[r] = q1[r] * r02 + q2[r] * r12 + q3[r] * r22;
-        // stress (mpm_utils.py:125-177) with R = [r00 r01 r02; 0 r11 r12; 0 0 r22]
-        const float F11 = r00 * iD11, F12 = r00 * iD12 + r01 * iD22, F22 = r11 * iD22;
-        const float pa = F11 + F22, pb = F12;
-        const float pin = rsqrtf(pa * pa + pb * pb);
-        const float c = pa * pin, s = pb * pin;  // Rot = [[c, s], [-s, c]]
-        const float J = F11 * F22;
-        const float lj = lam * (J - 1.0f);
-        const float k00 = 2.0f * mu * (F11 - c) + lj * F22;
-        const float k01 = 2.0f * mu * (F12 - s);
-        const float k11 = 2.0f * mu * (F22 - c) + lj * F11;  // K2[1,0] is never used (mpm_utils.py:146-148)
-        const float dr13 = gamma * r02, dr23 = gamma * r12;
-        const float dr33 = (r22 > 1.0f) ? 0.0f : -kappa * (1.0f - r22) * (1.0f - r22);
-        // K3 = dr * RiDT, RiDT = [F11 0 0; F12 F22 0; r02 r12 r22]
-        const float K00 = k00 * F11 + k01 * F12 + dr13 * r02;
-        const float K01 = k01 * F22 + dr13 * r12;
-        const float K02 = dr13 * r22;
-        const float K11 = k11 * F22 + dr23 * r12;
-        const float K12 = dr23 * r22;
-        const float K22 = dr33 * r22;
-        // inverse of lower-triangular RiDT (mpm_utils.py:87-99)
-        const float invdet = 1.0f / (F11 * F22 * r22);
-        const float I00 = F22 * r22 * invdet, I10 = -F12 * r22 * invdet, I11 = F11 * r22 * invdet;
-        const float I20 = (F12 * r12 - r02 * F22) * invdet, I21 = -F11 * r12 * invdet, I22 = F11 * F22 * invdet;
-        // M = K3sym * RiDT^-1
-        const float M00 = K00 * I00 + K01 * I10 + K02 * I20, M01 = K01 * I11 + K02 * I21, M02 = K02 * I22;
-        const float M10 = K01 * I00 + K11 * I10 + K12 * I20, M11 = K11 * I11 + K12 * I21, M12 = K12 * I22;
-        const float M20 = K02 * I00 + K12 * I10 + K22 * I20, M21 = K12 * I11 + K22 * I21, M22 = K22 * I22;
-        float P1[3], P2[3], P3[3];  // columns of P = Q M
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            P1[r] = q1[r] * M00 + q2[r] * M10 + q3[r] * M20;
-            P2[r] = q1[r] * M01 + q2[r] * M11 + q3[r] * M21;
-            P3[r] = q1[r] * M02 + q2[r] * M12 + q3[r] * M22;
-        }
-        float f1[3], f2[3], f3[3];
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            f2[r] = -vol * (iD11 * P1[r] + iD12 * P2[r]);
-            f3[r] = -vol * iD22 * P2[r];
-            f1[r] = -(f2[r] + f3[r]);
-        }
-        // vertex_force scatter (mpm_utils.py:172-175): one 16-byte vector atomic per corner
-        atomicAdd(&VF[face0], make_float4(f1[0], f1[1], f1[2], 0.f));
-        atomicAdd(&VF[face1], make_float4(f2[0], f2[1], f2[2], 0.f));
-        atomicAdd(&VF[face2], make_float4(f3[0], f3[1], f3[2], 0.f));
-        // stress = vol * P3 (x) d3 with the return-mapped d3 (mpm_utils.py:177)
-        float* so = sS + w.lane * S_F;
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int cc = 0; cc < 3; cc++) so[3 * r + cc] = vol * (P3[r] * nd3[cc]);
-        float* dd = sD + w.lane * ED_F;
-        dd[6] = nd3[0]; dd[7] = nd3[1]; dd[8] = nd3[2];
     }
-    slab_store2(w, sD, ED, ED_F, sS, ES, S_F);
+#pragma unroll
+    for (int r = 0; r < 3; r++) o.nd3[r] = q1[r] * r02 + q2[r] * r12 + q3[r] * r22;
+    // stress (mpm_utils.py:125-177) with R = [r00 r01 r02; 0 r11 r12; 0 0 r22]
+    const float F11 = r00 * k.iD11, F12 = r00 * k.iD12 + r01 * k.iD22, F22 = r11 * k.iD22;
+    const float pa = F11 + F22, pb = F12;
+    const float pin = rsqrtf(pa * pa + pb * pb);
+    const float c = pa * pin, s = pb * pin;  // Rot = [[c, s], [-s, c]]
+    const float J = F11 * F22;
+    const float lj = k.lam * (J - 1.0f);
+    const float k00 = 2.0f * k.mu * (F11 - c) + lj * F22;
+    const float k01 = 2.0f * k.mu * (F12 - s);
+    const float k11 = 2.0f * k.mu * (F22 - c) + lj * F11;  // K2[1,0] is never used (mpm_utils.py:146-148)
+    const float dr13 = k.gamma * r02, dr23 = k.gamma * r12;
+    const float dr33 = (r22 > 1.0f) ? 0.0f : -k.kappa * (1.0f - r22) * (1.0f - r22);
+    // K3 = dr * RiDT, RiDT = [F11 0 0; F12 F22 0; r02 r12 r22]
+    const float K00 = k00 * F11 + k01 * F12 + dr13 * r02;
+    const float K01 = k01 * F22 + dr13 * r12;
+    const float K02 = dr13 * r22;
+    const float K11 = k11 * F22 + dr23 * r12;
+    const float K12 = dr23 * r22;
+    const float K22 = dr33 * r22;
+    // inverse of lower-triangular RiDT (mpm_utils.py:87-99)
+    const float invdet = 1.0f / (F11 * F22 * r22);
+    const float I00 = F22 * r22 * invdet, I10 = -F12 * r22 * invdet, I11 = F11 * r22 * invdet;
+    const float I20 = (F12 * r12 - r02 * F22) * invdet, I21 = -F11 * r12 * invdet, I22 = F11 * F22 * invdet;
+    // M = K3sym * RiDT^-1
+    const float M00 = K00 * I00 + K01 * I10 + K02 * I20, M01 = K01 * I11 + K02 * I21, M02 = K02 * I22;
+    const float M10 = K01 * I00 + K11 * I10 + K12 * I20, M11 = K11 * I11 + K12 * I21, M12 = K12 * I22;
+    const float M20 = K02 * I00 + K12 * I10 + K22 * I20, M21 = K12 * I11 + K22 * I21, M22 = K22 * I22;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {  // columns of P = Q M
+        const float P1 = q1[r] * M00 + q2[r] * M10 + q3[r] * M20;
+        const float P2 = q1[r] * M01 + q2[r] * M11 + q3[r] * M21;
+        o.P3[r] = q1[r] * M02 + q2[r] * M12 + q3[r] * M22;
+        o.f2[r] = -k.vol * (k.iD11 * P1 + k.iD12 * P2);
+        o.f3[r] = -k.vol * k.iD22 * P2;
+        o.f1[r] = -(o.f2[r] + o.f3[r]);
+    }
 }
 
 // return mappings + stress for traditional particles (mpm_utils.py:1047-1103, 212-399, 8-84)
@@ -170,7 +153,7 @@ __global__ void __launch_bounds__(32 * STRESS_T_NW) k_stress_traditional(int Nt,
     if (!warp_begin<STRESS_T_NW, STRESS_T_WB>(w, Nt, smem)) return;
     float* sT = reinterpret_cast<float*>(w.buf);
     float* sS = sT + 32 * TF_F;
-    slab_load2(w, sT, TF, TF_F, nullptr, nullptr, 0);
+    slab_load(w, {Slab{sT, TF, TF_F}});
     if (w.lane < w.cnt) {
         float* a = sT + w.lane * TF_F;
         float F[9], Ft[9], U[9], V[9], sg[3];
@@ -280,7 +263,7 @@ __global__ void __launch_bounds__(32 * STRESS_T_NW) k_stress_traditional(int Nt,
         a[T_LAM] = lam;
         a[T_YS] = ys;
     }
-    slab_store2(w, sT, TF, TF_F, sS, TS, S_F);
+    slab_store(w, {Slab{sT, TF, TF_F}, Slab{sS, TS, S_F}});
 }
 
 // pre-P2G particle operations on one class (mpm_solver.py:260-279); v and mass sit at the same
@@ -306,60 +289,112 @@ __global__ void k_particle_ops(int n, float* __restrict__ rec, int F, const uint
     if (ch) { r[P_V] = vx; r[P_V + 1] = vy; r[P_V + 2] = vz; }
 }
 
-// ============================================================ P2G
-// p2g_apic_with_stress (mpm_utils.py:484-557), restructured for cell-sorted particles.
-//  stage 0  cp.async.bulk brings the warp's kinematics slab and stress (or vertex-force) slab into smem.
-//  stage 1  lane = particle (all 32 lanes busy, nothing computed twice): each lane evaluates the 27
-//           stencil contributions {dt*f + w m (v + C dpos), w m} of ITS particle and stores them as 27
-//           float4 in shared memory; a ballot marks where the cell id changes along the slab.
-//  stage 2  lane = stencil node (27 of 32 lanes): particles of one cell form a run; its 27 node sums
-//           are plain float4 adds down a shared-memory column, flushed with ONE REDG.E.ADD.F32x4 per
-//           node per run.  No intra-warp reduction, no shared-memory atomics; global atomics drop
-//           from 27*4 per particle to 27 per cell run.
-// KIND 0: element (S already holds vol*P3(x)d3), 1: traditional (stress*vol, :496), 2: vertex.
+// ============================================================ P2G (+ fused cloth stress)
+// p2g_apic_with_stress (mpm_utils.py:484-557), restructured for cell-sorted particles; for cloth
+// elements compute_stress_from_F_trial (mpm_utils.py:1017-1046) is fused in front of it, so the
+// stress never round-trips through HBM.
+//  stage 0  cp.async.bulk brings the warp's sub-record slabs into smem.
+//  stage 1  lane = particle.  (elements: return mapping + stress; the three corner forces leave as
+//           REDG.128 into VF, the return-mapped d3 as one coalesced STG.128.)  The contribution of a
+//           particle to stencil node (i,j,k), {dt*f + w m (v + C dpos), w m}, is separable:
+//             out(i,j,k) = w2k T_ij + (w0i w1j) Uz_k,      T_ij = w1j Ux_i + w0i Uy_j,
+//             Ux_i = w0i (A + i Bx) + dw0i S0,  Uy_j = w1j j By + dw1j S1,  Uz_k = w2k k Bz + dw2k S2
+//           (A = {m (v - dx C f) + dt f_vertex, m}, B_a = m dx C[:,a], S_a = -dt/dx stress[:,a]); each lane
+//           writes the 9 T_ij, the 3 {Uz_k, w2k} and the 9 w0i w1j of ITS particle to shared memory
+//           (228 B per particle instead of 27 float4).
+//  stage 2  lane = stencil node (27 of 32 lanes): particles of one cell form a run; the lane expands and
+//           accumulates its node along the run (3 broadcast LDS + 3 FFMA2 + 1 FFMA per particle) and
+//           flushes with ONE REDG.E.ADD.F32x4 per node per run (the node address of the next run is
+//           looked up while the current run is summed).  No intra-warp reduction, no shared-memory
+//           atomics; global atomics drop from 27*4 per particle to 27 per cell run.
+// KIND 0: cloth element, 1: traditional (stress*vol, :496), 2: cloth vertex.
 constexpr int P2G_NW = 4;
-constexpr int P2G_WB = (32 * 27 + 8) * 16 + 128;  // 27 float4 per particle (+ slack for lanes 27..31) + cell ids
+constexpr int P2G_T_B = 32 * 9 * 16, P2G_U_B = 32 * 3 * 16, P2G_W_B = 32 * 9 * 4;
+constexpr int P2G_WB = P2G_T_B + P2G_U_B + P2G_W_B;  // 7296 B; the raw slabs (<= 4864 B) are overlaid on it
 constexpr int P2G_SMEM = 128 + P2G_NW * P2G_WB;
 
+struct P2GIn {
+    const float* KP;   // EP / TP / VP
+    const float* SF;   // TS (KIND 1) or VF (KIND 2)
+    const float* E12;  // KIND 0 only from here
+    float4* D3;
+    const int* EF;
+    const float* EK;
+    float4* VF;
+    float friction_coeff;
+};
+
 template <int KIND>
-__global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, const float* __restrict__ KP, const float* __restrict__ SF, int n,
-                                                      float dt, float rpic) {
+__global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, float dt, float rpic) {
     constexpr int F0 = (KIND == 2) ? VP_F : KP_F;  // kinematics record
-    constexpr int F1 = (KIND == 2) ? VF_F : S_F;   // vertex force / stress record
     extern __shared__ __align__(128) unsigned char smem[];
     Warp w;
     if (!warp_begin<P2G_NW, P2G_WB>(w, n, smem)) return;
+    PHASE_BEGIN();
     float* buf = reinterpret_cast<float*>(w.buf);
+    // ---- stage 0
     float* raw1 = buf + 32 * F0;
-    slab_load2(w, buf, KP, F0, raw1, SF, F1);
+    float* s12 = buf + 32 * KP_F;
+    float* sD3 = s12 + 32 * E12_F;
+    float* sEF = sD3 + 32 * 4;
+    float* sEK = sEF + 32 * EF_F;
+    if (KIND == 0) slab_load(w, {Slab{buf, in.KP, KP_F}, Slab{s12, in.E12, E12_F}, Slab{sD3, in.D3, 4}, Slab{sEF, in.EF, EF_F}, Slab{sEK, in.EK, EK_F}});
+    if (KIND == 1) slab_load(w, {Slab{buf, in.KP, KP_F}, Slab{raw1, in.SF, S_F}});
+    if (KIND == 2) slab_load(w, {Slab{buf, in.KP, VP_F}, Slab{raw1, in.SF, VF_F}});
+    PHASE(g, KIND, 0);  // slab load
     // ---- stage 1
-    float x[3], m, v[3], C[9], Sp[9], fv[3] = {0.f, 0.f, 0.f};
-    if (w.lane < w.cnt) {
+    const bool valid = w.lane < w.cnt;
+    float x[3] = {0.f, 0.f, 0.f}, m = 0.f, v[3] = {0.f, 0.f, 0.f}, C[9], Sp[9], fv[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 9; i++) { C[i] = 0.f; Sp[i] = 0.f; }
+    if (valid) {
         const float* r = buf + w.lane * F0;
-        const float* s = raw1 + w.lane * F1;
         if (KIND == 2) {
             const float4* r4 = reinterpret_cast<const float4*>(r);
             const float4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
             x[0] = a.x; x[1] = a.y; x[2] = a.z; m = a.w;
             v[0] = b.x; v[1] = b.y; v[2] = b.z;
             C[0] = b.w; C[1] = c.x; C[2] = c.y; C[3] = c.z; C[4] = c.w; C[5] = d.x; C[6] = d.y; C[7] = d.z; C[8] = d.w;
-            const float4 f4 = *reinterpret_cast<const float4*>(s);
+            const float4 f4 = reinterpret_cast<const float4*>(raw1)[w.lane];
             fv[0] = f4.x; fv[1] = f4.y; fv[2] = f4.z;
-#pragma unroll
-            for (int i = 0; i < 9; i++) Sp[i] = 0.f;
         } else {
             x[0] = r[0]; x[1] = r[1]; x[2] = r[2]; m = r[P_M];
             v[0] = r[P_V]; v[1] = r[P_V + 1]; v[2] = r[P_V + 2];
-            const float sc = -dt * g.inv_dx * ((KIND == 1) ? r[P_VOL] : 1.0f);
 #pragma unroll
-            for (int i = 0; i < 9; i++) { C[i] = r[P_C + i]; Sp[i] = sc * s[i]; }
+            for (int i = 0; i < 9; i++) C[i] = r[P_C + i];
+            if (KIND == 1) {
+                const float sc = -dt * g.inv_dx * r[P_VOL];
+                const float* s = raw1 + w.lane * S_F;
+#pragma unroll
+                for (int i = 0; i < 9; i++) Sp[i] = sc * s[i];
+            }
         }
-    } else {
-        x[0] = x[1] = x[2] = 0.f; m = 0.f; v[0] = v[1] = v[2] = 0.f;
+        if (KIND == 0) {
+            const float2* e2 = reinterpret_cast<const float2*>(s12 + w.lane * E12_F);
+            const float2 da = e2[0], db = e2[1], dc = e2[2];
+            const float4 d3v = reinterpret_cast<const float4*>(sD3)[w.lane];
+            const float d1[3] = {da.x, da.y, db.x}, d2[3] = {db.y, dc.x, dc.y}, d3[3] = {d3v.x, d3v.y, d3v.z};
+            const int* fc = reinterpret_cast<const int*>(sEF) + w.lane * EF_F;
+            const int face0 = fc[0], face1 = fc[1], face2 = fc[2];
+            const float4 k0 = reinterpret_cast<const float4*>(sEK + w.lane * EK_F)[0], k1 = reinterpret_cast<const float4*>(sEK + w.lane * EK_F)[1];
+            const ElemConst ek{k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+            ElemStress es;
+            element_stress(d1, d2, d3, ek, in.friction_coeff, es);
+            // vertex_force scatter (mpm_utils.py:172-175): one 16-byte vector atomic per corner
+            atomicAdd(&in.VF[face0], make_float4(es.f1[0], es.f1[1], es.f1[2], 0.f));
+            atomicAdd(&in.VF[face1], make_float4(es.f2[0], es.f2[1], es.f2[2], 0.f));
+            atomicAdd(&in.VF[face2], make_float4(es.f3[0], es.f3[1], es.f3[2], 0.f));
+            in.D3[w.p0 + w.lane] = make_float4(es.nd3[0], es.nd3[1], es.nd3[2], 0.f);
+            // stress = vol * P3 (x) nd3 already carries the volume (mpm_utils.py:177, :494)
+            const float sc = -dt * g.inv_dx * ek.vol;
 #pragma unroll
-        for (int i = 0; i < 9; i++) { C[i] = 0.f; Sp[i] = 0.f; }
+            for (int rr = 0; rr < 3; rr++)
+#pragma unroll
+                for (int cc = 0; cc < 3; cc++) Sp[3 * rr + cc] = sc * (es.P3[rr] * es.nd3[cc]);
+        }
     }
     __syncwarp();  // the contributions overwrite the raw slabs
+    PHASE(g, KIND, 1);  // unpack (+ stress)
     int mycell;
     {
         if (rpic != 0.0f) {  // mpm_utils.py:528-542
@@ -384,67 +419,91 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, const float* __rest
         }
         // w m (v + C dpos) + dt w f_vertex = w (A + B_x i + B_y j + B_z k), dpos = (ijk - f) dx
         const float mdx = m * g.dx;
-        float A[3], B[9];
+        float A[3];
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
+        for (int c = 0; c < 3; c++)
             A[c] = m * (v[c] - g.dx * (C[3 * c] * f[0] + C[3 * c + 1] * f[1] + C[3 * c + 2] * f[2])) + dt * fv[c];
+        const V4 A4 = v4(A[0], A[1], A[2], m);
+        const V4 Bx = v4(mdx * C[0], mdx * C[3], mdx * C[6], 0.f), By = v4(mdx * C[1], mdx * C[4], mdx * C[7], 0.f),
+                 Bz = v4(mdx * C[2], mdx * C[5], mdx * C[8], 0.f);
+        V4 Ux[3], Uy[3], Uz[3];
+        Ux[0] = mul4(wgt[0][0], A4);
+        Ux[1] = mul4(wgt[0][1], add4(A4, Bx));
+        Ux[2] = mul4(wgt[0][2], fma4(2.0f, Bx, A4));
+        Uy[0] = v4(0.f, 0.f, 0.f, 0.f);
+        Uy[1] = mul4(wgt[1][1], By);
+        Uy[2] = mul4(2.0f * wgt[1][2], By);
+        Uz[0] = v4(0.f, 0.f, 0.f, 0.f);
+        Uz[1] = mul4(wgt[2][1], Bz);
+        Uz[2] = mul4(2.0f * wgt[2][2], Bz);
+        if (KIND != 2) {  // dt * (-stress grad w), stress pre-scaled in Sp
+            const V4 S0 = v4(Sp[0], Sp[3], Sp[6], 0.f), S1 = v4(Sp[1], Sp[4], Sp[7], 0.f), S2 = v4(Sp[2], Sp[5], Sp[8], 0.f);
 #pragma unroll
-            for (int a = 0; a < 3; a++) B[3 * c + a] = mdx * C[3 * c + a];
-        }
-        float4* out = reinterpret_cast<float4*>(buf) + w.lane * 27;
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const float Ai[3] = {A[0] + B[0] * (float)i, A[1] + B[3] * (float)i, A[2] + B[6] * (float)i};
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const float wxy = wgt[0][i] * wgt[1][j];
-                const float gxy0 = dwg[0][i] * wgt[1][j], gxy1 = wgt[0][i] * dwg[1][j];
-                const float Aij[3] = {Ai[0] + B[1] * (float)j, Ai[1] + B[4] * (float)j, Ai[2] + B[7] * (float)j};
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const float ww = wxy * wgt[2][k];
-                    float4 o;
-                    o.x = ww * (Aij[0] + B[2] * (float)k);
-                    o.y = ww * (Aij[1] + B[5] * (float)k);
-                    o.z = ww * (Aij[2] + B[8] * (float)k);
-                    o.w = ww * m;
-                    if (KIND != 2) {  // dt * (-stress grad w), stress pre-scaled in Sp
-                        const float g0 = gxy0 * wgt[2][k], g1 = gxy1 * wgt[2][k], g2 = wxy * dwg[2][k];
-                        o.x += Sp[0] * g0 + Sp[1] * g1 + Sp[2] * g2;
-                        o.y += Sp[3] * g0 + Sp[4] * g1 + Sp[5] * g2;
-                        o.z += Sp[6] * g0 + Sp[7] * g1 + Sp[8] * g2;
-                    }
-                    out[(i * 3 + j) * 3 + k] = o;
-                }
+            for (int i = 0; i < 3; i++) {
+                Ux[i] = fma4(dwg[0][i], S0, Ux[i]);
+                Uy[i] = fma4(dwg[1][i], S1, Uy[i]);
+                Uz[i] = fma4(dwg[2][i], S2, Uz[i]);
             }
         }
-        mycell = (clampi(b[0] + 2, 0, 1023)) | (clampi(b[1] + 2, 0, 1023) << 10) | (clampi(b[2] + 2, 0, 1023) << 20);
-        if (w.lane >= w.cnt) mycell = -1 - w.lane;
+        float4* tT = reinterpret_cast<float4*>(w.buf) + w.lane * 9;
+        float4* tU = reinterpret_cast<float4*>(w.buf + P2G_T_B) + w.lane * 3;
+        float* tW = reinterpret_cast<float*>(w.buf + P2G_T_B + P2G_U_B) + w.lane * 9;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const V4 T = fma4(wgt[1][j], Ux[i], mul4(wgt[0][i], Uy[j]));
+                tT[i * 3 + j] = make_float4(T.lo.x, T.lo.y, T.hi.x, T.hi.y);
+                tW[i * 3 + j] = wgt[0][i] * wgt[1][j];
+            }
+#pragma unroll
+        for (int k = 0; k < 3; k++) tU[k] = make_float4(Uz[k].lo.x, Uz[k].lo.y, Uz[k].hi.x, wgt[2][k]);
+        mycell = valid ? pack_cell(b[0], b[1], b[2]) : -1 - w.lane;
     }
-    const int prev = __shfl_up_sync(0xffffffffu, mycell, 1);
-    unsigned starts = __ballot_sync(0xffffffffu, w.lane < w.cnt && (w.lane == 0 || mycell != prev));
+    const Runs R = find_runs(w.lane, w.cnt, mycell);
     __syncwarp();
+    PHASE(g, KIND, 2);  // stage 1
     // ---- stage 2
     const bool act = w.lane < 27;
     const int li = act ? w.lane / 9 : 0, lj = act ? (w.lane / 3) % 3 : 0, lk = act ? w.lane % 3 : 0;
-    const float4* P = reinterpret_cast<const float4*>(buf) + w.lane;
-    while (starts) {
-        const int s0 = __ffs(starts) - 1;
-        starts &= starts - 1;
-        const int e0 = starts ? (__ffs(starts) - 1) : w.cnt;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int q = s0; q < e0; q++) {
-            const float4 t = P[q * 27];
-            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-        }
-        const int c = __shfl_sync(0xffffffffu, mycell, s0);
-        if (act && (acc.w != 0.0f || acc.x != 0.0f || acc.y != 0.0f || acc.z != 0.0f)) {
-            int ni = node_index(g, (c & 1023) - 2 + li, ((c >> 10) & 1023) - 2 + lj, ((c >> 20) & 1023) - 2 + lk);
-            if (ni >= 0) atomicAdd(&g.acc[ni], acc);
+    const float4* pT = reinterpret_cast<const float4*>(w.buf) + (li * 3 + lj);
+    const float4* pU = reinterpret_cast<const float4*>(w.buf + P2G_T_B) + lk;
+    const float* pW = reinterpret_cast<const float*>(w.buf + P2G_T_B + P2G_U_B) + (li * 3 + lj);
+    // one pass over the slab with a fixed trip count (loads of later particles are in flight while earlier
+    // ones are accumulated); a warp-uniform test of `starts` closes a run: one REDG.128 per node
+    auto flush = [&](int c, float2 lo, float2 hi) {
+        if (act && (hi.y != 0.0f || lo.x != 0.0f || lo.y != 0.0f || hi.x != 0.0f)) {
+            const int ni = node_index(g, (c & 1023) - 2 + li, ((c >> 10) & 1023) - 2 + lj, ((c >> 20) & 1023) - 2 + lk);
+            if (ni >= 0) atomicAdd(&g.acc[ni], make_float4(lo.x, lo.y, hi.x, hi.y));
             else g.flags[1] = 1;
         }
+    };
+    float2 alo = make_float2(0.f, 0.f), ahi = alo;
+    int c = __shfl_sync(0xffffffffu, mycell, 0);
+    float4 Tn = pT[0], Un = pU[0];
+    float wn = pW[0];
+#pragma unroll 8
+    for (int q = 0; q < 32; q++) {  // records past cnt contribute zeros
+        const float4 T = Tn, U = Un;
+        const float wij = wn;
+        if (q < 31) {  // the loads of particle q+1 are in flight while particle q is accumulated
+            Tn = pT[(q + 1) * 9];
+            Un = pU[(q + 1) * 3];
+            wn = pW[(q + 1) * 9];
+        }
+        if (q > 0 && ((R.starts >> q) & 1u)) {
+            flush(c, alo, ahi);
+            alo = ahi = make_float2(0.f, 0.f);
+            c = __shfl_sync(0xffffffffu, mycell, q);
+        }
+        alo = fma2(U.w, make_float2(T.x, T.y), alo);
+        ahi = fma2(U.w, make_float2(T.z, T.w), ahi);
+        alo = fma2(wij, make_float2(U.x, U.y), alo);
+        ahi.x = fmaf(wij, U.z, ahi.x);
     }
+    flush(c, alo, ahi);
+    PHASE(g, KIND, 3);  // stage 2
+    PHASE_END(g, KIND);
 }
 
 // ============================================================ collider / mover scatter
@@ -511,7 +570,7 @@ __global__ void __launch_bounds__(128) k_collider_scatter(Grid g, int Mf, const 
         for (int j = 0; j < 3; j++)
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                int ni = stencil_node(sl, sp.b[0], sp.b[1], sp.b[2], i, j, k);
+                int ni = stencil_node(g, sl, sp.b[0], sp.b[1], sp.b[2], i, j, k);
                 if (ni < 0) continue;
                 float ww = sp.w[0][i] * sp.w[1][j] * sp.w[2][k];
                 atomicAdd(&g.colv[ni], make_float4(ww * fv[0], ww * fv[1], ww * fv[2], ww));
@@ -546,7 +605,7 @@ __global__ void __launch_bounds__(128) k_mover_scatter(Grid g, int njt, int njv,
         for (int j = 0; j < 3; j++)
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                int ni = stencil_node(sl, sp.b[0], sp.b[1], sp.b[2], i, j, k);
+                int ni = stencil_node(g, sl, sp.b[0], sp.b[1], sp.b[2], i, j, k);
                 if (ni < 0) { g.flags[1] = 1; continue; }
                 float ww = sp.w[0][i] * sp.w[1][j] * sp.w[2][k];
                 atomicAdd(&g.mov[ni], make_float4(ww * v0, ww * v1, ww * v2, ww));
@@ -567,13 +626,15 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
     const int total = n_slots * BN;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int slot = idx >> 6, l = idx & 63;
+        const int co = g.slot_coord[slot];
+        const int ni = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023) * BN + l;
         // all four accumulator loads are issued before any use (memory-level parallelism)
-        const float4 a = g.acc[idx];
-        const float4 mv = g.mov[idx];
+        const float4 a = g.acc[ni];
+        const float4 mv = g.mov[ni];
         float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), cn = cv;
-        if (use_collider) { cv = g.colv[idx]; cn = g.coln[idx]; }
+        if (use_collider) { cv = g.colv[ni]; cn = g.coln[ni]; }
         float vx = 0.f, vy = 0.f, vz = 0.f;
-        if (g.dbg_acc) g.dbg_acc[idx] = a;
+        if (g.dbg_acc) g.dbg_acc[ni] = a;
         if (a.w > 1e-15f) {
             float inv = 1.0f / a.w;
             vx = a.x * inv + dt * md.gx;
@@ -581,15 +642,15 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
             vz = a.z * inv + dt * md.gz;
         }
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.w != 0.0f || a.x != 0.0f || a.y != 0.0f || a.z != 0.0f) g.acc[idx] = zero4;
+        if (a.w != 0.0f || a.x != 0.0f || a.y != 0.0f || a.z != 0.0f) g.acc[ni] = zero4;
         if (md.damping < 1.0f) {
             vx -= (1.0f - md.damping) * vx;
             vy -= (1.0f - md.damping) * vy;
             vz -= (1.0f - md.damping) * vz;
         }
         if (use_collider && cv.w != 0.0f) {
-            g.colv[idx] = zero4;
-            g.coln[idx] = zero4;
+            g.colv[ni] = zero4;
+            g.coln[ni] = zero4;
             if (cv.w > 1e-15f) {
                 float inv = 1.0f / cv.w;
                 float mx = cv.x * inv, my = cv.y * inv, mz = cv.z * inv;
@@ -610,14 +671,13 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
         }
         // the mover accumulators are consumed (and cleared) even on steps without joint inputs
         if (mv.w != 0.0f || mv.x != 0.0f || mv.y != 0.0f || mv.z != 0.0f) {
-            g.mov[idx] = zero4;
+            g.mov[ni] = zero4;
             if (use_mover && mv.w > 1e-15f) {
                 float inv = 1.0f / mv.w;
                 vx = mv.x * inv; vy = mv.y * inv; vz = mv.z * inv;
             }
         }
         if (n_bc > 0) {
-            const int co = g.slot_coord[slot];
             const int ix = ((co & 1023) << 2) + (l >> 4), iy = (((co >> 10) & 1023) << 2) + ((l >> 2) & 3),
                       iz = (((co >> 20) & 1023) << 2) + (l & 3);
             for (int k = 0; k < n_bc; k++) {
@@ -664,7 +724,7 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
                 }
             }
         }
-        g.vout[idx] = make_float4(vx, vy, vz, 0.0f);
+        g.vout[ni] = make_float4(vx, vy, vz, 0.0f);
     }
 }
 __global__ void k_reset_k(StepState* st) { st->k = 0; }
@@ -675,80 +735,155 @@ struct Gathered {
     float C[9];
     float G[9];  // grad v
 };
-// Shared gather of g2p_v / g2p_e (mpm_utils.py:726-763, 798-836) by sum factorisation: the 27-node
-// sums v = sum w v_n, C = 4/dx sum w v_n (x) (ijk - f), grad v = sum v_n (x) grad w are separable, so
-// contract over k, then j, then i (441 FMA) instead of 27 x 33 flops.  Per axis a:
-//   w_a[i]  weight,  c_a[i] = w_a[i] (i - f_a) 4/dx  (APIC),  d_a[i] = dw_a[i] / dx  (gradient)
-__device__ __forceinline__ void g2p_gather(const Grid& g, float x, float y, float z, Gathered& o) {
-    const float gp[3] = {x * g.inv_dx, y * g.inv_dx, z * g.inv_dx};
-    int b[3];
-    float w[3][3], cw[3][3], dw[3][3];
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-        b[a] = (int)(gp[a] - 0.5f);
-        const float f = gp[a] - (float)b[a];
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            float ww, dd;
-            bspline(f, i, ww, dd);
-            w[a][i] = ww;
-            cw[a][i] = ww * ((float)i - f) * (g.inv_dx * 4.0f);
-            dw[a][i] = dd * g.inv_dx;
-        }
-    }
-    int sl[8];
-    load_slots8(g, b[0], b[1], b[2], sl);
-#pragma unroll
-    for (int i = 0; i < 3; i++) o.v[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 9; i++) { o.C[i] = 0.f; o.G[i] = 0.f; }
-    const int X0 = b[0] >> 2, Y0 = b[1] >> 2, Z0 = b[2] >> 2;
+// Contraction of one 27-node tile (g2p_v / g2p_e, mpm_utils.py:726-763, 798-836) by sum factorisation:
+// v = sum w v_n, C = 4/dx sum w v_n (x) (ijk - f), grad v = sum v_n (x) grad w are separable, so contract
+// over k, then j, then i.  Per axis a:  W weight,  CW = W (i - f_a) 4/dx (APIC),  DW = dw / dx (gradient).
+// Written on packed fp32 pairs (FFMA2): the x,y components of a node velocity ride in one pair with the
+// weight broadcast, the z components of two different sums share a pair with a PAIR of weights.
+// Outputs that the caller does not use are removed by the compiler.
+__device__ __forceinline__ void g2p_contract(const float4* __restrict__ T, const float (&W)[3][3], const float (&CW)[3][3],
+                                             const float (&DW)[3][3], Gathered& o) {
+    const float2 z2 = make_float2(0.f, 0.f);
+    float2 v_xy = z2, C0_xy = z2, C1_xy = z2, C2_xy = z2, G0_xy = z2, G1_xy = z2, G2_xy = z2;
+    float2 vz_c1z = z2, c2z_g2z = z2, c0z_g0z = z2;
+    float g1z = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        float A0[3] = {0, 0, 0}, A1[3] = {0, 0, 0}, A2[3] = {0, 0, 0}, B0[3] = {0, 0, 0}, C0[3] = {0, 0, 0};
-        const int ix = b[0] + i, ox = (ix >> 2) - X0;
+        float2 A0_xy = z2, A1_xy = z2, A2_xy = z2, B0_xy = z2, C0q_xy = z2, A0z_A1z = z2, B0z_C0z = z2;
+        float A2z = 0.f;
+        // one i-plane (9 nodes, 36 registers) is fetched at a time; the compiler barrier keeps ptxas from
+        // hoisting all 27 LDS.128 (108 registers) to the top and spilling
+        float4 pl[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) pl[q] = T[i * 9 + q];
+        asm volatile("" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            const int iy = b[1] + j, oy = (iy >> 2) - Y0;
-            const int xy = (ox << 2) | (oy << 1);
-            // the z-run of three nodes spans at most two blocks
-            const int sA = (xy == 0) ? sl[0] : (xy == 2) ? sl[2] : (xy == 4) ? sl[4] : sl[6];
-            const int sB = (xy == 0) ? sl[1] : (xy == 2) ? sl[3] : (xy == 4) ? sl[5] : sl[7];
-            const int off = ((ix & 3) << 4) + ((iy & 3) << 2);
-            float a[3] = {0, 0, 0}, bb[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+            float2 a_xy = z2, b_xy = z2, c_xy = z2, bz_cz = z2;
+            float az = 0.f;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                const int iz = b[2] + k;
-                const int sk = ((iz >> 2) == Z0) ? sA : sB;
-                float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (sk >= 0) gv = g.vout[sk * BN + off + (iz & 3)];
-                else if (b[0] >= 0 && b[1] >= 0 && b[2] >= 0 && ix < g.n && iy < g.n && iz < g.n) g.flags[1] = 1;
-                a[0] += w[2][k] * gv.x; a[1] += w[2][k] * gv.y; a[2] += w[2][k] * gv.z;
-                bb[0] += cw[2][k] * gv.x; bb[1] += cw[2][k] * gv.y; bb[2] += cw[2][k] * gv.z;
-                c[0] += dw[2][k] * gv.x; c[1] += dw[2][k] * gv.y; c[2] += dw[2][k] * gv.z;
+                const float4 gv = pl[j * 3 + k];
+                const float2 gxy = make_float2(gv.x, gv.y);
+                a_xy = fma2(W[2][k], gxy, a_xy);
+                b_xy = fma2(CW[2][k], gxy, b_xy);
+                c_xy = fma2(DW[2][k], gxy, c_xy);
+                az = fmaf(W[2][k], gv.z, az);
+                bz_cz = fma2(make_float2(CW[2][k], DW[2][k]), gv.z, bz_cz);
             }
+            A0_xy = fma2(W[1][j], a_xy, A0_xy);
+            A1_xy = fma2(CW[1][j], a_xy, A1_xy);
+            A2_xy = fma2(DW[1][j], a_xy, A2_xy);
+            B0_xy = fma2(W[1][j], b_xy, B0_xy);
+            C0q_xy = fma2(W[1][j], c_xy, C0q_xy);
+            A0z_A1z = fma2(make_float2(W[1][j], CW[1][j]), az, A0z_A1z);
+            A2z = fmaf(DW[1][j], az, A2z);
+            B0z_C0z = fma2(W[1][j], bz_cz, B0z_C0z);
+        }
+        v_xy = fma2(W[0][i], A0_xy, v_xy);
+        C0_xy = fma2(CW[0][i], A0_xy, C0_xy);
+        C1_xy = fma2(W[0][i], A1_xy, C1_xy);
+        C2_xy = fma2(W[0][i], B0_xy, C2_xy);
+        G0_xy = fma2(DW[0][i], A0_xy, G0_xy);
+        G1_xy = fma2(W[0][i], A2_xy, G1_xy);
+        G2_xy = fma2(W[0][i], C0q_xy, G2_xy);
+        vz_c1z = fma2(W[0][i], A0z_A1z, vz_c1z);
+        c2z_g2z = fma2(W[0][i], B0z_C0z, c2z_g2z);
+        c0z_g0z = fma2(make_float2(CW[0][i], DW[0][i]), A0z_A1z.x, c0z_g0z);
+        g1z = fmaf(W[0][i], A2z, g1z);
+    }
+    o.v[0] = v_xy.x; o.v[1] = v_xy.y; o.v[2] = vz_c1z.x;
+    o.C[0] = C0_xy.x; o.C[3] = C0_xy.y; o.C[6] = c0z_g0z.x;
+    o.C[1] = C1_xy.x; o.C[4] = C1_xy.y; o.C[7] = vz_c1z.y;
+    o.C[2] = C2_xy.x; o.C[5] = C2_xy.y; o.C[8] = c2z_g2z.x;
+    o.G[0] = G0_xy.x; o.G[3] = G0_xy.y; o.G[6] = c0z_g0z.y;
+    o.G[1] = G1_xy.x; o.G[4] = G1_xy.y; o.G[7] = g1z;
+    o.G[2] = G2_xy.x; o.G[5] = G2_xy.y; o.G[8] = c2z_g2z.y;
+}
+
+// Warp-collective gather.  The particles of a warp form a few same-cell runs; for each run lanes 0..26
+// fetch the run's 27 node velocities ONCE (one table lookup + one LDG.128 per lane, up to G2P_RMAX runs
+// in flight) into a shared-memory tile, then lane = particle contracts its run's tile with broadcast
+// reads.  Replaces 8 table lookups + 27 dependent gathers per particle.
+constexpr int G2P_RMAX = 8;   // runs per contraction pass (tile capacity)
+constexpr int G2P_RLOAD = 4;  // runs whose node loads are in flight together
+constexpr int G2P_TILE_B = 128 + G2P_RMAX * 27 * 16;  // run cells | tiles
+struct Gather {
+    const Grid& g;
+    const Warp& w;
+    int* runcell;
+    float4* tile;
+    Runs R;
+    bool valid;
+    float f[3];
+    int b[3];
+    __device__ __forceinline__ Gather(const Grid& g_, const Warp& w_, unsigned char* tile_mem, bool valid_, float x, float y, float z)
+        : g(g_), w(w_), runcell(reinterpret_cast<int*>(tile_mem)), tile(reinterpret_cast<float4*>(tile_mem + 128)), valid(valid_) {
+        const float gp[3] = {x * g.inv_dx, y * g.inv_dx, z * g.inv_dx};
 #pragma unroll
-            for (int r = 0; r < 3; r++) {
-                A0[r] += w[1][j] * a[r];
-                A1[r] += cw[1][j] * a[r];
-                A2[r] += dw[1][j] * a[r];
-                B0[r] += w[1][j] * bb[r];
-                C0[r] += w[1][j] * c[r];
+        for (int a = 0; a < 3; a++) {
+            b[a] = (int)(gp[a] - 0.5f);
+            f[a] = gp[a] - (float)b[a];
+        }
+        const int cell = valid ? pack_cell(b[0], b[1], b[2]) : -1 - w.lane;
+        R = find_runs(w.lane, w.cnt, cell);
+        if ((R.starts >> w.lane) & 1u) runcell[R.mine] = cell;
+        __syncwarp();
+    }
+    // lanes 0..26 load the nodes of runs [r0, r0 + G2P_RMAX) into the tile
+    __device__ __forceinline__ void stage(int r0) const {
+        const int nrp = min(G2P_RMAX, R.nr - r0);
+        if (w.lane < 27) {
+            const int li = w.lane / 9, lj = (w.lane / 3) % 3, lk = w.lane % 3;
+            for (int rb = 0; rb < nrp; rb += G2P_RLOAD) {
+                float4 val[G2P_RLOAD];
+#pragma unroll
+                for (int r = 0; r < G2P_RLOAD; r++) {
+                    val[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rb + r < nrp) {
+                        const int c = runcell[r0 + rb + r];
+                        const int ni = node_index(g, (c & 1023) - 2 + li, ((c >> 10) & 1023) - 2 + lj, ((c >> 20) & 1023) - 2 + lk);
+                        if (ni >= 0) val[r] = g.vout[ni];
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < G2P_RLOAD; r++)
+                    if (rb + r < nrp) tile[(rb + r) * 27 + w.lane] = val[r];
             }
         }
+        __syncwarp();
+    }
+    // lane = particle: contract the tile of my run if it is staged
+    __device__ __forceinline__ void contract(int r0, Gathered& o) const {
+        if (valid && R.mine >= r0 && R.mine < r0 + G2P_RMAX) {
+            float W[3][3], CW[3][3], DW[3][3];
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-            o.v[r] += w[0][i] * A0[r];
-            o.C[3 * r + 0] += cw[0][i] * A0[r];
-            o.C[3 * r + 1] += w[0][i] * A1[r];
-            o.C[3 * r + 2] += w[0][i] * B0[r];
-            o.G[3 * r + 0] += dw[0][i] * A0[r];
-            o.G[3 * r + 1] += w[0][i] * A2[r];
-            o.G[3 * r + 2] += w[0][i] * C0[r];
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    float ww, dd;
+                    bspline(f[a], i, ww, dd);
+                    W[a][i] = ww;
+                    CW[a][i] = ww * ((float)i - f[a]) * (g.inv_dx * 4.0f);
+                    DW[a][i] = dd * g.inv_dx;
+                }
+            g2p_contract(tile + (R.mine - r0) * 27, W, CW, DW, o);
         }
     }
-}
+    // stage + contract every run of the warp (one pass unless the warp spans more than G2P_RMAX cells)
+    __device__ __forceinline__ void run(Gathered& o) const {
+        for (int r0 = 0; r0 < R.nr; r0 += G2P_RMAX) {
+            if (r0) __syncwarp();
+            stage(r0);
+            contract(r0, o);
+        }
+    }
+};
 __device__ __forceinline__ float clampf(float x, float a, float b) { return fminf(fmaxf(x, a), b); }
+// the blocks under the particle's new stencil exist already unless its base cell changed
+__device__ __forceinline__ void ensure_if_moved(const Grid& g, const int (&b)[3], float x, float y, float z) {
+    if (base_of(x, g.inv_dx) != b[0] || base_of(y, g.inv_dx) != b[1] || base_of(z, g.inv_dx) != b[2]) ensure_stencil_blocks(g, x, y, z);
+}
 
 // end of substep: self.time += dt (mpm_solver.py:536), substep counter, moving cuboids (:975-981);
 // run by one thread of the LAST kernel of the substep
@@ -767,22 +902,34 @@ struct Advance {
 };
 
 constexpr int G2P_NW = 4;
+constexpr int G2P_MINB = 5;  // resident CTAs per SM the register allocation must allow (<= 96 registers)
 // g2p_v for cloth vertices (mpm_utils.py:716-786); also clears vertex_force for the next substep
 // (replaces set_vec3_to_zero, mpm_solver.py:251-256) and allocates grid blocks for the new position.
-constexpr int G2P_V_WB = VP_F * 32 * 4;
-__global__ void __launch_bounds__(32 * G2P_NW, 4) k_g2p_vertices(Grid g, int Nv, float* __restrict__ VP, float4* __restrict__ VF,
-                                                                  float dt, float* __restrict__ dbg_f, Advance adv) {
+constexpr int G2P_V_WB = VP_F * 32 * 4 + G2P_TILE_B;
+__global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_vertices(Grid g, int Nv, float* __restrict__ VP, float4* __restrict__ VF,
+                                                               float dt, float* __restrict__ dbg_f, Advance adv) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
     Warp w;
     if (!warp_begin<G2P_NW, G2P_V_WB>(w, Nv, smem)) return;
+    PHASE_BEGIN();
     float* sP = reinterpret_cast<float*>(w.buf);
-    slab_load2(w, sP, VP, VP_F, nullptr, nullptr, 0);
-    if (w.lane < w.cnt) {
-        float4* r4 = reinterpret_cast<float4*>(sP + w.lane * VP_F);
-        float4 xm = r4[0];
-        Gathered o;
-        g2p_gather(g, xm.x, xm.y, xm.z, o);
+    slab_load(w, {Slab{sP, VP, VP_F}});
+    PHASE(g, 3, 0);
+    const bool valid = w.lane < w.cnt;
+    float4* r4 = reinterpret_cast<float4*>(sP + w.lane * VP_F);
+    float4 xm = valid ? r4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+    Gathered o;
+    const Gather G(g, w, w.buf + VP_F * 32 * 4, valid, xm.x, xm.y, xm.z);
+    PHASE(g, 3, 1);
+    for (int r0 = 0; r0 < G.R.nr; r0 += G2P_RMAX) {  // one pass unless the warp spans more than G2P_RMAX cells
+        if (r0) __syncwarp();
+        G.stage(r0);
+        PHASE(g, 3, 2);
+        G.contract(r0, o);
+        PHASE(g, 3, 3);
+    }
+    if (valid) {
         const float dxc = 1.0f / g.inv_dx, a_min = dxc * 2.0f, a_max = g.lim - dxc * 2.0f;
         xm.x = clampf(xm.x + dt * o.v[0], a_min, a_max);
         xm.y = clampf(xm.y + dt * o.v[1], a_min, a_max);
@@ -794,28 +941,33 @@ __global__ void __launch_bounds__(32 * G2P_NW, 4) k_g2p_vertices(Grid g, int Nv,
         const int p = w.p0 + w.lane;
         if (dbg_f) { float4 f = VF[p]; dbg_f[3 * p] = f.x; dbg_f[3 * p + 1] = f.y; dbg_f[3 * p + 2] = f.z; }
         VF[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ensure_stencil_blocks(g, xm.x, xm.y, xm.z);
+        ensure_if_moved(g, G.b, xm.x, xm.y, xm.z);
     }
-    slab_store2(w, sP, VP, VP_F, nullptr, nullptr, 0);
+    PHASE(g, 3, 4);
+    slab_store(w, {Slab{sP, VP, VP_F}});
+    PHASE(g, 3, 5);
+    PHASE_END(g, 3);
 }
 
 // g2p_v for traditional particles: additionally F_trial = (I + dt grad v) F (mpm_utils.py:783-786)
-constexpr int G2P_T_WB = (KP_F + TF_F) * 32 * 4;
-__global__ void __launch_bounds__(32 * G2P_NW, 4) k_g2p_traditional(Grid g, int Nt, float* __restrict__ TP, float* __restrict__ TF,
-                                                                     float dt, Advance adv) {
+constexpr int G2P_T_WB = (KP_F + TF_F) * 32 * 4 + G2P_TILE_B;
+__global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_traditional(Grid g, int Nt, float* __restrict__ TP, float* __restrict__ TF,
+                                                                  float dt, Advance adv) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
     Warp w;
     if (!warp_begin<G2P_NW, G2P_T_WB>(w, Nt, smem)) return;
     float* sP = reinterpret_cast<float*>(w.buf);
     float* sT = sP + 32 * KP_F;
-    slab_load2(w, sP, TP, KP_F, sT, TF, TF_F);
-    if (w.lane < w.cnt) {
-        float* r = sP + w.lane * KP_F;
+    slab_load(w, {Slab{sP, TP, KP_F}, Slab{sT, TF, TF_F}});
+    const bool valid = w.lane < w.cnt;
+    float* r = sP + w.lane * KP_F;
+    float x = valid ? r[0] : 0.f, y = valid ? r[1] : 0.f, z = valid ? r[2] : 0.f;
+    Gathered o;
+    const Gather G(g, w, w.buf + (KP_F + TF_F) * 32 * 4, valid, x, y, z);
+    G.run(o);
+    if (valid) {
         float* t = sT + w.lane * TF_F;
-        float x = r[0], y = r[1], z = r[2];
-        Gathered o;
-        g2p_gather(g, x, y, z, o);
         const float dxc = 1.0f / g.inv_dx, a_min = dxc * 2.0f, a_max = g.lim - dxc * 2.0f;
         x = clampf(x + dt * o.v[0], a_min, a_max);
         y = clampf(y + dt * o.v[1], a_min, a_max);
@@ -831,42 +983,71 @@ __global__ void __launch_bounds__(32 * G2P_NW, 4) k_g2p_traditional(Grid g, int 
         mat_mul(M, F, Ft);
 #pragma unroll
         for (int i = 0; i < 9; i++) t[T_FT + i] = Ft[i];
-        ensure_stencil_blocks(g, x, y, z);
+        ensure_if_moved(g, G.b, x, y, z);
     }
-    slab_store2(w, sP, TP, KP_F, sT, TF, TF_F);
+    slab_store(w, {Slab{sP, TP, KP_F}, Slab{sT, TF, TF_F}});
 }
 
 // g2p_e (mpm_utils.py:788-857): C and grad v at the OLD centroid, x/v = mean of the three
-// already-updated corner vertices, d = [x2-x1, x3-x1, (I + dt grad v) d3]
-constexpr int G2P_E_WB = (KP_F + ED_F) * 32 * 4;
-__global__ void __launch_bounds__(32 * G2P_NW, 4) k_g2p_elements(Grid g, int Ne, float* __restrict__ EP, float* __restrict__ ED,
-                                                                  const float* __restrict__ VP, float dt, Advance adv) {
+// already-updated corner vertices, d = [x2-x1, x3-x1, (I + dt grad v) d3].  Reads the return-mapped d3
+// of direction buffer `cur`, writes d1,d2,d3 of buffer `cur^1` (see mpm_device.cuh).
+constexpr int G2P_E_WB = (KP_F + EF_F + E12_F) * 32 * 4 + G2P_TILE_B;
+__global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_elements(Grid g, int Ne, float* __restrict__ EP, const int* __restrict__ EF,
+                                                               const float4* __restrict__ D3in, float* __restrict__ E12out,
+                                                               float4* __restrict__ D3out, const float* __restrict__ VP, float dt,
+                                                               Advance adv) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
     Warp w;
     if (!warp_begin<G2P_NW, G2P_E_WB>(w, Ne, smem)) return;
     float* sP = reinterpret_cast<float*>(w.buf);
-    float* sD = sP + 32 * KP_F;
-    slab_load2(w, sP, EP, KP_F, sD, ED, ED_F);
-    if (w.lane < w.cnt) {
-        float* r = sP + w.lane * KP_F;
-        float4* d4 = reinterpret_cast<float4*>(sD + w.lane * ED_F);
-        const float4 q1v = d4[1], q2v = d4[2];
-        const float d3[3] = {q1v.z, q1v.w, q2v.x};
-        const int f0 = __float_as_int(q2v.y), f1 = __float_as_int(q2v.z), f2 = __float_as_int(q2v.w);
-        // corner gathers first (one 32-byte sector per corner: {x,y,z,m | vx,vy,vz,C0}); they do not
-        // depend on the grid gather
+    int* sF = reinterpret_cast<int*>(sP + 32 * KP_F);
+    float* s12 = reinterpret_cast<float*>(sF + 32 * EF_F);
+    PHASE_BEGIN();
+    slab_load(w, {Slab{sP, EP, KP_F}, Slab{sF, EF, EF_F}});
+    PHASE(g, 5, 0);
+    const bool valid = w.lane < w.cnt;
+    float* r = sP + w.lane * KP_F;
+    const int p = w.p0 + w.lane;
+    // corner gathers first (one 32-byte sector per corner: {x,y,z,m | vx,vy,vz,C0}) and d3; none of
+    // them depends on the grid gather, and their results are parked in the shared-memory records before
+    // the register-hungry contraction starts
+    float4 x1, v1, x2, v2, x3, v3, d3v;
+    x1 = v1 = x2 = v2 = x3 = v3 = d3v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (valid) {
+        const int f0 = sF[w.lane * EF_F], f1 = sF[w.lane * EF_F + 1], f2 = sF[w.lane * EF_F + 2];
         const float4* c0 = reinterpret_cast<const float4*>(VP + (size_t)f0 * VP_F);
         const float4* c1 = reinterpret_cast<const float4*>(VP + (size_t)f1 * VP_F);
         const float4* c2 = reinterpret_cast<const float4*>(VP + (size_t)f2 * VP_F);
-        const float4 x1 = c0[0], v1 = c0[1], x2 = c1[0], v2 = c1[1], x3 = c2[0], v3 = c2[1];
-        Gathered o;
-        g2p_gather(g, r[0], r[1], r[2], o);
-        const float nx = (x1.x + x2.x + x3.x) / 3.0f, ny = (x1.y + x2.y + x3.y) / 3.0f, nz = (x1.z + x2.z + x3.z) / 3.0f;
-        r[0] = nx; r[1] = ny; r[2] = nz;
-        r[P_V] = (v1.x + v2.x + v3.x) / 3.0f;
-        r[P_V + 1] = (v1.y + v2.y + v3.y) / 3.0f;
-        r[P_V + 2] = (v1.z + v2.z + v3.z) / 3.0f;
+        x1 = c0[0]; v1 = c0[1]; x2 = c1[0]; v2 = c1[1]; x3 = c2[0]; v3 = c2[1];
+        d3v = D3in[p];
+        ox = r[0]; oy = r[1]; oz = r[2];
+    }
+    const Gather G(g, w, w.buf + (KP_F + EF_F + E12_F) * 32 * 4, valid, ox, oy, oz);
+    PHASE(g, 5, 1);
+    Gathered o;
+    for (int r0 = 0; r0 < G.R.nr; r0 += G2P_RMAX) {  // one pass unless the warp spans more than G2P_RMAX cells
+        if (r0) __syncwarp();
+        G.stage(r0);
+        PHASE(g, 5, 2);
+        if (r0 == 0 && valid) {
+            const float nx = (x1.x + x2.x + x3.x) / 3.0f, ny = (x1.y + x2.y + x3.y) / 3.0f, nz = (x1.z + x2.z + x3.z) / 3.0f;
+            r[0] = nx; r[1] = ny; r[2] = nz;
+            r[P_V] = (v1.x + v2.x + v3.x) / 3.0f;
+            r[P_V + 1] = (v1.y + v2.y + v3.y) / 3.0f;
+            r[P_V + 2] = (v1.z + v2.z + v3.z) / 3.0f;
+            float2* e2 = reinterpret_cast<float2*>(s12 + w.lane * E12_F);
+            e2[0] = make_float2(x2.x - x1.x, x2.y - x1.y);
+            e2[1] = make_float2(x2.z - x1.z, x3.x - x1.x);
+            e2[2] = make_float2(x3.y - x1.y, x3.z - x1.z);
+            ensure_if_moved(g, G.b, nx, ny, nz);
+        }
+        PHASE(g, 5, 3);  // corner consume
+        G.contract(r0, o);
+    }
+    PHASE(g, 5, 4);  // contraction
+    if (valid) {
 #pragma unroll
         for (int i = 0; i < 9; i++) r[P_C + i] = o.C[i];
         float nd3[3];
@@ -875,14 +1056,13 @@ __global__ void __launch_bounds__(32 * G2P_NW, 4) k_g2p_elements(Grid g, int Ne,
             float m0 = o.G[3 * rr] * dt + (rr == 0 ? 1.0f : 0.0f);
             float m1 = o.G[3 * rr + 1] * dt + (rr == 1 ? 1.0f : 0.0f);
             float m2 = o.G[3 * rr + 2] * dt + (rr == 2 ? 1.0f : 0.0f);
-            nd3[rr] = m0 * d3[0] + m1 * d3[1] + m2 * d3[2];
+            nd3[rr] = m0 * d3v.x + m1 * d3v.y + m2 * d3v.z;
         }
-        d4[0] = make_float4(x2.x - x1.x, x2.y - x1.y, x2.z - x1.z, x3.x - x1.x);
-        d4[1] = make_float4(x3.y - x1.y, x3.z - x1.z, nd3[0], nd3[1]);
-        d4[2] = make_float4(nd3[2], q2v.y, q2v.z, q2v.w);
-        ensure_stencil_blocks(g, nx, ny, nz);
+        D3out[p] = make_float4(nd3[0], nd3[1], nd3[2], 0.f);
     }
-    slab_store2(w, sP, EP, KP_F, sD, ED, ED_F);
+    slab_store(w, {Slab{sP, EP, KP_F}, Slab{s12, E12out, E12_F}});
+    PHASE(g, 5, 5);  // epilogue + store
+    PHASE_END(g, 5);
 }
 
 }  // namespace mpm
