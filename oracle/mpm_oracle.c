@@ -6,14 +6,21 @@
  * bench.py's cpu_baseline / --impl reference legs can check and time the
  * reference algorithm on the host.
  *
- * PARITY UNPINNED: the reference (KAISTChangmin/MPMAvatar) ships no tests,
- * golden vectors or fixtures for this path and its
- * runtime, warp_lang==0.10.1 (requirements.txt:36), is a third-party
- * dependency that is neither vendored under /root/reference nor installable
- * offline, so the reference itself cannot be executed here.  This file is a
- * line-by-line restatement of the reference's Python/Warp kernels (each
- * function cites the file:line it follows) and is pinned only by the
- * analytic known-answer tests in tests/test_oracle_kat.py.
+ * PINNING: the reference (KAISTChangmin/MPMAvatar) ships no tests, golden
+ * vectors or fixtures for this path and its runtime,
+ * warp_lang==0.10.1 (requirements.txt:36), is a third-party dependency that
+ * is neither vendored under /root/reference nor installable offline.  This
+ * file is a line-by-line restatement of the reference's Python/Warp kernels
+ * (each function cites the file:line it follows) and is pinned by
+ *   (a) the analytic known-answer tests in tests/test_oracle_kat.py, and
+ *   (b) golden vectors produced by executing the reference's OWN source
+ *       (warp_mpm/mpm_solver.py, mpm_utils.py, mpm_data_structure.py,
+ *       unmodified) under oracle/warp_emu.py, a sequential Python stand-in
+ *       for the Warp API: tests/golden/make_golden.py -> tests/golden/*.npz,
+ *       checked by tests/test_golden.py (fp64 build: 1e-9 relative on every
+ *       state and grid field, all materials, collider, mover, plane).
+ * What remains an assumption is the convention of the two third-party
+ * numerical routines below (their source is not readable offline).
  *
  * Third-party pieces restated from their published behaviour (warp-lang 0.10.x):
  *   wp.qr3   -> Givens (rotation) QR, det Q = +1; only its sign-normalised

@@ -2,8 +2,11 @@
 
 TEST INFRASTRUCTURE ONLY -- see the header of mpm_oracle.c.  Only tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
-import this module.  PARITY UNPINNED (the reference has no tests or golden
-vectors and warp-lang is not installable offline); pinned by analytic KATs.
+import this module.  The reference has no tests or golden vectors and warp-lang is
+not installable offline; the oracle is pinned (a) by analytic KATs
+(tests/test_oracle_kat.py) and (b) against the reference's OWN kernel source executed
+under oracle/warp_emu.py (tests/golden/*.npz, tests/test_golden.py: 1e-9 in fp64).
+What stays assumed: the conventions of wp.qr3 / wp.svd3 (see warp_emu.py).
 
 The Python surface mirrors the reference's call order (mpm_solver.py:229-536):
 build an OracleSim from the canonical particle arrays, then call p2g2p().

@@ -1,0 +1,168 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by executing the REFERENCE's own solver source -- unmodified, imported from
+/root/reference/warp_mpm -- under oracle/warp_emu.py (a sequential pure-Python stand-in for the Warp API;
+warp-lang 0.10.1 is not installable offline).  Only runs in the build container (the GPU box has no
+/root/reference); the .npz files it writes are committed and are what tests/ compare against.
+
+    python tests/golden/make_golden.py            # regenerate every fixture (about a minute)
+
+Each fixture stores the canonical inputs (so the tests do not depend on synthetic.py staying unchanged), the
+per-substep solver inputs, and the reference's state after N substeps in fp64 emulation ("ref64_*": pins the
+algorithm) and in fp32 emulation ("ref32_*": Warp's storage / arithmetic width, sequential atomics).
+The call sequence is the caller's: train_material_params.py:403-506 (setup) and :589-626 (rollout).
+Assumptions about wp.qr3 / wp.svd3 are stated in oracle/warp_emu.py.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference/warp_mpm"
+
+from oracle import warp_emu  # noqa: E402
+from mpmavatar_b200 import synthetic as S  # noqa: E402
+
+
+def import_reference():
+    wp = warp_emu.install()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import mpm_data_structure as ds  # the reference's files
+    import mpm_solver as sv
+    return wp, ds, sv
+
+
+def tiny_scenes():
+    out = {}
+    for mat, n in (("jelly", 120), ("metal", 60), ("sand", 60), ("foam", 60), ("plasticine", 60), ("snow", 40)):
+        sc = S.scene_c1(n=n, n_grid=12, seed=21, material=mat)
+        out[f"trad_{mat}"] = (sc, 2, None)
+    sc = S._cloth_scene("golden_cloth_body", 5, 14, 8, 20, with_body=True)
+    sc.body_verts, sc.body_faces = S.capsule_mesh(segs=14, rings_cyl=6, rings_cap=3, radius=0.22, cyl_len=0.7,
+                                                  center=(1.0, 1.0, 1.0))
+    # pre-stretch + a velocity field so that stress, vertex forces and the collider all act
+    Ne = sc.n_elements
+    rng = np.random.default_rng(3)
+    verts = sc.x[Ne:] * np.array([1.0, 1.04, 1.0], np.float32) + np.array([0, -0.04, 0], np.float32)
+    sc.x = sc.x.copy()
+    sc.x[Ne:] = verts
+    sc.x[:Ne] = verts[sc.faces].mean(1)
+    sc.v = (0.3 * rng.normal(size=sc.x.shape)).astype(np.float32)
+    d1 = verts[sc.faces[:, 1]] - verts[sc.faces[:, 0]]
+    d2 = verts[sc.faces[:, 2]] - verts[sc.faces[:, 0]]
+    d3 = np.cross(d1, d2)
+    d3 /= np.linalg.norm(d3, axis=1, keepdims=True)
+    d3 = d3 * (1.0 + 0.05 * rng.normal(size=(Ne, 1))) + 0.05 * rng.normal(size=(Ne, 3))  # both return-map branches
+    sc.d = np.stack([d1, d2, d3], -1).astype(np.float32)
+    out["cloth_body_joints"] = (sc, 3, None)
+    sd = S.scene_demo_like(Nu=10, Nr=6, n_sand=80, n_grid=20, seed=7)
+    sd.body_verts, sd.body_faces = S.capsule_mesh(segs=10, rings_cyl=4, rings_cap=2, radius=0.22, cyl_len=0.7,
+                                                  center=(1.0, 1.0, 1.0))
+    sd.v = (0.2 * np.random.default_rng(4).normal(size=sd.x.shape)).astype(np.float32)
+    out["demo_sand_plane_pinned"] = (sd, 2, np.zeros((sd.num_joint_t, 3), np.float32))
+    return out
+
+
+def run_reference(sc, nsub, joint_t, precision):
+    """setup_simulation + rollout exactly as the reference's caller does, on the emulated Warp."""
+    warp_emu.set_precision(precision)
+    wp, ds, sv = import_reference()
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32)
+    N, Ne, Nv, Nt = sc.n_particles, sc.n_elements, sc.n_vertices, sc.n_traditional
+    dev = "cpu"
+    with contextlib.redirect_stdout(io.StringIO()):
+        state = ds.MPMStateStruct()
+        state.init(N, Ne, Nv, device=dev, requires_grad=True)
+        trad = np.zeros(N, np.int32); trad[Ne:Ne + Nt] = 1
+        vert = np.zeros(N, np.int32); vert[Ne + Nt:] = 1
+        elem = np.zeros(N, np.int32); elem[:Ne] = 1
+        d = T(sc.d) if Ne else torch.zeros(0, 3, 3)
+        R_inv = T(sc.R_inv) if Ne else torch.zeros(0, 3)
+        faces = T(sc.faces.astype(np.float32)) if Ne else torch.zeros(0, 3)
+        D_inv = torch.linalg.inv(d) if Ne else d
+        state.from_torch(T(sc.x), T(sc.vol), D_inv, R_inv, faces, trad, vert, elem, torch.zeros(N - Nv, 6),
+                         device=dev, requires_grad=True, n_grid=sc.n_grid, grid_lim=sc.grid_lim)
+        model = ds.MPMModelStruct()
+        model.init(N, device=dev, requires_grad=True)
+        model.init_other_params(n_grid=sc.n_grid, grid_lim=sc.grid_lim, device=dev)
+        solver = sv.MPMWARP(N, Ne, Nv, n_grid=sc.n_grid, grid_lim=sc.grid_lim, mesh_vertices=sc.body_verts,
+                            mesh_faces=sc.body_faces, num_joint_t=sc.num_joint_t, num_joint_v=sc.num_joint_v,
+                            num_joint_f=sc.num_joint_f, device=dev)
+        solver.set_parameters_dict(model, state, {"material": sc.material, "g": list(sc.g), "density": 1.0,
+                                                  "grid_v_damping_scale": sc.grid_v_damping_scale,
+                                                  "friction_angle": sc.friction_angle,
+                                                  "rpic_damping": sc.rpic_damping}, device=dev)
+        for b in sc.surface_colliders:
+            solver.add_surface_collider(**b)
+        if sc.body_verts is not None:
+            solver.add_mesh_collider(solver.mesh.id, n_grid=sc.n_grid, friction=sc.mesh_friction)
+        if sc.num_joint_v or sc.num_joint_f:
+            solver.add_particle_mover(n_grid=sc.n_grid)
+        # rollout reset: train_material_params.py:584-610
+        state.reset_state(Nv, T(sc.x).clone(), d, None, T(sc.v).clone(), tensor_R_inv=R_inv, device=dev,
+                          requires_grad=True)
+        if sc.F_trial is not None:
+            state.particle_F_trial = wp.from_numpy(sc.F_trial, dtype=wp.mat33)
+        state.reset_density(T(sc.density), None, dev, update_mass=True)
+        solver.set_E_nu_from_torch(model, T(sc.E), T(sc.nu), T(sc.gamma), T(sc.kappa), dev)
+        if sc.yield_stress is not None:
+            model.yield_stress = wp.from_numpy(sc.yield_stress, dtype=float)
+        solver.prepare_mu_lam(model, state, dev)
+        fi = sc.frame_inputs(0)
+        t = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32)
+        for k in range(nsub):
+            mx = None if fi["mesh_x"] is None else fi["mesh_x"] + np.float32(sc.dt * k) * fi["mesh_v"]
+            solver.p2g2p(model, state, sc.dt, mesh_x=t(mx), mesh_v=t(fi["mesh_v"]), joint_traditional_v=t(joint_t),
+                         joint_verts_v=t(fi["joint_verts_v"]), joint_faces_v=t(fi["joint_faces_v"]), device=dev)
+    g = lambda a: np.array(a.numpy(), dtype=np.float64)
+    out = dict(x=g(state.particle_x), v=g(state.particle_v), C=g(state.particle_C), F=g(state.particle_F),
+               F_trial=g(state.particle_F_trial), stress=g(state.particle_stress), d=g(state.particle_d),
+               vertex_force=g(state.vertex_force), grid_m=g(state.grid_m), grid_v_in=g(state.grid_v_in),
+               grid_v_out=g(state.grid_v_out), time=np.float64(solver.time))
+    return out
+
+
+SCENE_FIELDS = ("x", "v", "vol", "density", "E", "nu", "gamma", "kappa", "faces", "d", "R_inv", "F_trial",
+                "yield_stress", "body_verts", "body_faces")
+SCENE_SCALARS = ("name", "n_grid", "grid_lim", "dt", "material", "n_elements", "n_traditional", "n_vertices",
+                 "friction_angle", "grid_v_damping_scale", "rpic_damping", "substeps_per_frame", "mesh_friction",
+                 "num_joint_v", "num_joint_f", "num_joint_t")
+
+
+def main():
+    for name, (sc, nsub, joint_t) in tiny_scenes().items():
+        rec = {"nsub": np.int64(nsub), "g": np.asarray(sc.g, np.float64)}
+        for f in SCENE_FIELDS:
+            v = getattr(sc, f)
+            if v is not None:
+                rec["in_" + f] = np.asarray(v)
+        for f in SCENE_SCALARS:
+            rec["sc_" + f] = np.asarray(getattr(sc, f))
+        fi = sc.frame_inputs(0)
+        for k, v in fi.items():
+            if v is not None:
+                rec["fi_" + k] = v
+        if joint_t is not None:
+            rec["fi_joint_traditional_v"] = joint_t
+        if sc.surface_colliders:
+            rec["plane_point"] = np.asarray(sc.surface_colliders[0]["point"], np.float64)
+            rec["plane_normal"] = np.asarray(sc.surface_colliders[0]["normal"], np.float64)
+        for prec, tag in (("f64", "ref64_"), ("f32", "ref32_")):
+            r = run_reference(sc, nsub, joint_t, prec)
+            for k, v in r.items():
+                if k.startswith("grid_") and tag == "ref32_":
+                    continue
+                rec[tag + k] = v.astype(np.float64 if tag == "ref64_" else np.float32)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **rec)
+        print(f"{name}: N={sc.n_particles} grid={sc.n_grid} nsub={nsub} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

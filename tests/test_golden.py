@@ -1,0 +1,109 @@
+"""Pins the CPU oracle -- and, on the GPU box, the CUDA path -- to golden vectors produced by the
+REFERENCE's own kernel source (warp_mpm/*.py, unmodified) executed under oracle/warp_emu.py; see
+tests/golden/make_golden.py.  Covers every traditional material branch, the cloth return mapping / stress,
+vertex forces, APIC P2G/G2P, the body-mesh collider, the particle mover (joint vertices, faces and pinned
+traditional tail) and the sticky plane.
+
+Tolerances: the fp64 oracle must reproduce the fp64 reference run to round-off (1e-9 relative: the only
+difference is the SVD/QR routine, both accurate to 1e-15); fp32 oracle and CUDA are held to BASELINE.json's
+1e-4 relative on x, v and 1e-3 of max|.| on the other fields."""
+import numpy as np
+import pytest
+
+from tests.golden_util import golden_names, load
+
+NAMES = golden_names()
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def run_oracle(sc, nsub, precision):
+    from oracle.oracle import OracleSim
+    o = OracleSim.from_scene(sc, precision, threads=1)
+    fi = sc.frame_inputs(0)
+    for k in range(nsub):
+        mx = None if fi["mesh_x"] is None else fi["mesh_x"] + np.float32(sc.dt * k) * fi["mesh_v"]
+        o.p2g2p(sc.dt, mx, fi["mesh_v"], fi["joint_traditional_v"], fi["joint_verts_v"], fi["joint_faces_v"])
+    return o
+
+
+def test_fixtures_present():
+    assert len(NAMES) >= 8, NAMES
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_f64_reproduces_reference_source(name):
+    sc, nsub, ref, _ = load(name)
+    o = run_oracle(sc, nsub, "f64")
+    Ne, Nt = sc.n_elements, sc.n_traditional
+    assert rel(o.x, ref["x"]) < 1e-9
+    assert rel(o.v, ref["v"]) < 1e-9
+    assert np.abs(o.C - ref["C"]).max() < 1e-7 * max(np.abs(ref["C"]).max(), 1.0)
+    assert rel(o.grid_m.reshape(-1), ref["grid_m"].reshape(-1)) < 1e-10
+    assert rel(o.grid_v_in.reshape(-1, 3), ref["grid_v_in"].reshape(-1, 3)) < 1e-9
+    assert rel(o.grid_v_out.reshape(-1, 3), ref["grid_v_out"].reshape(-1, 3)) < 1e-9
+    if Ne:
+        assert rel(o.d, ref["d"]) < 1e-9
+        assert rel(o.stress[:Ne], ref["stress"][:Ne]) < 1e-7
+        assert rel(o.vertex_force, ref["vertex_force"]) < 1e-7
+    if Nt:
+        sl = slice(Ne, Ne + Nt)
+        assert rel(o.F_trial[sl], ref["F_trial"][sl]) < 1e-9
+        assert rel(o.F[sl], ref["F"][sl]) < 1e-8
+        assert np.abs(o.stress[sl] - ref["stress"][sl]).max() < 1e-7 * max(np.abs(ref["stress"][sl]).max(), 1e-30)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_f32_within_tolerance_of_reference_source(name):
+    sc, nsub, ref, ref32 = load(name)
+    o = run_oracle(sc, nsub, "f32")
+    for r in (ref, ref32):
+        assert rel(o.x, r["x"]) < 1e-4
+        assert rel(o.v, r["v"]) < 1e-4
+    if sc.n_elements:
+        assert rel(o.d, ref["d"]) < 1e-3
+
+
+def _run_cuda(sc, nsub):
+    import torch
+    from mpmavatar_b200.scene_setup import build_from_scene
+    solver, model, state = build_from_scene(sc)
+    solver.set_debug(True)
+    fi = sc.frame_inputs(0)
+    T = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32, device="cuda")
+    for k in range(nsub):
+        mx = None if fi["mesh_x"] is None else T(fi["mesh_x"] + np.float32(sc.dt * k) * fi["mesh_v"])
+        solver.p2g2p(model, state, sc.dt, mesh_x=mx, mesh_v=T(fi["mesh_v"]), joint_traditional_v=T(fi["joint_traditional_v"]),
+                     joint_verts_v=T(fi["joint_verts_v"]), joint_faces_v=T(fi["joint_faces_v"]))
+    assert solver.stats()["overflow"] == 0
+    return solver, state
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_matches_reference_source(name):
+    sc, nsub, ref, _ = load(name)
+    solver, state = _run_cuda(sc, nsub)
+    Ne, Nt = sc.n_elements, sc.n_traditional
+    x, v = state.particle_x.cpu().numpy(), state.particle_v.cpu().numpy()
+    assert rel(x, ref["x"]) < 1e-4, rel(x, ref["x"])
+    assert rel(v, ref["v"]) < 1e-4, rel(v, ref["v"])
+    inv_dx = sc.n_grid / sc.grid_lim
+    c_tol = 1e-3 * np.abs(ref["C"]).max() + 1e-4 * np.abs(ref["v"]).max() * 4.0 * inv_dx
+    assert np.abs(state.particle_C.cpu().numpy() - ref["C"]).max() < c_tol
+    gm, gvi, gvo = state.export_grid()
+    assert rel(gm.cpu().numpy().reshape(-1), ref["grid_m"].reshape(-1)) < 1e-5
+    assert rel(gvi.cpu().numpy().reshape(-1, 3), ref["grid_v_in"].reshape(-1, 3)) < 1e-4
+    if Ne:
+        assert rel(state.particle_d.cpu().numpy(), ref["d"]) < 1e-3
+        assert rel(state.particle_stress.cpu().numpy()[:Ne], ref["stress"][:Ne]) < 1e-3
+        assert rel(state.vertex_force.cpu().numpy(), ref["vertex_force"]) < 1e-3
+    if Nt:
+        sl = slice(Ne, Ne + Nt)
+        assert rel(state.particle_F_trial.cpu().numpy()[sl], ref["F_trial"][sl]) < 1e-3
+        assert rel(state.particle_F.cpu().numpy()[sl], ref["F"][sl]) < 1e-3
+        s_ref = ref["stress"][sl]
+        assert np.abs(state.particle_stress.cpu().numpy()[sl] - s_ref).max() < 1e-3 * max(np.abs(s_ref).max(), 1e-30)
