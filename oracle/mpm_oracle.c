@@ -16,7 +16,7 @@
  *   (b) golden vectors produced by executing the reference's OWN source
  *       (warp_mpm/mpm_solver.py, mpm_utils.py, mpm_data_structure.py,
  *       unmodified) under oracle/warp_emu.py, a sequential Python stand-in
- *       for the Warp API: tests/golden/make_golden.py -> tests/golden/*.npz,
+ *       for the Warp API: tests/golden/make_golden.py -> the .npz files beside it,
  *       checked by tests/test_golden.py (fp64 build: 1e-9 relative on every
  *       state and grid field, all materials, collider, mover, plane).
  * What remains an assumption is the convention of the two third-party
