@@ -135,6 +135,23 @@ int mpm_add_particle_op(MpmSolver *s, int kind, const float vec[3], const int *m
  * (train_material_params.py:622-626); nsub = 1 is exactly one p2g2p call. */
 int mpm_step(MpmSolver *s, float dt, int nsub, const MpmFrameInputs *in, void *stream);
 
+/* ---- sharded runs (the reference is single-GPU, so these have no reference counterpart).
+ * One p2g2p substep split around the grid: mpm_step_scatter = constitutive update + P2G + body / joint
+ * scatters, mpm_step_gather = grid update + G2P.  Between the two the caller sum-reduces the packed
+ * buffer of the grid blocks shared with other ranks (one all-reduce per substep):
+ *   mpm_shared_pack -> all-reduce(buf, n_shared*64*8 floats) -> mpm_shared_unpack.
+ * Ghost copies of vertices owned by another rank are ordinary vertex particles with mass 0: their
+ * scatter is then exactly the force term dt*w*f, which is linear, so partial vertex forces need no
+ * exchange of their own.  mpm_get_active_blocks synchronises; coords are bx | by<<10 | bz<<20. */
+int mpm_step_scatter(MpmSolver *s, float dt, const MpmFrameInputs *in, void *stream);
+int mpm_step_gather(MpmSolver *s, float dt, void *stream);
+int mpm_get_active_blocks(MpmSolver *s, int *coords, int cap, int *n, void *stream);
+/* blocks this rank can activate while its particles move at most `margin` cells (synchronises) */
+int mpm_get_potential_blocks(MpmSolver *s, int margin, int *coords, int cap, int *n, void *stream);
+int mpm_set_shared_blocks(MpmSolver *s, const int *coords, int n, void *stream);
+int mpm_shared_pack(MpmSolver *s, float *buf, void *stream);
+int mpm_shared_unpack(MpmSolver *s, const float *buf, void *stream);
+
 /* self.time (mpm_solver.py:28,536) */
 int mpm_set_time(MpmSolver *s, double t);
 

@@ -65,6 +65,13 @@ SYMBOLS = {
     "mpm_enforce_grid_velocity_by_mask": (C.c_int, [_P, _P, _P]),
     "mpm_add_particle_op": (C.c_int, [_P, C.c_int, _F3, _P, C.c_float, C.c_float, _P]),
     "mpm_step": (C.c_int, [_P, C.c_float, C.c_int, C.POINTER(MpmFrameInputs), _P]),
+    "mpm_step_scatter": (C.c_int, [_P, C.c_float, C.POINTER(MpmFrameInputs), _P]),
+    "mpm_step_gather": (C.c_int, [_P, C.c_float, _P]),
+    "mpm_get_active_blocks": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int), _P]),
+    "mpm_get_potential_blocks": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]),
+    "mpm_set_shared_blocks": (C.c_int, [_P, _P, C.c_int, _P]),
+    "mpm_shared_pack": (C.c_int, [_P, _P, _P]),
+    "mpm_shared_unpack": (C.c_int, [_P, _P, _P]),
     "mpm_set_time": (C.c_int, [_P, C.c_double]),
     "mpm_export_grid": (C.c_int, [_P, _P, _P, _P, _P]),
     "mpm_set_debug": (C.c_int, [_P, C.c_int]),

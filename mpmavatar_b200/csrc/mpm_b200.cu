@@ -115,7 +115,7 @@ __global__ void k_export_E(int Ne, const uint32_t* __restrict__ perm, Canon c, R
         const float d1[3] = {q[0], q[1], q[2]}, d2[3] = {q[3], q[4], q[5]}, d3p[3] = {q3.x, q3.y, q3.z};
         const ElemConst kc{ek[K_RINV], ek[K_RINV + 1], ek[K_RINV + 2], ek[K_MU], ek[K_LAM], ek[K_GAMMA], ek[K_KAPPA], ek[K_VOL]};
         ElemStress es;
-        element_stress(d1, d2, d3p, kc, friction_coeff, es);
+        element_stress<false>(d1, d2, d3p, kc, friction_coeff, es);
         for (int rr = 0; rr < 3; rr++)
             for (int cc = 0; cc < 3; cc++) c.stress[9 * (size_t)s + 3 * rr + cc] = kc.vol * (es.P3[rr] * es.nd3[cc]);
     }
@@ -193,6 +193,42 @@ __global__ void k_popc(const unsigned long long* mask, int n, unsigned long long
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+// blocks under the stencil of any particle displaced by up to `margin` cells in every direction: what this
+// rank can activate before the shared-block list is rebuilt
+__global__ void k_mark_potential(Grid g, int n, const float* __restrict__ rec, int F, int margin, unsigned char* __restrict__ mark) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* x = rec + (size_t)i * F;
+    int lo[3], hi[3];
+    for (int a = 0; a < 3; a++) {
+        int b = clampi(base_of(x[a], g.inv_dx), 0, g.n - 1);
+        lo[a] = clampi(b - margin, 0, g.n - 1) >> 2;
+        hi[a] = clampi(b + 2 + margin, 0, g.n - 1) >> 2;
+    }
+    for (int a = lo[0]; a <= hi[0]; a++)
+        for (int b = lo[1]; b <= hi[1]; b++)
+            for (int c = lo[2]; c <= hi[2]; c++) mark[table_index(g, a, b, c)] = 1;
+}
+// ---- sharded runs: the grid blocks shared with other ranks travel through one packed buffer
+// [n_shared][64 nodes][acc float4 | mov float4]; inactive blocks pack zeros and ignore the result
+__global__ void k_shared_pack(Grid g, const int* __restrict__ shared, int n_shared, float4* __restrict__ buf) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_shared * BN) return;
+    const int co = shared[idx >> 6], l = idx & 63;
+    const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), m = a;
+    if (g.table[blk] >= 0) { a = g.acc[blk * BN + l]; m = g.mov[blk * BN + l]; }
+    buf[2 * idx] = a;
+    buf[2 * idx + 1] = m;
+}
+__global__ void k_shared_unpack(Grid g, const int* __restrict__ shared, int n_shared, const float4* __restrict__ buf) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_shared * BN) return;
+    const int co = shared[idx >> 6], l = idx & 63;
+    const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
+    if (g.table[blk] >= 0) { g.acc[blk * BN + l] = buf[2 * idx]; g.mov[blk * BN + l] = buf[2 * idx + 1]; }
+}
+
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
@@ -228,6 +264,10 @@ struct MpmSolver {
     // state flags
     bool have_state = false, need_sort = true, canon_stale = false;
     int since_sort = 0, resort_interval = 128;
+    unsigned char* d_mark = nullptr;  // sharded runs: potential-block marks
+    std::vector<unsigned char> h_mark;
+    int* d_shared = nullptr;  // sharded runs: coordinates of the blocks shared with other ranks
+    int n_shared = 0, shared_cap = 0;
     int cur = 0;             // direction buffer (E12/D3) holding the current d
     bool have_prev = false;  // buffer cur^1 holds the d of the last stress evaluation
     int n_resorts = 0;
@@ -235,6 +275,7 @@ struct MpmSolver {
     int launches = 0;
     double host_time = 0.0;
     bool debug = false, profiling = false;
+    bool pending_mover = false;  // mover flag of the scatter half, consumed by the gather half
     float* dbg_f = nullptr;
     unsigned long long* node_mask = nullptr;
     // device block count mirrored (asynchronously) into pinned host memory after each re-sort
@@ -329,19 +370,27 @@ struct SubstepArgs {
 // the grid update grid-strides over the allocated blocks (count on the device): 8 CTAs of 256 threads per SM
 constexpr int GRID_UPDATE_CTAS = 148 * 8;
 
-static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
+// A substep has two halves around the grid: everything that SCATTERS to it (constitutive update, P2G,
+// body-mesh and joint scatters) and everything that reads it back (grid update, G2P).  Single-GPU
+// stepping runs them back to back; a sharded run reduces the shared grid blocks in between (mpm_shared_*).
+enum { HALF_SCATTER = 1, HALF_GATHER = 2, HALF_BOTH = 3 };
+
+static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, int halves = HALF_BOTH) {
     const int n_bc = (int)s->h_bcs.size(), n_ops = (int)s->h_ops.size();
     cudaEvent_t* ev = nullptr;
     std::array<cudaEvent_t, 9> evs;
-    if (s->profiling) {
+    if (s->profiling && halves == HALF_BOTH) {
         for (auto& e : evs) CK(cudaEventCreate(&e));
         ev = evs.data();
         CK(cudaEventRecord(ev[0], q));
     }
     const Recs& R = s->R;
+    auto sm = [](int nw, int wb) { return (size_t)(128 + nw * wb); };
+    const int cur = s->cur;
+    if (halves & HALF_SCATTER) {
     // the two scatter kernels only need the block table and the particle positions, both fixed since
     // the end of the previous substep: fork them onto a side stream (a parallel branch of the graph)
-    const bool fork = !s->profiling && (a.collider || a.mover);
+    const bool fork = !s->profiling && (a.collider || a.mover) && (halves & HALF_SCATTER);
     if (fork) {
         CK(cudaEventRecord(s->ev_fork, q));
         CK(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
@@ -352,8 +401,6 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
         if (s->Nv) k_particle_ops<<<cdiv(s->Nv, 256), 256, 0, q>>>(s->Nv, R.VP, VP_F, s->permV, s->Nnv, s->d_ops, n_ops, s->st, a.dt);
         s->launches += 3;
     }
-    auto sm = [](int nw, int wb) { return (size_t)(128 + nw * wb); };
-    const int cur = s->cur;
     if (s->Nt) {
         k_stress_traditional<<<cdiv(s->Nt, 32 * STRESS_T_NW), 32 * STRESS_T_NW, sm(STRESS_T_NW, STRESS_T_WB), q>>>(s->Nt, R.TF, R.TS, s->md, a.dt);
         s->launches++;
@@ -396,8 +443,9 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
             CK(cudaStreamWaitEvent(q, s->ev_join, 0));
         }
     }
-    // one thread per node of the allocated blocks; the block count lives on the device, so the grid is
-    // sized from the last value copied back (a hint: the kernel grid-strides over the true count)
+    }  // HALF_SCATTER
+    if (!(halves & HALF_GATHER)) return;
+    // one thread per node of the active blocks, grid-strided over the device-side block count
     k_grid_update<<<GRID_UPDATE_CTAS, 256, 0, q>>>(s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, s->d_bcs, n_bc, s->st);
     s->launches++;
     if (ev) CK(cudaEventRecord(ev[5], q));
@@ -811,6 +859,126 @@ int mpm_step(MpmSolver* s, float dt, int nsub, const MpmFrameInputs* in, void* s
         left -= chunk;
     }
     CK(cudaGetLastError());
+    API_END(s)
+}
+
+// ---- sharded stepping (one substep, split around the exchange of the shared grid blocks)
+static void begin_half_step(MpmSolver* s, const MpmFrameInputs* in, SubstepArgs& a, float dt, cudaStream_t q) {
+    if (!s->have_state) throw std::string("mpm_step_* before mpm_import_state");
+    a.dt = dt;
+    a.collider = s->has_collider;
+    a.advance_mesh = false;
+    a.mover = s->has_mover && in && in->joint_verts_v && in->joint_faces_v;
+    a.njt = 0;
+}
+
+int mpm_step_scatter(MpmSolver* s, float dt, const MpmFrameInputs* in, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    MpmFrameInputs none{};
+    if (!in) in = &none;
+    SubstepArgs a{};
+    begin_half_step(s, in, a, dt, q);
+    if (in->n_joint_t > 0) throw std::string("sharded stepping does not support pinned traditional particles yet");
+    upload_lists(s, q);
+    size_t mv3 = 3 * (size_t)s->cfg.n_mesh_v * sizeof(float);
+    if (in->mesh_x && mv3) CK(cudaMemcpyAsync(s->mesh_x, in->mesh_x, mv3, cudaMemcpyDefault, q));
+    if (in->mesh_v && mv3) CK(cudaMemcpyAsync(s->mesh_v, in->mesh_v, mv3, cudaMemcpyDefault, q));
+    if (a.mover) {
+        if (s->cfg.num_joint_v) CK(cudaMemcpyAsync(s->joint_v, in->joint_verts_v, 3 * (size_t)s->cfg.num_joint_v * sizeof(float), cudaMemcpyDefault, q));
+        if (s->cfg.num_joint_f) CK(cudaMemcpyAsync(s->joint_f, in->joint_faces_v, 3 * (size_t)s->cfg.num_joint_f * sizeof(float), cudaMemcpyDefault, q));
+    }
+    if (s->need_sort || s->since_sort >= s->resort_interval) resort(s, q);
+    s->pending_mover = a.mover;
+    launch_substep(s, a, q, HALF_SCATTER);
+    CK(cudaGetLastError());
+    API_END(s)
+}
+
+int mpm_step_gather(MpmSolver* s, float dt, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    SubstepArgs a{};
+    begin_half_step(s, nullptr, a, dt, q);
+    a.mover = s->pending_mover;
+    launch_substep(s, a, q, HALF_GATHER);
+    s->since_sort++;
+    s->n_substeps++;
+    s->canon_stale = true;
+    s->host_time += (double)dt;
+    CK(cudaGetLastError());
+    API_END(s)
+}
+
+int mpm_get_active_blocks(MpmSolver* s, int* coords, int cap, int* n, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    if (s->need_sort && s->have_state) resort(s, q);
+    int ns = 0;
+    CK(cudaMemcpyAsync(&ns, s->g.n_slots, sizeof(int), cudaMemcpyDeviceToHost, q));
+    CK(cudaStreamSynchronize(q));
+    ns = std::min(ns, s->g.cap);
+    *n = ns;
+    if (coords && cap > 0) CK(cudaMemcpy(coords, s->g.slot_coord, (size_t)std::min(ns, cap) * sizeof(int), cudaMemcpyDefault));
+    API_END(s)
+}
+
+int mpm_get_potential_blocks(MpmSolver* s, int margin, int* coords, int cap, int* n, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    if (s->need_sort && s->have_state) resort(s, q);
+    const size_t nt = (size_t)s->g.nb * s->g.nb * s->g.nb;
+    if (!s->d_mark) {
+        s->d_mark = s->dalloc<unsigned char>(nt);
+        s->h_mark.resize(nt);
+    }
+    CK(cudaMemsetAsync(s->d_mark, 0, nt, q));
+    if (s->Ne) k_mark_potential<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.EP, KP_F, margin, s->d_mark);
+    if (s->Nt) k_mark_potential<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F, margin, s->d_mark);
+    if (s->Nv) k_mark_potential<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, margin, s->d_mark);
+    s->launches += 3;
+    CK(cudaMemcpyAsync(s->h_mark.data(), s->d_mark, nt, cudaMemcpyDeviceToHost, q));
+    CK(cudaStreamSynchronize(q));
+    int cnt = 0;
+    const int nb = s->g.nb;
+    for (size_t t = 0; t < nt; t++)
+        if (s->h_mark[t]) {
+            if (coords && cnt < cap) {
+                int bz = (int)(t % nb), by = (int)((t / nb) % nb), bx = (int)(t / ((size_t)nb * nb));
+                coords[cnt] = bx | (by << 10) | (bz << 20);
+            }
+            cnt++;
+        }
+    *n = cnt;
+    API_END(s)
+}
+
+int mpm_set_shared_blocks(MpmSolver* s, const int* coords, int n, void* stream) {
+    API_BEGIN(s)
+    if (n > s->shared_cap) {
+        s->shared_cap = std::max(2 * n, 1024);
+        s->d_shared = s->dalloc<int>(s->shared_cap);
+    }
+    if (n) CK(cudaMemcpyAsync(s->d_shared, coords, (size_t)n * sizeof(int), cudaMemcpyDefault, (cudaStream_t)stream));
+    s->n_shared = n;
+    API_END(s)
+}
+
+int mpm_shared_pack(MpmSolver* s, float* buf, void* stream) {
+    API_BEGIN(s)
+    if (s->n_shared) {
+        k_shared_pack<<<cdiv((long long)s->n_shared * BN, 256), 256, 0, (cudaStream_t)stream>>>(s->g, s->d_shared, s->n_shared, (float4*)buf);
+        s->launches++;
+    }
+    API_END(s)
+}
+
+int mpm_shared_unpack(MpmSolver* s, const float* buf, void* stream) {
+    API_BEGIN(s)
+    if (s->n_shared) {
+        k_shared_unpack<<<cdiv((long long)s->n_shared * BN, 256), 256, 0, (cudaStream_t)stream>>>(s->g, s->d_shared, s->n_shared, (const float4*)buf);
+        s->launches++;
+    }
     API_END(s)
 }
 

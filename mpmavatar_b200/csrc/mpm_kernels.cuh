@@ -76,6 +76,10 @@ struct ElemStress {
     float f1[3], f2[3], f3[3];   // corner forces (mpm_utils.py:163-175)
     float P3[3];                 // stress = vol * P3 (x) nd3 (mpm_utils.py:177)
 };
+// RETURN_MAP = false evaluates the stress of a d whose third column is ALREADY return mapped (what
+// kirchoff_stress_Anisotropy sees in the reference); the mapping must not be applied twice: its R22 > 1
+// branch keeps the shear while a second pass through the cone branch (fn = 0 at R22 = 1) would zero it.
+template <bool RETURN_MAP = true>
 __device__ __forceinline__ void element_stress(const float* d1, const float* d2, const float* d3, const ElemConst& k,
                                                float friction_coeff, ElemStress& o) {
     // rotation QR, sign-normalised (R00>0, R11>0, det Q=+1): Gram-Schmidt with q3 = q1 x q2, in
@@ -92,7 +96,8 @@ __device__ __forceinline__ void element_stress(const float* d1, const float* d2,
                          __fsub_rn(__fmul_rn(q1[0], q2[1]), __fmul_rn(q1[1], q2[0]))};
     float r02 = dot3_rn(q1, d3), r12 = dot3_rn(q2, d3), r22 = dot3_rn(q3, d3);
     // return mapping (mpm_utils.py:196-204)
-    if (r22 > 1.0f) {
+    if (!RETURN_MAP) {
+    } else if (r22 > 1.0f) {
         r22 = 1.0f;
     } else {
         float fn = k.kappa * (1.0f - r22) * (1.0f - r22);

@@ -1,0 +1,143 @@
+"""One MPM garment simulation sharded over the GPUs of a box: one process per GPU (torch.distributed,
+NCCL over NVLink), one sum-reduction of the shared grid blocks per substep.
+
+The reference is single-GPU, so this class has no reference counterpart; it drives the same C-ABI
+(include/mpm_b200.h, mpm_step_scatter / mpm_shared_* / mpm_step_gather) and the same warp_mpm mirror on each
+rank's sub-scene (mpmavatar_b200/sharding.py explains the scheme).  No CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, sharding as sh
+from .scene_setup import build_from_scene
+
+
+class ShardedMPM:
+    def __init__(self, sc, device, group=None, refresh=16, margin=1, resort_interval=0):
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.group, self.sc, self.device = group, sc, torch.device(device)
+        self.refresh, self.margin = int(refresh), int(margin)
+        self.part = sh.partition(sc.x, sc.faces, sc.n_elements, sc.n_vertices, sc.n_grid, sc.grid_lim, self.world,
+                                 sc.num_joint_v, sc.num_joint_f)[self.rank]
+        self.local = sh.local_scene(sc, self.part)
+        self.solver, self.model, self.state = build_from_scene(self.local, device=device, resort_interval=resort_interval)
+        self.solver._bind(self.model, self.state)
+        self.lib, self.h = self.solver._libh, self.solver._h
+        self.nb = (sc.n_grid + 3) // 4
+        self.buf = None
+        self.n_shared = 0
+        self.k = 0  # substeps since the last shared-list rebuild
+        self.stats = {"rebuilds": 0, "shared_blocks": 0, "exchange_bytes": 0}
+
+    # collectives: NCCL works on device tensors; with gloo (CPU tests, or two ranks sharing one GPU) they are
+    # staged through host memory
+    def _host_staged(self):
+        return dist.get_backend(self.group) != "nccl"
+
+    def _all_gather(self, t):
+        if self._host_staged():
+            out = [torch.empty(t.shape, dtype=t.dtype) for _ in range(self.world)]
+            dist.all_gather(out, t.cpu(), group=self.group)
+            return [o.to(self.device) for o in out]
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t, group=self.group)
+        return out
+
+    def _all_reduce(self, t):
+        if self._host_staged():
+            h = t.cpu()
+            dist.all_reduce(h, group=self.group)
+            t.copy_(h)
+        else:
+            dist.all_reduce(t, group=self.group)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError("libmpm_b200: " + self.lib.mpm_last_error(self.h).decode())
+
+    def rebuild_shared(self):
+        cap = self.nb ** 3
+        coords = np.empty(cap, np.int32)
+        n = C.c_int(0)
+        self._ck(self.lib.mpm_get_potential_blocks(self.h, self.margin, coords.ctypes.data_as(C.c_void_p), cap, C.byref(n), self._stream()))
+        mine = torch.from_numpy(coords[: n.value].copy()).to(self.device)
+        sizes = [int(s.item()) for s in self._all_gather(torch.tensor([n.value], dtype=torch.int64, device=self.device))]
+        pad = max(sizes)
+        send = torch.full((pad,), -1, dtype=torch.int32, device=self.device)
+        send[: n.value] = mine
+        recv = self._all_gather(send)
+        lists = [r[:s].cpu().numpy() for r, s in zip(recv, sizes)]
+        shared = np.ascontiguousarray(sh.shared_blocks(lists))
+        self._shared_keep = torch.from_numpy(shared).to(self.device)
+        self._ck(self.lib.mpm_set_shared_blocks(self.h, C.c_void_p(self._shared_keep.data_ptr()), len(shared), self._stream()))
+        self.n_shared = len(shared)
+        need = max(self.n_shared, 1) * 64 * 8
+        if self.buf is None or self.buf.numel() < need:
+            self.buf = torch.zeros(int(need * 1.5), dtype=torch.float32, device=self.device)
+        self.k = 0
+        self.stats["rebuilds"] += 1
+        self.stats["shared_blocks"] = self.n_shared
+        self.stats["exchange_bytes"] = self.n_shared * 64 * 8 * 4
+
+    def step(self, dt, nsub, mesh_x=None, mesh_v=None, joint_verts_v=None, joint_faces_v=None):
+        """nsub substeps; substep k sees body points mesh_x + dt*k*mesh_v (the callers' inner loop,
+        train_material_params.py:622-626).  Joint velocity arrays are the GLOBAL ones."""
+        dev = self.device
+        T = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32, device=dev).contiguous()
+        mesh_x, mesh_v = T(mesh_x), T(mesh_v)
+        jv = jf = None
+        if joint_verts_v is not None and joint_faces_v is not None:
+            p = self.part
+            vi = torch.as_tensor(p.verts[:p.num_joint_v], device=dev, dtype=torch.long)
+            fi = torch.as_tensor(p.elems[:p.num_joint_f], device=dev, dtype=torch.long)
+            jv = T(joint_verts_v)[vi].contiguous() if p.num_joint_v else torch.zeros(1, 3, device=dev)
+            jf = T(joint_faces_v)[fi].contiguous() if p.num_joint_f else torch.zeros(1, 3, device=dev)
+        st = self._stream()
+        for k in range(int(nsub)):
+            fin = _lib.MpmFrameInputs()
+            mx = None if mesh_x is None else (mesh_x + float(np.float32(dt * k)) * mesh_v if k else mesh_x)
+            fin.mesh_x = None if mx is None else C.c_void_p(mx.data_ptr())
+            fin.mesh_v = None if mesh_v is None else C.c_void_p(mesh_v.data_ptr())
+            if jv is not None:
+                fin.joint_verts_v, fin.joint_faces_v = C.c_void_p(jv.data_ptr()), C.c_void_p(jf.data_ptr())
+            self._ck(self.lib.mpm_step_scatter(self.h, C.c_float(dt), C.byref(fin), st))
+            if self.buf is None or self.k >= self.refresh:
+                self.rebuild_shared()
+            if self.n_shared:
+                view = self.buf[: self.n_shared * 64 * 8]
+                self._ck(self.lib.mpm_shared_pack(self.h, C.c_void_p(view.data_ptr()), st))
+                self._all_reduce(view)
+                self._ck(self.lib.mpm_shared_unpack(self.h, C.c_void_p(view.data_ptr()), st))
+            self._ck(self.lib.mpm_step_gather(self.h, C.c_float(dt), st))
+            self.k += 1
+        self.state._stale = True
+        self.state._solver = self.solver
+
+    def gather_positions(self):
+        """Full canonical particle_x / particle_v on every rank (original particle order)."""
+        p, sc, dev = self.part, self.sc, self.device
+        Ne_l = len(p.elems)
+        x, v = self.state.particle_x, self.state.particle_v
+        ids = torch.as_tensor(np.concatenate([p.elems, sc.n_elements + p.verts[:p.n_owned_v]]), device=dev, dtype=torch.long)
+        own = torch.cat([x[: Ne_l + p.n_owned_v], v[: Ne_l + p.n_owned_v]], 1).contiguous()
+        sizes = [int(s.item()) for s in self._all_gather(torch.tensor([own.shape[0]], dtype=torch.int64, device=dev))]
+        pad = max(sizes)
+        send = torch.zeros(pad, 7, device=dev)
+        send[: own.shape[0], :6] = own
+        send[: own.shape[0], 6] = ids.to(torch.float32)  # ids < 2^24 are exact in fp32
+        if sc.n_particles >= (1 << 24):
+            raise NotImplementedError("gather_positions packs ids in fp32")
+        recv = self._all_gather(send)
+        X = torch.empty(sc.n_particles, 3, device=dev)
+        V = torch.empty(sc.n_particles, 3, device=dev)
+        for r, s in zip(recv, sizes):
+            i = r[:s, 6].to(torch.long)
+            X[i], V[i] = r[:s, :3], r[:s, 3:6]
+        return X, V
