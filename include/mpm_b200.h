@@ -144,6 +144,14 @@ int mpm_step(MpmSolver *s, float dt, int nsub, const MpmFrameInputs *in, void *s
  * scatter is then exactly the force term dt*w*f, which is linear, so partial vertex forces need no
  * exchange of their own.  mpm_get_active_blocks synchronises; coords are bx | by<<10 | bz<<20. */
 int mpm_step_scatter(MpmSolver *s, float dt, const MpmFrameInputs *in, void *stream);
+/* The same, nsub substeps driven from C.  `exchange` must enqueue a sum-reduction of buf[0..n_floats) over
+ * the ranks on `stream` (the caller owns the communicator); `rebuild` must call mpm_get_potential_blocks,
+ * agree on the shared list with the other ranks and call mpm_set_shared_blocks; it is invoked every
+ * `refresh` substeps.  buf must hold 512 floats per shared block.  Both return 0 on success. */
+typedef int (*MpmExchangeFn)(void *ctx, float *buf, int n_floats);
+typedef int (*MpmRebuildFn)(void *ctx);
+int mpm_step_sharded(MpmSolver *s, float dt, int nsub, const MpmFrameInputs *in, float *buf, int refresh,
+                     MpmExchangeFn exchange, MpmRebuildFn rebuild, void *ctx, void *stream);
 int mpm_step_gather(MpmSolver *s, float dt, void *stream);
 int mpm_get_active_blocks(MpmSolver *s, int *coords, int cap, int *n, void *stream);
 /* blocks this rank can activate while its particles move at most `margin` cells (synchronises) */

@@ -46,6 +46,9 @@ class MpmProfile(C.Structure):
                                          "g2p_v_ms", "g2p_e_ms", "resort_ms")] + [("n_substeps", C.c_longlong)]
 
 
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)
+REBUILD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
 # every symbol include/mpm_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _F3 = C.POINTER(C.c_float)
@@ -67,6 +70,7 @@ SYMBOLS = {
     "mpm_step": (C.c_int, [_P, C.c_float, C.c_int, C.POINTER(MpmFrameInputs), _P]),
     "mpm_step_scatter": (C.c_int, [_P, C.c_float, C.POINTER(MpmFrameInputs), _P]),
     "mpm_step_gather": (C.c_int, [_P, C.c_float, _P]),
+    "mpm_step_sharded": (C.c_int, [_P, C.c_float, C.c_int, C.POINTER(MpmFrameInputs), _P, C.c_int, EXCHANGE_FN, REBUILD_FN, _P, _P]),
     "mpm_get_active_blocks": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int), _P]),
     "mpm_get_potential_blocks": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]),
     "mpm_set_shared_blocks": (C.c_int, [_P, _P, C.c_int, _P]),

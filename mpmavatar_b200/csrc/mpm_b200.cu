@@ -51,8 +51,9 @@ struct Recs {  // sorted sub-record arrays (see mpm_device.cuh)
     float4* D3[2];  // ping-pong d3
     int* EF;
     float4* VF;
+    int *CE, *CV;  // packed stencil base cell per element / vertex (lets G2P start its node loads early)
 };
-__global__ void k_import_E(int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R, int cur, const int* __restrict__ invV) {
+__global__ void k_import_E(Grid g, int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R, int cur, const int* __restrict__ invV) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Ne) return;
     int s = perm[i];  // canonical element index == canonical particle index
@@ -66,6 +67,7 @@ __global__ void k_import_E(int Ne, const uint32_t* __restrict__ perm, Canon c, R
     for (int row = 0; row < 3; row++) { e[row] = ds[3 * row]; e[3 + row] = ds[3 * row + 1]; }
     R.D3[cur][i] = make_float4(ds[2], ds[5], ds[8], 0.f);
     for (int k = 0; k < 3; k++) R.EF[(size_t)i * EF_F + k] = invV[(int)c.faces[3 * s + k]];  // int(face[k]), mpm_utils.py:172
+    R.CE[i] = pack_cell(base_of(p[0], g.inv_dx), base_of(p[1], g.inv_dx), base_of(p[2], g.inv_dx));
     float* ek = R.EK + (size_t)i * EK_F;
     for (int k = 0; k < 3; k++) ek[K_RINV + k] = c.Rinv[3 * s + k];
     ek[K_MU] = c.mu[s]; ek[K_LAM] = c.lam[s]; ek[K_GAMMA] = c.gamma[s]; ek[K_KAPPA] = c.kappa[s]; ek[K_VOL] = c.vol[s];
@@ -83,7 +85,7 @@ __global__ void k_import_T(int Nt, int Ne, const uint32_t* __restrict__ perm, Ca
     for (int k = 0; k < 9; k++) { t[T_F + k] = c.F[9 * (size_t)s + k]; t[T_FT + k] = c.Ft[9 * (size_t)s + k]; }
     t[T_MU] = c.mu[s]; t[T_LAM] = c.lam[s]; t[T_YS] = c.ys[s];
 }
-__global__ void k_import_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, Canon c, Recs R) {
+__global__ void k_import_V(Grid g, int Nv, int Nnv, const uint32_t* __restrict__ perm, Canon c, Recs R) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Nv) return;
     int s = Nnv + perm[i];
@@ -92,6 +94,7 @@ __global__ void k_import_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, C
     p[V_M] = c.mass[s];
     for (int k = 0; k < 9; k++) p[V_C + k] = c.C[9 * (size_t)s + k];
     R.VF[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    R.CV[i] = pack_cell(base_of(p[0], g.inv_dx), base_of(p[1], g.inv_dx), base_of(p[2], g.inv_dx));
 }
 // d from direction buffer `cur`; the element stress of the LAST substep is re-evaluated from buffer
 // `cur^1`, which still holds the d1,d2 and the return-mapped d3 that substep's stress was computed from
@@ -267,7 +270,7 @@ struct MpmSolver {
     unsigned char* d_mark = nullptr;  // sharded runs: potential-block marks
     std::vector<unsigned char> h_mark;
     int* d_shared = nullptr;  // sharded runs: coordinates of the blocks shared with other ranks
-    int n_shared = 0, shared_cap = 0;
+    int n_shared = 0, shared_cap = 0, shared_age = -1;
     int cur = 0;             // direction buffer (E12/D3) holding the current d
     bool have_prev = false;  // buffer cur^1 holds the d of the last stress evaluation
     int n_resorts = 0;
@@ -283,6 +286,7 @@ struct MpmSolver {
     int slots_seen = 0;
     void* graph_cache_ptr = nullptr;
     bool use_graphs = true;
+    bool use_pdl = true;  // MPM_B200_PDL=0 disables programmatic dependent launch
     cudaStream_t cap_stream = nullptr;
     cudaStream_t side = nullptr;       // body-collider / mover scatter run concurrently with stress + P2G
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -329,10 +333,10 @@ static void resort(MpmSolver* s, cudaStream_t q) {
     sort_class(s, s->Ne, 0, s->permE, s->invE, q);
     sort_class(s, s->Nt, s->Ne, s->permT, s->invT, q);
     sort_class(s, s->Nv, s->Nnv, s->permV, s->invV, q);
-    if (s->Ne) k_import_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->permE, s->canon, s->R, s->cur, s->invV);
+    if (s->Ne) k_import_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->permE, s->canon, s->R, s->cur, s->invV);
     s->have_prev = false;
     if (s->Nt) k_import_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->permT, s->canon, s->R);
-    if (s->Nv) k_import_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->Nnv, s->permV, s->canon, s->R);
+    if (s->Nv) k_import_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->Nnv, s->permV, s->canon, s->R);
     // all accumulators are zero between substeps, so rebuilding the table needs no pool sweep
     size_t nt = (size_t)s->g.nb * s->g.nb * s->g.nb;
     k_fill_int<<<std::min(cdiv((long long)nt, 256), 1184), 256, 0, q>>>(s->g.table, nt, -1);
@@ -367,6 +371,23 @@ struct SubstepArgs {
     int njt;
 };
 
+// Launch with programmatic stream serialization (PDL): the kernel may be scheduled while its predecessor in
+// the stream drains; it calls griddepcontrol.wait before touching global memory (mpm_device.cuh pdl_wait).
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t q, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = q;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+}
+
 // the grid update grid-strides over the allocated blocks (count on the device): 8 CTAs of 256 threads per SM
 constexpr int GRID_UPDATE_CTAS = 148 * 8;
 
@@ -387,6 +408,7 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
     const Recs& R = s->R;
     auto sm = [](int nw, int wb) { return (size_t)(128 + nw * wb); };
     const int cur = s->cur;
+    const bool pdl = s->use_pdl && !s->profiling;
     if (halves & HALF_SCATTER) {
     // the two scatter kernels only need the block table and the particle positions, both fixed since
     // the end of the previous substep: fork them onto a side stream (a parallel branch of the graph)
@@ -409,17 +431,17 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
     const int ppb = 32 * P2G_NW;  // particles per P2G block
     if (s->Ne) {  // cloth stress fused in front of the element scatter; VF must be complete before the vertex scatter
         P2GIn in{R.EP, nullptr, R.E12[cur], R.D3[cur], R.EF, R.EK, R.VF, s->md.friction_coeff};
-        k_p2g<0><<<cdiv(s->Ne, ppb), ppb, P2G_SMEM, q>>>(s->g, in, s->Ne, a.dt, s->md.rpic);
+        launch_pdl(k_p2g<0>, cdiv(s->Ne, ppb), ppb, P2G_SMEM, q, pdl, s->g, in, s->Ne, a.dt, s->md.rpic);
         s->launches++;
     }
     if (s->Nt) {
         P2GIn in{R.TP, R.TS, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
-        k_p2g<1><<<cdiv(s->Nt, ppb), ppb, P2G_SMEM, q>>>(s->g, in, s->Nt, a.dt, s->md.rpic);
+        launch_pdl(k_p2g<1>, cdiv(s->Nt, ppb), ppb, P2G_SMEM, q, pdl, s->g, in, s->Nt, a.dt, s->md.rpic);
         s->launches++;
     }
     if (s->Nv) {
         P2GIn in{R.VP, (const float*)R.VF, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
-        k_p2g<2><<<cdiv(s->Nv, ppb), ppb, P2G_SMEM, q>>>(s->g, in, s->Nv, a.dt, s->md.rpic);
+        launch_pdl(k_p2g<2>, cdiv(s->Nv, ppb), ppb, P2G_SMEM, q, pdl, s->g, in, s->Nv, a.dt, s->md.rpic);
         s->launches++;
     }
     if (ev) CK(cudaEventRecord(ev[2], q));
@@ -452,11 +474,11 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
     Advance none{nullptr, nullptr, 0}, adv{s->st, s->d_bcs, n_bc};
     const int last = s->Ne ? 2 : (s->Nt ? 1 : 0);  // the last kernel of the substep advances time
     const int gpb = 32 * G2P_NW;
-    if (s->Nv) { k_g2p_vertices<<<cdiv(s->Nv, gpb), gpb, sm(G2P_NW, G2P_V_WB), q>>>(s->g, s->Nv, R.VP, R.VF, a.dt, s->debug ? s->dbg_f : nullptr, last == 0 ? adv : none); s->launches++; }
-    if (s->Nt) { k_g2p_traditional<<<cdiv(s->Nt, gpb), gpb, sm(G2P_NW, G2P_T_WB), q>>>(s->g, s->Nt, R.TP, R.TF, a.dt, last == 1 ? adv : none); s->launches++; }
+    if (s->Nv) { launch_pdl(k_g2p_vertices, cdiv(s->Nv, gpb), gpb, sm(G2P_NW, G2P_V_WB), q, pdl, s->g, s->Nv, R.VP, R.VF, R.CV, a.dt, s->debug ? s->dbg_f : nullptr, last == 0 ? adv : none); s->launches++; }
+    if (s->Nt) { launch_pdl(k_g2p_traditional, cdiv(s->Nt, gpb), gpb, sm(G2P_NW, G2P_T_WB), q, pdl, s->g, s->Nt, R.TP, R.TF, a.dt, last == 1 ? adv : none); s->launches++; }
     if (ev) CK(cudaEventRecord(ev[6], q));
     if (s->Ne) {
-        k_g2p_elements<<<cdiv(s->Ne, gpb), gpb, sm(G2P_NW, G2P_E_WB), q>>>(s->g, s->Ne, R.EP, R.EF, R.D3[cur], R.E12[cur ^ 1], R.D3[cur ^ 1], R.VP, a.dt, last == 2 ? adv : none);
+        launch_pdl(k_g2p_elements, cdiv(s->Ne, gpb), gpb, sm(G2P_NW, G2P_E_WB), q, pdl, s->g, s->Ne, R.EP, (const int*)R.EF, (const float4*)R.D3[cur], R.E12[cur ^ 1], R.D3[cur ^ 1], R.CE, (const float*)R.VP, a.dt, last == 2 ? adv : none);
         s->launches++;
         s->cur ^= 1;
         s->have_prev = true;
@@ -584,6 +606,9 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         if (s->N <= 0 || s->Ne < 0 || s->Nv < 0 || s->Nt < 0 || cfg->n_grid < 8 || cfg->n_grid > 1020)
             throw std::string("invalid particle counts or n_grid (8..1020)");
         if (cfg->resort_interval > 0) s->resort_interval = cfg->resort_interval;
+        if (const char* e = getenv("MPM_B200_RESORT")) { if (cfg->resort_interval <= 0 && atoi(e) > 0) s->resort_interval = atoi(e); }
+        if (const char* e = getenv("MPM_B200_PDL")) s->use_pdl = atoi(e) != 0;
+        if (const char* e = getenv("MPM_B200_GRAPHS")) s->use_graphs = atoi(e) != 0;
         Grid& g = s->g;
         g.n = cfg->n_grid;
         g.nb = (g.n + BS - 1) / BS;
@@ -611,6 +636,7 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
             size_t ne = (size_t)s->Ne + 32, nt = (size_t)s->Nt + 32, nv = (size_t)s->Nv + 32;
             s->R.EP = s->dalloc<float>(ne * KP_F); s->R.EK = s->dalloc<float>(ne * EK_F);
             s->R.EF = s->dalloc<int>(ne * EF_F);
+            s->R.CE = s->dalloc<int>(ne); s->R.CV = s->dalloc<int>(nv);
             for (int b = 0; b < 2; b++) { s->R.E12[b] = s->dalloc<float>(ne * E12_F); s->R.D3[b] = s->dalloc<float4>(ne); }
             s->R.TP = s->dalloc<float>(nt * KP_F); s->R.TS = s->dalloc<float>(nt * S_F); s->R.TF = s->dalloc<float>(nt * TF_F);
             s->R.VP = s->dalloc<float>(nv * VP_F); s->R.VF = s->dalloc<float4>(nv);
@@ -906,6 +932,52 @@ int mpm_step_gather(MpmSolver* s, float dt, void* stream) {
     s->n_substeps++;
     s->canon_stale = true;
     s->host_time += (double)dt;
+    CK(cudaGetLastError());
+    API_END(s)
+}
+
+// nsub sharded substeps driven from C: per substep the host only enqueues ~9 kernels and calls `exchange`
+// (the caller's all-reduce on its communicator, e.g. torch.distributed / NCCL) once
+int mpm_step_sharded(MpmSolver* s, float dt, int nsub, const MpmFrameInputs* in, float* buf, int refresh,
+                     MpmExchangeFn exchange, MpmRebuildFn rebuild, void* ctx, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    MpmFrameInputs none{};
+    if (!in) in = &none;
+    SubstepArgs a{};
+    begin_half_step(s, in, a, dt, q);
+    if (in->n_joint_t > 0) throw std::string("sharded stepping does not support pinned traditional particles yet");
+    upload_lists(s, q);
+    size_t mv3 = 3 * (size_t)s->cfg.n_mesh_v * sizeof(float);
+    if (in->mesh_x && mv3) CK(cudaMemcpyAsync(s->mesh_x, in->mesh_x, mv3, cudaMemcpyDefault, q));
+    if (in->mesh_v && mv3) CK(cudaMemcpyAsync(s->mesh_v, in->mesh_v, mv3, cudaMemcpyDefault, q));
+    if (a.mover) {
+        if (s->cfg.num_joint_v) CK(cudaMemcpyAsync(s->joint_v, in->joint_verts_v, 3 * (size_t)s->cfg.num_joint_v * sizeof(float), cudaMemcpyDefault, q));
+        if (s->cfg.num_joint_f) CK(cudaMemcpyAsync(s->joint_f, in->joint_faces_v, 3 * (size_t)s->cfg.num_joint_f * sizeof(float), cudaMemcpyDefault, q));
+    }
+    a.advance_mesh = in->mesh_x != nullptr && nsub > 1;  // substep k sees mesh_x + dt*k*mesh_v (device-side counter)
+    k_reset_k<<<1, 1, 0, q>>>(s->st);
+    s->launches++;
+    for (int k = 0; k < nsub; k++) {
+        if (s->need_sort || s->since_sort >= s->resort_interval) resort(s, q);
+        launch_substep(s, a, q, HALF_SCATTER);
+        if (s->shared_age < 0 || s->shared_age >= refresh) {
+            if (rebuild(ctx) != 0) throw std::string("shared-block rebuild callback failed");
+            s->shared_age = 0;
+        }
+        if (s->n_shared) {
+            k_shared_pack<<<cdiv((long long)s->n_shared * BN, 256), 256, 0, q>>>(s->g, s->d_shared, s->n_shared, (float4*)buf);
+            if (exchange(ctx, buf, s->n_shared * BN * 8) != 0) throw std::string("exchange callback failed");
+            k_shared_unpack<<<cdiv((long long)s->n_shared * BN, 256), 256, 0, q>>>(s->g, s->d_shared, s->n_shared, (const float4*)buf);
+            s->launches += 2;
+        }
+        launch_substep(s, a, q, HALF_GATHER);
+        s->shared_age++;
+        s->since_sort++;
+        s->n_substeps++;
+        s->host_time += (double)dt;
+    }
+    s->canon_stale = true;
     CK(cudaGetLastError());
     API_END(s)
 }

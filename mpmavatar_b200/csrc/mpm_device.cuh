@@ -404,6 +404,19 @@ __device__ __forceinline__ void bulk_commit_wait() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// 16-byte cp.async (SASS LDGSTS): global -> shared without passing through registers
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor drains; pdl_wait() blocks until the predecessor's memory is visible, pdl_trigger()
+// lets the successor's CTAs be scheduled as soon as every CTA of this grid has started
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (TMA store)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // bytes of a slab of cnt records of F floats, rounded up to the 16-byte bulk-copy granule

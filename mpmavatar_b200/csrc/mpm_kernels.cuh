@@ -38,7 +38,7 @@ struct Slab {
 };
 // one cp.async.bulk per sub-record slab, all completing on the warp's mbarrier
 template <int N>
-__device__ __forceinline__ void slab_load(const Warp& w, const Slab (&sl)[N]) {
+__device__ __forceinline__ void slab_issue(const Warp& w, const Slab (&sl)[N]) {
     if (w.lane == 0) {
         uint32_t tot = 0;
 #pragma unroll
@@ -48,7 +48,14 @@ __device__ __forceinline__ void slab_load(const Warp& w, const Slab (&sl)[N]) {
         for (int i = 0; i < N; i++)
             bulk_g2s(sl[i].s, static_cast<const float*>(sl[i].g) + (size_t)w.p0 * sl[i].F, slab_bytes(w.cnt, sl[i].F), w.bar);
     }
+}
+__device__ __forceinline__ void slab_wait(const Warp& w) {
     while (!mbar_try_wait(w.bar, 0)) {}
+}
+template <int N>
+__device__ __forceinline__ void slab_load(const Warp& w, const Slab (&sl)[N]) {
+    slab_issue(w, sl);
+    slab_wait(w);
 }
 template <int N>
 __device__ __forceinline__ void slab_store(const Warp& w, const Slab (&sl)[N]) {
@@ -337,6 +344,8 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
     if (!warp_begin<P2G_NW, P2G_WB>(w, n, smem)) return;
     PHASE_BEGIN();
     float* buf = reinterpret_cast<float*>(w.buf);
+    pdl_wait();     // everything above overlapped the predecessor's tail (programmatic dependent launch)
+    pdl_trigger();  // let the successor's CTAs be scheduled into the slots this grid frees
     // ---- stage 0
     float* raw1 = buf + 32 * F0;
     float* s12 = buf + 32 * KP_F;
@@ -626,6 +635,7 @@ __global__ void __launch_bounds__(128) k_mover_scatter(Grid g, int njt, int njv,
 __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float dt, int use_collider, float col_friction,
                                                      int use_mover, const BCDesc* __restrict__ bcs, int n_bc,
                                                      const StepState* __restrict__ st) {
+    pdl_trigger();  // the G2P kernels behind this one may take the slots it frees (they wait for its completion)
     const int n_slots = min(*g.n_slots, g.cap);
     const float time = (float)st->time;
     const int total = n_slots * BN;
@@ -756,19 +766,19 @@ __device__ __forceinline__ void g2p_contract(const float4* __restrict__ T, const
     for (int i = 0; i < 3; i++) {
         float2 A0_xy = z2, A1_xy = z2, A2_xy = z2, B0_xy = z2, C0q_xy = z2, A0z_A1z = z2, B0z_C0z = z2;
         float A2z = 0.f;
-        // one i-plane (9 nodes, 36 registers) is fetched at a time; the compiler barrier keeps ptxas from
-        // hoisting all 27 LDS.128 (108 registers) to the top and spilling
-        float4 pl[9];
-#pragma unroll
-        for (int q = 0; q < 9; q++) pl[q] = T[i * 9 + q];
-        asm volatile("" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 3; j++) {
+            // one z-row (3 nodes, 12 registers) is fetched at a time; the compiler barrier keeps ptxas from
+            // hoisting all 27 LDS.128 (108 registers) to the top and spilling
+            float4 pl[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) pl[q] = T[(i * 3 + j) * 3 + q];
+            asm volatile("" ::: "memory");
             float2 a_xy = z2, b_xy = z2, c_xy = z2, bz_cz = z2;
             float az = 0.f;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                const float4 gv = pl[j * 3 + k];
+                const float4 gv = pl[k];
                 const float2 gxy = make_float2(gv.x, gv.y);
                 a_xy = fma2(W[2][k], gxy, a_xy);
                 b_xy = fma2(CW[2][k], gxy, b_xy);
@@ -810,8 +820,7 @@ __device__ __forceinline__ void g2p_contract(const float4* __restrict__ T, const
 // fetch the run's 27 node velocities ONCE (one table lookup + one LDG.128 per lane, up to G2P_RMAX runs
 // in flight) into a shared-memory tile, then lane = particle contracts its run's tile with broadcast
 // reads.  Replaces 8 table lookups + 27 dependent gathers per particle.
-constexpr int G2P_RMAX = 8;   // runs per contraction pass (tile capacity)
-constexpr int G2P_RLOAD = 4;  // runs whose node loads are in flight together
+constexpr int G2P_RMAX = 8;  // runs per contraction pass (tile capacity)
 constexpr int G2P_TILE_B = 128 + G2P_RMAX * 27 * 16;  // run cells | tiles
 struct Gather {
     const Grid& g;
@@ -822,40 +831,43 @@ struct Gather {
     bool valid;
     float f[3];
     int b[3];
-    __device__ __forceinline__ Gather(const Grid& g_, const Warp& w_, unsigned char* tile_mem, bool valid_, float x, float y, float z)
-        : g(g_), w(w_), runcell(reinterpret_cast<int*>(tile_mem)), tile(reinterpret_cast<float4*>(tile_mem + 128)), valid(valid_) {
+    __device__ __forceinline__ Gather(const Grid& g_, const Warp& w_, unsigned char* tile_mem, bool valid_)
+        : g(g_), w(w_), runcell(reinterpret_cast<int*>(tile_mem)), tile(reinterpret_cast<float4*>(tile_mem + 128)), valid(valid_) {}
+    // the packed stencil base of every lane's particle is all the staging needs: with the per-particle cell
+    // arrays (CV / CE) the node loads are issued before the particle slab has arrived
+    __device__ __forceinline__ void begin(int cell) {
+        if (!valid) cell = -1 - w.lane;
+        R = find_runs(w.lane, w.cnt, cell);
+        if ((R.starts >> w.lane) & 1u) runcell[R.mine] = cell;
+        __syncwarp();
+        stage_issue(0);
+    }
+    __device__ __forceinline__ int set_position(float x, float y, float z) {
         const float gp[3] = {x * g.inv_dx, y * g.inv_dx, z * g.inv_dx};
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             b[a] = (int)(gp[a] - 0.5f);
             f[a] = gp[a] - (float)b[a];
         }
-        const int cell = valid ? pack_cell(b[0], b[1], b[2]) : -1 - w.lane;
-        R = find_runs(w.lane, w.cnt, cell);
-        if ((R.starts >> w.lane) & 1u) runcell[R.mine] = cell;
-        __syncwarp();
+        return pack_cell(b[0], b[1], b[2]);
     }
-    // lanes 0..26 load the nodes of runs [r0, r0 + G2P_RMAX) into the tile
-    __device__ __forceinline__ void stage(int r0) const {
+    // lanes 0..26 copy the nodes of runs [r0, r0 + G2P_RMAX) into the tile with cp.async (LDGSTS): global ->
+    // shared without staging registers, every run of the pass in flight at once
+    __device__ __forceinline__ void stage_issue(int r0) const {
         const int nrp = min(G2P_RMAX, R.nr - r0);
         if (w.lane < 27) {
             const int li = w.lane / 9, lj = (w.lane / 3) % 3, lk = w.lane % 3;
-            for (int rb = 0; rb < nrp; rb += G2P_RLOAD) {
-                float4 val[G2P_RLOAD];
-#pragma unroll
-                for (int r = 0; r < G2P_RLOAD; r++) {
-                    val[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rb + r < nrp) {
-                        const int c = runcell[r0 + rb + r];
-                        const int ni = node_index(g, (c & 1023) - 2 + li, ((c >> 10) & 1023) - 2 + lj, ((c >> 20) & 1023) - 2 + lk);
-                        if (ni >= 0) val[r] = g.vout[ni];
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < G2P_RLOAD; r++)
-                    if (rb + r < nrp) tile[(rb + r) * 27 + w.lane] = val[r];
+            for (int r = 0; r < nrp; r++) {
+                const int c = runcell[r0 + r];
+                const int ni = node_index(g, (c & 1023) - 2 + li, ((c >> 10) & 1023) - 2 + lj, ((c >> 20) & 1023) - 2 + lk);
+                float4* dst = tile + r * 27 + w.lane;
+                if (ni >= 0) cp_async16(dst, g.vout + ni);
+                else *dst = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+    }
+    __device__ __forceinline__ void stage_wait() const {
+        cp_async_wait_all();
         __syncwarp();
     }
     // lane = particle: contract the tile of my run if it is staged
@@ -875,11 +887,12 @@ struct Gather {
             g2p_contract(tile + (R.mine - r0) * 27, W, CW, DW, o);
         }
     }
-    // stage + contract every run of the warp (one pass unless the warp spans more than G2P_RMAX cells)
-    __device__ __forceinline__ void run(Gathered& o) const {
-        for (int r0 = 0; r0 < R.nr; r0 += G2P_RMAX) {
-            if (r0) __syncwarp();
-            stage(r0);
+    // passes beyond the first (a warp spanning more than G2P_RMAX cells): stage, then contract
+    __device__ __forceinline__ void remaining_passes(Gathered& o) const {
+        for (int r0 = G2P_RMAX; r0 < R.nr; r0 += G2P_RMAX) {
+            __syncwarp();
+            stage_issue(r0);
+            stage_wait();
             contract(r0, o);
         }
     }
@@ -912,28 +925,32 @@ constexpr int G2P_MINB = 5;  // resident CTAs per SM the register allocation mus
 // (replaces set_vec3_to_zero, mpm_solver.py:251-256) and allocates grid blocks for the new position.
 constexpr int G2P_V_WB = VP_F * 32 * 4 + G2P_TILE_B;
 __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_vertices(Grid g, int Nv, float* __restrict__ VP, float4* __restrict__ VF,
-                                                               float dt, float* __restrict__ dbg_f, Advance adv) {
+                                                               int* __restrict__ CV, float dt, float* __restrict__ dbg_f, Advance adv) {
     extern __shared__ __align__(128) unsigned char smem[];
-    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
+    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); advance_step(adv.st, dt, adv.bcs, adv.n_bc); }
     Warp w;
     if (!warp_begin<G2P_NW, G2P_V_WB>(w, Nv, smem)) return;
     PHASE_BEGIN();
     float* sP = reinterpret_cast<float*>(w.buf);
-    slab_load(w, {Slab{sP, VP, VP_F}});
-    PHASE(g, 3, 0);
+    pdl_wait();
+    pdl_trigger();
+    slab_issue(w, {Slab{sP, VP, VP_F}});
     const bool valid = w.lane < w.cnt;
+    const int p = w.p0 + w.lane;
+    Gather G(g, w, w.buf + VP_F * 32 * 4, valid);
+    G.begin(valid ? CV[p] : 0);  // node loads are in flight before the slab lands
+    PHASE(g, 3, 1);
+    slab_wait(w);
+    PHASE(g, 3, 0);
     float4* r4 = reinterpret_cast<float4*>(sP + w.lane * VP_F);
     float4 xm = valid ? r4[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+    G.set_position(xm.x, xm.y, xm.z);
+    G.stage_wait();
+    PHASE(g, 3, 2);
     Gathered o;
-    const Gather G(g, w, w.buf + VP_F * 32 * 4, valid, xm.x, xm.y, xm.z);
-    PHASE(g, 3, 1);
-    for (int r0 = 0; r0 < G.R.nr; r0 += G2P_RMAX) {  // one pass unless the warp spans more than G2P_RMAX cells
-        if (r0) __syncwarp();
-        G.stage(r0);
-        PHASE(g, 3, 2);
-        G.contract(r0, o);
-        PHASE(g, 3, 3);
-    }
+    G.contract(0, o);
+    G.remaining_passes(o);
+    PHASE(g, 3, 3);
     if (valid) {
         const float dxc = 1.0f / g.inv_dx, a_min = dxc * 2.0f, a_max = g.lim - dxc * 2.0f;
         xm.x = clampf(xm.x + dt * o.v[0], a_min, a_max);
@@ -943,10 +960,13 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_vertices(Grid g, 
         r4[1] = make_float4(o.v[0], o.v[1], o.v[2], o.C[0]);
         r4[2] = make_float4(o.C[1], o.C[2], o.C[3], o.C[4]);
         r4[3] = make_float4(o.C[5], o.C[6], o.C[7], o.C[8]);
-        const int p = w.p0 + w.lane;
         if (dbg_f) { float4 f = VF[p]; dbg_f[3 * p] = f.x; dbg_f[3 * p + 1] = f.y; dbg_f[3 * p + 2] = f.z; }
         VF[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ensure_if_moved(g, G.b, xm.x, xm.y, xm.z);
+        const int nb0 = base_of(xm.x, g.inv_dx), nb1 = base_of(xm.y, g.inv_dx), nb2 = base_of(xm.z, g.inv_dx);
+        if (nb0 != G.b[0] || nb1 != G.b[1] || nb2 != G.b[2]) {  // the blocks under the new stencil exist unless the cell changed
+            ensure_stencil_blocks(g, xm.x, xm.y, xm.z);
+            CV[p] = pack_cell(nb0, nb1, nb2);
+        }
     }
     PHASE(g, 3, 4);
     slab_store(w, {Slab{sP, VP, VP_F}});
@@ -959,18 +979,23 @@ constexpr int G2P_T_WB = (KP_F + TF_F) * 32 * 4 + G2P_TILE_B;
 __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_traditional(Grid g, int Nt, float* __restrict__ TP, float* __restrict__ TF,
                                                                   float dt, Advance adv) {
     extern __shared__ __align__(128) unsigned char smem[];
-    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
+    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); advance_step(adv.st, dt, adv.bcs, adv.n_bc); }
     Warp w;
     if (!warp_begin<G2P_NW, G2P_T_WB>(w, Nt, smem)) return;
     float* sP = reinterpret_cast<float*>(w.buf);
     float* sT = sP + 32 * KP_F;
+    pdl_wait();
+    pdl_trigger();
     slab_load(w, {Slab{sP, TP, KP_F}, Slab{sT, TF, TF_F}});
     const bool valid = w.lane < w.cnt;
     float* r = sP + w.lane * KP_F;
     float x = valid ? r[0] : 0.f, y = valid ? r[1] : 0.f, z = valid ? r[2] : 0.f;
     Gathered o;
-    const Gather G(g, w, w.buf + (KP_F + TF_F) * 32 * 4, valid, x, y, z);
-    G.run(o);
+    Gather G(g, w, w.buf + (KP_F + TF_F) * 32 * 4, valid);
+    G.begin(G.set_position(x, y, z));
+    G.stage_wait();
+    G.contract(0, o);
+    G.remaining_passes(o);
     if (valid) {
         float* t = sT + w.lane * TF_F;
         const float dxc = 1.0f / g.inv_dx, a_min = dxc * 2.0f, a_max = g.lim - dxc * 2.0f;
@@ -996,61 +1021,69 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_traditional(Grid 
 // g2p_e (mpm_utils.py:788-857): C and grad v at the OLD centroid, x/v = mean of the three
 // already-updated corner vertices, d = [x2-x1, x3-x1, (I + dt grad v) d3].  Reads the return-mapped d3
 // of direction buffer `cur`, writes d1,d2,d3 of buffer `cur^1` (see mpm_device.cuh).
-constexpr int G2P_E_WB = (KP_F + EF_F + E12_F) * 32 * 4 + G2P_TILE_B;
+constexpr int G2P_E_WB = (KP_F + E12_F) * 32 * 4 + G2P_TILE_B;
 __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_elements(Grid g, int Ne, float* __restrict__ EP, const int* __restrict__ EF,
                                                                const float4* __restrict__ D3in, float* __restrict__ E12out,
-                                                               float4* __restrict__ D3out, const float* __restrict__ VP, float dt,
-                                                               Advance adv) {
+                                                               float4* __restrict__ D3out, int* __restrict__ CE,
+                                                               const float* __restrict__ VP, float dt, Advance adv) {
     extern __shared__ __align__(128) unsigned char smem[];
-    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
+    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); advance_step(adv.st, dt, adv.bcs, adv.n_bc); }
     Warp w;
     if (!warp_begin<G2P_NW, G2P_E_WB>(w, Ne, smem)) return;
     float* sP = reinterpret_cast<float*>(w.buf);
-    int* sF = reinterpret_cast<int*>(sP + 32 * KP_F);
-    float* s12 = reinterpret_cast<float*>(sF + 32 * EF_F);
+    float* s12 = sP + 32 * KP_F;
     PHASE_BEGIN();
-    slab_load(w, {Slab{sP, EP, KP_F}, Slab{sF, EF, EF_F}});
-    PHASE(g, 5, 0);
+    pdl_wait();
+    pdl_trigger();
+    slab_issue(w, {Slab{sP, EP, KP_F}});
     const bool valid = w.lane < w.cnt;
     float* r = sP + w.lane * KP_F;
     const int p = w.p0 + w.lane;
-    // corner gathers first (one 32-byte sector per corner: {x,y,z,m | vx,vy,vz,C0}) and d3; none of
-    // them depends on the grid gather, and their results are parked in the shared-memory records before
-    // the register-hungry contraction starts
-    float4 x1, v1, x2, v2, x3, v3, d3v;
-    x1 = v1 = x2 = v2 = x3 = v3 = d3v = make_float4(0.f, 0.f, 0.f, 0.f);
-    float ox = 0.f, oy = 0.f, oz = 0.f;
+    // three independent two-hop chains are started before the slab lands: cell -> stencil nodes (cp.async
+    // into the tile), corner slots -> corner vertices {x,y,z,m | vx,vy,vz,C0}, and d3
+    int cell = 0, f0 = 0, f1 = 0, f2 = 0;
+    float4 d3v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
-        const int f0 = sF[w.lane * EF_F], f1 = sF[w.lane * EF_F + 1], f2 = sF[w.lane * EF_F + 2];
+        cell = CE[p];
+        f0 = EF[(size_t)p * EF_F]; f1 = EF[(size_t)p * EF_F + 1]; f2 = EF[(size_t)p * EF_F + 2];
+        d3v = D3in[p];
+    }
+    Gather G(g, w, w.buf + (KP_F + E12_F) * 32 * 4, valid);
+    G.begin(cell);
+    float4 x1, v1, x2, v2, x3, v3;
+    x1 = v1 = x2 = v2 = x3 = v3 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
         const float4* c0 = reinterpret_cast<const float4*>(VP + (size_t)f0 * VP_F);
         const float4* c1 = reinterpret_cast<const float4*>(VP + (size_t)f1 * VP_F);
         const float4* c2 = reinterpret_cast<const float4*>(VP + (size_t)f2 * VP_F);
         x1 = c0[0]; v1 = c0[1]; x2 = c1[0]; v2 = c1[1]; x3 = c2[0]; v3 = c2[1];
-        d3v = D3in[p];
-        ox = r[0]; oy = r[1]; oz = r[2];
     }
-    const Gather G(g, w, w.buf + (KP_F + EF_F + E12_F) * 32 * 4, valid, ox, oy, oz);
     PHASE(g, 5, 1);
-    Gathered o;
-    for (int r0 = 0; r0 < G.R.nr; r0 += G2P_RMAX) {  // one pass unless the warp spans more than G2P_RMAX cells
-        if (r0) __syncwarp();
-        G.stage(r0);
-        PHASE(g, 5, 2);
-        if (r0 == 0 && valid) {
-            const float nx = (x1.x + x2.x + x3.x) / 3.0f, ny = (x1.y + x2.y + x3.y) / 3.0f, nz = (x1.z + x2.z + x3.z) / 3.0f;
-            r[0] = nx; r[1] = ny; r[2] = nz;
-            r[P_V] = (v1.x + v2.x + v3.x) / 3.0f;
-            r[P_V + 1] = (v1.y + v2.y + v3.y) / 3.0f;
-            r[P_V + 2] = (v1.z + v2.z + v3.z) / 3.0f;
-            float2* e2 = reinterpret_cast<float2*>(s12 + w.lane * E12_F);
-            e2[0] = make_float2(x2.x - x1.x, x2.y - x1.y);
-            e2[1] = make_float2(x2.z - x1.z, x3.x - x1.x);
-            e2[2] = make_float2(x3.y - x1.y, x3.z - x1.z);
-            ensure_if_moved(g, G.b, nx, ny, nz);
+    slab_wait(w);
+    PHASE(g, 5, 0);
+    G.set_position(valid ? r[0] : 0.f, valid ? r[1] : 0.f, valid ? r[2] : 0.f);
+    G.stage_wait();
+    PHASE(g, 5, 2);
+    if (valid) {  // park the corner results in the shared-memory records before the register-hungry contraction
+        const float nx = (x1.x + x2.x + x3.x) / 3.0f, ny = (x1.y + x2.y + x3.y) / 3.0f, nz = (x1.z + x2.z + x3.z) / 3.0f;
+        r[0] = nx; r[1] = ny; r[2] = nz;
+        r[P_V] = (v1.x + v2.x + v3.x) / 3.0f;
+        r[P_V + 1] = (v1.y + v2.y + v3.y) / 3.0f;
+        r[P_V + 2] = (v1.z + v2.z + v3.z) / 3.0f;
+        float2* e2 = reinterpret_cast<float2*>(s12 + w.lane * E12_F);
+        e2[0] = make_float2(x2.x - x1.x, x2.y - x1.y);
+        e2[1] = make_float2(x2.z - x1.z, x3.x - x1.x);
+        e2[2] = make_float2(x3.y - x1.y, x3.z - x1.z);
+        const int nb0 = base_of(nx, g.inv_dx), nb1 = base_of(ny, g.inv_dx), nb2 = base_of(nz, g.inv_dx);
+        if (nb0 != G.b[0] || nb1 != G.b[1] || nb2 != G.b[2]) {
+            ensure_stencil_blocks(g, nx, ny, nz);
+            CE[p] = pack_cell(nb0, nb1, nb2);
         }
-        PHASE(g, 5, 3);  // corner consume
-        G.contract(r0, o);
     }
+    PHASE(g, 5, 3);  // corner consume
+    Gathered o;
+    G.contract(0, o);
+    G.remaining_passes(o);
     PHASE(g, 5, 4);  // contraction
     if (valid) {
 #pragma unroll

@@ -79,8 +79,10 @@ class ShardedMPM:
         self._ck(self.lib.mpm_set_shared_blocks(self.h, C.c_void_p(self._shared_keep.data_ptr()), len(shared), self._stream()))
         self.n_shared = len(shared)
         need = max(self.n_shared, 1) * 64 * 8
-        if self.buf is None or self.buf.numel() < need:
-            self.buf = torch.zeros(int(need * 1.5), dtype=torch.float32, device=self.device)
+        if self.buf is None:
+            self.buf = torch.zeros(max(int(need * 2), 1 << 20), dtype=torch.float32, device=self.device)
+        elif self.buf.numel() < need:  # the C loop holds the buffer's address: it cannot move mid-step
+            raise RuntimeError("shared-block buffer too small; construct ShardedMPM with a larger reserve")
         self.k = 0
         self.stats["rebuilds"] += 1
         self.stats["shared_blocks"] = self.n_shared
@@ -88,35 +90,50 @@ class ShardedMPM:
 
     def step(self, dt, nsub, mesh_x=None, mesh_v=None, joint_verts_v=None, joint_faces_v=None):
         """nsub substeps; substep k sees body points mesh_x + dt*k*mesh_v (the callers' inner loop,
-        train_material_params.py:622-626).  Joint velocity arrays are the GLOBAL ones."""
+        train_material_params.py:622-626).  Joint velocity arrays are the GLOBAL ones.  The substep loop
+        runs in C (mpm_step_sharded); per substep it calls back once for the all-reduce."""
         dev = self.device
         T = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32, device=dev).contiguous()
         mesh_x, mesh_v = T(mesh_x), T(mesh_v)
         jv = jf = None
         if joint_verts_v is not None and joint_faces_v is not None:
             p = self.part
-            vi = torch.as_tensor(p.verts[:p.num_joint_v], device=dev, dtype=torch.long)
-            fi = torch.as_tensor(p.elems[:p.num_joint_f], device=dev, dtype=torch.long)
-            jv = T(joint_verts_v)[vi].contiguous() if p.num_joint_v else torch.zeros(1, 3, device=dev)
-            jf = T(joint_faces_v)[fi].contiguous() if p.num_joint_f else torch.zeros(1, 3, device=dev)
-        st = self._stream()
-        for k in range(int(nsub)):
-            fin = _lib.MpmFrameInputs()
-            mx = None if mesh_x is None else (mesh_x + float(np.float32(dt * k)) * mesh_v if k else mesh_x)
-            fin.mesh_x = None if mx is None else C.c_void_p(mx.data_ptr())
-            fin.mesh_v = None if mesh_v is None else C.c_void_p(mesh_v.data_ptr())
-            if jv is not None:
-                fin.joint_verts_v, fin.joint_faces_v = C.c_void_p(jv.data_ptr()), C.c_void_p(jf.data_ptr())
-            self._ck(self.lib.mpm_step_scatter(self.h, C.c_float(dt), C.byref(fin), st))
-            if self.buf is None or self.k >= self.refresh:
+            if not hasattr(self, "_jidx"):
+                self._jidx = (torch.as_tensor(p.verts[:p.num_joint_v], device=dev, dtype=torch.long),
+                              torch.as_tensor(p.elems[:p.num_joint_f], device=dev, dtype=torch.long))
+            jv = T(joint_verts_v)[self._jidx[0]].contiguous() if p.num_joint_v else torch.zeros(1, 3, device=dev)
+            jf = T(joint_faces_v)[self._jidx[1]].contiguous() if p.num_joint_f else torch.zeros(1, 3, device=dev)
+        if self.buf is None:
+            self.rebuild_shared()
+        fin = _lib.MpmFrameInputs()
+        fin.mesh_x = None if mesh_x is None else C.c_void_p(mesh_x.data_ptr())
+        fin.mesh_v = None if mesh_v is None else C.c_void_p(mesh_v.data_ptr())
+        if jv is not None:
+            fin.joint_verts_v, fin.joint_faces_v = C.c_void_p(jv.data_ptr()), C.c_void_p(jf.data_ptr())
+        err = []
+
+        def exchange(ctx, buf, n):
+            try:
+                self._all_reduce(self.buf[:n])
+                return 0
+            except Exception as e:  # noqa: BLE001 -- must not unwind through C
+                err.append(e)
+                return 1
+
+        def rebuild(ctx):
+            try:
                 self.rebuild_shared()
-            if self.n_shared:
-                view = self.buf[: self.n_shared * 64 * 8]
-                self._ck(self.lib.mpm_shared_pack(self.h, C.c_void_p(view.data_ptr()), st))
-                self._all_reduce(view)
-                self._ck(self.lib.mpm_shared_unpack(self.h, C.c_void_p(view.data_ptr()), st))
-            self._ck(self.lib.mpm_step_gather(self.h, C.c_float(dt), st))
-            self.k += 1
+                return 0
+            except Exception as e:  # noqa: BLE001
+                err.append(e)
+                return 1
+        ex, rb = _lib.EXCHANGE_FN(exchange), _lib.REBUILD_FN(rebuild)
+        rc = self.lib.mpm_step_sharded(self.h, C.c_float(dt), int(nsub), C.byref(fin), C.c_void_p(self.buf.data_ptr()),
+                                       self.refresh, ex, rb, None, self._stream())
+        if err:
+            raise err[0]
+        self._ck(rc)
+        self._keep = (mesh_x, mesh_v, jv, jf)
         self.state._stale = True
         self.state._solver = self.solver
 
