@@ -321,6 +321,10 @@ __global__ void k_particle_ops(int n, float* __restrict__ rec, int F, const uint
 //           atomics; global atomics drop from 27*4 per particle to 27 per cell run.
 // KIND 0: cloth element, 1: traditional (stress*vol, :496), 2: cloth vertex.
 constexpr int P2G_NW = 4;
+#ifndef MPM_P2G_PF
+#define MPM_P2G_PF 2
+#endif
+constexpr int P2G_PF = MPM_P2G_PF;  // stage-2 prefetch depth (particles), divides 8
 constexpr int P2G_T_B = 32 * 9 * 16, P2G_U_B = 32 * 3 * 16, P2G_W_B = 32 * 9 * 4;
 constexpr int P2G_WB = P2G_T_B + P2G_U_B + P2G_W_B;  // 7296 B; the raw slabs (<= 4864 B) are overlaid on it
 constexpr int P2G_SMEM = 128 + P2G_NW * P2G_WB;
@@ -344,8 +348,15 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
     if (!warp_begin<P2G_NW, P2G_WB>(w, n, smem)) return;
     PHASE_BEGIN();
     float* buf = reinterpret_cast<float*>(w.buf);
-    pdl_wait();     // everything above overlapped the predecessor's tail (programmatic dependent launch)
-    pdl_trigger();  // let the successor's CTAs be scheduled into the slots this grid frees
+    // PDL invariant of this file: a kernel triggers its dependents only AFTER its own griddepcontrol.wait, so
+    // "my grid has started" implies "my predecessor's predecessor has completed" -- that is what the code in
+    // front of a wait may rely on.
+    // The vertex scatter only needs its predecessor (the element kernel) for the vertex forces: the VP slab is
+    // loaded and unpacked while the element kernel drains, griddepcontrol.wait sits in front of the VF read.
+    if (KIND != 2) {
+        pdl_wait();
+        pdl_trigger();  // let the successor's CTAs be scheduled into the slots this grid frees
+    }
     // ---- stage 0
     float* raw1 = buf + 32 * F0;
     float* s12 = buf + 32 * KP_F;
@@ -354,7 +365,7 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
     float* sEK = sEF + 32 * EF_F;
     if (KIND == 0) slab_load(w, {Slab{buf, in.KP, KP_F}, Slab{s12, in.E12, E12_F}, Slab{sD3, in.D3, 4}, Slab{sEF, in.EF, EF_F}, Slab{sEK, in.EK, EK_F}});
     if (KIND == 1) slab_load(w, {Slab{buf, in.KP, KP_F}, Slab{raw1, in.SF, S_F}});
-    if (KIND == 2) slab_load(w, {Slab{buf, in.KP, VP_F}, Slab{raw1, in.SF, VF_F}});
+    if (KIND == 2) slab_load(w, {Slab{buf, in.KP, VP_F}});
     PHASE(g, KIND, 0);  // slab load
     // ---- stage 1
     const bool valid = w.lane < w.cnt;
@@ -369,8 +380,6 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
             x[0] = a.x; x[1] = a.y; x[2] = a.z; m = a.w;
             v[0] = b.x; v[1] = b.y; v[2] = b.z;
             C[0] = b.w; C[1] = c.x; C[2] = c.y; C[3] = c.z; C[4] = c.w; C[5] = d.x; C[6] = d.y; C[7] = d.z; C[8] = d.w;
-            const float4 f4 = reinterpret_cast<const float4*>(raw1)[w.lane];
-            fv[0] = f4.x; fv[1] = f4.y; fv[2] = f4.z;
         } else {
             x[0] = r[0]; x[1] = r[1]; x[2] = r[2]; m = r[P_M];
             v[0] = r[P_V]; v[1] = r[P_V + 1]; v[2] = r[P_V + 2];
@@ -431,6 +440,14 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
 #pragma unroll
             for (int i = 0; i < 3; i++) bspline(f[a], i, wgt[a][i], dwg[a][i]);
         }
+        if (KIND == 2) {  // the weights above were computed while the element kernel drained
+            pdl_wait();
+            pdl_trigger();
+            if (valid) {
+                const float4 f4 = __ldcg(reinterpret_cast<const float4*>(in.SF) + w.p0 + w.lane);  // written by L2 atomics
+                fv[0] = f4.x; fv[1] = f4.y; fv[2] = f4.z;
+            }
+        }
         // w m (v + C dpos) + dt w f_vertex = w (A + B_x i + B_y j + B_z k), dpos = (ijk - f) dx
         const float mdx = m * g.dx;
         float A[3];
@@ -488,32 +505,43 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
     auto flush = [&](int c, float2 lo, float2 hi) {
         if (act && (hi.y != 0.0f || lo.x != 0.0f || lo.y != 0.0f || hi.x != 0.0f)) {
             const int ni = node_index(g, (c & 1023) - 2 + li, ((c >> 10) & 1023) - 2 + lj, ((c >> 20) & 1023) - 2 + lk);
+#ifdef MPM_NO_RED  // analysis build: everything but the atomics (results are wrong)
+            if (ni == -12345) atomicAdd(&g.acc[0], make_float4(lo.x, lo.y, hi.x, hi.y));
+#else
             if (ni >= 0) atomicAdd(&g.acc[ni], make_float4(lo.x, lo.y, hi.x, hi.y));
             else g.flags[1] = 1;
+#endif
         }
     };
     float2 alo = make_float2(0.f, 0.f), ahi = alo;
     int c = __shfl_sync(0xffffffffu, mycell, 0);
-    float4 Tn = pT[0], Un = pU[0];
-    float wn = pW[0];
-#pragma unroll 8
-    for (int q = 0; q < 32; q++) {  // records past cnt contribute zeros
-        const float4 T = Tn, U = Un;
-        const float wij = wn;
-        if (q < 31) {  // the loads of particle q+1 are in flight while particle q is accumulated
-            Tn = pT[(q + 1) * 9];
-            Un = pU[(q + 1) * 3];
-            wn = pW[(q + 1) * 9];
+    // register ring of P2G_PF particles: the shared-memory loads run P2G_PF iterations ahead of the
+    // accumulation, so the loop is bound by issue slots and not by LDS latency
+    float4 Tq[P2G_PF], Uq[P2G_PF];
+    float wq[P2G_PF];
+#pragma unroll
+    for (int d = 0; d < P2G_PF; d++) { Tq[d] = pT[d * 9]; Uq[d] = pU[d * 3]; wq[d] = pW[d * 9]; }
+#pragma unroll 1
+    for (int q0 = 0; q0 < 32; q0 += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {  // records past cnt contribute zeros
+            const int q = q0 + j;
+            const float4 T = Tq[j % P2G_PF], U = Uq[j % P2G_PF];
+            const float wij = wq[j % P2G_PF];
+            const int qn = min(q + P2G_PF, 31);
+            Tq[j % P2G_PF] = pT[qn * 9];
+            Uq[j % P2G_PF] = pU[qn * 3];
+            wq[j % P2G_PF] = pW[qn * 9];
+            if (q > 0 && ((R.starts >> q) & 1u)) {
+                flush(c, alo, ahi);
+                alo = ahi = make_float2(0.f, 0.f);
+                c = __shfl_sync(0xffffffffu, mycell, q);
+            }
+            alo = fma2(U.w, make_float2(T.x, T.y), alo);
+            ahi = fma2(U.w, make_float2(T.z, T.w), ahi);
+            alo = fma2(wij, make_float2(U.x, U.y), alo);
+            ahi.x = fmaf(wij, U.z, ahi.x);
         }
-        if (q > 0 && ((R.starts >> q) & 1u)) {
-            flush(c, alo, ahi);
-            alo = ahi = make_float2(0.f, 0.f);
-            c = __shfl_sync(0xffffffffu, mycell, q);
-        }
-        alo = fma2(U.w, make_float2(T.x, T.y), alo);
-        ahi = fma2(U.w, make_float2(T.z, T.w), ahi);
-        alo = fma2(wij, make_float2(U.x, U.y), alo);
-        ahi.x = fmaf(wij, U.z, ahi.x);
     }
     flush(c, alo, ahi);
     PHASE(g, KIND, 3);  // stage 2
@@ -840,7 +868,6 @@ struct Gather {
         R = find_runs(w.lane, w.cnt, cell);
         if ((R.starts >> w.lane) & 1u) runcell[R.mine] = cell;
         __syncwarp();
-        stage_issue(0);
     }
     __device__ __forceinline__ int set_position(float x, float y, float z) {
         const float gp[3] = {x * g.inv_dx, y * g.inv_dx, z * g.inv_dx};
@@ -920,7 +947,10 @@ struct Advance {
 };
 
 constexpr int G2P_NW = 4;
-constexpr int G2P_MINB = 5;  // resident CTAs per SM the register allocation must allow (<= 96 registers)
+#ifndef MPM_G2P_MINB
+#define MPM_G2P_MINB 4
+#endif
+constexpr int G2P_MINB = MPM_G2P_MINB;  // resident CTAs per SM the register allocation must allow (4: <= 128 registers, no spills)
 // g2p_v for cloth vertices (mpm_utils.py:716-786); also clears vertex_force for the next substep
 // (replaces set_vec3_to_zero, mpm_solver.py:251-256) and allocates grid blocks for the new position.
 constexpr int G2P_V_WB = VP_F * 32 * 4 + G2P_TILE_B;
@@ -932,13 +962,16 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_vertices(Grid g, 
     if (!warp_begin<G2P_NW, G2P_V_WB>(w, Nv, smem)) return;
     PHASE_BEGIN();
     float* sP = reinterpret_cast<float*>(w.buf);
-    pdl_wait();
-    pdl_trigger();
+    // VP and CV were last written by the previous substep's G2P: the slab load and the run search overlap the
+    // tail of the grid update; only the node velocities need the predecessor
     slab_issue(w, {Slab{sP, VP, VP_F}});
     const bool valid = w.lane < w.cnt;
     const int p = w.p0 + w.lane;
     Gather G(g, w, w.buf + VP_F * 32 * 4, valid);
-    G.begin(valid ? CV[p] : 0);  // node loads are in flight before the slab lands
+    G.begin(valid ? CV[p] : 0);
+    pdl_wait();
+    pdl_trigger();
+    G.stage_issue(0);  // node loads are in flight before the slab lands
     PHASE(g, 3, 1);
     slab_wait(w);
     PHASE(g, 3, 0);
@@ -993,6 +1026,7 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_traditional(Grid 
     Gathered o;
     Gather G(g, w, w.buf + (KP_F + TF_F) * 32 * 4, valid);
     G.begin(G.set_position(x, y, z));
+    G.stage_issue(0);
     G.stage_wait();
     G.contract(0, o);
     G.remaining_passes(o);
@@ -1033,14 +1067,14 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_elements(Grid g, 
     float* sP = reinterpret_cast<float*>(w.buf);
     float* s12 = sP + 32 * KP_F;
     PHASE_BEGIN();
-    pdl_wait();
-    pdl_trigger();
+    // Everything up to the corner reads is independent of the predecessor (the vertex G2P): EP / CE / EF / D3 were
+    // last written by earlier kernels and the grid velocities by the grid update, whose completion every CTA
+    // of the predecessor has waited for before this grid could start.  So the gather and the contraction
+    // of this kernel fill the predecessor's tail; griddepcontrol.wait sits in front of the corner reads.
     slab_issue(w, {Slab{sP, EP, KP_F}});
     const bool valid = w.lane < w.cnt;
     float* r = sP + w.lane * KP_F;
     const int p = w.p0 + w.lane;
-    // three independent two-hop chains are started before the slab lands: cell -> stencil nodes (cp.async
-    // into the tile), corner slots -> corner vertices {x,y,z,m | vx,vy,vz,C0}, and d3
     int cell = 0, f0 = 0, f1 = 0, f2 = 0;
     float4 d3v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
@@ -1050,21 +1084,39 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_elements(Grid g, 
     }
     Gather G(g, w, w.buf + (KP_F + E12_F) * 32 * 4, valid);
     G.begin(cell);
-    float4 x1, v1, x2, v2, x3, v3;
-    x1 = v1 = x2 = v2 = x3 = v3 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-        const float4* c0 = reinterpret_cast<const float4*>(VP + (size_t)f0 * VP_F);
-        const float4* c1 = reinterpret_cast<const float4*>(VP + (size_t)f1 * VP_F);
-        const float4* c2 = reinterpret_cast<const float4*>(VP + (size_t)f2 * VP_F);
-        x1 = c0[0]; v1 = c0[1]; x2 = c1[0]; v2 = c1[1]; x3 = c2[0]; v3 = c2[1];
-    }
+    G.stage_issue(0);
     PHASE(g, 5, 1);
     slab_wait(w);
     PHASE(g, 5, 0);
     G.set_position(valid ? r[0] : 0.f, valid ? r[1] : 0.f, valid ? r[2] : 0.f);
     G.stage_wait();
     PHASE(g, 5, 2);
-    if (valid) {  // park the corner results in the shared-memory records before the register-hungry contraction
+    {
+        Gathered o;
+        G.contract(0, o);
+        G.remaining_passes(o);
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) r[P_C + i] = o.C[i];
+            float nd3[3];
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) {
+                float m0 = o.G[3 * rr] * dt + (rr == 0 ? 1.0f : 0.0f);
+                float m1 = o.G[3 * rr + 1] * dt + (rr == 1 ? 1.0f : 0.0f);
+                float m2 = o.G[3 * rr + 2] * dt + (rr == 2 ? 1.0f : 0.0f);
+                nd3[rr] = m0 * d3v.x + m1 * d3v.y + m2 * d3v.z;
+            }
+            D3out[p] = make_float4(nd3[0], nd3[1], nd3[2], 0.f);
+        }
+    }
+    PHASE(g, 5, 4);  // contraction
+    pdl_wait();      // the corner vertices must have been moved by the vertex G2P
+    pdl_trigger();
+    if (valid) {
+        const float4* c0 = reinterpret_cast<const float4*>(VP + (size_t)f0 * VP_F);
+        const float4* c1 = reinterpret_cast<const float4*>(VP + (size_t)f1 * VP_F);
+        const float4* c2 = reinterpret_cast<const float4*>(VP + (size_t)f2 * VP_F);
+        const float4 x1 = c0[0], v1 = c0[1], x2 = c1[0], v2 = c1[1], x3 = c2[0], v3 = c2[1];
         const float nx = (x1.x + x2.x + x3.x) / 3.0f, ny = (x1.y + x2.y + x3.y) / 3.0f, nz = (x1.z + x2.z + x3.z) / 3.0f;
         r[0] = nx; r[1] = ny; r[2] = nz;
         r[P_V] = (v1.x + v2.x + v3.x) / 3.0f;
@@ -1080,24 +1132,7 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_elements(Grid g, 
             CE[p] = pack_cell(nb0, nb1, nb2);
         }
     }
-    PHASE(g, 5, 3);  // corner consume
-    Gathered o;
-    G.contract(0, o);
-    G.remaining_passes(o);
-    PHASE(g, 5, 4);  // contraction
-    if (valid) {
-#pragma unroll
-        for (int i = 0; i < 9; i++) r[P_C + i] = o.C[i];
-        float nd3[3];
-#pragma unroll
-        for (int rr = 0; rr < 3; rr++) {
-            float m0 = o.G[3 * rr] * dt + (rr == 0 ? 1.0f : 0.0f);
-            float m1 = o.G[3 * rr + 1] * dt + (rr == 1 ? 1.0f : 0.0f);
-            float m2 = o.G[3 * rr + 2] * dt + (rr == 2 ? 1.0f : 0.0f);
-            nd3[rr] = m0 * d3v.x + m1 * d3v.y + m2 * d3v.z;
-        }
-        D3out[p] = make_float4(nd3[0], nd3[1], nd3[2], 0.f);
-    }
+    PHASE(g, 5, 3);  // corner reads
     slab_store(w, {Slab{sP, EP, KP_F}, Slab{s12, E12out, E12_F}});
     PHASE(g, 5, 5);  // epilogue + store
     PHASE_END(g, 5);
