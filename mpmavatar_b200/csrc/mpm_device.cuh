@@ -408,6 +408,10 @@ __device__ __forceinline__ void bulk_commit_wait() {
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+// the same with src_bytes (0 or 16) read from global and the rest of the 16 bytes zero-filled
+__device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");

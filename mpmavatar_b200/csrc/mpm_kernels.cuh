@@ -790,6 +790,11 @@ __device__ __forceinline__ void g2p_contract(const float4* __restrict__ T, const
     float2 v_xy = z2, C0_xy = z2, C1_xy = z2, C2_xy = z2, G0_xy = z2, G1_xy = z2, G2_xy = z2;
     float2 vz_c1z = z2, c2z_g2z = z2, c0z_g0z = z2;
     float g1z = 0.f;
+#ifdef MPM_G2P_ROWPF
+    float4 nx[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) nx[q] = T[q];
+#endif
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         float2 A0_xy = z2, A1_xy = z2, A2_xy = z2, B0_xy = z2, C0q_xy = z2, A0z_A1z = z2, B0z_C0z = z2;
@@ -799,9 +804,19 @@ __device__ __forceinline__ void g2p_contract(const float4* __restrict__ T, const
             // one z-row (3 nodes, 12 registers) is fetched at a time; the compiler barrier keeps ptxas from
             // hoisting all 27 LDS.128 (108 registers) to the top and spilling
             float4 pl[3];
+#ifdef MPM_G2P_ROWPF  // two z-rows in flight: the next row is fetched before the current one is consumed
+#pragma unroll
+            for (int q = 0; q < 3; q++) pl[q] = nx[q];
+            if (i * 3 + j < 8) {
+#pragma unroll
+                for (int q = 0; q < 3; q++) nx[q] = T[(i * 3 + j + 1) * 3 + q];
+            }
+            asm volatile("" ::: "memory");
+#else
 #pragma unroll
             for (int q = 0; q < 3; q++) pl[q] = T[(i * 3 + j) * 3 + q];
             asm volatile("" ::: "memory");
+#endif
             float2 a_xy = z2, b_xy = z2, c_xy = z2, bz_cz = z2;
             float az = 0.f;
 #pragma unroll
@@ -879,17 +894,25 @@ struct Gather {
         return pack_cell(b[0], b[1], b[2]);
     }
     // lanes 0..26 copy the nodes of runs [r0, r0 + G2P_RMAX) into the tile with cp.async (LDGSTS): global ->
-    // shared without staging registers, every run of the pass in flight at once
+    // shared without staging registers, every run of the pass in flight at once.  Four runs are addressed per
+    // trip so that their (dependent, integer) index chains interleave; a node outside the grid and the unused
+    // slots of the last trip are zero-filled by a cp.async of source size 0 instead of a branch.
     __device__ __forceinline__ void stage_issue(int r0) const {
         const int nrp = min(G2P_RMAX, R.nr - r0);
         if (w.lane < 27) {
-            const int li = w.lane / 9, lj = (w.lane / 3) % 3, lk = w.lane % 3;
-            for (int r = 0; r < nrp; r++) {
-                const int c = runcell[r0 + r];
-                const int ni = node_index(g, (c & 1023) - 2 + li, ((c >> 10) & 1023) - 2 + lj, ((c >> 20) & 1023) - 2 + lk);
-                float4* dst = tile + r * 27 + w.lane;
-                if (ni >= 0) cp_async16(dst, g.vout + ni);
-                else *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int li = w.lane / 9 - 2, lj = (w.lane / 3) % 3 - 2, lk = w.lane % 3 - 2;
+            float4* dst = tile + w.lane;
+            for (int rb = 0; rb < nrp; rb += 4) {
+                int c[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) c[u] = runcell[r0 + min(rb + u, nrp - 1)];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const unsigned ix = (c[u] & 1023) + li, iy = ((c[u] >> 10) & 1023) + lj, iz = ((unsigned)c[u] >> 20) + lk;
+                    const bool ok = max(max(ix, iy), iz) < (unsigned)g.n && rb + u < nrp;
+                    const unsigned ni = ((((ix >> 2) * g.nb + (iy >> 2)) * g.nb + (iz >> 2)) << 6) + (((ix & 3) << 4) | ((iy & 3) << 2) | (iz & 3));
+                    cp_async16_zfill(dst + (rb + u) * 27, g.vout + (ok ? ni : 0u), ok ? 16 : 0);
+                }
             }
         }
     }
@@ -1075,12 +1098,20 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_elements(Grid g, 
     const bool valid = w.lane < w.cnt;
     float* r = sP + w.lane * KP_F;
     const int p = w.p0 + w.lane;
-    int cell = 0, f0 = 0, f1 = 0, f2 = 0;
-    float4 d3v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-        cell = CE[p];
-        f0 = EF[(size_t)p * EF_F]; f1 = EF[(size_t)p * EF_F + 1]; f2 = EF[(size_t)p * EF_F + 2];
-        d3v = D3in[p];
+    int cell = 0;
+    {   // corner slots and d3 are not needed before the contraction is done: park them in the (still unused)
+        // E12 staging area of this lane to keep them out of the register-hungry contraction
+        int f0 = 0, f1 = 0, f2 = 0;
+        float4 d3v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            cell = CE[p];
+            f0 = EF[(size_t)p * EF_F]; f1 = EF[(size_t)p * EF_F + 1]; f2 = EF[(size_t)p * EF_F + 2];
+            d3v = D3in[p];
+        }
+        float4* park = reinterpret_cast<float4*>(s12 + w.lane * E12_F);  // 24 bytes per lane, 8-byte aligned
+        reinterpret_cast<int2*>(park)[0] = make_int2(f0, f1);
+        reinterpret_cast<float2*>(park)[1] = make_float2(__int_as_float(f2), d3v.x);
+        reinterpret_cast<float2*>(park)[2] = make_float2(d3v.y, d3v.z);
     }
     Gather G(g, w, w.buf + (KP_F + E12_F) * 32 * 4, valid);
     G.begin(cell);
@@ -1098,6 +1129,9 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_elements(Grid g, 
         if (valid) {
 #pragma unroll
             for (int i = 0; i < 9; i++) r[P_C + i] = o.C[i];
+            const float2* park = reinterpret_cast<const float2*>(s12 + w.lane * E12_F);
+            const float2 pk1 = park[1], pk2 = park[2];
+            const float3 d3v = make_float3(pk1.y, pk2.x, pk2.y);
             float nd3[3];
 #pragma unroll
             for (int rr = 0; rr < 3; rr++) {
@@ -1113,6 +1147,8 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_elements(Grid g, 
     pdl_wait();      // the corner vertices must have been moved by the vertex G2P
     pdl_trigger();
     if (valid) {
+        const int2 pk0 = reinterpret_cast<const int2*>(s12 + w.lane * E12_F)[0];
+        const int f0 = pk0.x, f1 = pk0.y, f2 = __float_as_int(reinterpret_cast<const float2*>(s12 + w.lane * E12_F)[1].x);
         const float4* c0 = reinterpret_cast<const float4*>(VP + (size_t)f0 * VP_F);
         const float4* c1 = reinterpret_cast<const float4*>(VP + (size_t)f1 * VP_F);
         const float4* c2 = reinterpret_cast<const float4*>(VP + (size_t)f2 * VP_F);
