@@ -410,13 +410,6 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
     const int cur = s->cur;
     const bool pdl = s->use_pdl && !s->profiling;
     if (halves & HALF_SCATTER) {
-    // the two scatter kernels only need the block table and the particle positions, both fixed since
-    // the end of the previous substep: fork them onto a side stream (a parallel branch of the graph)
-    const bool fork = !s->profiling && (a.collider || a.mover) && (halves & HALF_SCATTER);
-    if (fork) {
-        CK(cudaEventRecord(s->ev_fork, q));
-        CK(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
-    }
     if (n_ops) {
         if (s->Ne) k_particle_ops<<<cdiv(s->Ne, 256), 256, 0, q>>>(s->Ne, R.EP, KP_F, s->permE, 0, s->d_ops, n_ops, s->st, a.dt);
         if (s->Nt) k_particle_ops<<<cdiv(s->Nt, 256), 256, 0, q>>>(s->Nt, R.TP, KP_F, s->permT, s->Ne, s->d_ops, n_ops, s->st, a.dt);
@@ -445,30 +438,25 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
         s->launches++;
     }
     if (ev) CK(cudaEventRecord(ev[2], q));
-    {
-        cudaStream_t qs = fork ? s->side : q;
-        if (a.collider) {
-            k_collider_scatter<<<cdiv(s->cfg.n_mesh_f, 128), 128, 0, qs>>>(s->g, s->cfg.n_mesh_f, s->mesh_faces, s->mesh_x, s->mesh_v, s->st, a.dt, a.advance_mesh ? 1 : 0);
+    {   // body-mesh collider and joint movers (mpm_solver.py:382-472): one launch behind the P2G kernels
+        const int tot = a.mover ? a.njt + s->cfg.num_joint_v + s->cfg.num_joint_f : 0;
+        ColliderArgs ca{a.collider ? s->cfg.n_mesh_f : 0, s->mesh_faces, s->mesh_x, s->mesh_v, s->st, a.dt, a.advance_mesh ? 1 : 0};
+        MoverArgs ma{a.mover ? a.njt : 0, a.mover ? s->cfg.num_joint_v : 0, a.mover ? s->cfg.num_joint_f : 0, s->Nt,
+                     s->joint_t, s->joint_v, s->joint_f, R.EP, R.TP, R.VP, s->invE, s->invT, s->invV};
+        if (ev) {  // profiling: separate launches so that the two phases are timed separately
+            if (ca.Mf) { k_collider_scatter<<<cdiv(ca.Mf, 128), 128, 0, q>>>(s->g, ca); s->launches++; }
+            CK(cudaEventRecord(ev[3], q));
+            if (tot) { k_mover_scatter<<<cdiv(tot, 128), 128, 0, q>>>(s->g, ma); s->launches++; }
+            CK(cudaEventRecord(ev[4], q));
+        } else if (ca.Mf + tot) {
+            launch_pdl(k_body_scatter, cdiv(ca.Mf + tot, 128), 128, 0, q, pdl, s->g, ca, ma);
             s->launches++;
-        }
-        if (ev) CK(cudaEventRecord(ev[3], q));
-        if (a.mover) {
-            int tot = a.njt + s->cfg.num_joint_v + s->cfg.num_joint_f;
-            if (tot) {
-                k_mover_scatter<<<cdiv(tot, 128), 128, 0, qs>>>(s->g, a.njt, s->cfg.num_joint_v, s->cfg.num_joint_f, s->Nt, s->joint_t, s->joint_v, s->joint_f, R.EP, R.TP, R.VP, s->invE, s->invT, s->invV);
-                s->launches++;
-            }
-        }
-        if (ev) CK(cudaEventRecord(ev[4], q));
-        if (fork) {
-            CK(cudaEventRecord(s->ev_join, s->side));
-            CK(cudaStreamWaitEvent(q, s->ev_join, 0));
         }
     }
     }  // HALF_SCATTER
     if (!(halves & HALF_GATHER)) return;
     // one thread per node of the active blocks, grid-strided over the device-side block count
-    k_grid_update<<<GRID_UPDATE_CTAS, 256, 0, q>>>(s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, s->d_bcs, n_bc, s->st);
+    launch_pdl(k_grid_update, GRID_UPDATE_CTAS, 256, 0, q, pdl, s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, (const BCDesc*)s->d_bcs, n_bc, (const StepState*)s->st);
     s->launches++;
     if (ev) CK(cudaEventRecord(ev[5], q));
     Advance none{nullptr, nullptr, 0}, adv{s->st, s->d_bcs, n_bc};

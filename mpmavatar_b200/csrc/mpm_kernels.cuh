@@ -320,7 +320,10 @@ __global__ void k_particle_ops(int n, float* __restrict__ rec, int F, const uint
 //           looked up while the current run is summed).  No intra-warp reduction, no shared-memory
 //           atomics; global atomics drop from 27*4 per particle to 27 per cell run.
 // KIND 0: cloth element, 1: traditional (stress*vol, :496), 2: cloth vertex.
-constexpr int P2G_NW = 4;
+#ifndef MPM_P2G_NW
+#define MPM_P2G_NW 1
+#endif
+constexpr int P2G_NW = MPM_P2G_NW;  // warps (= slabs) per CTA
 #ifndef MPM_P2G_PF
 #define MPM_P2G_PF 2
 #endif
@@ -573,11 +576,21 @@ __device__ __forceinline__ bool scatter_ok(const Grid& g, const Stencil& s) {
 // compute_mesh (mpm_solver.py:829-880).  Only nodes of ALLOCATED blocks are written: a node
 // outside every particle stencil is never read by G2P, so the body mesh never allocates grid
 // (and faces far from the cloth cost eight table reads and nothing else).
-__global__ void __launch_bounds__(128) k_collider_scatter(Grid g, int Mf, const int* __restrict__ faces,
-                                                          const float* __restrict__ px, const float* __restrict__ pv,
-                                                          const StepState* __restrict__ st, float dt, int advance) {
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= Mf) return;
+struct ColliderArgs {
+    int Mf;
+    const int* faces;
+    const float *px, *pv;
+    const StepState* st;
+    float dt;
+    int advance;
+};
+__device__ __forceinline__ void collider_scatter_face(const Grid& g, const ColliderArgs& ca, int f) {
+    const int* __restrict__ faces = ca.faces;
+    const float* __restrict__ px = ca.px;
+    const float* __restrict__ pv = ca.pv;
+    const StepState* __restrict__ st = ca.st;
+    const float dt = ca.dt;
+    const int advance = ca.advance;
     const float s = advance ? (float)((double)dt * (double)st->k) : 0.0f;
     int id[3] = {faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]};
     float P[3][3], fv[3] = {0, 0, 0}, fp[3] = {0, 0, 0};
@@ -619,17 +632,23 @@ __global__ void __launch_bounds__(128) k_collider_scatter(Grid g, int Mf, const 
                 atomicAdd(&g.coln[ni], make_float4(ww * nx, ww * ny, ww * nz, 0.0f));
             }
 }
+__global__ void __launch_bounds__(128) k_collider_scatter(Grid g, ColliderArgs ca) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < ca.Mf) collider_scatter_face(g, ca, f);
+}
 
 // add_velocity_traditional / _verts / _faces (mpm_solver.py:677-788) in one launch:
 // threads [0,njt) pinned traditional tail, [njt, njt+njv) joint vertices, then joint faces.
-__global__ void __launch_bounds__(128) k_mover_scatter(Grid g, int njt, int njv, int njf, int Nt,
-                                                       const float* __restrict__ vt, const float* __restrict__ vvv,
-                                                       const float* __restrict__ vf, const float* __restrict__ EP,
-                                                       const float* __restrict__ TP, const float* __restrict__ VP,
-                                                       const int* __restrict__ invE, const int* __restrict__ invT,
-                                                       const int* __restrict__ invV) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= njt + njv + njf) return;
+struct MoverArgs {
+    int njt, njv, njf, Nt;
+    const float *vt, *vvv, *vf, *EP, *TP, *VP;
+    const int *invE, *invT, *invV;
+};
+__device__ __forceinline__ void mover_scatter_one(const Grid& g, const MoverArgs& ma, int t) {
+    const int njt = ma.njt, njv = ma.njv, Nt = ma.Nt;
+    const float *__restrict__ vt = ma.vt, *__restrict__ vvv = ma.vvv, *__restrict__ vf = ma.vf;
+    const float *__restrict__ EP = ma.EP, *__restrict__ TP = ma.TP, *__restrict__ VP = ma.VP;
+    const int *__restrict__ invE = ma.invE, *__restrict__ invT = ma.invT, *__restrict__ invV = ma.invV;
     const float* xr;
     const float* vel;
     if (t < njt) { xr = TP + (size_t)invT[Nt - njt + t] * KP_F; vel = vt + 3 * t; }
@@ -653,6 +672,20 @@ __global__ void __launch_bounds__(128) k_mover_scatter(Grid g, int njt, int njv,
                 atomicAdd(&g.mov[ni], make_float4(ww * v0, ww * v1, ww * v2, ww));
             }
 }
+__global__ void __launch_bounds__(128) k_mover_scatter(Grid g, MoverArgs ma) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ma.njt + ma.njv + ma.njf) mover_scatter_one(g, ma, t);
+}
+// Both scatters in one launch, placed behind the vertex P2G in the stream: it does not depend on it (different
+// accumulators), so under programmatic dependent launch its CTAs fill the tail of the P2G kernels; the wait at the
+// end only keeps the chain transitive (see the PDL invariant in k_p2g).  Threads [0, Mf) faces, then the movers.
+__global__ void __launch_bounds__(128) k_body_scatter(Grid g, ColliderArgs ca, MoverArgs ma) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ca.Mf) collider_scatter_face(g, ca, t);
+    else if (t - ca.Mf < ma.njt + ma.njv + ma.njf) mover_scatter_one(g, ma, t - ca.Mf);
+    pdl_wait();
+    pdl_trigger();
+}
 
 // ============================================================ grid update
 // One pass over the nodes of the allocated blocks that fuses
@@ -663,13 +696,22 @@ __global__ void __launch_bounds__(128) k_mover_scatter(Grid g, int njt, int njv,
 __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float dt, int use_collider, float col_friction,
                                                      int use_mover, const BCDesc* __restrict__ bcs, int n_bc,
                                                      const StepState* __restrict__ st) {
-    pdl_trigger();  // the G2P kernels behind this one may take the slots it frees (they wait for its completion)
+    // the active list was last changed by the previous substep's G2P: the node address is computed while the
+    // scatter kernels in front of this one drain (PDL invariant: wait, then trigger)
     const int n_slots = min(*g.n_slots, g.cap);
-    const float time = (float)st->time;
     const int total = n_slots * BN;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int slot = idx >> 6, l = idx & 63;
-        const int co = g.slot_coord[slot];
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int co_next = idx < total ? g.slot_coord[idx >> 6] : 0;
+    pdl_wait();
+    pdl_trigger();  // the G2P kernels behind this one may take the slots it frees (they wait for its completion)
+    const float time = (float)st->time;
+    for (; idx < total; idx += gridDim.x * blockDim.x) {
+        const int l = idx & 63;
+        const int co = co_next;
+        {
+            const int nidx = idx + gridDim.x * blockDim.x;
+            if (nidx < total) co_next = g.slot_coord[nidx >> 6];
+        }
         const int ni = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023) * BN + l;
         // all four accumulator loads are issued before any use (memory-level parallelism)
         const float4 a = g.acc[ni];
@@ -969,11 +1011,11 @@ struct Advance {
     int n_bc;
 };
 
-constexpr int G2P_NW = 4;
-#ifndef MPM_G2P_MINB
-#define MPM_G2P_MINB 4
+#ifndef MPM_G2P_NW
+#define MPM_G2P_NW 1
 #endif
-constexpr int G2P_MINB = MPM_G2P_MINB;  // resident CTAs per SM the register allocation must allow (4: <= 128 registers, no spills)
+constexpr int G2P_NW = MPM_G2P_NW;  // warps (= slabs) per CTA
+constexpr int G2P_MINB = 16 / G2P_NW;  // 16 resident warps per SM: <= 128 registers, no spills
 // g2p_v for cloth vertices (mpm_utils.py:716-786); also clears vertex_force for the next substep
 // (replaces set_vec3_to_zero, mpm_solver.py:251-256) and allocates grid blocks for the new position.
 constexpr int G2P_V_WB = VP_F * 32 * 4 + G2P_TILE_B;
