@@ -152,6 +152,17 @@ typedef int (*MpmExchangeFn)(void *ctx, float *buf, int n_floats);
 typedef int (*MpmRebuildFn)(void *ctx);
 int mpm_step_sharded(MpmSolver *s, float dt, int nsub, const MpmFrameInputs *in, float *buf, int refresh,
                      MpmExchangeFn exchange, MpmRebuildFn rebuild, void *ctx, void *stream);
+/* The same again with the exchange done inside the library: mpm_attach_comm gives the solver its own NCCL
+ * communicator (id = ncclUniqueId bytes from mpm_comm_unique_id on rank 0, distributed by the caller; libnccl.so.2
+ * is dlopen'ed, inside a torch process that is torch's own copy), and mpm_step_sharded_nccl replays captured
+ * windows of 8 substeps -- kernels AND the ncclAllReduce of the shared blocks in one CUDA graph -- so that no
+ * host code runs between substeps.  Every `refresh` substeps the shared list is rebuilt on the stream as well
+ * (blocks reachable within `margin` cells are marked, the marks byte-summed over the ranks, blocks with count >= 2
+ * compacted in ascending order); only buffer growth synchronises.  mpm_shared_info synchronises. */
+int mpm_comm_unique_id(char *out128);
+int mpm_attach_comm(MpmSolver *s, const char *id128, int rank, int nranks);
+int mpm_step_sharded_nccl(MpmSolver *s, float dt, int nsub, const MpmFrameInputs *in, int refresh, int margin, void *stream);
+int mpm_shared_info(MpmSolver *s, int *n_shared, int *cap_blocks, int *n_rebuilds, void *stream);
 int mpm_step_gather(MpmSolver *s, float dt, void *stream);
 int mpm_get_active_blocks(MpmSolver *s, int *coords, int cap, int *n, void *stream);
 /* blocks this rank can activate while its particles move at most `margin` cells (synchronises) */

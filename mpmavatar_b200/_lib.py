@@ -71,6 +71,10 @@ SYMBOLS = {
     "mpm_step_scatter": (C.c_int, [_P, C.c_float, C.POINTER(MpmFrameInputs), _P]),
     "mpm_step_gather": (C.c_int, [_P, C.c_float, _P]),
     "mpm_step_sharded": (C.c_int, [_P, C.c_float, C.c_int, C.POINTER(MpmFrameInputs), _P, C.c_int, EXCHANGE_FN, REBUILD_FN, _P, _P]),
+    "mpm_comm_unique_id": (C.c_int, [_P]),
+    "mpm_attach_comm": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "mpm_step_sharded_nccl": (C.c_int, [_P, C.c_float, C.c_int, C.POINTER(MpmFrameInputs), C.c_int, C.c_int, _P]),
+    "mpm_shared_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
     "mpm_get_active_blocks": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int), _P]),
     "mpm_get_potential_blocks": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]),
     "mpm_set_shared_blocks": (C.c_int, [_P, _P, C.c_int, _P]),

@@ -10,7 +10,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libmpm_b200.so")
 SOURCES = ["mpm_b200.cu", "mpm_kernels.cuh", "mpm_device.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "-Wno-deprecated-declarations"]
 
 
 def _nvcc() -> str:

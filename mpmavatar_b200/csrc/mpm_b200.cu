@@ -1,7 +1,11 @@
 // libmpm_b200.so -- host side of the B200 MPM substep solver and its C-ABI (include/mpm_b200.h).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: libnccl.so.2 is dlopen'ed by mpm_attach_comm (no link-time dependency)
 
 #include <algorithm>
 #include <array>
@@ -214,23 +218,45 @@ __global__ void k_mark_potential(Grid g, int n, const float* __restrict__ rec, i
 }
 // ---- sharded runs: the grid blocks shared with other ranks travel through one packed buffer
 // [n_shared][64 nodes][acc float4 | mov float4]; inactive blocks pack zeros and ignore the result
-__global__ void k_shared_pack(Grid g, const int* __restrict__ shared, int n_shared, float4* __restrict__ buf) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_shared * BN) return;
-    const int co = shared[idx >> 6], l = idx & 63;
-    const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), m = a;
-    if (g.table[blk] >= 0) { a = g.acc[blk * BN + l]; m = g.mov[blk * BN + l]; }
-    buf[2 * idx] = a;
-    buf[2 * idx + 1] = m;
+// n_dev (device int) overrides n_shared when non-null: the captured sharded graphs keep a fixed launch geometry
+// (capacity) while the shared list is rebuilt underneath them
+__global__ void k_shared_pack(Grid g, const int* __restrict__ shared, int n_shared, const int* __restrict__ n_dev, float4* __restrict__ buf) {
+    if (n_dev) n_shared = *n_dev;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_shared * BN; idx += gridDim.x * blockDim.x) {
+        const int co = shared[idx >> 6], l = idx & 63;
+        const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), m = a;
+        if (g.table[blk] >= 0) { a = g.acc[blk * BN + l]; m = g.mov[blk * BN + l]; }
+        buf[2 * idx] = a;
+        buf[2 * idx + 1] = m;
+    }
 }
-__global__ void k_shared_unpack(Grid g, const int* __restrict__ shared, int n_shared, const float4* __restrict__ buf) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_shared * BN) return;
-    const int co = shared[idx >> 6], l = idx & 63;
-    const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
-    if (g.table[blk] >= 0) { g.acc[blk * BN + l] = buf[2 * idx]; g.mov[blk * BN + l] = buf[2 * idx + 1]; }
+__global__ void k_shared_unpack(Grid g, const int* __restrict__ shared, int n_shared, const int* __restrict__ n_dev, const float4* __restrict__ buf) {
+    if (n_dev) n_shared = *n_dev;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_shared * BN; idx += gridDim.x * blockDim.x) {
+        const int co = shared[idx >> 6], l = idx & 63;
+        const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
+        if (g.table[blk] >= 0) { g.acc[blk * BN + l] = buf[2 * idx]; g.mov[blk * BN + l] = buf[2 * idx + 1]; }
+    }
 }
+
+// device-side rebuild of the shared-block list: mark[] holds, after a byte-wise sum over the ranks, how many ranks
+// can touch each block; the blocks with count >= 2 are compacted in ascending order (the same list on every rank)
+struct SharedPred {
+    const unsigned char* mark;
+    __device__ bool operator()(int i) const { return mark[i] >= 2; }
+};
+__global__ void k_shared_coords(Grid g, const int* __restrict__ lin, int* __restrict__ n_sel, int cap, int* __restrict__ coords) {
+    const int n = *n_sel;
+    if (n > cap && blockIdx.x == 0 && threadIdx.x == 0) g.flags[0] = 1;  // reported as overflow
+    const int m = min(n, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const int t = lin[i];
+        const int bz = t % g.nb, by = (t / g.nb) % g.nb, bx = t / (g.nb * g.nb);
+        coords[i] = bx | (by << 10) | (bz << 20);
+    }
+}
+__global__ void k_clamp_count(int* n, int cap) { if (*n > cap) *n = cap; }
 
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
@@ -271,9 +297,19 @@ struct MpmSolver {
     std::vector<unsigned char> h_mark;
     int* d_shared = nullptr;  // sharded runs: coordinates of the blocks shared with other ranks
     int n_shared = 0, shared_cap = 0, shared_age = -1;
+    int* d_n_shared = nullptr;     // device copy of n_shared (read by the captured pack / unpack launches)
+    ncclComm_t comm = nullptr;     // mpm_attach_comm: this solver's own communicator
+    int comm_rank = 0, comm_size = 1;
+    float* xbuf = nullptr;         // exchange buffer of the in-graph path, xcap_blocks * 512 floats
+    int xcap_blocks = 0;
+    void* shard_graphs = nullptr;  // cache of captured sharded windows
+    int* d_sel = nullptr;          // compaction output (linear block indices), [nb^3]
+    void* sel_tmp = nullptr;
+    size_t sel_bytes = 0;
+    int* h_nshared = nullptr;      // pinned mirror of the device-side count (read one rebuild late)
     int cur = 0;             // direction buffer (E12/D3) holding the current d
     bool have_prev = false;  // buffer cur^1 holds the d of the last stress evaluation
-    int n_resorts = 0;
+    int n_resorts = 0, n_rebuilds = 0;
     long long n_substeps = 0;
     int launches = 0;
     double host_time = 0.0;
@@ -288,8 +324,6 @@ struct MpmSolver {
     bool use_graphs = true;
     bool use_pdl = true;  // MPM_B200_PDL=0 disables programmatic dependent launch
     cudaStream_t cap_stream = nullptr;
-    cudaStream_t side = nullptr;       // body-collider / mover scatter run concurrently with stress + P2G
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // profiling
     cudaEvent_t ev[10]{};
     MpmProfile prof{};
@@ -524,6 +558,7 @@ static void destroy_graphs(MpmSolver* s) {
     delete &v;
     s->graph_cache_ptr = nullptr;
 }
+static void destroy_sharded(MpmSolver* s);  // communicator + captured sharded windows (defined with the NCCL path)
 static void run_substeps(MpmSolver* s, SubstepArgs a, int count, cudaStream_t q) {
     const bool graphs = s->use_graphs && !s->profiling;
     while (count > 0) {
@@ -660,9 +695,6 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         s->st = s->dalloc<StepState>(1);
         CK(cudaHostAlloc((void**)&s->h_nslots, sizeof(int), cudaHostAllocDefault));
         *s->h_nslots = 0;
-        CK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
         // model defaults (mpm_data_structure.py:686-715)
         s->md.material = 0; s->md.hardening = 0; s->md.friction_coeff = 0.f; s->md.alpha = 0.f;
         s->md.gx = s->md.gy = s->md.gz = 0.f; s->md.rpic = 0.f; s->md.damping = 1.1f;
@@ -687,10 +719,8 @@ void mpm_destroy(MpmSolver* s) {
     cudaSetDevice(s->cfg.device);
     cudaDeviceSynchronize();
     destroy_graphs(s);
+    destroy_sharded(s);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
-    if (s->side) cudaStreamDestroy(s->side);
-    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
-    if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->h_nslots) cudaFreeHost(s->h_nslots);
     for (void* p : s->allocs) cudaFree(p);
     delete s;
@@ -954,9 +984,9 @@ int mpm_step_sharded(MpmSolver* s, float dt, int nsub, const MpmFrameInputs* in,
             s->shared_age = 0;
         }
         if (s->n_shared) {
-            k_shared_pack<<<cdiv((long long)s->n_shared * BN, 256), 256, 0, q>>>(s->g, s->d_shared, s->n_shared, (float4*)buf);
+            k_shared_pack<<<cdiv((long long)s->n_shared * BN, 256), 256, 0, q>>>(s->g, s->d_shared, s->n_shared, nullptr, (float4*)buf);
             if (exchange(ctx, buf, s->n_shared * BN * 8) != 0) throw std::string("exchange callback failed");
-            k_shared_unpack<<<cdiv((long long)s->n_shared * BN, 256), 256, 0, q>>>(s->g, s->d_shared, s->n_shared, (const float4*)buf);
+            k_shared_unpack<<<cdiv((long long)s->n_shared * BN, 256), 256, 0, q>>>(s->g, s->d_shared, s->n_shared, nullptr, (const float4*)buf);
             s->launches += 2;
         }
         launch_substep(s, a, q, HALF_GATHER);
@@ -970,6 +1000,250 @@ int mpm_step_sharded(MpmSolver* s, float dt, int nsub, const MpmFrameInputs* in,
     API_END(s)
 }
 
+}  // extern "C" (re-opened after the sharded helpers)
+
+// ---- in-graph sharded stepping over this solver's own NCCL communicator
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    if (api.lib) return &api;
+    // the soname torch's own NCCL carries: inside a torch process this resolves to the library already loaded
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) throw std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+    auto sym = [&](const char* name) {
+        void* p = dlsym(lib, name);
+        if (!p) throw std::string("libnccl.so.2 lacks ") + name;
+        return p;
+    };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.lib = lib;
+    return &api;
+}
+#define NCK(call)                                                                            \
+    do {                                                                                     \
+        ncclResult_t r_ = (call);                                                            \
+        if (r_ != ncclSuccess) throw std::string(#call " failed: ") + nccl_api()->GetErrorString(r_); \
+    } while (0)
+
+struct ShardGraphKey {
+    float dt;
+    int collider, mover, advance_mesh, cur, n_bc, n_ops, xcap, len;
+    const void* shared_ptr;
+    bool operator==(const ShardGraphKey& o) const { return memcmp(this, &o, sizeof(ShardGraphKey)) == 0; }
+};
+struct ShardGraph {
+    ShardGraphKey key;
+    cudaGraphExec_t exec;
+    int launches;
+};
+std::vector<ShardGraph>& shard_graphs(MpmSolver* s) {
+    if (!s->shard_graphs) s->shard_graphs = new std::vector<ShardGraph>();
+    return *static_cast<std::vector<ShardGraph>*>(s->shard_graphs);
+}
+// one sharded substep on stream q: scatter half, pack, all-reduce, unpack, gather half
+void sharded_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
+    launch_substep(s, a, q, HALF_SCATTER);
+    const int ctas = std::max(1, std::min(cdiv((long long)s->xcap_blocks * BN, 256), 148 * 8));
+    k_shared_pack<<<ctas, 256, 0, q>>>(s->g, s->d_shared, 0, s->d_n_shared, (float4*)s->xbuf);
+    NCK(nccl_api()->AllReduce(s->xbuf, s->xbuf, (size_t)s->xcap_blocks * BN * 8, ncclFloat, ncclSum, s->comm, q));
+    k_shared_unpack<<<ctas, 256, 0, q>>>(s->g, s->d_shared, 0, s->d_n_shared, (const float4*)s->xbuf);
+    s->launches += 3;
+    launch_substep(s, a, q, HALF_GATHER);
+}
+}  // namespace
+
+// Rebuild of the shared-block list entirely on the stream: mark, byte-sum over the ranks, ordered compaction.
+// The host only learns the count one rebuild later (pinned mirror), which is enough to grow the buffers in time.
+static void mark_potential(MpmSolver* s, int margin, cudaStream_t q) {
+    const size_t nt = (size_t)s->g.nb * s->g.nb * s->g.nb;
+    if (!s->d_mark) {
+        s->d_mark = s->dalloc<unsigned char>(nt);
+        s->h_mark.resize(nt);
+    }
+    CK(cudaMemsetAsync(s->d_mark, 0, nt, q));
+    if (s->Ne) k_mark_potential<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.EP, KP_F, margin, s->d_mark);
+    if (s->Nt) k_mark_potential<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F, margin, s->d_mark);
+    if (s->Nv) k_mark_potential<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, margin, s->d_mark);
+    s->launches += 3;
+}
+static void rebuild_shared_on_device(MpmSolver* s, int margin, cudaStream_t q) {
+    const size_t nt = (size_t)s->g.nb * s->g.nb * s->g.nb;
+    if (!s->d_sel) {
+        s->d_sel = s->dalloc<int>(nt);
+        s->d_n_shared = s->d_n_shared ? s->d_n_shared : s->dalloc<int>(1);
+        CK(cudaMallocHost(&s->h_nshared, sizeof(int)));
+        *s->h_nshared = -1;
+        cub::CountingInputIterator<int> it(0);
+        CK(cub::DeviceSelect::If(nullptr, s->sel_bytes, it, s->d_sel, s->d_n_shared, (int)nt, SharedPred{s->d_mark}, q));
+        s->sel_tmp = s->dalloc<unsigned char>(s->sel_bytes);
+    }
+    const bool first = *s->h_nshared < 0;
+    if (!first && *s->h_nshared * 10 > s->xcap_blocks * 7) {  // the list (as of the previous rebuild) nears the capacity
+        CK(cudaStreamSynchronize(q));
+        s->xcap_blocks = 0;
+    }
+    mark_potential(s, margin, q);
+    NCK(nccl_api()->AllReduce(s->d_mark, s->d_mark, nt, ncclUint8, ncclSum, s->comm, q));
+    cub::CountingInputIterator<int> it(0);
+    size_t tmp = s->sel_bytes;
+    CK(cub::DeviceSelect::If(s->sel_tmp, tmp, it, s->d_sel, s->d_n_shared, (int)nt, SharedPred{s->d_mark}, q));
+    s->launches += 2;
+    if (first || s->xcap_blocks == 0) {  // size the buffers from the actual count (the only synchronising rebuilds)
+        int n = 0;
+        CK(cudaMemcpyAsync(&n, s->d_n_shared, sizeof(int), cudaMemcpyDeviceToHost, q));
+        CK(cudaStreamSynchronize(q));
+        s->xcap_blocks = std::max(128, (2 * n + 63) / 64 * 64);
+        s->xbuf = s->dalloc<float>((size_t)s->xcap_blocks * BN * 8);
+        s->shared_cap = s->xcap_blocks;
+        s->d_shared = s->dalloc<int>(s->shared_cap);
+    }
+    k_shared_coords<<<std::max(1, std::min(cdiv(s->xcap_blocks, 256), 64)), 256, 0, q>>>(s->g, s->d_sel, s->d_n_shared, s->xcap_blocks, s->d_shared);
+    k_clamp_count<<<1, 1, 0, q>>>(s->d_n_shared, s->xcap_blocks);
+    CK(cudaMemcpyAsync(s->h_nshared, s->d_n_shared, sizeof(int), cudaMemcpyDeviceToHost, q));
+    s->launches += 2;
+    s->n_rebuilds++;
+}
+
+static void destroy_sharded(MpmSolver* s) {
+    if (s->h_nshared) { cudaFreeHost(s->h_nshared); s->h_nshared = nullptr; }
+    if (s->shard_graphs) {
+        auto& v = shard_graphs(s);
+        for (auto& e : v) cudaGraphExecDestroy(e.exec);
+        delete &v;
+        s->shard_graphs = nullptr;
+    }
+    if (s->comm) {
+        nccl_api()->CommDestroy(s->comm);
+        s->comm = nullptr;
+    }
+}
+
+extern "C" {
+
+int mpm_comm_unique_id(char* out128) {
+    try {
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+        ncclUniqueId id;
+        NCK(nccl_api()->GetUniqueId(&id));
+        memcpy(out128, &id, sizeof id);
+    } catch (const std::string& e) {
+        g_create_error = e;
+        return -2;
+    }
+    return 0;
+}
+
+int mpm_attach_comm(MpmSolver* s, const char* id128, int rank, int nranks) {
+    API_BEGIN(s)
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    if (s->comm) { nccl_api()->CommDestroy(s->comm); s->comm = nullptr; }
+    NCK(nccl_api()->CommInitRank(&s->comm, nranks, id, rank));
+    s->comm_rank = rank;
+    s->comm_size = nranks;
+    // connection set-up happens on first use: do it here, outside any stream capture
+    float* tmp = s->dalloc<float>(256);
+    NCK(nccl_api()->AllReduce(tmp, tmp, 256, ncclFloat, ncclSum, s->comm, 0));
+    CK(cudaStreamSynchronize(0));
+    API_END(s)
+}
+
+int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs* in, int refresh, int margin, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    if (!s->comm) throw std::string("mpm_step_sharded_nccl before mpm_attach_comm");
+    MpmFrameInputs none{};
+    if (!in) in = &none;
+    SubstepArgs a{};
+    begin_half_step(s, in, a, dt, q);
+    if (in->n_joint_t > 0) throw std::string("sharded stepping does not support pinned traditional particles yet");
+    upload_lists(s, q);
+    size_t mv3 = 3 * (size_t)s->cfg.n_mesh_v * sizeof(float);
+    if (in->mesh_x && mv3) CK(cudaMemcpyAsync(s->mesh_x, in->mesh_x, mv3, cudaMemcpyDefault, q));
+    if (in->mesh_v && mv3) CK(cudaMemcpyAsync(s->mesh_v, in->mesh_v, mv3, cudaMemcpyDefault, q));
+    if (a.mover) {
+        if (s->cfg.num_joint_v) CK(cudaMemcpyAsync(s->joint_v, in->joint_verts_v, 3 * (size_t)s->cfg.num_joint_v * sizeof(float), cudaMemcpyDefault, q));
+        if (s->cfg.num_joint_f) CK(cudaMemcpyAsync(s->joint_f, in->joint_faces_v, 3 * (size_t)s->cfg.num_joint_f * sizeof(float), cudaMemcpyDefault, q));
+    }
+    a.advance_mesh = in->mesh_x != nullptr && nsub > 1;
+    k_reset_k<<<1, 1, 0, q>>>(s->st);
+    s->launches++;
+    constexpr int W = 8;  // substeps per captured window (even: the direction ping-pong returns to its start)
+    int left = nsub;
+    while (left > 0) {
+        if (s->need_sort || s->since_sort >= s->resort_interval) resort(s, q);
+        if (s->shared_age < 0 || s->shared_age >= refresh) {
+            rebuild_shared_on_device(s, margin, q);
+            s->shared_age = 0;
+        }
+        const int room = std::min({left, refresh - s->shared_age, s->resort_interval - s->since_sort});
+        int done = 1;
+        if (s->use_graphs && room >= W) {
+            ShardGraphKey key{};
+            key.dt = a.dt; key.collider = a.collider; key.mover = a.mover; key.advance_mesh = a.advance_mesh; key.cur = s->cur;
+            key.n_bc = (int)s->h_bcs.size(); key.n_ops = (int)s->h_ops.size(); key.xcap = s->xcap_blocks; key.len = W;
+            key.shared_ptr = s->d_shared;
+            auto& cache = shard_graphs(s);
+            ShardGraph* hit = nullptr;
+            for (auto& e : cache) if (e.key == key) hit = &e;
+            if (!hit) {
+                if (!s->cap_stream) CK(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+                const int before = s->launches;
+                cudaGraph_t graph;
+                CK(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
+                for (int i = 0; i < W; i++) sharded_substep(s, a, s->cap_stream);
+                CK(cudaStreamEndCapture(s->cap_stream, &graph));
+                ShardGraph e;
+                e.key = key;
+                e.launches = s->launches - before;
+                s->launches = before;
+                CK(cudaGraphInstantiate(&e.exec, graph, 0));
+                cudaGraphDestroy(graph);
+                cache.push_back(e);
+                hit = &cache.back();
+            }
+            CK(cudaGraphLaunch(hit->exec, q));
+            s->launches += hit->launches;
+            if (s->Ne) s->have_prev = true;
+            done = W;
+        } else {
+            sharded_substep(s, a, q);
+        }
+        s->shared_age += done;
+        s->since_sort += done;
+        s->n_substeps += done;
+        for (int k = 0; k < done; k++) s->host_time += (double)dt;
+        left -= done;
+    }
+    s->canon_stale = true;
+    CK(cudaGetLastError());
+    API_END(s)
+}
+
+int mpm_shared_info(MpmSolver* s, int* n_shared, int* cap_blocks, int* n_rebuilds, void* stream) {
+    API_BEGIN(s)
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (n_shared) *n_shared = s->h_nshared ? *s->h_nshared : s->n_shared;
+    if (cap_blocks) *cap_blocks = s->xcap_blocks;
+    if (n_rebuilds) *n_rebuilds = s->n_rebuilds;
+    API_END(s)
+}
+
+}  // extern "C"
+
+extern "C" {
 int mpm_get_active_blocks(MpmSolver* s, int* coords, int cap, int* n, void* stream) {
     API_BEGIN(s)
     cudaStream_t q = (cudaStream_t)stream;
@@ -988,15 +1262,7 @@ int mpm_get_potential_blocks(MpmSolver* s, int margin, int* coords, int cap, int
     cudaStream_t q = (cudaStream_t)stream;
     if (s->need_sort && s->have_state) resort(s, q);
     const size_t nt = (size_t)s->g.nb * s->g.nb * s->g.nb;
-    if (!s->d_mark) {
-        s->d_mark = s->dalloc<unsigned char>(nt);
-        s->h_mark.resize(nt);
-    }
-    CK(cudaMemsetAsync(s->d_mark, 0, nt, q));
-    if (s->Ne) k_mark_potential<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.EP, KP_F, margin, s->d_mark);
-    if (s->Nt) k_mark_potential<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F, margin, s->d_mark);
-    if (s->Nv) k_mark_potential<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, margin, s->d_mark);
-    s->launches += 3;
+    mark_potential(s, margin, q);
     CK(cudaMemcpyAsync(s->h_mark.data(), s->d_mark, nt, cudaMemcpyDeviceToHost, q));
     CK(cudaStreamSynchronize(q));
     int cnt = 0;
@@ -1021,13 +1287,15 @@ int mpm_set_shared_blocks(MpmSolver* s, const int* coords, int n, void* stream) 
     }
     if (n) CK(cudaMemcpyAsync(s->d_shared, coords, (size_t)n * sizeof(int), cudaMemcpyDefault, (cudaStream_t)stream));
     s->n_shared = n;
+    if (!s->d_n_shared) s->d_n_shared = s->dalloc<int>(1);
+    CK(cudaMemcpyAsync(s->d_n_shared, &s->n_shared, sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     API_END(s)
 }
 
 int mpm_shared_pack(MpmSolver* s, float* buf, void* stream) {
     API_BEGIN(s)
     if (s->n_shared) {
-        k_shared_pack<<<cdiv((long long)s->n_shared * BN, 256), 256, 0, (cudaStream_t)stream>>>(s->g, s->d_shared, s->n_shared, (float4*)buf);
+        k_shared_pack<<<cdiv((long long)s->n_shared * BN, 256), 256, 0, (cudaStream_t)stream>>>(s->g, s->d_shared, s->n_shared, nullptr, (float4*)buf);
         s->launches++;
     }
     API_END(s)
@@ -1036,7 +1304,7 @@ int mpm_shared_pack(MpmSolver* s, float* buf, void* stream) {
 int mpm_shared_unpack(MpmSolver* s, const float* buf, void* stream) {
     API_BEGIN(s)
     if (s->n_shared) {
-        k_shared_unpack<<<cdiv((long long)s->n_shared * BN, 256), 256, 0, (cudaStream_t)stream>>>(s->g, s->d_shared, s->n_shared, (const float4*)buf);
+        k_shared_unpack<<<cdiv((long long)s->n_shared * BN, 256), 256, 0, (cudaStream_t)stream>>>(s->g, s->d_shared, s->n_shared, nullptr, (const float4*)buf);
         s->launches++;
     }
     API_END(s)

@@ -536,9 +536,12 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
             Uq[j % P2G_PF] = pU[qn * 3];
             wq[j % P2G_PF] = pW[qn * 9];
             if (q > 0 && ((R.starts >> q) & 1u)) {
-                flush(c, alo, ahi);
-                alo = ahi = make_float2(0.f, 0.f);
-                c = __shfl_sync(0xffffffffu, mycell, q);
+                const int cn = __shfl_sync(0xffffffffu, mycell, q);
+                {
+                    flush(c, alo, ahi);
+                    alo = ahi = make_float2(0.f, 0.f);
+                }
+                c = cn;
             }
             alo = fma2(U.w, make_float2(T.x, T.y), alo);
             ahi = fma2(U.w, make_float2(T.z, T.w), ahi);

@@ -7,6 +7,7 @@ rank's sub-scene (mpmavatar_b200/sharding.py explains the scheme).  No CPU fallb
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -32,6 +33,20 @@ class ShardedMPM:
         self.n_shared = 0
         self.k = 0  # substeps since the last shared-list rebuild
         self.stats = {"rebuilds": 0, "shared_blocks": 0, "exchange_bytes": 0}
+        # NCCL backend: the solver gets its own communicator and replays captured windows (kernels + the
+        # all-reduce in one CUDA graph); gloo (CPU rendezvous, ranks sharing a GPU) keeps the callback path
+        self.in_graph = dist.get_backend(group) == "nccl" and os.environ.get("MPM_B200_SHARD_GRAPH", "1") != "0"
+        if self.in_graph:
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if self.rank == 0:
+                raw = (C.c_char * 128)()
+                if self.lib.mpm_comm_unique_id(raw) != 0:
+                    raise RuntimeError("libmpm_b200: " + self.lib.mpm_last_error(None).decode())
+                uid = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+            uid = uid.to(self.device)
+            dist.broadcast(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            self._uid = bytes(uid.cpu().numpy().tobytes())
+            self._ck(self.lib.mpm_attach_comm(self.h, self._uid, self.rank, self.world))
 
     # collectives: NCCL works on device tensors; with gloo (CPU tests, or two ranks sharing one GPU) they are
     # staged through host memory
@@ -79,7 +94,9 @@ class ShardedMPM:
         self._ck(self.lib.mpm_set_shared_blocks(self.h, C.c_void_p(self._shared_keep.data_ptr()), len(shared), self._stream()))
         self.n_shared = len(shared)
         need = max(self.n_shared, 1) * 64 * 8
-        if self.buf is None:
+        if self.in_graph:
+            self.buf = self.buf if self.buf is not None else torch.zeros(1, device=self.device)  # the library owns the exchange buffer
+        elif self.buf is None:
             self.buf = torch.zeros(max(int(need * 2), 1 << 20), dtype=torch.float32, device=self.device)
         elif self.buf.numel() < need:  # the C loop holds the buffer's address: it cannot move mid-step
             raise RuntimeError("shared-block buffer too small; construct ShardedMPM with a larger reserve")
@@ -103,7 +120,7 @@ class ShardedMPM:
                               torch.as_tensor(p.elems[:p.num_joint_f], device=dev, dtype=torch.long))
             jv = T(joint_verts_v)[self._jidx[0]].contiguous() if p.num_joint_v else torch.zeros(1, 3, device=dev)
             jf = T(joint_faces_v)[self._jidx[1]].contiguous() if p.num_joint_f else torch.zeros(1, 3, device=dev)
-        if self.buf is None:
+        if self.buf is None and not self.in_graph:
             self.rebuild_shared()
         fin = _lib.MpmFrameInputs()
         fin.mesh_x = None if mesh_x is None else C.c_void_p(mesh_x.data_ptr())
@@ -128,14 +145,26 @@ class ShardedMPM:
                 err.append(e)
                 return 1
         ex, rb = _lib.EXCHANGE_FN(exchange), _lib.REBUILD_FN(rebuild)
-        rc = self.lib.mpm_step_sharded(self.h, C.c_float(dt), int(nsub), C.byref(fin), C.c_void_p(self.buf.data_ptr()),
-                                       self.refresh, ex, rb, None, self._stream())
+        if self.in_graph:
+            rc = self.lib.mpm_step_sharded_nccl(self.h, C.c_float(dt), int(nsub), C.byref(fin), self.refresh, self.margin, self._stream())
+        else:
+            rc = self.lib.mpm_step_sharded(self.h, C.c_float(dt), int(nsub), C.byref(fin), C.c_void_p(self.buf.data_ptr()),
+                                           self.refresh, ex, rb, None, self._stream())
         if err:
             raise err[0]
         self._ck(rc)
+        if self.in_graph:
+            self.refresh_stats()
         self._keep = (mesh_x, mesh_v, jv, jf)
         self.state._stale = True
         self.state._solver = self.solver
+
+    def refresh_stats(self):
+        """in-graph path: the shared list lives in the library (synchronises)"""
+        n, cap, rb = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self.lib.mpm_shared_info(self.h, C.byref(n), C.byref(cap), C.byref(rb), self._stream()))
+        self.n_shared = n.value
+        self.stats.update(rebuilds=rb.value, shared_blocks=n.value, exchange_bytes=cap.value * 64 * 8 * 4)
 
     def gather_positions(self):
         """Full canonical particle_x / particle_v on every rank (original particle order)."""
