@@ -50,13 +50,16 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index=0, enabled=True):
+        # one sampler per job (rank 0): concurrent nvidia-smi pollers on every rank perturb the launches they watch
+        self.rows, self.proc, self.index, self.enabled = [], None, index, enabled
 
     def start(self):
+        if not self.enabled:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -67,6 +70,8 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if not self.enabled:
+            return None
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -183,7 +188,7 @@ def run_sharded(args, sc, rank, local_rank, world, dev, barrier):
     for _ in range(args.warmup):
         step(fi, False); fi += 1
     st0 = sm.solver.stats()
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank, enabled=(rank == 0))
     barrier()
     clocks.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -317,7 +322,7 @@ def main():
     for _ in range(args.warmup):
         step_dev(fi); fi += 1
     st0 = solver.stats()
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank, enabled=(rank == 0))
     barrier()
     clocks.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

@@ -202,9 +202,13 @@ __global__ void k_popc(const unsigned long long* mask, int n, unsigned long long
 
 // blocks under the stencil of any particle displaced by up to `margin` cells in every direction: what this
 // rank can activate before the shared-block list is rebuilt
-__global__ void k_mark_potential(Grid g, int n, const float* __restrict__ rec, int F, int margin, unsigned char* __restrict__ mark) {
+// markj (optional): blocks reachable by prescribed-velocity (joint) particles, the first njoint of the class in
+// canonical order -- only those blocks carry mover accumulators
+__global__ void k_mark_potential(Grid g, int n, const float* __restrict__ rec, int F, int margin, unsigned char* __restrict__ mark,
+                                 unsigned char* __restrict__ markj = nullptr, const uint32_t* __restrict__ perm = nullptr, int njoint = 0) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const bool joint = markj && perm && (int)perm[i] < njoint;
     const float* x = rec + (size_t)i * F;
     int lo[3], hi[3];
     for (int a = 0; a < 3; a++) {
@@ -214,7 +218,10 @@ __global__ void k_mark_potential(Grid g, int n, const float* __restrict__ rec, i
     }
     for (int a = lo[0]; a <= hi[0]; a++)
         for (int b = lo[1]; b <= hi[1]; b++)
-            for (int c = lo[2]; c <= hi[2]; c++) mark[table_index(g, a, b, c)] = 1;
+            for (int c = lo[2]; c <= hi[2]; c++) {
+                mark[table_index(g, a, b, c)] = 1;
+                if (joint) markj[table_index(g, a, b, c)] = 1;
+            }
 }
 // ---- sharded runs: the grid blocks shared with other ranks travel through one packed buffer
 // [n_shared][64 nodes][acc float4 | mov float4]; inactive blocks pack zeros and ignore the result
@@ -244,8 +251,37 @@ __global__ void k_shared_unpack(Grid g, const int* __restrict__ shared, int n_sh
 // can touch each block; the blocks with count >= 2 are compacted in ascending order (the same list on every rank)
 struct SharedPred {
     const unsigned char* mark;
-    __device__ bool operator()(int i) const { return mark[i] >= 2; }
+    const unsigned char* markj;  // non-null: additionally some rank has joint particles there
+    __device__ bool operator()(int i) const { return mark[i] >= 2 && (!markj || markj[i] >= 1); }
 };
+// in-graph exchange buffer: [capA blocks x 64 acc float4 | capM blocks x 64 mov float4]; list A = blocks at least
+// two ranks can touch, list M = the subset that can carry mover (joint) accumulators
+struct SharedLists {
+    const int *A, *nA, *M, *nM;
+    int capA, capM;
+};
+__global__ void k_shared_pack2(Grid g, SharedLists L, float4* __restrict__ buf) {
+    const int nA = min(*L.nA, L.capA) * BN, nM = min(*L.nM, L.capM) * BN;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nA + nM; idx += gridDim.x * blockDim.x) {
+        const bool mv = idx >= nA;
+        const int j = mv ? idx - nA : idx;
+        const int co = (mv ? L.M : L.A)[j >> 6], l = j & 63;
+        const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.table[blk] >= 0) a = (mv ? g.mov : g.acc)[blk * BN + l];
+        buf[mv ? (size_t)L.capA * BN + j : j] = a;
+    }
+}
+__global__ void k_shared_unpack2(Grid g, SharedLists L, const float4* __restrict__ buf) {
+    const int nA = min(*L.nA, L.capA) * BN, nM = min(*L.nM, L.capM) * BN;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nA + nM; idx += gridDim.x * blockDim.x) {
+        const bool mv = idx >= nA;
+        const int j = mv ? idx - nA : idx;
+        const int co = (mv ? L.M : L.A)[j >> 6], l = j & 63;
+        const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
+        if (g.table[blk] >= 0) (mv ? g.mov : g.acc)[blk * BN + l] = buf[mv ? (size_t)L.capA * BN + j : j];
+    }
+}
 __global__ void k_shared_coords(Grid g, const int* __restrict__ lin, int* __restrict__ n_sel, int cap, int* __restrict__ coords) {
     const int n = *n_sel;
     if (n > cap && blockIdx.x == 0 && threadIdx.x == 0) g.flags[0] = 1;  // reported as overflow
@@ -256,7 +292,6 @@ __global__ void k_shared_coords(Grid g, const int* __restrict__ lin, int* __rest
         coords[i] = bx | (by << 10) | (bz << 20);
     }
 }
-__global__ void k_clamp_count(int* n, int cap) { if (*n > cap) *n = cap; }
 
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
@@ -306,7 +341,9 @@ struct MpmSolver {
     int* d_sel = nullptr;          // compaction output (linear block indices), [nb^3]
     void* sel_tmp = nullptr;
     size_t sel_bytes = 0;
-    int* h_nshared = nullptr;      // pinned mirror of the device-side count (read one rebuild late)
+    int* h_nshared = nullptr;      // pinned mirror of the device-side counts {A, M} (read one rebuild late)
+    int *d_sharedM = nullptr, *d_nM = nullptr;  // list M (mover blocks)
+    int xcapM = 0;
     int cur = 0;             // direction buffer (E12/D3) holding the current d
     bool have_prev = false;  // buffer cur^1 holds the d of the last stress evaluation
     int n_resorts = 0, n_rebuilds = 0;
@@ -1055,10 +1092,11 @@ std::vector<ShardGraph>& shard_graphs(MpmSolver* s) {
 // one sharded substep on stream q: scatter half, pack, all-reduce, unpack, gather half
 void sharded_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
     launch_substep(s, a, q, HALF_SCATTER);
-    const int ctas = std::max(1, std::min(cdiv((long long)s->xcap_blocks * BN, 256), 148 * 8));
-    k_shared_pack<<<ctas, 256, 0, q>>>(s->g, s->d_shared, 0, s->d_n_shared, (float4*)s->xbuf);
-    NCK(nccl_api()->AllReduce(s->xbuf, s->xbuf, (size_t)s->xcap_blocks * BN * 8, ncclFloat, ncclSum, s->comm, q));
-    k_shared_unpack<<<ctas, 256, 0, q>>>(s->g, s->d_shared, 0, s->d_n_shared, (const float4*)s->xbuf);
+    const int ctas = std::max(1, std::min(cdiv((long long)(s->xcap_blocks + s->xcapM) * BN, 256), 148 * 8));
+    const SharedLists L{s->d_shared, s->d_n_shared, s->d_sharedM, s->d_nM, s->xcap_blocks, s->xcapM};
+    k_shared_pack2<<<ctas, 256, 0, q>>>(s->g, L, (float4*)s->xbuf);
+    NCK(nccl_api()->AllReduce(s->xbuf, s->xbuf, (size_t)(s->xcap_blocks + s->xcapM) * BN * 4, ncclFloat, ncclSum, s->comm, q));
+    k_shared_unpack2<<<ctas, 256, 0, q>>>(s->g, L, (const float4*)s->xbuf);
     s->launches += 3;
     launch_substep(s, a, q, HALF_GATHER);
 }
@@ -1069,49 +1107,55 @@ void sharded_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
 static void mark_potential(MpmSolver* s, int margin, cudaStream_t q) {
     const size_t nt = (size_t)s->g.nb * s->g.nb * s->g.nb;
     if (!s->d_mark) {
-        s->d_mark = s->dalloc<unsigned char>(nt);
+        s->d_mark = s->dalloc<unsigned char>(2 * nt);  // [rank count | joint-rank count]
         s->h_mark.resize(nt);
     }
-    CK(cudaMemsetAsync(s->d_mark, 0, nt, q));
-    if (s->Ne) k_mark_potential<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.EP, KP_F, margin, s->d_mark);
+    unsigned char* mj = s->d_mark + nt;
+    CK(cudaMemsetAsync(s->d_mark, 0, 2 * nt, q));
+    if (s->Ne) k_mark_potential<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.EP, KP_F, margin, s->d_mark, mj, s->permE, s->cfg.num_joint_f);
     if (s->Nt) k_mark_potential<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F, margin, s->d_mark);
-    if (s->Nv) k_mark_potential<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, margin, s->d_mark);
+    if (s->Nv) k_mark_potential<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, margin, s->d_mark, mj, s->permV, s->cfg.num_joint_v);
     s->launches += 3;
 }
 static void rebuild_shared_on_device(MpmSolver* s, int margin, cudaStream_t q) {
     const size_t nt = (size_t)s->g.nb * s->g.nb * s->g.nb;
+    cub::CountingInputIterator<int> it(0);
     if (!s->d_sel) {
-        s->d_sel = s->dalloc<int>(nt);
+        s->d_sel = s->dalloc<int>(2 * nt);
         s->d_n_shared = s->d_n_shared ? s->d_n_shared : s->dalloc<int>(1);
-        CK(cudaMallocHost(&s->h_nshared, sizeof(int)));
-        *s->h_nshared = -1;
-        cub::CountingInputIterator<int> it(0);
-        CK(cub::DeviceSelect::If(nullptr, s->sel_bytes, it, s->d_sel, s->d_n_shared, (int)nt, SharedPred{s->d_mark}, q));
+        s->d_nM = s->dalloc<int>(1);
+        CK(cudaMallocHost(&s->h_nshared, 2 * sizeof(int)));
+        s->h_nshared[0] = s->h_nshared[1] = -1;
+        CK(cub::DeviceSelect::If(nullptr, s->sel_bytes, it, s->d_sel, s->d_n_shared, (int)nt, SharedPred{s->d_mark, s->d_mark}, q));
         s->sel_tmp = s->dalloc<unsigned char>(s->sel_bytes);
     }
-    const bool first = *s->h_nshared < 0;
-    if (!first && *s->h_nshared * 10 > s->xcap_blocks * 7) {  // the list (as of the previous rebuild) nears the capacity
-        CK(cudaStreamSynchronize(q));
-        s->xcap_blocks = 0;
-    }
+    const bool first = s->h_nshared[0] < 0;
+    // the lists (as of the previous rebuild) near their capacities: re-size from the actual counts below
+    bool resize = first || s->h_nshared[0] * 10 > s->xcap_blocks * 9 || s->h_nshared[1] * 10 > s->xcapM * 9;
     mark_potential(s, margin, q);
-    NCK(nccl_api()->AllReduce(s->d_mark, s->d_mark, nt, ncclUint8, ncclSum, s->comm, q));
-    cub::CountingInputIterator<int> it(0);
+    NCK(nccl_api()->AllReduce(s->d_mark, s->d_mark, 2 * nt, ncclUint8, ncclSum, s->comm, q));
     size_t tmp = s->sel_bytes;
-    CK(cub::DeviceSelect::If(s->sel_tmp, tmp, it, s->d_sel, s->d_n_shared, (int)nt, SharedPred{s->d_mark}, q));
-    s->launches += 2;
-    if (first || s->xcap_blocks == 0) {  // size the buffers from the actual count (the only synchronising rebuilds)
-        int n = 0;
-        CK(cudaMemcpyAsync(&n, s->d_n_shared, sizeof(int), cudaMemcpyDeviceToHost, q));
+    CK(cub::DeviceSelect::If(s->sel_tmp, tmp, it, s->d_sel, s->d_n_shared, (int)nt, SharedPred{s->d_mark, nullptr}, q));
+    tmp = s->sel_bytes;
+    CK(cub::DeviceSelect::If(s->sel_tmp, tmp, it, s->d_sel + nt, s->d_nM, (int)nt, SharedPred{s->d_mark, s->d_mark + nt}, q));
+    s->launches += 3;
+    if (resize) {  // the only synchronising rebuilds
+        int n[2] = {0, 0};
+        CK(cudaMemcpyAsync(&n[0], s->d_n_shared, sizeof(int), cudaMemcpyDeviceToHost, q));
+        CK(cudaMemcpyAsync(&n[1], s->d_nM, sizeof(int), cudaMemcpyDeviceToHost, q));
         CK(cudaStreamSynchronize(q));
-        s->xcap_blocks = std::max(128, (2 * n + 63) / 64 * 64);
-        s->xbuf = s->dalloc<float>((size_t)s->xcap_blocks * BN * 8);
+        auto room = [](int k) { return (k + k / 4 + 32 + 31) / 32 * 32; };
+        s->xcap_blocks = room(n[0]);
+        s->xcapM = room(n[1]);
+        s->xbuf = s->dalloc<float>((size_t)(s->xcap_blocks + s->xcapM) * BN * 4);
         s->shared_cap = s->xcap_blocks;
-        s->d_shared = s->dalloc<int>(s->shared_cap);
+        s->d_shared = s->dalloc<int>(s->xcap_blocks);
+        s->d_sharedM = s->dalloc<int>(s->xcapM);
     }
     k_shared_coords<<<std::max(1, std::min(cdiv(s->xcap_blocks, 256), 64)), 256, 0, q>>>(s->g, s->d_sel, s->d_n_shared, s->xcap_blocks, s->d_shared);
-    k_clamp_count<<<1, 1, 0, q>>>(s->d_n_shared, s->xcap_blocks);
-    CK(cudaMemcpyAsync(s->h_nshared, s->d_n_shared, sizeof(int), cudaMemcpyDeviceToHost, q));
+    k_shared_coords<<<std::max(1, std::min(cdiv(s->xcapM, 256), 64)), 256, 0, q>>>(s->g, s->d_sel + nt, s->d_nM, s->xcapM, s->d_sharedM);
+    CK(cudaMemcpyAsync(&s->h_nshared[0], s->d_n_shared, sizeof(int), cudaMemcpyDeviceToHost, q));
+    CK(cudaMemcpyAsync(&s->h_nshared[1], s->d_nM, sizeof(int), cudaMemcpyDeviceToHost, q));
     s->launches += 2;
     s->n_rebuilds++;
 }
@@ -1193,7 +1237,7 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
         if (s->use_graphs && room >= W) {
             ShardGraphKey key{};
             key.dt = a.dt; key.collider = a.collider; key.mover = a.mover; key.advance_mesh = a.advance_mesh; key.cur = s->cur;
-            key.n_bc = (int)s->h_bcs.size(); key.n_ops = (int)s->h_ops.size(); key.xcap = s->xcap_blocks; key.len = W;
+            key.n_bc = (int)s->h_bcs.size(); key.n_ops = (int)s->h_ops.size(); key.xcap = s->xcap_blocks * 65536 + s->xcapM; key.len = W;
             key.shared_ptr = s->d_shared;
             auto& cache = shard_graphs(s);
             ShardGraph* hit = nullptr;
@@ -1235,8 +1279,8 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
 int mpm_shared_info(MpmSolver* s, int* n_shared, int* cap_blocks, int* n_rebuilds, void* stream) {
     API_BEGIN(s)
     CK(cudaStreamSynchronize((cudaStream_t)stream));
-    if (n_shared) *n_shared = s->h_nshared ? *s->h_nshared : s->n_shared;
-    if (cap_blocks) *cap_blocks = s->xcap_blocks;
+    if (n_shared) *n_shared = s->h_nshared ? s->h_nshared[0] : s->n_shared;
+    if (cap_blocks) *cap_blocks = (s->xcap_blocks + s->xcapM + 1) / 2;  // in units of 512 floats (the callback path's block payload)
     if (n_rebuilds) *n_rebuilds = s->n_rebuilds;
     API_END(s)
 }
