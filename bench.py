@@ -33,6 +33,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SUBSTEPS_PER_STEP = 400
+# dram__bytes_read.sum + dram__bytes_write.sum of the six P2G / G2P launches of one substep (ncu --set full, cold caches;
+# profiles/r1_v14_ncu_full_summary.txt); None until captured for the current kernels
+TRAFFIC_NCU = None
 METRIC = "mpm_substeps_per_sec_500k_particles_256grid"
 
 
@@ -59,7 +62,7 @@ class ClockSampler:
             return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -185,12 +188,12 @@ def run_sharded(args, sc, rank, local_rank, world, dev, barrier):
         sm.step(sc.dt, S_PER, f["mesh_x"], f["mesh_v"], f["joint_verts_v"], f["joint_faces_v"])
 
     fi = 0
+    clocks = ClockSampler(local_rank, enabled=(rank == 0))
+    clocks.start()  # sampled through warm-up and the timed region (the same load)
     for _ in range(args.warmup):
         step(fi, False); fi += 1
     st0 = sm.solver.stats()
-    clocks = ClockSampler(local_rank, enabled=(rank == 0))
     barrier()
-    clocks.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k in range(args.steps):
         flush_buf.fill_(k)
@@ -319,12 +322,12 @@ def main():
 
     # ---------------- value: inputs resident in HBM
     fi = 0
+    clocks = ClockSampler(local_rank, enabled=(rank == 0))
+    clocks.start()  # sampled through warm-up and the timed region (the same load)
     for _ in range(args.warmup):
         step_dev(fi); fi += 1
     st0 = solver.stats()
-    clocks = ClockSampler(local_rank, enabled=(rank == 0))
     barrier()
-    clocks.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k in range(args.steps):
         flush_buf.fill_(k)  # L2 flush between timed steps (not timed)
@@ -395,14 +398,23 @@ def main():
     solver.enable_profiling(False)
     n = max(prof["n_substeps"], 1)
     per = {k: prof[k] / n for k in prof if k.endswith("_ms")}
-    t_pg = (per["p2g_ms"] + per["g2p_v_ms"] + per["g2p_e_ms"]) * 1e-3
+    t_ev = (per["p2g_ms"] + per["g2p_v_ms"] + per["g2p_e_ms"]) * 1e-3
+    # the same phases inside the running chain: first-start / last-end stamps of the kernels on the GPU global timer
+    # (the kernels overlap under programmatic dependent launch; events around them would serialise the chain)
+    from mpmavatar_b200.timeline import measure, summarise
+    tl = summarise(measure(solver, sc.dt, dev_frames[-1], 32))
+    t_pg = (tl["p2g_union_us"] + tl["g2p_union_us"]) * 1e-6
     peak, peak_src = measured_peaks()
     bytes_pg = algorithmic_bytes(sc, A)
     achieved = bytes_pg / t_pg / 1e9
     roofline = {"bound": "hbm", "kernel": "p2g + g2p (k_p2g<0,1,2>, k_g2p_vertices, k_g2p_traditional, k_g2p_elements)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "algorithmic_bytes_per_substep": bytes_pg, "active_nodes": A,
-                "phase_us_per_substep": {k[:-3]: round(v * 1e3, 2) for k, v in per.items()}}
+                "traffic": TRAFFIC_NCU, "algorithmic_bytes_per_substep": bytes_pg, "active_nodes": A,
+                "timing": "P2G phase + G2P phase per substep = first CTA start to last CTA end of their kernels on the GPU "
+                          "global timer (mpm_measure_timeline), median over 28 graph-replayed substeps",
+                "timeline_us": tl,
+                "achieved_events_serialised": bytes_pg / t_ev / 1e9,
+                "phase_us_per_substep_events_serialised": {k[:-3]: round(v * 1e3, 2) for k, v in per.items()}}
 
     line = {"metric": METRIC, "value": value, "unit": "substeps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",

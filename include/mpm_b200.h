@@ -183,6 +183,11 @@ int mpm_set_profiling(MpmSolver *s, int on); /* per-phase CUDA events; disables 
 int mpm_get_profile(MpmSolver *s, MpmProfile *out);   /* synchronises */
 int mpm_get_stats(MpmSolver *s, MpmStats *out, void *stream); /* synchronises */
 int mpm_force_resort(MpmSolver *s);
+/* timeline probe: n <= 64 substeps with per-kernel first-start / last-end stamps of the GPU global timer;
+ * out[n][8][2] ns relative to the first stamp (-1: kernel not launched).  Kernel ids: 0 P2G elements (+ cloth stress),
+ * 1 P2G traditional, 2 P2G vertices, 3 body/joint scatter, 4 grid update, 5 G2P vertices, 6 G2P traditional,
+ * 7 G2P elements.  The kernels overlap under programmatic dependent launch, which CUDA events cannot resolve. */
+int mpm_measure_timeline(MpmSolver *s, float dt, int n, const MpmFrameInputs *in, long long *out, void *stream);
 /* latency analysis (builds with -DMPM_CLK only fill it): 8 kernels x 8 per-warp phase cycle sums; synchronises */
 int mpm_debug_phase_clocks(MpmSolver *s, unsigned long long *out64, int reset);
 

@@ -80,6 +80,7 @@ SYMBOLS = {
     "mpm_set_shared_blocks": (C.c_int, [_P, _P, C.c_int, _P]),
     "mpm_shared_pack": (C.c_int, [_P, _P, _P]),
     "mpm_shared_unpack": (C.c_int, [_P, _P, _P]),
+    "mpm_measure_timeline": (C.c_int, [_P, C.c_float, C.c_int, C.POINTER(MpmFrameInputs), _P, _P]),
     "mpm_set_time": (C.c_int, [_P, C.c_double]),
     "mpm_export_grid": (C.c_int, [_P, _P, _P, _P, _P]),
     "mpm_set_debug": (C.c_int, [_P, C.c_int]),

@@ -460,7 +460,7 @@ static void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem,
 }
 
 // the grid update grid-strides over the allocated blocks (count on the device): 8 CTAs of 256 threads per SM
-constexpr int GRID_UPDATE_CTAS = 148 * 8;
+constexpr int GRID_UPDATE_CTAS = 148 * 5;  // one wave at 48 registers x 256 threads
 
 // A substep has two halves around the grid: everything that SCATTERS to it (constitutive update, P2G,
 // body-mesh and joint scatters) and everything that reads it back (grid update, G2P).  Single-GPU
@@ -503,13 +503,9 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
         launch_pdl(k_p2g<1>, cdiv(s->Nt, ppb), ppb, P2G_SMEM, q, pdl, s->g, in, s->Nt, a.dt, s->md.rpic);
         s->launches++;
     }
-    if (s->Nv) {
-        P2GIn in{R.VP, (const float*)R.VF, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
-        launch_pdl(k_p2g<2>, cdiv(s->Nv, ppb), ppb, P2G_SMEM, q, pdl, s->g, in, s->Nv, a.dt, s->md.rpic);
-        s->launches++;
-    }
-    if (ev) CK(cudaEventRecord(ev[2], q));
-    {   // body-mesh collider and joint movers (mpm_solver.py:382-472): one launch behind the P2G kernels
+    // body-mesh collider and joint movers (mpm_solver.py:382-472): one launch behind the P2G kernels
+    // (profiling: two launches, so that the two phases are timed separately)
+    auto scatter_launch = [&]() {
         const int tot = a.mover ? a.njt + s->cfg.num_joint_v + s->cfg.num_joint_f : 0;
         ColliderArgs ca{a.collider ? s->cfg.n_mesh_f : 0, s->mesh_faces, s->mesh_x, s->mesh_v, s->st, a.dt, a.advance_mesh ? 1 : 0};
         MoverArgs ma{a.mover ? a.njt : 0, a.mover ? s->cfg.num_joint_v : 0, a.mover ? s->cfg.num_joint_f : 0, s->Nt,
@@ -523,7 +519,14 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
             launch_pdl(k_body_scatter, cdiv(ca.Mf + tot, 128), 128, 0, q, pdl, s->g, ca, ma);
             s->launches++;
         }
+    };
+    if (s->Nv) {
+        P2GIn in{R.VP, (const float*)R.VF, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
+        launch_pdl(k_p2g<2>, cdiv(s->Nv, ppb), ppb, P2G_SMEM, q, pdl, s->g, in, s->Nv, a.dt, s->md.rpic);
+        s->launches++;
     }
+    if (ev) CK(cudaEventRecord(ev[2], q));
+    scatter_launch();
     }  // HALF_SCATTER
     if (!(halves & HALF_GATHER)) return;
     // one thread per node of the active blocks, grid-strided over the device-side block count
@@ -691,6 +694,7 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         g.mov = s->dalloc<float4>(pn);
         g.dbg_acc = nullptr;
         g.clk = s->dalloc<unsigned long long>(64 * 64);
+        g.ts = nullptr;
         k_fill_int<<<1184, 256>>>(g.table, nt, -1);
         {   // sorted sub-records, each with 32 records of slack for the 16-byte bulk-copy granule
             size_t ne = (size_t)s->Ne + 32, nt = (size_t)s->Nt + 32, nv = (size_t)s->Nv + 32;
@@ -1350,6 +1354,75 @@ int mpm_shared_unpack(MpmSolver* s, const float* buf, void* stream) {
     if (s->n_shared) {
         k_shared_unpack<<<cdiv((long long)s->n_shared * BN, 256), 256, 0, (cudaStream_t)stream>>>(s->g, s->d_shared, s->n_shared, nullptr, (const float4*)buf);
         s->launches++;
+    }
+    API_END(s)
+}
+
+// n substeps (<= 64) launched eagerly (same kernels, same programmatic-dependent-launch chain as mpm_step) with the
+// timeline probe on; out[n][TS_KERNELS][2] = first-CTA start / last-CTA end in ns relative to the first stamp, -1 for
+// kernels that did not run.  Synchronises.
+int mpm_measure_timeline(MpmSolver* s, float dt, int n, const MpmFrameInputs* in, long long* out, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    if (n < 1 || n > 64) throw std::string("mpm_measure_timeline: 1 <= n <= 64");
+    if (!s->have_state) throw std::string("mpm_measure_timeline before mpm_import_state");
+    MpmFrameInputs none{};
+    if (!in) in = &none;
+    SubstepArgs a{};
+    begin_half_step(s, in, a, dt, q);
+    a.njt = 0;
+    a.advance_mesh = false;  // the body stays where the last step left it
+    const size_t per = 2 * TS_KERNELS;
+    std::vector<unsigned long long> h((size_t)n * per);
+    for (size_t i = 0; i < h.size(); i++) h[i] = (i & 1) ? 0ull : ~0ull;
+    unsigned long long* d = s->dalloc<unsigned long long>(h.size());
+    CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, q));
+    if (s->need_sort) resort(s, q);
+    const bool prof = s->profiling;
+    s->profiling = false;
+    if (s->use_graphs && n % 2 == 0) {  // as mpm_step runs them: one captured graph, replayed (twice: the second is timed)
+        if (!s->cap_stream) CK(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+        const int before = s->launches;
+        cudaGraph_t graph;
+        cudaGraphExec_t exec;
+        CK(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < n; i++) {
+            s->g.ts = d + (size_t)i * per;
+            launch_substep(s, a, s->cap_stream);
+        }
+        CK(cudaStreamEndCapture(s->cap_stream, &graph));
+        s->g.ts = nullptr;
+        CK(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        CK(cudaGraphLaunch(exec, q));
+        CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, q));
+        CK(cudaGraphLaunch(exec, q));
+        CK(cudaStreamSynchronize(q));
+        cudaGraphExecDestroy(exec);
+        s->launches = before + 2 * (s->launches - before);
+        s->since_sort += n;
+        s->n_substeps += n;
+        for (int k = 0; k < n; k++) s->host_time += (double)dt;
+    } else {
+        for (int i = 0; i < n; i++) {
+            s->g.ts = d + (size_t)i * per;
+            launch_substep(s, a, q);
+        }
+        s->g.ts = nullptr;
+    }
+    s->profiling = prof;
+    s->since_sort += n;
+    s->n_substeps += n;
+    s->canon_stale = true;
+    for (int k = 0; k < n; k++) s->host_time += (double)dt;
+    CK(cudaMemcpyAsync(h.data(), d, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, q));
+    CK(cudaStreamSynchronize(q));
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < h.size(); i += 2) t0 = std::min(t0, h[i]);
+    for (size_t i = 0; i < h.size(); i += 2) {
+        const bool ran = h[i] != ~0ull;
+        out[i] = ran ? (long long)(h[i] - t0) : -1;
+        out[i + 1] = ran ? (long long)(h[i + 1] - t0) : -1;
     }
     API_END(s)
 }

@@ -73,7 +73,26 @@ struct Grid {
     float4* dbg_acc;  // copy of acc taken by the grid update when debugging (else null)
     int* flags;       // [0] pool overflow, [1] scatter/gather hit an unallocated block
     unsigned long long* clk;  // phase-clock accumulators (only read by -DMPM_CLK builds, tools/phase_clocks.py)
+    unsigned long long* ts;   // timeline probe (mpm_measure_timeline): [kernel id][first start, last end] in ns, else null
 };
+// Timeline probe: first CTA start / last CTA end of a kernel on the GPU's global timer.  CUDA events cannot
+// time kernels that overlap under programmatic dependent launch; these stamps can.  One 64-bit atomic per warp
+// at each end, only when g.ts is set.
+enum { TS_P2G_E = 0, TS_P2G_T, TS_P2G_V, TS_SCATTER, TS_GRID, TS_G2P_V, TS_G2P_T, TS_G2P_E, TS_KERNELS };
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// CTAs start in blockIdx order, so the first start is among the first CTAs and the last end (almost surely) among
+// the last ones: only the first / last 512 CTAs stamp, which keeps the probe's same-address atomics off the
+// measured path (stamping every warp cost ~10 % of a substep).
+__device__ __forceinline__ void ts_begin(const Grid& g, int k) {
+    if (g.ts && threadIdx.x == 0 && blockIdx.x < 512) atomicMin(&g.ts[2 * k], globaltimer_ns());
+}
+__device__ __forceinline__ void ts_end(const Grid& g, int k) {
+    if (g.ts && threadIdx.x == 0 && blockIdx.x + 512 >= gridDim.x) atomicMax(&g.ts[2 * k + 1], globaltimer_ns());
+}
 
 // Per-warp phase clocks for latency analysis: PHASE_BEGIN at kernel entry, PHASE(k, i) after phase i of
 // kernel k adds the elapsed SM cycles to a per-thread accumulator, PHASE_END(k) flushes lane 0's sums to

@@ -349,11 +349,13 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
     extern __shared__ __align__(128) unsigned char smem[];
     Warp w;
     if (!warp_begin<P2G_NW, P2G_WB>(w, n, smem)) return;
+    ts_begin(g, TS_P2G_E + KIND);
     PHASE_BEGIN();
     float* buf = reinterpret_cast<float*>(w.buf);
-    // PDL invariant of this file: a kernel triggers its dependents only AFTER its own griddepcontrol.wait, so
-    // "my grid has started" implies "my predecessor's predecessor has completed" -- that is what the code in
-    // front of a wait may rely on.
+    // PDL invariants of this file: (1) every kernel executes griddepcontrol.wait before it exits, so completion is
+    // transitive along the stream; (2) a kernel whose successor runs code in front of its own wait triggers
+    // only AFTER its wait, so "my grid has started" implies "my predecessor's predecessor has completed" -- that
+    // is what the code in front of a wait may rely on.
     // The vertex scatter only needs its predecessor (the element kernel) for the vertex forces: the VP slab is
     // loaded and unpacked while the element kernel drains, griddepcontrol.wait sits in front of the VF read.
     if (KIND != 2) {
@@ -552,6 +554,7 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
     flush(c, alo, ahi);
     PHASE(g, KIND, 3);  // stage 2
     PHASE_END(g, KIND);
+    ts_end(g, TS_P2G_E + KIND);
 }
 
 // ============================================================ collider / mover scatter
@@ -679,15 +682,19 @@ __global__ void __launch_bounds__(128) k_mover_scatter(Grid g, MoverArgs ma) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < ma.njt + ma.njv + ma.njf) mover_scatter_one(g, ma, t);
 }
-// Both scatters in one launch, placed behind the vertex P2G in the stream: it does not depend on it (different
-// accumulators), so under programmatic dependent launch its CTAs fill the tail of the P2G kernels; the wait at the
-// end only keeps the chain transitive (see the PDL invariant in k_p2g).  Threads [0, Mf) faces, then the movers.
+// Both scatters in one launch, placed behind the vertex P2G in the stream.  It depends on neither P2G kernel
+// (different accumulators; the block table and the positions are those of the previous substep), so its CTAs fill
+// the tail of the vertex P2G; the wait before exit keeps completion transitive.  (Placing it between the two P2G
+// kernels was measured: its ~1.1 M vector atomics then collide with the element kernel's and slow that kernel by
+// more than the scatter's own exposed time.)  Threads [0, Mf) faces, then the movers.
 __global__ void __launch_bounds__(128) k_body_scatter(Grid g, ColliderArgs ca, MoverArgs ma) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    ts_begin(g, TS_SCATTER);
     if (t < ca.Mf) collider_scatter_face(g, ca, t);
     else if (t - ca.Mf < ma.njt + ma.njv + ma.njf) mover_scatter_one(g, ma, t - ca.Mf);
+    ts_end(g, TS_SCATTER);  // before the wait: the stamp is the end of this kernel's own work
     pdl_wait();
-    pdl_trigger();
 }
 
 // ============================================================ grid update
@@ -701,6 +708,7 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
                                                      const StepState* __restrict__ st) {
     // the active list was last changed by the previous substep's G2P: the node address is computed while the
     // scatter kernels in front of this one drain (PDL invariant: wait, then trigger)
+    ts_begin(g, TS_GRID);
     const int n_slots = min(*g.n_slots, g.cap);
     const int total = n_slots * BN;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -814,6 +822,7 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
         }
         g.vout[ni] = make_float4(vx, vy, vz, 0.0f);
     }
+    ts_end(g, TS_GRID);
 }
 __global__ void k_reset_k(StepState* st) { st->k = 0; }
 
@@ -1028,6 +1037,7 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_vertices(Grid g, 
     if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); advance_step(adv.st, dt, adv.bcs, adv.n_bc); }
     Warp w;
     if (!warp_begin<G2P_NW, G2P_V_WB>(w, Nv, smem)) return;
+    ts_begin(g, TS_G2P_V);
     PHASE_BEGIN();
     float* sP = reinterpret_cast<float*>(w.buf);
     // VP and CV were last written by the previous substep's G2P: the slab load and the run search overlap the
@@ -1073,6 +1083,7 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_vertices(Grid g, 
     slab_store(w, {Slab{sP, VP, VP_F}});
     PHASE(g, 3, 5);
     PHASE_END(g, 3);
+    ts_end(g, TS_G2P_V);
 }
 
 // g2p_v for traditional particles: additionally F_trial = (I + dt grad v) F (mpm_utils.py:783-786)
@@ -1083,6 +1094,7 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_traditional(Grid 
     if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); advance_step(adv.st, dt, adv.bcs, adv.n_bc); }
     Warp w;
     if (!warp_begin<G2P_NW, G2P_T_WB>(w, Nt, smem)) return;
+    ts_begin(g, TS_G2P_T);
     float* sP = reinterpret_cast<float*>(w.buf);
     float* sT = sP + 32 * KP_F;
     pdl_wait();
@@ -1118,6 +1130,7 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_traditional(Grid 
         ensure_if_moved(g, G.b, x, y, z);
     }
     slab_store(w, {Slab{sP, TP, KP_F}, Slab{sT, TF, TF_F}});
+    ts_end(g, TS_G2P_T);
 }
 
 // g2p_e (mpm_utils.py:788-857): C and grad v at the OLD centroid, x/v = mean of the three
@@ -1132,6 +1145,7 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_elements(Grid g, 
     if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); advance_step(adv.st, dt, adv.bcs, adv.n_bc); }
     Warp w;
     if (!warp_begin<G2P_NW, G2P_E_WB>(w, Ne, smem)) return;
+    ts_begin(g, TS_G2P_E);
     float* sP = reinterpret_cast<float*>(w.buf);
     float* s12 = sP + 32 * KP_F;
     PHASE_BEGIN();
@@ -1217,6 +1231,7 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_elements(Grid g, 
     slab_store(w, {Slab{sP, EP, KP_F}, Slab{s12, E12out, E12_F}});
     PHASE(g, 5, 5);  // epilogue + store
     PHASE_END(g, 5);
+    ts_end(g, TS_G2P_E);
 }
 
 }  // namespace mpm
