@@ -324,13 +324,9 @@ __global__ void k_particle_ops(int n, float* __restrict__ rec, int F, const uint
 #define MPM_P2G_NW 1
 #endif
 constexpr int P2G_NW = MPM_P2G_NW;  // warps (= slabs) per CTA
-#ifndef MPM_P2G_PF
-#define MPM_P2G_PF 2
-#endif
-constexpr int P2G_PF = MPM_P2G_PF;  // stage-2 prefetch depth (particles), divides 8
 constexpr int P2G_T_B = 32 * 9 * 16, P2G_U_B = 32 * 3 * 16, P2G_W_B = 32 * 9 * 4;
 constexpr int P2G_WB = P2G_T_B + P2G_U_B + P2G_W_B;  // 7296 B; the raw slabs (<= 4864 B) are overlaid on it
-constexpr int P2G_SMEM = 128 + P2G_NW * P2G_WB;
+constexpr int P2G_SMEM = 128 + P2G_NW * P2G_WB + 64;  // + slack for the stage-2 look-ahead loads
 
 struct P2GIn {
     const float* KP;   // EP / TP / VP
@@ -520,36 +516,27 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
     };
     float2 alo = make_float2(0.f, 0.f), ahi = alo;
     int c = __shfl_sync(0xffffffffu, mycell, 0);
-    // register ring of P2G_PF particles: the shared-memory loads run P2G_PF iterations ahead of the
-    // accumulation, so the loop is bound by issue slots and not by LDS latency
-    float4 Tq[P2G_PF], Uq[P2G_PF];
-    float wq[P2G_PF];
-#pragma unroll
-    for (int d = 0; d < P2G_PF; d++) { Tq[d] = pT[d * 9]; Uq[d] = pU[d * 3]; wq[d] = pW[d * 9]; }
-#pragma unroll 1
-    for (int q0 = 0; q0 < 32; q0 += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) {  // records past cnt contribute zeros
-            const int q = q0 + j;
-            const float4 T = Tq[j % P2G_PF], U = Uq[j % P2G_PF];
-            const float wij = wq[j % P2G_PF];
-            const int qn = min(q + P2G_PF, 31);
-            Tq[j % P2G_PF] = pT[qn * 9];
-            Uq[j % P2G_PF] = pU[qn * 3];
-            wq[j % P2G_PF] = pW[qn * 9];
-            if (q > 0 && ((R.starts >> q) & 1u)) {
-                const int cn = __shfl_sync(0xffffffffu, mycell, q);
-                {
-                    flush(c, alo, ahi);
-                    alo = ahi = make_float2(0.f, 0.f);
-                }
-                c = cn;
-            }
-            alo = fma2(U.w, make_float2(T.x, T.y), alo);
-            ahi = fma2(U.w, make_float2(T.z, T.w), ahi);
-            alo = fma2(wij, make_float2(U.x, U.y), alo);
-            ahi.x = fmaf(wij, U.z, ahi.x);
+    // one pass over the slab; the shared-memory loads of particle q+1 are in flight while particle q is accumulated
+    // (deeper prefetch was measured: no gain, more address arithmetic).  The loads of "particle 32" read a few bytes
+    // past the tiles, inside the CTA's allocation (P2G_SMEM carries the slack), and are never used.
+    float4 Tn = pT[0], Un = pU[0];
+    float wn = pW[0];
+#pragma unroll 8
+    for (int q = 0; q < 32; q++) {  // records past cnt contribute zeros
+        const float4 T = Tn, U = Un;
+        const float wij = wn;
+        Tn = pT[(q + 1) * 9];
+        Un = pU[(q + 1) * 3];
+        wn = pW[(q + 1) * 9];
+        if (q > 0 && ((R.starts >> q) & 1u)) {
+            flush(c, alo, ahi);
+            alo = ahi = make_float2(0.f, 0.f);
+            c = __shfl_sync(0xffffffffu, mycell, q);
         }
+        alo = fma2(U.w, make_float2(T.x, T.y), alo);
+        ahi = fma2(U.w, make_float2(T.z, T.w), ahi);
+        alo = fma2(wij, make_float2(U.x, U.y), alo);
+        ahi.x = fmaf(wij, U.z, ahi.x);
     }
     flush(c, alo, ahi);
     PHASE(g, KIND, 3);  // stage 2
