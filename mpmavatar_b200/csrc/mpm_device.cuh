@@ -28,7 +28,7 @@
 //   EK     constants   {Rinv[3], mu, lam, gamma, kappa, vol} 8 floats read-only
 //   TS     stress      {S[9]}                              9 floats  written by the traditional stress kernel
 //   TF     trad state  {F[9], Ft[9], mu, lam, ys}         21 floats  written by stress (F,..) and G2P (Ft)
-//   VP     kinematics  {x,y,z,m, vx,vy,vz, C[9]}          16 floats  written by G2P
+//   VP     kinematics  {x,y,z,m, vx,vy,vz, C[9], pad[4]}  20 floats  written by G2P
 //   VF     force       float4 {fx,fy,fz,-}                           REDG.128 by stress, zeroed by G2P
 // E12 / D3 are double buffered: G2P reads buffer `cur` and writes buffer `cur^1`, so the directions the
 // last stress evaluation saw stay available and the element stress (state.particle_stress) is
@@ -54,7 +54,8 @@ constexpr int E12_F = 6;
 constexpr int EF_F = 3;
 constexpr int EK_F = 8;
 constexpr int TF_F = 21;
-constexpr int VP_F = 16;
+constexpr int VP_F = 20;  // 16 used + 4 pad: an 80-byte stride makes lane = particle LDS.128 / STS.128 bank-conflict free
+                          // (at 64 bytes they were 4-way conflicted: 64 of the ~290 shared-memory wavefronts of a G2P warp)
 constexpr int VF_F = 4;
 // field offsets
 constexpr int P_X = 0, P_M = 3, P_V = 4, P_VOL = 7, P_C = 8;  // EP / TP

@@ -900,6 +900,97 @@ __device__ __forceinline__ void g2p_contract(const float4* __restrict__ T, const
     o.G[2] = G2_xy.x; o.G[5] = G2_xy.y; o.G[8] = c2z_g2z.y;
 }
 
+// Register-lean variants of the same contraction for the two cloth kernels.  The unrolled version above keeps the 27
+// weights, three levels of partial sums and hoisted tile rows live (112-121 registers, 16 warps per SM); here the x
+// axis is a ROLLED loop whose weights are evaluated in the loop, and only what the kernel uses is accumulated:
+//   MODE 0 (vertices)  v and C;
+//   MODE 1 (elements)  C and (grad v) d3 -- g2p_e only uses grad v in F d3 = d3 + dt (grad v) d3 (mpm_utils.py:850-855), so
+//                      the three gradient weights are folded with d3 and ONE vector is accumulated instead of nine sums.
+template <int MODE>
+__device__ __forceinline__ void g2p_contract_lean(const float4* __restrict__ T, const float (&f)[3], float inv_dx, const float (&d3)[3],
+                                                  Gathered& o) {
+    float W1[3], CW1[3], W2[3], CW2[3], D1[3], D2[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float ww, dd;
+        bspline(f[1], i, ww, dd);
+        W1[i] = ww; CW1[i] = ww * ((float)i - f[1]) * (inv_dx * 4.0f); D1[i] = dd * inv_dx * d3[1];
+        bspline(f[2], i, ww, dd);
+        W2[i] = ww; CW2[i] = ww * ((float)i - f[2]) * (inv_dx * 4.0f); D2[i] = dd * inv_dx * d3[2];
+    }
+    const float2 z2 = make_float2(0.f, 0.f);
+    float2 v_xy = z2, C0_xy = z2, C1_xy = z2, C2_xy = z2, g_xy = z2;
+    float vz = 0.f, c0z = 0.f, c1z = 0.f, c2z = 0.f, gz = 0.f;
+#pragma unroll 1
+    for (int i = 0; i < 3; i++) {
+        // bspline(f[0], i) with a run-time i (same arithmetic as the unrolled form)
+        const float fi = (float)i;
+        const float A = (i == 1) ? -1.0f : 0.5f, B = (i == 1) ? 0.75f : 0.0f;
+        const float t = f[0] - (1.5f - 0.5f * fi);
+        const float w0 = A * t * t + B;
+        const float cw0 = w0 * (fi - f[0]) * (inv_dx * 4.0f);
+        const float d0 = (2.0f * A * t) * inv_dx * d3[0];
+        const float4* __restrict__ Ti = T + i * 9;
+        float2 A0_xy = z2, A1_xy = z2, B0_xy = z2, E_xy = z2;
+        float A0z = 0.f, A1z = 0.f, B0z = 0.f, Ez = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            float4 pl[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) pl[q] = Ti[j * 3 + q];
+            asm volatile("" ::: "memory");  // one z-row in flight: keeps the loads from being hoisted into 100+ registers
+            float2 a_xy = z2, b_xy = z2, c_xy = z2, bz_cz = z2;
+            float az = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float2 gxy = make_float2(pl[k].x, pl[k].y);
+                a_xy = fma2(W2[k], gxy, a_xy);
+                b_xy = fma2(CW2[k], gxy, b_xy);
+                az = fmaf(W2[k], pl[k].z, az);
+                if (MODE == 1) {
+                    c_xy = fma2(D2[k], gxy, c_xy);
+                    bz_cz = fma2(make_float2(CW2[k], D2[k]), pl[k].z, bz_cz);
+                } else {
+                    bz_cz.x = fmaf(CW2[k], pl[k].z, bz_cz.x);
+                }
+            }
+            A0_xy = fma2(W1[j], a_xy, A0_xy);
+            A1_xy = fma2(CW1[j], a_xy, A1_xy);
+            B0_xy = fma2(W1[j], b_xy, B0_xy);
+            A0z = fmaf(W1[j], az, A0z);
+            A1z = fmaf(CW1[j], az, A1z);
+            B0z = fmaf(W1[j], bz_cz.x, B0z);
+            if (MODE == 1) {  // E = sum_j (w1j c' + dw1j d3y a): the y and z terms of (grad w . d3) for this i
+                E_xy = fma2(W1[j], c_xy, E_xy);
+                E_xy = fma2(D1[j], a_xy, E_xy);
+                Ez = fmaf(W1[j], bz_cz.y, Ez);
+                Ez = fmaf(D1[j], az, Ez);
+            }
+        }
+        if (MODE == 0) {
+            v_xy = fma2(w0, A0_xy, v_xy);
+            vz = fmaf(w0, A0z, vz);
+        }
+        C0_xy = fma2(cw0, A0_xy, C0_xy);
+        C1_xy = fma2(w0, A1_xy, C1_xy);
+        C2_xy = fma2(w0, B0_xy, C2_xy);
+        c0z = fmaf(cw0, A0z, c0z);
+        c1z = fmaf(w0, A1z, c1z);
+        c2z = fmaf(w0, B0z, c2z);
+        if (MODE == 1) {
+            g_xy = fma2(w0, E_xy, g_xy);
+            g_xy = fma2(d0, A0_xy, g_xy);
+            gz = fmaf(w0, Ez, gz);
+            gz = fmaf(d0, A0z, gz);
+        }
+    }
+    o.v[0] = v_xy.x; o.v[1] = v_xy.y; o.v[2] = vz;
+    o.C[0] = C0_xy.x; o.C[3] = C0_xy.y; o.C[6] = c0z;
+    o.C[1] = C1_xy.x; o.C[4] = C1_xy.y; o.C[7] = c1z;
+    o.C[2] = C2_xy.x; o.C[5] = C2_xy.y; o.C[8] = c2z;
+    o.G[0] = g_xy.x; o.G[1] = g_xy.y; o.G[2] = gz;  // MODE 1: (grad v) d3
+}
+
 // Warp-collective gather.  The particles of a warp form a few same-cell runs; for each run lanes 0..26
 // fetch the run's 27 node velocities ONCE (one table lookup + one LDG.128 per lane, up to G2P_RMAX runs
 // in flight) into a shared-memory tile, then lane = particle contracts its run's tile with broadcast
@@ -961,6 +1052,20 @@ struct Gather {
         cp_async_wait_all();
         __syncwarp();
     }
+    // the register-lean contractions (MODE 0: v, C; MODE 1: C, (grad v) d3)
+    template <int MODE>
+    __device__ __forceinline__ void contract_lean(int r0, const float (&d3)[3], Gathered& o) const {
+        if (valid && R.mine >= r0 && R.mine < r0 + G2P_RMAX) g2p_contract_lean<MODE>(tile + (R.mine - r0) * 27, f, g.inv_dx, d3, o);
+    }
+    template <int MODE>
+    __device__ __forceinline__ void remaining_passes_lean(const float (&d3)[3], Gathered& o) const {
+        for (int r0 = G2P_RMAX; r0 < R.nr; r0 += G2P_RMAX) {
+            __syncwarp();
+            stage_issue(r0);
+            stage_wait();
+            contract_lean<MODE>(r0, d3, o);
+        }
+    }
     // lane = particle: contract the tile of my run if it is staged
     __device__ __forceinline__ void contract(int r0, Gathered& o) const {
         if (valid && R.mine >= r0 && R.mine < r0 + G2P_RMAX) {
@@ -1014,11 +1119,18 @@ struct Advance {
 #define MPM_G2P_NW 1
 #endif
 constexpr int G2P_NW = MPM_G2P_NW;  // warps (= slabs) per CTA
-constexpr int G2P_MINB = 16 / G2P_NW;  // 16 resident warps per SM: <= 128 registers, no spills
+constexpr int G2P_MINB = 16 / G2P_NW;  // unrolled contraction (traditional particles): 16 resident warps per SM, <= 128 registers
+#ifndef MPM_G2P_V_WARPS
+#define MPM_G2P_V_WARPS 20
+#endif
+#ifndef MPM_G2P_E_WARPS
+#define MPM_G2P_E_WARPS 20
+#endif
+constexpr int G2P_V_MINB = MPM_G2P_V_WARPS / G2P_NW, G2P_E_MINB = MPM_G2P_E_WARPS / G2P_NW;  // lean contractions
 // g2p_v for cloth vertices (mpm_utils.py:716-786); also clears vertex_force for the next substep
 // (replaces set_vec3_to_zero, mpm_solver.py:251-256) and allocates grid blocks for the new position.
 constexpr int G2P_V_WB = VP_F * 32 * 4 + G2P_TILE_B;
-__global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_vertices(Grid g, int Nv, float* __restrict__ VP, float4* __restrict__ VF,
+__global__ void __launch_bounds__(32 * G2P_NW, G2P_V_MINB) k_g2p_vertices(Grid g, int Nv, float* __restrict__ VP, float4* __restrict__ VF,
                                                                int* __restrict__ CV, float dt, float* __restrict__ dbg_f, Advance adv) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); advance_step(adv.st, dt, adv.bcs, adv.n_bc); }
@@ -1046,8 +1158,11 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_vertices(Grid g, 
     G.stage_wait();
     PHASE(g, 3, 2);
     Gathered o;
-    G.contract(0, o);
-    G.remaining_passes(o);
+    {
+        const float no_d3[3] = {0.f, 0.f, 0.f};
+        G.contract_lean<0>(0, no_d3, o);
+        G.remaining_passes_lean<0>(no_d3, o);
+    }
     PHASE(g, 3, 3);
     if (valid) {
         const float dxc = 1.0f / g.inv_dx, a_min = dxc * 2.0f, a_max = g.lim - dxc * 2.0f;
@@ -1124,7 +1239,7 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_traditional(Grid 
 // already-updated corner vertices, d = [x2-x1, x3-x1, (I + dt grad v) d3].  Reads the return-mapped d3
 // of direction buffer `cur`, writes d1,d2,d3 of buffer `cur^1` (see mpm_device.cuh).
 constexpr int G2P_E_WB = (KP_F + E12_F) * 32 * 4 + G2P_TILE_B;
-__global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_elements(Grid g, int Ne, float* __restrict__ EP, const int* __restrict__ EF,
+__global__ void __launch_bounds__(32 * G2P_NW, G2P_E_MINB) k_g2p_elements(Grid g, int Ne, float* __restrict__ EP, const int* __restrict__ EF,
                                                                const float4* __restrict__ D3in, float* __restrict__ E12out,
                                                                float4* __restrict__ D3out, int* __restrict__ CE,
                                                                const float* __restrict__ VP, float dt, Advance adv) {
@@ -1170,23 +1285,16 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_elements(Grid g, 
     PHASE(g, 5, 2);
     {
         Gathered o;
-        G.contract(0, o);
-        G.remaining_passes(o);
+        const float2* park = reinterpret_cast<const float2*>(s12 + w.lane * E12_F);
+        const float2 pk1 = park[1], pk2 = park[2];
+        const float d3v[3] = {pk1.y, pk2.x, pk2.y};
+        G.contract_lean<1>(0, d3v, o);
+        G.remaining_passes_lean<1>(d3v, o);
         if (valid) {
 #pragma unroll
             for (int i = 0; i < 9; i++) r[P_C + i] = o.C[i];
-            const float2* park = reinterpret_cast<const float2*>(s12 + w.lane * E12_F);
-            const float2 pk1 = park[1], pk2 = park[2];
-            const float3 d3v = make_float3(pk1.y, pk2.x, pk2.y);
-            float nd3[3];
-#pragma unroll
-            for (int rr = 0; rr < 3; rr++) {
-                float m0 = o.G[3 * rr] * dt + (rr == 0 ? 1.0f : 0.0f);
-                float m1 = o.G[3 * rr + 1] * dt + (rr == 1 ? 1.0f : 0.0f);
-                float m2 = o.G[3 * rr + 2] * dt + (rr == 2 ? 1.0f : 0.0f);
-                nd3[rr] = m0 * d3v.x + m1 * d3v.y + m2 * d3v.z;
-            }
-            D3out[p] = make_float4(nd3[0], nd3[1], nd3[2], 0.f);
+            // d3 <- (I + dt grad v) d3 (mpm_utils.py:850-855), with (grad v) d3 accumulated directly
+            D3out[p] = make_float4(fmaf(dt, o.G[0], d3v[0]), fmaf(dt, o.G[1], d3v[1]), fmaf(dt, o.G[2], d3v[2]), 0.f);
         }
     }
     PHASE(g, 5, 4);  // contraction
