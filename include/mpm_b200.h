@@ -163,6 +163,10 @@ int mpm_comm_unique_id(char *out128);
 int mpm_attach_comm(MpmSolver *s, const char *id128, int rank, int nranks);
 int mpm_step_sharded_nccl(MpmSolver *s, float dt, int nsub, const MpmFrameInputs *in, int refresh, int margin, void *stream);
 int mpm_shared_info(MpmSolver *s, int *n_shared, int *cap_blocks, int *n_rebuilds, void *stream);
+/* how the shared blocks travel: 0 caller's collective (callbacks), 1 ncclAllReduce inside the captured windows,
+ * 2 peer-to-peer: with <= 8 ranks on one NVLink domain every rank maps every peer's receive area (CUDA IPC) and the
+ * push / pull kernels move the parts directly (MPM_B200_P2P=0 forces 1) */
+int mpm_shared_mode(MpmSolver *s);
 int mpm_step_gather(MpmSolver *s, float dt, void *stream);
 int mpm_get_active_blocks(MpmSolver *s, int *coords, int cap, int *n, void *stream);
 /* blocks this rank can activate while its particles move at most `margin` cells (synchronises) */

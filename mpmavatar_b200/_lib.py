@@ -74,6 +74,7 @@ SYMBOLS = {
     "mpm_comm_unique_id": (C.c_int, [_P]),
     "mpm_attach_comm": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "mpm_step_sharded_nccl": (C.c_int, [_P, C.c_float, C.c_int, C.POINTER(MpmFrameInputs), C.c_int, C.c_int, _P]),
+    "mpm_shared_mode": (C.c_int, [_P]),
     "mpm_shared_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
     "mpm_get_active_blocks": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int), _P]),
     "mpm_get_potential_blocks": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]),

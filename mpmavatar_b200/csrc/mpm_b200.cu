@@ -202,13 +202,16 @@ __global__ void k_popc(const unsigned long long* mask, int n, unsigned long long
 
 // blocks under the stencil of any particle displaced by up to `margin` cells in every direction: what this
 // rank can activate before the shared-block list is rebuilt
+// g_bit: the value written (1, or 1 << rank so that a byte-sum over <= 8 ranks is the set of ranks that can touch a block)
 // markj (optional): blocks reachable by prescribed-velocity (joint) particles, the first njoint of the class in
 // canonical order -- only those blocks carry mover accumulators
 __global__ void k_mark_potential(Grid g, int n, const float* __restrict__ rec, int F, int margin, unsigned char* __restrict__ mark,
-                                 unsigned char* __restrict__ markj = nullptr, const uint32_t* __restrict__ perm = nullptr, int njoint = 0) {
+                                 unsigned char* __restrict__ markj = nullptr, const uint32_t* __restrict__ perm = nullptr, int njoint = 0,
+                                 int g_bit = 1) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const bool joint = markj && perm && (int)perm[i] < njoint;
+    const unsigned char bit = (unsigned char)g_bit;
     const float* x = rec + (size_t)i * F;
     int lo[3], hi[3];
     for (int a = 0; a < 3; a++) {
@@ -219,8 +222,8 @@ __global__ void k_mark_potential(Grid g, int n, const float* __restrict__ rec, i
     for (int a = lo[0]; a <= hi[0]; a++)
         for (int b = lo[1]; b <= hi[1]; b++)
             for (int c = lo[2]; c <= hi[2]; c++) {
-                mark[table_index(g, a, b, c)] = 1;
-                if (joint) markj[table_index(g, a, b, c)] = 1;
+                mark[table_index(g, a, b, c)] = bit;
+                if (joint) markj[table_index(g, a, b, c)] = bit;
             }
 }
 // ---- sharded runs: the grid blocks shared with other ranks travel through one packed buffer
@@ -252,7 +255,11 @@ __global__ void k_shared_unpack(Grid g, const int* __restrict__ shared, int n_sh
 struct SharedPred {
     const unsigned char* mark;
     const unsigned char* markj;  // non-null: additionally some rank has joint particles there
-    __device__ bool operator()(int i) const { return mark[i] >= 2 && (!markj || markj[i] >= 1); }
+    int bits;                    // 1: mark[] is a set of rank bits, 0: a count
+    __device__ bool operator()(int i) const {
+        const int m = mark[i];
+        return (bits ? __popc(m) >= 2 : m >= 2) && (!markj || markj[i] >= 1);
+    }
 };
 // in-graph exchange buffer: [capA blocks x 64 acc float4 | capM blocks x 64 mov float4]; list A = blocks at least
 // two ranks can touch, list M = the subset that can carry mover (joint) accumulators
@@ -282,7 +289,8 @@ __global__ void k_shared_unpack2(Grid g, SharedLists L, const float4* __restrict
         if (g.table[blk] >= 0) (mv ? g.mov : g.acc)[blk * BN + l] = buf[mv ? (size_t)L.capA * BN + j : j];
     }
 }
-__global__ void k_shared_coords(Grid g, const int* __restrict__ lin, int* __restrict__ n_sel, int cap, int* __restrict__ coords) {
+__global__ void k_shared_coords(Grid g, const int* __restrict__ lin, int* __restrict__ n_sel, int cap, int* __restrict__ coords,
+                                const unsigned char* __restrict__ mark, unsigned char* __restrict__ members) {
     const int n = *n_sel;
     if (n > cap && blockIdx.x == 0 && threadIdx.x == 0) g.flags[0] = 1;  // reported as overflow
     const int m = min(n, cap);
@@ -290,6 +298,100 @@ __global__ void k_shared_coords(Grid g, const int* __restrict__ lin, int* __rest
         const int t = lin[i];
         const int bz = t % g.nb, by = (t / g.nb) % g.nb, bx = t / (g.nb * g.nb);
         coords[i] = bx | (by << 10) | (bz << 20);
+        members[i] = mark[t];  // the ranks that can touch the block (peer-to-peer exchange)
+    }
+}
+
+// ---- peer-to-peer exchange of the shared blocks over NVLink (replaces pack -> ncclAllReduce -> unpack)
+// Every rank owns a receive area [2 epochs parity][nranks senders][capA + capM blocks][64 float4] and flags
+// [2][nranks], both mapped into every peer (CUDA IPC).  k_shared_push writes this rank's partial sums of every block
+// it is a member of straight into the receive areas of the block's other members and then raises its flag there;
+// k_shared_pull waits for the flags of all peers and adds the members' parts IN RANK ORDER (own part included at its
+// position), so every member computes bit-identical sums.  Two parities suffice: a rank can only push epoch e+2 after
+// its pull of e+1, which needed every peer's push of e+1, which follows that peer's pull of e.
+struct PeerArea {
+    unsigned char* base[8];  // receive area of every rank as mapped here (base[rank] is the local one)
+    unsigned long long slot_bytes, flags_off;
+    int rank, nranks;
+    unsigned* epoch;    // completed exchanges (device)
+    unsigned* counter;  // last-CTA detection: [0] push, [1] pull
+};
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(256) k_shared_push(Grid g, SharedLists L, const unsigned char* __restrict__ memA,
+                                                     const unsigned char* __restrict__ memM, PeerArea P) {
+    const unsigned E = *P.epoch;  // written by the previous pull, which completed before the scatter half started
+    const int par = E & 1;
+    const int nA = min(*L.nA, L.capA) * BN, nM = min(*L.nM, L.capM) * BN;
+    pdl_wait();     // every scatter into acc / mov of this substep is complete
+    pdl_trigger();  // the pull may start polling the peers' flags while this rank still sends
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nA + nM; idx += gridDim.x * blockDim.x) {
+        const bool mv = idx >= nA;
+        const int j = mv ? idx - nA : idx;
+        const int mem = (mv ? memM : memA)[j >> 6];
+        if (!((mem >> P.rank) & 1)) continue;  // not a member: nothing to send, nobody reads this slot
+        const int co = (mv ? L.M : L.A)[j >> 6], l = j & 63;
+        const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.table[blk] >= 0) a = (mv ? g.mov : g.acc)[blk * BN + l];
+        const size_t off = ((size_t)par * P.nranks + P.rank) * P.slot_bytes + ((mv ? (size_t)L.capA * BN + j : j) << 4);
+        for (int r = 0; r < P.nranks; r++)
+            if (r != P.rank && ((mem >> r) & 1)) *reinterpret_cast<float4*>(P.base[r] + off) = a;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(&P.counter[0], 1u);
+        if (done == gridDim.x - 1) {  // the last CTA: every part is written and fenced
+            P.counter[0] = 0;
+            __threadfence_system();
+            for (int r = 0; r < P.nranks; r++)
+                if (r != P.rank) st_release_sys(reinterpret_cast<unsigned*>(P.base[r] + P.flags_off) + par * P.nranks + P.rank, E + 1);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_shared_pull(Grid g, SharedLists L, const unsigned char* __restrict__ memA,
+                                                     const unsigned char* __restrict__ memM, PeerArea P) {
+    const unsigned E = *P.epoch;
+    const int par = E & 1;
+    if (threadIdx.x < P.nranks && threadIdx.x != P.rank) {
+        const unsigned* f = reinterpret_cast<const unsigned*>(P.base[P.rank] + P.flags_off) + par * P.nranks + threadIdx.x;
+        while (ld_acquire_sys(f) < E + 1) __nanosleep(64);
+    }
+    __syncthreads();
+    pdl_wait();  // this rank's push has completed: it reads the very accumulators (and the epoch) that are updated below
+    pdl_trigger();
+    const int nA = min(*L.nA, L.capA) * BN, nM = min(*L.nM, L.capM) * BN;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nA + nM; idx += gridDim.x * blockDim.x) {
+        const bool mv = idx >= nA;
+        const int j = mv ? idx - nA : idx;
+        const int mem = (mv ? memM : memA)[j >> 6];
+        if (!((mem >> P.rank) & 1)) continue;
+        const int co = (mv ? L.M : L.A)[j >> 6], l = j & 63;
+        const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
+        if (g.table[blk] < 0) continue;  // not under any of my stencils: my G2P never reads it
+        float4* mine = (mv ? g.mov : g.acc) + blk * BN + l;
+        const size_t off = (size_t)par * P.nranks * P.slot_bytes + ((mv ? (size_t)L.capA * BN + j : j) << 4);
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < P.nranks; r++) {
+            if (!((mem >> r) & 1)) continue;
+            const float4 v = (r == P.rank) ? *mine : __ldcv(reinterpret_cast<const float4*>(P.base[P.rank] + off + (size_t)r * P.slot_bytes));
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        *mine = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(&P.counter[1], 1u);
+        if (done == gridDim.x - 1) {
+            P.counter[1] = 0;
+            *P.epoch = E + 1;
+        }
     }
 }
 
@@ -344,6 +446,11 @@ struct MpmSolver {
     int* h_nshared = nullptr;      // pinned mirror of the device-side counts {A, M} (read one rebuild late)
     int *d_sharedM = nullptr, *d_nM = nullptr;  // list M (mover blocks)
     int xcapM = 0;
+    unsigned char *d_memA = nullptr, *d_memM = nullptr;  // member ranks of every listed block
+    bool use_p2p = true, p2p_ready = false;  // MPM_B200_P2P=0: ncclAllReduce instead of the peer-to-peer exchange
+    unsigned char* peer_local = nullptr;     // this rank's receive area (cudaMalloc, exported over CUDA IPC)
+    void* peer_open[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    PeerArea peer{};
     int cur = 0;             // direction buffer (E12/D3) holding the current d
     bool have_prev = false;  // buffer cur^1 holds the d of the last stress evaluation
     int n_resorts = 0, n_rebuilds = 0;
@@ -672,6 +779,7 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         if (const char* e = getenv("MPM_B200_RESORT")) { if (cfg->resort_interval <= 0 && atoi(e) > 0) s->resort_interval = atoi(e); }
         if (const char* e = getenv("MPM_B200_PDL")) s->use_pdl = atoi(e) != 0;
         if (const char* e = getenv("MPM_B200_GRAPHS")) s->use_graphs = atoi(e) != 0;
+        if (const char* e = getenv("MPM_B200_P2P")) s->use_p2p = atoi(e) != 0;
         Grid& g = s->g;
         g.n = cfg->n_grid;
         g.nb = (g.n + BS - 1) / BS;
@@ -1096,12 +1204,19 @@ std::vector<ShardGraph>& shard_graphs(MpmSolver* s) {
 // one sharded substep on stream q: scatter half, pack, all-reduce, unpack, gather half
 void sharded_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
     launch_substep(s, a, q, HALF_SCATTER);
-    const int ctas = std::max(1, std::min(cdiv((long long)(s->xcap_blocks + s->xcapM) * BN, 256), 148 * 8));
+    const int ctas = std::max(1, std::min(cdiv((long long)(s->xcap_blocks + s->xcapM) * BN, 256), 148 * 4));
     const SharedLists L{s->d_shared, s->d_n_shared, s->d_sharedM, s->d_nM, s->xcap_blocks, s->xcapM};
-    k_shared_pack2<<<ctas, 256, 0, q>>>(s->g, L, (float4*)s->xbuf);
-    NCK(nccl_api()->AllReduce(s->xbuf, s->xbuf, (size_t)(s->xcap_blocks + s->xcapM) * BN * 4, ncclFloat, ncclSum, s->comm, q));
-    k_shared_unpack2<<<ctas, 256, 0, q>>>(s->g, L, (const float4*)s->xbuf);
-    s->launches += 3;
+    if (s->p2p_ready) {
+        const bool pdl = s->use_pdl;
+        launch_pdl(k_shared_push, ctas, 256, 0, q, pdl, s->g, L, (const unsigned char*)s->d_memA, (const unsigned char*)s->d_memM, s->peer);
+        launch_pdl(k_shared_pull, ctas, 256, 0, q, pdl, s->g, L, (const unsigned char*)s->d_memA, (const unsigned char*)s->d_memM, s->peer);
+        s->launches += 2;
+    } else {
+        k_shared_pack2<<<ctas, 256, 0, q>>>(s->g, L, (float4*)s->xbuf);
+        NCK(nccl_api()->AllReduce(s->xbuf, s->xbuf, (size_t)(s->xcap_blocks + s->xcapM) * BN * 4, ncclFloat, ncclSum, s->comm, q));
+        k_shared_unpack2<<<ctas, 256, 0, q>>>(s->g, L, (const float4*)s->xbuf);
+        s->launches += 3;
+    }
     launch_substep(s, a, q, HALF_GATHER);
 }
 }  // namespace
@@ -1116,11 +1231,80 @@ static void mark_potential(MpmSolver* s, int margin, cudaStream_t q) {
     }
     unsigned char* mj = s->d_mark + nt;
     CK(cudaMemsetAsync(s->d_mark, 0, 2 * nt, q));
-    if (s->Ne) k_mark_potential<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.EP, KP_F, margin, s->d_mark, mj, s->permE, s->cfg.num_joint_f);
-    if (s->Nt) k_mark_potential<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F, margin, s->d_mark);
-    if (s->Nv) k_mark_potential<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, margin, s->d_mark, mj, s->permV, s->cfg.num_joint_v);
+    const int bit = (s->comm && s->comm_size <= 8) ? (1 << s->comm_rank) : 1;  // rank set for <= 8 ranks, else a count
+    if (s->Ne) k_mark_potential<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.EP, KP_F, margin, s->d_mark, mj, s->permE, s->cfg.num_joint_f, bit);
+    if (s->Nt) k_mark_potential<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F, margin, s->d_mark, nullptr, nullptr, 0, bit);
+    if (s->Nv) k_mark_potential<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, margin, s->d_mark, mj, s->permV, s->cfg.num_joint_v, bit);
     s->launches += 3;
 }
+// (Re)allocate this rank's receive area for the current capacities and map every peer's (CUDA IPC; the handles travel
+// through ncclAllGather).  Collective: every rank resizes at the same rebuild because the lists are global.  Any
+// failure (no peer access, more than 8 ranks, MPM_B200_P2P=0) leaves the ncclAllReduce exchange in place.
+static void close_peer_areas(MpmSolver* s) {
+    for (int r = 0; r < 8; r++)
+        if (s->peer_open[r]) { cudaIpcCloseMemHandle(s->peer_open[r]); s->peer_open[r] = nullptr; }
+    if (s->peer_local) { cudaFree(s->peer_local); s->peer_local = nullptr; }
+    s->p2p_ready = false;
+}
+static void setup_peer_areas(MpmSolver* s, cudaStream_t q) {
+    const int n = s->comm_size;
+    if (!s->use_p2p || !s->comm || n < 2 || n > 8) return;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) =
+        (decltype(AllGather))dlsym(nccl_api()->lib, "ncclAllGather");
+    if (!AllGather) return;
+    CK(cudaStreamSynchronize(q));
+    // every rank has finished every exchange that used the old areas (it is inside this collective).  Imported
+    // mappings are closed first; the old local area is freed only after the all-gather below, i.e. after every peer
+    // has closed its mapping of it
+    for (int r = 0; r < 8; r++)
+        if (s->peer_open[r]) { cudaIpcCloseMemHandle(s->peer_open[r]); s->peer_open[r] = nullptr; }
+    unsigned char* old_local = s->peer_local;
+    s->peer_local = nullptr;
+    s->p2p_ready = false;
+    const size_t slot = (size_t)(s->xcap_blocks + s->xcapM) * BN * sizeof(float4);
+    const size_t flags_off = 2 * (size_t)n * slot;
+    const size_t total = flags_off + 2 * (size_t)n * sizeof(unsigned);
+    struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+    Msg mine{};
+    mine.ok = cudaMalloc(&s->peer_local, total) == cudaSuccess && cudaMemset(s->peer_local, 0, total) == cudaSuccess &&
+              cudaDeviceSynchronize() == cudaSuccess && cudaIpcGetMemHandle(&mine.h, s->peer_local) == cudaSuccess;
+    cudaGetLastError();
+    Msg* d_msgs = s->dalloc<Msg>(n + 1);
+    CK(cudaMemcpyAsync(d_msgs + n, &mine, sizeof(Msg), cudaMemcpyHostToDevice, q));
+    NCK(AllGather(d_msgs + n, d_msgs, sizeof(Msg), ncclUint8, s->comm, q));
+    std::vector<Msg> all(n);
+    CK(cudaMemcpyAsync(all.data(), d_msgs, n * sizeof(Msg), cudaMemcpyDeviceToHost, q));
+    CK(cudaStreamSynchronize(q));
+    if (old_local) cudaFree(old_local);
+    bool ok = true;
+    for (int r = 0; r < n; r++) ok = ok && all[r].ok;
+    PeerArea P{};
+    for (int r = 0; r < n && ok; r++) {
+        if (r == s->comm_rank) { P.base[r] = s->peer_local; continue; }
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+        s->peer_open[r] = ptr;
+        P.base[r] = (unsigned char*)ptr;
+    }
+    // agree on the outcome: one rank failing to map a peer must switch every rank to the NCCL exchange
+    int* d_ok = s->dalloc<int>(1);
+    int h_ok = ok ? 1 : 0;
+    CK(cudaMemcpyAsync(d_ok, &h_ok, sizeof(int), cudaMemcpyHostToDevice, q));
+    NCK(nccl_api()->AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, s->comm, q));
+    CK(cudaMemcpyAsync(&h_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, q));
+    CK(cudaStreamSynchronize(q));
+    if (!h_ok) { close_peer_areas(s); return; }
+    P.slot_bytes = slot;
+    P.flags_off = flags_off;
+    P.rank = s->comm_rank;
+    P.nranks = n;
+    unsigned* ctr = s->dalloc<unsigned>(4);  // zeroed: epoch, push counter, pull counter
+    P.epoch = ctr;
+    P.counter = ctr + 1;
+    s->peer = P;
+    s->p2p_ready = true;
+}
+
 static void rebuild_shared_on_device(MpmSolver* s, int margin, cudaStream_t q) {
     const size_t nt = (size_t)s->g.nb * s->g.nb * s->g.nb;
     cub::CountingInputIterator<int> it(0);
@@ -1130,7 +1314,7 @@ static void rebuild_shared_on_device(MpmSolver* s, int margin, cudaStream_t q) {
         s->d_nM = s->dalloc<int>(1);
         CK(cudaMallocHost(&s->h_nshared, 2 * sizeof(int)));
         s->h_nshared[0] = s->h_nshared[1] = -1;
-        CK(cub::DeviceSelect::If(nullptr, s->sel_bytes, it, s->d_sel, s->d_n_shared, (int)nt, SharedPred{s->d_mark, s->d_mark}, q));
+        CK(cub::DeviceSelect::If(nullptr, s->sel_bytes, it, s->d_sel, s->d_n_shared, (int)nt, SharedPred{s->d_mark, s->d_mark, 1}, q));
         s->sel_tmp = s->dalloc<unsigned char>(s->sel_bytes);
     }
     const bool first = s->h_nshared[0] < 0;
@@ -1138,10 +1322,11 @@ static void rebuild_shared_on_device(MpmSolver* s, int margin, cudaStream_t q) {
     bool resize = first || s->h_nshared[0] * 10 > s->xcap_blocks * 9 || s->h_nshared[1] * 10 > s->xcapM * 9;
     mark_potential(s, margin, q);
     NCK(nccl_api()->AllReduce(s->d_mark, s->d_mark, 2 * nt, ncclUint8, ncclSum, s->comm, q));
+    const int bits = s->comm_size <= 8 ? 1 : 0;
     size_t tmp = s->sel_bytes;
-    CK(cub::DeviceSelect::If(s->sel_tmp, tmp, it, s->d_sel, s->d_n_shared, (int)nt, SharedPred{s->d_mark, nullptr}, q));
+    CK(cub::DeviceSelect::If(s->sel_tmp, tmp, it, s->d_sel, s->d_n_shared, (int)nt, SharedPred{s->d_mark, nullptr, bits}, q));
     tmp = s->sel_bytes;
-    CK(cub::DeviceSelect::If(s->sel_tmp, tmp, it, s->d_sel + nt, s->d_nM, (int)nt, SharedPred{s->d_mark, s->d_mark + nt}, q));
+    CK(cub::DeviceSelect::If(s->sel_tmp, tmp, it, s->d_sel + nt, s->d_nM, (int)nt, SharedPred{s->d_mark, s->d_mark + nt, bits}, q));
     s->launches += 3;
     if (resize) {  // the only synchronising rebuilds
         int n[2] = {0, 0};
@@ -1155,9 +1340,12 @@ static void rebuild_shared_on_device(MpmSolver* s, int margin, cudaStream_t q) {
         s->shared_cap = s->xcap_blocks;
         s->d_shared = s->dalloc<int>(s->xcap_blocks);
         s->d_sharedM = s->dalloc<int>(s->xcapM);
+        s->d_memA = s->dalloc<unsigned char>(s->xcap_blocks);
+        s->d_memM = s->dalloc<unsigned char>(s->xcapM);
+        setup_peer_areas(s, q);
     }
-    k_shared_coords<<<std::max(1, std::min(cdiv(s->xcap_blocks, 256), 64)), 256, 0, q>>>(s->g, s->d_sel, s->d_n_shared, s->xcap_blocks, s->d_shared);
-    k_shared_coords<<<std::max(1, std::min(cdiv(s->xcapM, 256), 64)), 256, 0, q>>>(s->g, s->d_sel + nt, s->d_nM, s->xcapM, s->d_sharedM);
+    k_shared_coords<<<std::max(1, std::min(cdiv(s->xcap_blocks, 256), 64)), 256, 0, q>>>(s->g, s->d_sel, s->d_n_shared, s->xcap_blocks, s->d_shared, s->d_mark, s->d_memA);
+    k_shared_coords<<<std::max(1, std::min(cdiv(s->xcapM, 256), 64)), 256, 0, q>>>(s->g, s->d_sel + nt, s->d_nM, s->xcapM, s->d_sharedM, s->d_mark, s->d_memM);
     CK(cudaMemcpyAsync(&s->h_nshared[0], s->d_n_shared, sizeof(int), cudaMemcpyDeviceToHost, q));
     CK(cudaMemcpyAsync(&s->h_nshared[1], s->d_nM, sizeof(int), cudaMemcpyDeviceToHost, q));
     s->launches += 2;
@@ -1166,6 +1354,7 @@ static void rebuild_shared_on_device(MpmSolver* s, int margin, cudaStream_t q) {
 
 static void destroy_sharded(MpmSolver* s) {
     if (s->h_nshared) { cudaFreeHost(s->h_nshared); s->h_nshared = nullptr; }
+    close_peer_areas(s);
     if (s->shard_graphs) {
         auto& v = shard_graphs(s);
         for (auto& e : v) cudaGraphExecDestroy(e.exec);
@@ -1241,7 +1430,7 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
         if (s->use_graphs && room >= W) {
             ShardGraphKey key{};
             key.dt = a.dt; key.collider = a.collider; key.mover = a.mover; key.advance_mesh = a.advance_mesh; key.cur = s->cur;
-            key.n_bc = (int)s->h_bcs.size(); key.n_ops = (int)s->h_ops.size(); key.xcap = s->xcap_blocks * 65536 + s->xcapM; key.len = W;
+            key.n_bc = (int)s->h_bcs.size(); key.n_ops = (int)s->h_ops.size(); key.xcap = s->xcap_blocks * 65536 + s->xcapM; key.len = W + (s->p2p_ready ? 1000 : 0);
             key.shared_ptr = s->d_shared;
             auto& cache = shard_graphs(s);
             ShardGraph* hit = nullptr;
@@ -1279,6 +1468,8 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
     CK(cudaGetLastError());
     API_END(s)
 }
+
+int mpm_shared_mode(MpmSolver* s) { return !s ? -1 : (s->p2p_ready ? 2 : (s->comm ? 1 : 0)); }
 
 int mpm_shared_info(MpmSolver* s, int* n_shared, int* cap_blocks, int* n_rebuilds, void* stream) {
     API_BEGIN(s)

@@ -164,7 +164,8 @@ class ShardedMPM:
         n, cap, rb = C.c_int(0), C.c_int(0), C.c_int(0)
         self._ck(self.lib.mpm_shared_info(self.h, C.byref(n), C.byref(cap), C.byref(rb), self._stream()))
         self.n_shared = n.value
-        self.stats.update(rebuilds=rb.value, shared_blocks=n.value, exchange_bytes=cap.value * 64 * 8 * 4)
+        mode = {0: "callback", 1: "nccl all-reduce in graph", 2: "peer-to-peer push/pull in graph"}.get(self.lib.mpm_shared_mode(self.h), "?")
+        self.stats.update(rebuilds=rb.value, shared_blocks=n.value, exchange_bytes=cap.value * 64 * 8 * 4, exchange=mode)
 
     def gather_positions(self):
         """Full canonical particle_x / particle_v on every rank (original particle order)."""
