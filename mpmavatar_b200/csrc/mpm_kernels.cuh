@@ -312,10 +312,10 @@ __global__ void k_particle_ops(int n, float* __restrict__ rec, int F, const uint
 //             out(i,j,k) = w2k T_ij + (w0i w1j) Uz_k,      T_ij = w1j Ux_i + w0i Uy_j,
 //             Ux_i = w0i (A + i Bx) + dw0i S0,  Uy_j = w1j j By + dw1j S1,  Uz_k = w2k k Bz + dw2k S2
 //           (A = {m (v - dx C f) + dt f_vertex, m}, B_a = m dx C[:,a], S_a = -dt/dx stress[:,a]); each lane
-//           writes the 9 T_ij, the 3 {Uz_k, w2k} and the 9 w0i w1j of ITS particle to shared memory
-//           (228 B per particle instead of 27 float4).
+//           writes the 9 T_ij and the 3 {Uz_k / m, w2k} of ITS particle to shared memory (192 B per particle instead
+//           of 27 float4; w0i w1j is recovered from the mass component of T_ij, see below).
 //  stage 2  lane = stencil node (27 of 32 lanes): particles of one cell form a run; the lane expands and
-//           accumulates its node along the run (3 broadcast LDS + 3 FFMA2 + 1 FFMA per particle) and
+//           accumulates its node along the run (2 broadcast LDS.128 + 3 FFMA2 + 1 FFMA per particle) and
 //           flushes with ONE REDG.E.ADD.F32x4 per node per run (the node address of the next run is
 //           looked up while the current run is summed).  No intra-warp reduction, no shared-memory
 //           atomics; global atomics drop from 27*4 per particle to 27 per cell run.
@@ -324,8 +324,8 @@ __global__ void k_particle_ops(int n, float* __restrict__ rec, int F, const uint
 #define MPM_P2G_NW 1
 #endif
 constexpr int P2G_NW = MPM_P2G_NW;  // warps (= slabs) per CTA
-constexpr int P2G_T_B = 32 * 9 * 16, P2G_U_B = 32 * 3 * 16, P2G_W_B = 32 * 9 * 4;
-constexpr int P2G_WB = P2G_T_B + P2G_U_B + P2G_W_B;  // 7296 B; the raw slabs (<= 4864 B) are overlaid on it
+constexpr int P2G_T_B = 32 * 9 * 16, P2G_U_B = 32 * 3 * 16;
+constexpr int P2G_WB = P2G_T_B + P2G_U_B;  // 6144 B; the raw slabs (<= 4864 B) are overlaid on it
 constexpr int P2G_SMEM = 128 + P2G_NW * P2G_WB + 64;  // + slack for the stage-2 look-ahead loads
 
 struct P2GIn {
@@ -477,19 +477,31 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
                 Uz[i] = fma4(dwg[2][i], S2, Uz[i]);
             }
         }
+        // The second term of out(i,j,k) needs w0i w1j, and the mass component of T_ij IS m w0i w1j: with Uz_k stored
+        // as Uz_k / m the term becomes T_ij.w * (Uz_k / m) and stage 2 reads 8 words per particle instead of 9 (no
+        // separate weight tile).  m = 0 (ghost vertices of a sharded run): Uz_k = 0 for vertices, exact.  A massless
+        // element / traditional particle (volume > 0, density 0) still exerts its stress force: rare slow path below.
+        const float inv_m = (m != 0.0f) ? 1.0f / m : 0.0f;
+        if (KIND != 2 && valid && m == 0.0f) {
+#pragma unroll  // static indices: a rolled loop would push wgt / Uz into local memory for the whole kernel
+            for (int n = 0; n < 27; n++) {
+                const int i = n / 9, j = (n / 3) % 3, k = n % 3;
+                const float wij = wgt[0][i] * wgt[1][j];
+                const int ni = node_index(g, b[0] + i, b[1] + j, b[2] + k);
+                if (ni >= 0) atomicAdd(&g.acc[ni], make_float4(wij * Uz[k].lo.x, wij * Uz[k].lo.y, wij * Uz[k].hi.x, 0.f));
+            }
+        }
         float4* tT = reinterpret_cast<float4*>(w.buf) + w.lane * 9;
         float4* tU = reinterpret_cast<float4*>(w.buf + P2G_T_B) + w.lane * 3;
-        float* tW = reinterpret_cast<float*>(w.buf + P2G_T_B + P2G_U_B) + w.lane * 9;
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
             for (int j = 0; j < 3; j++) {
                 const V4 T = fma4(wgt[1][j], Ux[i], mul4(wgt[0][i], Uy[j]));
                 tT[i * 3 + j] = make_float4(T.lo.x, T.lo.y, T.hi.x, T.hi.y);
-                tW[i * 3 + j] = wgt[0][i] * wgt[1][j];
             }
 #pragma unroll
-        for (int k = 0; k < 3; k++) tU[k] = make_float4(Uz[k].lo.x, Uz[k].lo.y, Uz[k].hi.x, wgt[2][k]);
+        for (int k = 0; k < 3; k++) tU[k] = make_float4(Uz[k].lo.x * inv_m, Uz[k].lo.y * inv_m, Uz[k].hi.x * inv_m, wgt[2][k]);
         mycell = valid ? pack_cell(b[0], b[1], b[2]) : -1 - w.lane;
     }
     const Runs R = find_runs(w.lane, w.cnt, mycell);
@@ -500,7 +512,6 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
     const int li = act ? w.lane / 9 : 0, lj = act ? (w.lane / 3) % 3 : 0, lk = act ? w.lane % 3 : 0;
     const float4* pT = reinterpret_cast<const float4*>(w.buf) + (li * 3 + lj);
     const float4* pU = reinterpret_cast<const float4*>(w.buf + P2G_T_B) + lk;
-    const float* pW = reinterpret_cast<const float*>(w.buf + P2G_T_B + P2G_U_B) + (li * 3 + lj);
     // one pass over the slab with a fixed trip count (loads of later particles are in flight while earlier
     // ones are accumulated); a warp-uniform test of `starts` closes a run: one REDG.128 per node
     auto flush = [&](int c, float2 lo, float2 hi) {
@@ -520,14 +531,11 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
     // (deeper prefetch was measured: no gain, more address arithmetic).  The loads of "particle 32" read a few bytes
     // past the tiles, inside the CTA's allocation (P2G_SMEM carries the slack), and are never used.
     float4 Tn = pT[0], Un = pU[0];
-    float wn = pW[0];
 #pragma unroll 8
     for (int q = 0; q < 32; q++) {  // records past cnt contribute zeros
         const float4 T = Tn, U = Un;
-        const float wij = wn;
         Tn = pT[(q + 1) * 9];
         Un = pU[(q + 1) * 3];
-        wn = pW[(q + 1) * 9];
         if (q > 0 && ((R.starts >> q) & 1u)) {
             flush(c, alo, ahi);
             alo = ahi = make_float2(0.f, 0.f);
@@ -535,8 +543,8 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
         }
         alo = fma2(U.w, make_float2(T.x, T.y), alo);
         ahi = fma2(U.w, make_float2(T.z, T.w), ahi);
-        alo = fma2(wij, make_float2(U.x, U.y), alo);
-        ahi.x = fmaf(wij, U.z, ahi.x);
+        alo = fma2(T.w, make_float2(U.x, U.y), alo);  // (m w0i w1j) (Uz_k / m)
+        ahi.x = fmaf(T.w, U.z, ahi.x);
     }
     flush(c, alo, ahi);
     PHASE(g, KIND, 3);  // stage 2
