@@ -429,7 +429,7 @@ struct MpmSolver {
     StepState* st = nullptr;
     // state flags
     bool have_state = false, need_sort = true, canon_stale = false;
-    int since_sort = 0, resort_interval = 128;
+    int since_sort = 0, resort_interval = 64;
     unsigned char* d_mark = nullptr;  // sharded runs: potential-block marks
     std::vector<unsigned char> h_mark;
     int* d_shared = nullptr;  // sharded runs: coordinates of the blocks shared with other ranks
