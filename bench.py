@@ -33,9 +33,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SUBSTEPS_PER_STEP = 400
-# dram__bytes_read.sum + dram__bytes_write.sum of the six P2G / G2P launches of one substep (ncu --set full, cold caches;
-# profiles/r1_v14_ncu_full_summary.txt): 55.18 + 15.19 + 13.45 + 46.45 MB for k_p2g<0>, k_p2g<2>, k_g2p_vertices, k_g2p_elements
-TRAFFIC_NCU = 130.27e6
+# dram__bytes_read.sum + dram__bytes_write.sum of the P2G / G2P launches of one substep (ncu --set full, cold caches;
+# profiles/r1_v17_ncu_full_summary.txt): 55.29 + 17.86 + 16.12 + 49.81 MB for k_p2g<0>, k_p2g<2>, k_g2p_vertices,
+# k_g2p_elements (the vertex records carry 16 bytes of padding, see VP_F)
+TRAFFIC_NCU = 139.08e6
 METRIC = "mpm_substeps_per_sec_500k_particles_256grid"
 
 
