@@ -383,4 +383,11 @@ class OracleSim:
 
 
 def max_threads() -> int:
-    return int(_lib("f32").orc_max_threads())
+    """Host threads the oracle may use: the cores this process is allowed on.  omp_get_max_threads() alone is not
+    enough: torchrun exports OMP_NUM_THREADS=1, which would make the CPU arm of bench.py a one-thread run."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(int(_lib("f32").orc_max_threads()), n)
