@@ -74,3 +74,32 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"(import|from)\s+oracle|liboracle|oracle/", src), f"{f} uses the oracle"
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/mpm_b200.h is the boundary a non-Python host binds: it must compile as C (gcc -std=c99 -pedantic) and
+    link against the library.  The program only calls entry points that need no GPU."""
+    import shutil
+    import subprocess
+    from mpmavatar_b200 import build as b
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    lib = b.build_cuda()
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "mpm_b200.h"\n'
+                   "int main(void) {\n"
+                   "    MpmConfig cfg; MpmSolver *h = 0;\n"
+                   "    memset(&cfg, 0, sizeof cfg);\n"
+                   "    /* invalid particle counts: must be refused with a message, not crash */\n"
+                   "    int rc = mpm_create(&cfg, &h);\n"
+                   '    printf("%d %s\\n", rc, mpm_last_error(0));\n'
+                   "    return (rc != 0 && h == 0 && mpm_shared_mode(0) == -1) ? 0 : 1;\n"
+                   "}\n")
+    exe = tmp_path / "abi"
+    cmd = [gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           lib, "-Wl,-rpath," + os.path.dirname(lib)]
+    subprocess.run(cmd, check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.split()[0] != "0" and len(out.stdout.split()) > 1  # an error code and a message
