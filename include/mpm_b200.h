@@ -126,9 +126,16 @@ int mpm_enforce_grid_velocity_by_mask(MpmSolver *s, const int *mask, void *strea
 /* pre-P2G particle operations (mpm_solver.py:1058-1328, 1360-1417).  mask [N] int32 in canonical order.
  * kind 0: v += force/mass*dt where mask==1 (add_impulse_on_particles)
  * kind 1: v += force*dt where mask>=1      (add_impulse_on_particles_with_mask)
- * kind 2: v = velocity where mask==1        (enforce_particle_velocity_translation / _by_mask) */
+ * kind 2: v = velocity where mask==1        (enforce_particle_velocity_translation / _by_mask)
+ * Applied as the reference does: all impulses (kinds 0, 1) in the order added, then all velocity modifiers. */
 int mpm_add_particle_op(MpmSolver *s, int kind, const float vec[3], const int *mask, float start_time,
                         float end_time, void *stream);
+/* enforce_particle_velocity_rotation (mpm_solver.py:1156-1256): particles with mask==1 (the cylinder selection made by
+ * the caller at call time) get v = -h sin(t) rot * axis1 + h cos(t) rot * axis2 + translation_scale * normal, with
+ * h, t the polar coordinates of the particle about (point, normal); normal is unit, axis1/axis2 as the reference builds them */
+int mpm_add_particle_rotation(MpmSolver *s, const float point[3], const float normal[3], const float axis1[3],
+                              const float axis2[3], float rotation_scale, float translation_scale, const int *mask,
+                              float start_time, float end_time, void *stream);
 
 /* nsub substeps of MPMWARP.p2g2p (mpm_solver.py:229-536).  Substep k uses body points
  * mesh_x + (float)(dt*k) * mesh_v, which is what the callers compute on the host side

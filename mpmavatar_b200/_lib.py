@@ -67,6 +67,7 @@ SYMBOLS = {
     "mpm_add_bounding_box": (C.c_int, [_P, C.c_float, C.c_float]),
     "mpm_enforce_grid_velocity_by_mask": (C.c_int, [_P, _P, _P]),
     "mpm_add_particle_op": (C.c_int, [_P, C.c_int, _F3, _P, C.c_float, C.c_float, _P]),
+    "mpm_add_particle_rotation": (C.c_int, [_P, _F3, _F3, _F3, _F3, C.c_float, C.c_float, _P, C.c_float, C.c_float, _P]),
     "mpm_step": (C.c_int, [_P, C.c_float, C.c_int, C.POINTER(MpmFrameInputs), _P]),
     "mpm_step_scatter": (C.c_int, [_P, C.c_float, C.POINTER(MpmFrameInputs), _P]),
     "mpm_step_gather": (C.c_int, [_P, C.c_float, _P]),

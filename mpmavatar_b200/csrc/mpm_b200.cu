@@ -990,6 +990,16 @@ int mpm_enforce_grid_velocity_by_mask(MpmSolver* s, const int* mask, void* strea
     if (push_bc(s, b)) return -2;
     API_END(s)
 }
+}  // extern "C"
+// The reference applies every impulse (pre_p2g_operations) before every velocity modifier, each group in the order
+// it was added, whatever the order of the calls (mpm_solver.py:260-279): impulses go in front of the first modifier.
+static void insert_particle_op(MpmSolver* s, const ParticleOp& op) {
+    auto pos = s->h_ops.end();
+    if (op.kind <= 1) pos = std::find_if(s->h_ops.begin(), s->h_ops.end(), [](const ParticleOp& o) { return o.kind >= 2; });
+    s->h_ops.insert(pos, op);
+    s->ops_dirty = true;
+}
+extern "C" {
 int mpm_add_particle_op(MpmSolver* s, int kind, const float vec[3], const int* mask, float start_time, float end_time,
                         void* stream) {
     API_BEGIN(s)
@@ -999,8 +1009,23 @@ int mpm_add_particle_op(MpmSolver* s, int kind, const float vec[3], const int* m
     ParticleOp op{};
     op.kind = kind; op.mask = d; op.start_time = start_time; op.end_time = end_time;
     for (int i = 0; i < 3; i++) op.vec[i] = vec[i];
-    s->h_ops.push_back(op);
-    s->ops_dirty = true;
+    insert_particle_op(s, op);
+    API_END(s)
+}
+
+int mpm_add_particle_rotation(MpmSolver* s, const float point[3], const float normal[3], const float axis1[3], const float axis2[3],
+                              float rotation_scale, float translation_scale, const int* mask, float start_time, float end_time,
+                              void* stream) {
+    API_BEGIN(s)
+    if ((int)s->h_ops.size() >= MAX_OPS) throw std::string("too many particle operations");
+    int* d = s->dalloc<int>(s->N);
+    CK(cudaMemcpyAsync(d, mask, (size_t)s->N * sizeof(int), cudaMemcpyDefault, (cudaStream_t)stream));
+    ParticleOp op{};
+    op.kind = 3; op.mask = d; op.start_time = start_time; op.end_time = end_time;
+    for (int i = 0; i < 3; i++) { op.point[i] = point[i]; op.n[i] = normal[i]; op.h1[i] = axis1[i]; op.h2[i] = axis2[i]; }
+    op.rot = rotation_scale;
+    op.trans = translation_scale;
+    insert_particle_op(s, op);
     API_END(s)
 }
 

@@ -135,11 +135,13 @@ struct BCDesc {  // one grid_postprocess entry (mpm_solver.py:564-658, 929-1053,
     const int* mask;
 };
 
-struct ParticleOp {  // pre-P2G operations (mpm_solver.py:1058-1151, 1289-1328, 1360-1417)
-    int kind;        // 0 impulse/mass, 1 impulse, 2 set velocity
+struct ParticleOp {  // pre-P2G operations (mpm_solver.py:1058-1328, 1360-1417)
+    int kind;        // 0 impulse/mass, 1 impulse, 2 set velocity, 3 rotate about an axis (cylinder selection)
     float vec[3];
     float start_time, end_time;
     const int* mask;  // canonical order [N]
+    // kind 3 (enforce_particle_velocity_rotation, :1156-1256): v = -h sin(t) rot * h1 + h cos(t) rot * h2 + trans * n
+    float point[3], n[3], h1[3], h2[3], rot, trans;
 };
 
 struct ModelDev {

@@ -297,6 +297,18 @@ __global__ void k_particle_ops(int n, float* __restrict__ rec, int F, const uint
         if (op.kind == 0 && mk == 1) { vx += op.vec[0] / m * dt; vy += op.vec[1] / m * dt; vz += op.vec[2] / m * dt; ch = true; }
         if (op.kind == 1 && mk >= 1) { vx += op.vec[0] * dt; vy += op.vec[1] * dt; vz += op.vec[2] * dt; ch = true; }
         if (op.kind == 2 && mk == 1) { vx = op.vec[0]; vy = op.vec[1]; vz = op.vec[2]; ch = true; }
+        if (op.kind == 3 && mk == 1) {  // mpm_solver.py:1216-1254
+            const float ox = r[P_X] - op.point[0], oy = r[P_X + 1] - op.point[1], oz = r[P_X + 2] - op.point[2];
+            const float dn = ox * op.n[0] + oy * op.n[1] + oz * op.n[2];
+            const float hd = len3(ox - dn * op.n[0], oy - dn * op.n[1], oz - dn * op.n[2]);
+            float theta = acosf((ox * op.h1[0] + oy * op.h1[1] + oz * op.h1[2]) / hd);
+            if (!(ox * op.h2[0] + oy * op.h2[1] + oz * op.h2[2] > 0.0f)) theta = -theta;
+            const float a1 = -hd * sinf(theta) * op.rot, a2 = hd * cosf(theta) * op.rot;
+            vx = a1 * op.h1[0] + a2 * op.h2[0] + op.trans * op.n[0];
+            vy = a1 * op.h1[1] + a2 * op.h2[1] + op.trans * op.n[1];
+            vz = a1 * op.h1[2] + a2 * op.h2[2] + op.trans * op.n[2];
+            ch = true;
+        }
     }
     if (ch) { r[P_V] = vx; r[P_V + 1] = vy; r[P_V + 2] = vz; }
 }

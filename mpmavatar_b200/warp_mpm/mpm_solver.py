@@ -362,7 +362,12 @@ class MPMWARP(object):
     def add_impulse_on_particles_with_mask(self, mpm_state, force, dt, particle_mask, point=[1, 1, 1], size=[1, 1, 1],
                                            end_time=1, start_time=0.0, device="cuda:0"):
         assert len(particle_mask) == self.n_particles, "mask should have n_particles elements"
-        self._add_op(1, force, particle_mask, start_time, end_time)
+        # as the reference: the caller's mask tensor is aliased and then OVERWRITTEN by the box selection
+        # (mpm_solver.py:1381-1398), so the mask that acts is the box and the caller's tensor holds it afterwards
+        box = self._box_mask(mpm_state, point, size)
+        if isinstance(particle_mask, torch.Tensor):
+            particle_mask.copy_(box.to(particle_mask.device, particle_mask.dtype))
+        self._add_op(1, force, box, start_time, end_time)
         self.pre_p2g_operations.append("apply_force")
         self.impulse_params.append(None)
 
@@ -395,9 +400,33 @@ class MPMWARP(object):
             self.enforce_particle_velocity_translation(mpm_state, point, size, [0, 0, 0], start_time,
                                                        end_time_portion * (i + 1))
 
-    def enforce_particle_velocity_rotation(self, *args, **kwargs):
-        raise NotImplementedError("enforce_particle_velocity_rotation is not used by any caller of the hot path "
-                                  "(SURVEY.md 8a) and is not implemented in the B200 solver yet")
+    def enforce_particle_velocity_rotation(self, mpm_state, point, normal, half_height_and_radius, rotation_scale,
+                                           translation_scale, start_time, end_time, device="cuda:0"):
+        """mpm_solver.py:1156-1256: particles inside the cylinder (point, normal, half height, radius) AT CALL TIME rotate
+        about the axis with angular velocity rotation_scale and move along it with translation_scale."""
+        import math
+        ns = 1.0 / math.sqrt(float(normal[0] ** 2 + normal[1] ** 2 + normal[2] ** 2))
+        f32 = lambda v: torch.tensor([float(c) for c in v], dtype=torch.float32)
+        n = f32([ns * c for c in normal])
+        h1 = torch.ones(3, dtype=torch.float32)
+        if abs(float(torch.dot(n, h1))) < 0.01:
+            h1 = f32([0.72, 0.37, -0.67])
+        h1 = h1 - torch.dot(h1, n) * n
+        h1 = h1 * (1.0 / torch.linalg.norm(h1))
+        h2 = torch.linalg.cross(h1, n)
+        dev = self.device
+        off = mpm_state.particle_x - f32(point).to(dev)
+        nd = n.to(dev)
+        along = off @ nd
+        vert = along.abs()
+        hor = torch.linalg.norm(off - along[:, None] * nd, dim=1)
+        mask = ((vert < float(half_height_and_radius[0])) & (hor < float(half_height_and_radius[1]))).to(torch.int32).contiguous()
+        self._ck(self._libh.mpm_add_particle_rotation(self._h, _lib.f3(point), _lib.f3(n.tolist()), _lib.f3(h1.tolist()),
+                                                      _lib.f3(h2.tolist()), float(rotation_scale), float(translation_scale),
+                                                      _ptr(mask), float(start_time), float(end_time), self._stream()))
+        torch.cuda.current_stream(dev).synchronize()
+        self.particle_velocity_modifiers.append("rotation")
+        self.particle_velocity_modifier_params.append(None)
 
 
 class MPMSolverWarp(MPMWARP):

@@ -103,6 +103,7 @@ class OracleSim:
         assert self.lib.orc_sizeof_sim() == C.sizeof(self._Sim), "OrcSim layout mismatch"
         assert self.lib.orc_sizeof_bc() == C.sizeof(self._BC), "OrcBC layout mismatch"
         self.threads = threads
+        self._impulses, self._modifiers = [], []  # pre-P2G particle operations
         N, Ne, Nv = n_particles, n_elements, n_vertices
         Nnv = N - Nv
         self.N, self.Ne, self.Nv, self.Nnv, self.Nt = N, Ne, Nv, Nnv, Nnv - Ne
@@ -304,8 +305,92 @@ class OracleSim:
         self._keep.append(a)
         return self._ptr(a)
 
+    # ---- pre-P2G particle operations (mpm_solver.py:1058-1328, 1360-1417; selection kernels mpm_utils.py:1198-1248).
+    # They only touch particle_v, so they are restated here in numpy at the working precision instead of in C.
+    # Same method names and arguments as MPMWARP (the first, mpm_state, argument is ignored).
+    def _box_mask(self, point, size):
+        r = self.np_real
+        off = self.x.astype(r) - np.asarray(point, r)
+        return (np.abs(off) < np.asarray(size, r)).all(1).astype(np.int32)
+
+    def add_impulse_on_particles(self, mpm_state, force, dt, point=(1, 1, 1), size=(1, 1, 1), num_dt=1, start_time=0.0,
+                                 device=None):
+        r = self.np_real
+        self._impulses.append(dict(kind="per_mass", force=np.asarray(force, r), mask=self._box_mask(point, size),
+                                   t0=r(start_time), t1=r(r(start_time) + r(dt) * r(num_dt))))
+
+    def add_impulse_on_particles_with_mask(self, mpm_state, force, dt, particle_mask, point=(1, 1, 1), size=(1, 1, 1),
+                                           end_time=1, start_time=0.0, device=None):
+        # the reference aliases the caller's mask and then OVERWRITES it with the box selection (:1381-1398): the
+        # mask that acts is the box, and the caller's tensor holds it afterwards
+        r = self.np_real
+        assert len(particle_mask) == self.x.shape[0], "mask should have n_particles elements"
+        box = self._box_mask(point, size)
+        try:
+            particle_mask[...] = particle_mask.new_tensor(box) if hasattr(particle_mask, "new_tensor") else box
+        except Exception:  # noqa: BLE001 -- read-only input: the side effect is not observable
+            pass
+        self._impulses.append(dict(kind="plain", force=np.asarray(force, r), mask=box, t0=r(start_time), t1=r(end_time)))
+
+    def enforce_particle_velocity_translation(self, mpm_state, point, size, velocity, start_time, end_time, device=None):
+        r = self.np_real
+        self._modifiers.append(dict(kind="set", velocity=np.asarray(velocity, r), mask=self._box_mask(point, size),
+                                    t0=r(start_time), t1=r(end_time)))
+
+    def enforce_particle_velocity_by_mask(self, mpm_state, selection_mask, velocity, start_time, end_time):
+        r = self.np_real
+        self._modifiers.append(dict(kind="set", velocity=np.asarray(velocity, r),
+                                    mask=np.asarray(selection_mask).astype(np.int32), t0=r(start_time), t1=r(end_time)))
+
+    def enforce_particle_velocity_rotation(self, mpm_state, point, normal, half_height_and_radius, rotation_scale,
+                                           translation_scale, start_time, end_time, device=None):
+        r = self.np_real
+        n = np.asarray(normal, r)
+        n = n * (r(1.0) / np.sqrt(r(n[0] ** 2 + n[1] ** 2 + n[2] ** 2)))
+        h1 = np.ones(3, r)
+        if abs(np.dot(n, h1)) < 0.01:
+            h1 = np.asarray([0.72, 0.37, -0.67], r)
+        h1 = h1 - np.dot(h1, n) * n
+        h1 = h1 * (r(1.0) / np.sqrt(np.dot(h1, h1)))
+        h2 = np.cross(h1, n)
+        off = self.x.astype(r) - np.asarray(point, r)
+        vert = np.abs(off @ n)
+        hor = np.linalg.norm(off - (off @ n)[:, None] * n, axis=1)
+        mask = ((vert < r(half_height_and_radius[0])) & (hor < r(half_height_and_radius[1]))).astype(np.int32)
+        self._modifiers.append(dict(kind="rotate", point=np.asarray(point, r), n=n, h1=h1, h2=h2, rot=r(rotation_scale),
+                                    trans=r(translation_scale), mask=mask, t0=r(start_time), t1=r(end_time)))
+
+    def _apply_particle_ops(self, dt):
+        """mpm_solver.py:260-279: all impulses in the order added, then all velocity modifiers in the order added."""
+        r = self.np_real
+        t, dt = r(self.time), r(dt)
+        for op in self._impulses:
+            if t >= op["t0"] and t < op["t1"]:
+                if op["kind"] == "per_mass":
+                    sel = op["mask"] == 1
+                    self.v[sel] = (self.v[sel].astype(r) + op["force"][None, :] / self.mass[sel].astype(r)[:, None] * dt).astype(self.v.dtype)
+                else:
+                    sel = op["mask"] >= 1
+                    self.v[sel] = (self.v[sel].astype(r) + op["force"][None, :] * dt).astype(self.v.dtype)
+        for op in self._modifiers:
+            if not (t >= op["t0"] and t < op["t1"]):
+                continue
+            sel = op["mask"] == 1
+            if op["kind"] == "set":
+                self.v[sel] = op["velocity"].astype(self.v.dtype)
+            else:
+                off = self.x[sel].astype(r) - op["point"]
+                hd = np.linalg.norm(off - (off @ op["n"])[:, None] * op["n"], axis=1)
+                theta = np.arccos((off @ op["h1"]) / hd)
+                theta = np.where(off @ op["h2"] > 0, theta, -theta)
+                a1 = -hd * np.sin(theta) * op["rot"]
+                a2 = hd * np.cos(theta) * op["rot"]
+                self.v[sel] = (a1[:, None] * op["h1"] + a2[:, None] * op["h2"] + op["trans"] * op["n"]).astype(self.v.dtype)
+
     def p2g2p(self, dt, mesh_x=None, mesh_v=None, joint_traditional_v=None, joint_verts_v=None, joint_faces_v=None):
         """One substep, mpm_solver.py:229-536."""
+        if self._impulses or self._modifiers:
+            self._apply_particle_ops(dt)
         self.lib.orc_set_threads(C.c_int(self.threads))
         self._keep = []
         njt = 0 if joint_traditional_v is None else int(np.asarray(joint_traditional_v).shape[0])

@@ -66,10 +66,56 @@ def tiny_scenes():
                                                   center=(1.0, 1.0, 1.0))
     sd.v = (0.2 * np.random.default_rng(4).normal(size=sd.x.shape)).astype(np.float32)
     out["demo_sand_plane_pinned"] = (sd, 2, np.zeros((sd.num_joint_t, 3), np.float32))
+    # pre-P2G particle operations (mpm_solver.py:1058-1328, 1360-1417): every modifier the API offers, with time
+    # windows that open / close inside the 4 recorded substeps (dt = 1e-4)
+    so = S.scene_c1(n=150, n_grid=12, seed=22, material="jelly")
+    out["trad_jelly_particle_ops"] = (so, 4, None)
     return out
 
 
-def run_reference(sc, nsub, joint_t, precision):
+# (method, kwargs) in the order the caller issues them; replayed on the oracle / CUDA mirror by tests/test_golden.py.
+# The reference applies all impulses first, then all velocity modifiers, whatever the order of the calls
+# (mpm_solver.py:260-279) -- the translation below is therefore issued BEFORE the first impulse on purpose.
+PARTICLE_OPS = [
+    ("enforce_particle_velocity_translation", dict(point=[0.9, 1.0, 1.0], size=[0.06, 0.3, 0.3], velocity=[0.0, 0.2, -0.1],
+                                                   start_time=1.5e-4, end_time=10.0)),
+    ("add_impulse_on_particles", dict(force=[3e-4, 0.0, -1e-4], dt=1e-4, point=[1.1, 1.0, 1.0], size=[0.08, 0.3, 0.3], num_dt=2,
+                                      start_time=0.5e-4)),
+    ("add_impulse_on_particles_with_mask", dict(force=[0.0, 5.0, 0.0], dt=1e-4, particle_mask="first_third",
+                                                point=[1.0, 1.1, 1.0], size=[0.3, 0.07, 0.3], end_time=2.5e-4, start_time=0.0)),
+    ("enforce_particle_velocity_by_mask", dict(selection_mask="every_seventh", velocity=[0.05, 0.0, 0.0], start_time=0.0,
+                                               end_time=1.0)),
+    ("enforce_particle_velocity_rotation", dict(point=[1.0, 0.95, 1.0], normal=[0.0, 2.0, 0.0], half_height_and_radius=[0.08, 0.12],
+                                                rotation_scale=3.0, translation_scale=0.4, start_time=0.0, end_time=3.5e-4)),
+]
+
+
+def named_mask(name, n):
+    m = np.zeros(n, np.int32)
+    if name == "first_third":
+        m[: n // 3] = 1
+    elif name == "every_seventh":
+        m[::7] = 1
+    else:
+        raise KeyError(name)
+    return m
+
+
+def apply_particle_ops(solver, state, n, device=None, to_tensor=None):
+    """Issues PARTICLE_OPS on `solver` (the reference's MPMWARP or this repo's mirror: same method names and arguments)."""
+    import torch
+    for meth, kw in PARTICLE_OPS:
+        kw = dict(kw)
+        for k in ("particle_mask", "selection_mask"):
+            if k in kw:
+                t = torch.from_numpy(named_mask(kw[k], n))
+                kw[k] = to_tensor(t) if to_tensor else t
+        if device is not None and meth not in ("enforce_particle_velocity_by_mask",):
+            kw["device"] = device
+        getattr(solver, meth)(state, **kw)
+
+
+def run_reference(sc, nsub, joint_t, precision, with_ops=False):
     """setup_simulation + rollout exactly as the reference's caller does, on the emulated Warp."""
     warp_emu.set_precision(precision)
     wp, ds, sv = import_reference()
@@ -114,6 +160,8 @@ def run_reference(sc, nsub, joint_t, precision):
         if sc.yield_stress is not None:
             model.yield_stress = wp.from_numpy(sc.yield_stress, dtype=float)
         solver.prepare_mu_lam(model, state, dev)
+        if with_ops:
+            apply_particle_ops(solver, state, N, device=dev)
         fi = sc.frame_inputs(0)
         t = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32)
         for k in range(nsub):
@@ -136,7 +184,10 @@ SCENE_SCALARS = ("name", "n_grid", "grid_lim", "dt", "material", "n_elements", "
 
 
 def main():
+    only = set(sys.argv[1:])
     for name, (sc, nsub, joint_t) in tiny_scenes().items():
+        if only and name not in only:
+            continue
         rec = {"nsub": np.int64(nsub), "g": np.asarray(sc.g, np.float64)}
         for f in SCENE_FIELDS:
             v = getattr(sc, f)
@@ -150,11 +201,13 @@ def main():
                 rec["fi_" + k] = v
         if joint_t is not None:
             rec["fi_joint_traditional_v"] = joint_t
+        if name.endswith("particle_ops"):
+            rec["particle_ops"] = np.int64(1)  # replay tests/golden/make_golden.py PARTICLE_OPS
         if sc.surface_colliders:
             rec["plane_point"] = np.asarray(sc.surface_colliders[0]["point"], np.float64)
             rec["plane_normal"] = np.asarray(sc.surface_colliders[0]["normal"], np.float64)
         for prec, tag in (("f64", "ref64_"), ("f32", "ref32_")):
-            r = run_reference(sc, nsub, joint_t, prec)
+            r = run_reference(sc, nsub, joint_t, prec, with_ops=name.endswith("particle_ops"))
             for k, v in r.items():
                 if k.startswith("grid_") and tag == "ref32_":
                     continue

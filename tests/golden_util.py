@@ -17,6 +17,7 @@ def golden_names():
 class FixedScene(S.Scene):
     """Scene whose per-frame inputs are the recorded ones."""
     _fi = None
+    particle_ops = False
 
     def frame_inputs(self, i):
         assert i == 0
@@ -39,6 +40,7 @@ def load(name):
               for k in ("mesh_x", "mesh_v", "joint_verts_v", "joint_faces_v", "joint_traditional_v")}
     if "plane_point" in z.files:
         sc.surface_colliders = [dict(point=list(z["plane_point"]), normal=list(z["plane_normal"]))]
+    sc.particle_ops = "particle_ops" in z.files  # replay tests/golden/make_golden.py PARTICLE_OPS after the setup
     ref64 = {k[6:]: z[k] for k in z.files if k.startswith("ref64_")}
     ref32 = {k[6:]: z[k] for k in z.files if k.startswith("ref32_")}
     return sc, int(z["nsub"]), ref64, ref32

@@ -2,7 +2,8 @@
 REFERENCE's own kernel source (warp_mpm/*.py, unmodified) executed under oracle/warp_emu.py; see
 tests/golden/make_golden.py.  Covers every traditional material branch, the cloth return mapping / stress,
 vertex forces, APIC P2G/G2P, the body-mesh collider, the particle mover (joint vertices, faces and pinned
-traditional tail) and the sticky plane.
+traditional tail), the sticky plane, and every pre-P2G particle operation (impulses, velocity modifiers incl. the
+cylinder rotation).
 
 Tolerances: the fp64 oracle must reproduce the fp64 reference run to round-off (1e-9 relative: the only
 difference is the SVD/QR routine, both accurate to 1e-15); fp32 oracle and CUDA are held to BASELINE.json's
@@ -23,6 +24,9 @@ def rel(a, b):
 def run_oracle(sc, nsub, precision):
     from oracle.oracle import OracleSim
     o = OracleSim.from_scene(sc, precision, threads=1)
+    if sc.particle_ops:
+        from tests.golden.make_golden import apply_particle_ops
+        apply_particle_ops(o, None, sc.n_particles)
     fi = sc.frame_inputs(0)
     for k in range(nsub):
         mx = None if fi["mesh_x"] is None else fi["mesh_x"] + np.float32(sc.dt * k) * fi["mesh_v"]
@@ -72,6 +76,9 @@ def _run_cuda(sc, nsub):
     from mpmavatar_b200.scene_setup import build_from_scene
     solver, model, state = build_from_scene(sc)
     solver.set_debug(True)
+    if sc.particle_ops:
+        from tests.golden.make_golden import apply_particle_ops
+        apply_particle_ops(solver, state, sc.n_particles, to_tensor=lambda t: t.to("cuda"))
     fi = sc.frame_inputs(0)
     T = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32, device="cuda")
     for k in range(nsub):
