@@ -70,7 +70,52 @@ def tiny_scenes():
     # windows that open / close inside the 4 recorded substeps (dt = 1e-4)
     so = S.scene_c1(n=150, n_grid=12, seed=22, material="jelly")
     out["trad_jelly_particle_ops"] = (so, 4, None)
+    # grid boundary conditions beyond the sticky plane (mpm_solver.py:564-658, 929-1053, 1330-1355), grid damping
+    # (mpm_utils.py:1162-1174) and RPIC damping (:528-542): a jelly block next to the x = 0 wall
+    sg = S.scene_c1(n=150, n_grid=12, seed=23, material="jelly")
+    sg.x = (sg.x + np.array([-0.4, 0.0, 0.0], np.float32)).astype(np.float32)
+    sg.v = (0.3 * np.random.default_rng(5).normal(size=sg.x.shape)).astype(np.float32)
+    sg.grid_v_damping_scale = 0.98
+    sg.rpic_damping = 0.2
+    out["trad_jelly_grid_bcs"] = (sg, 4, None)
     return out
+
+
+# (method, kwargs) issued after the solver is set up; the order is the order the reference applies them in.
+# The first cuboid is long expired but has reset = 1: the reference then zeroes the WHOLE grid while
+# time < end_time + 15 dt (:966-970), here exactly for the first substep.  The second one switches on inside the run
+# and moves with its velocity (host-side modify_bc, :975-981).
+GRID_BCS = [
+    ("add_surface_collider", dict(point=[1.0, 0.86, 1.0], normal=[0.0, 1.0, 0.0], surface="slip", friction=0.3)),
+    ("set_velocity_on_cuboid", dict(point=[0.6, 1.0, 1.0], size=[0.1, 0.1, 0.1], velocity=[0.0, 0.0, 0.0], start_time=-1.0,
+                                    end_time=-14.5e-4, reset=1)),
+    ("set_velocity_on_cuboid", dict(point=[0.6, 1.0, 1.0], size=[0.12, 0.25, 0.25], velocity=[0.3, 0.0, 0.1], start_time=1.5e-4,
+                                    end_time=10.0, reset=0)),
+    ("add_bounding_box", dict(start_time=0.5e-4, end_time=999.0)),
+    ("enforce_grid_velocity_by_mask", dict(selection_mask="upper_y")),
+]
+
+
+def grid_mask(name, n):
+    m = np.zeros((n, n, n), np.int32)
+    if name == "upper_y":
+        m[:, 7:, :] = 1
+    else:
+        raise KeyError(name)
+    return m
+
+
+def apply_grid_bcs(solver, n_grid, to_mask=None):
+    """Issues GRID_BCS on `solver` (the reference's MPMWARP, this repo's mirror, or the oracle: same names and arguments);
+    to_mask converts the [n,n,n] int32 numpy mask into what the solver takes."""
+    import torch
+    for meth, kw in GRID_BCS:
+        kw = dict(kw)
+        if "selection_mask" in kw:
+            m = grid_mask(kw.pop("selection_mask"), n_grid)
+            getattr(solver, meth)(to_mask(m) if to_mask else torch.from_numpy(m))
+        else:
+            getattr(solver, meth)(**kw)
 
 
 # (method, kwargs) in the order the caller issues them; replayed on the oracle / CUDA mirror by tests/test_golden.py.
@@ -115,7 +160,7 @@ def apply_particle_ops(solver, state, n, device=None, to_tensor=None):
         getattr(solver, meth)(state, **kw)
 
 
-def run_reference(sc, nsub, joint_t, precision, with_ops=False):
+def run_reference(sc, nsub, joint_t, precision, with_ops=False, with_bcs=False):
     """setup_simulation + rollout exactly as the reference's caller does, on the emulated Warp."""
     warp_emu.set_precision(precision)
     wp, ds, sv = import_reference()
@@ -162,6 +207,8 @@ def run_reference(sc, nsub, joint_t, precision, with_ops=False):
         solver.prepare_mu_lam(model, state, dev)
         if with_ops:
             apply_particle_ops(solver, state, N, device=dev)
+        if with_bcs:
+            apply_grid_bcs(solver, sc.n_grid)
         fi = sc.frame_inputs(0)
         t = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32)
         for k in range(nsub):
@@ -201,13 +248,15 @@ def main():
                 rec["fi_" + k] = v
         if joint_t is not None:
             rec["fi_joint_traditional_v"] = joint_t
+        if name.endswith("grid_bcs"):
+            rec["grid_bcs"] = np.int64(1)  # replay tests/golden/make_golden.py GRID_BCS
         if name.endswith("particle_ops"):
             rec["particle_ops"] = np.int64(1)  # replay tests/golden/make_golden.py PARTICLE_OPS
         if sc.surface_colliders:
             rec["plane_point"] = np.asarray(sc.surface_colliders[0]["point"], np.float64)
             rec["plane_normal"] = np.asarray(sc.surface_colliders[0]["normal"], np.float64)
         for prec, tag in (("f64", "ref64_"), ("f32", "ref32_")):
-            r = run_reference(sc, nsub, joint_t, prec, with_ops=name.endswith("particle_ops"))
+            r = run_reference(sc, nsub, joint_t, prec, with_ops=name.endswith("particle_ops"), with_bcs=name.endswith("grid_bcs"))
             for k, v in r.items():
                 if k.startswith("grid_") and tag == "ref32_":
                     continue

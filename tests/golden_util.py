@@ -18,6 +18,7 @@ class FixedScene(S.Scene):
     """Scene whose per-frame inputs are the recorded ones."""
     _fi = None
     particle_ops = False
+    grid_bcs = False
 
     def frame_inputs(self, i):
         assert i == 0
@@ -41,6 +42,7 @@ def load(name):
     if "plane_point" in z.files:
         sc.surface_colliders = [dict(point=list(z["plane_point"]), normal=list(z["plane_normal"]))]
     sc.particle_ops = "particle_ops" in z.files  # replay tests/golden/make_golden.py PARTICLE_OPS after the setup
+    sc.grid_bcs = "grid_bcs" in z.files          # replay GRID_BCS
     ref64 = {k[6:]: z[k] for k in z.files if k.startswith("ref64_")}
     ref32 = {k[6:]: z[k] for k in z.files if k.startswith("ref32_")}
     return sc, int(z["nsub"]), ref64, ref32

@@ -3,7 +3,8 @@ REFERENCE's own kernel source (warp_mpm/*.py, unmodified) executed under oracle/
 tests/golden/make_golden.py.  Covers every traditional material branch, the cloth return mapping / stress,
 vertex forces, APIC P2G/G2P, the body-mesh collider, the particle mover (joint vertices, faces and pinned
 traditional tail), the sticky plane, and every pre-P2G particle operation (impulses, velocity modifiers incl. the
-cylinder rotation).
+cylinder rotation), and the remaining grid boundary conditions (slip plane, cuboids with reset / motion, bounding box,
+grid mask) with grid and RPIC damping.
 
 Tolerances: the fp64 oracle must reproduce the fp64 reference run to round-off (1e-9 relative: the only
 difference is the SVD/QR routine, both accurate to 1e-15); fp32 oracle and CUDA are held to BASELINE.json's
@@ -27,6 +28,9 @@ def run_oracle(sc, nsub, precision):
     if sc.particle_ops:
         from tests.golden.make_golden import apply_particle_ops
         apply_particle_ops(o, None, sc.n_particles)
+    if sc.grid_bcs:
+        from tests.golden.make_golden import apply_grid_bcs
+        apply_grid_bcs(o, sc.n_grid, to_mask=lambda m: m)
     fi = sc.frame_inputs(0)
     for k in range(nsub):
         mx = None if fi["mesh_x"] is None else fi["mesh_x"] + np.float32(sc.dt * k) * fi["mesh_v"]
@@ -35,7 +39,7 @@ def run_oracle(sc, nsub, precision):
 
 
 def test_fixtures_present():
-    assert len(NAMES) >= 8, NAMES
+    assert len(NAMES) >= 10, NAMES
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -79,6 +83,10 @@ def _run_cuda(sc, nsub):
     if sc.particle_ops:
         from tests.golden.make_golden import apply_particle_ops
         apply_particle_ops(solver, state, sc.n_particles, to_tensor=lambda t: t.to("cuda"))
+    if sc.grid_bcs:
+        import torch
+        from tests.golden.make_golden import apply_grid_bcs
+        apply_grid_bcs(solver, sc.n_grid, to_mask=lambda m: torch.from_numpy(m).to("cuda"))
     fi = sc.frame_inputs(0)
     T = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32, device="cuda")
     for k in range(nsub):
