@@ -78,7 +78,23 @@ def tiny_scenes():
     sg.grid_v_damping_scale = 0.98
     sg.rpic_damping = 0.2
     out["trad_jelly_grid_bcs"] = (sg, 4, None)
+    # non-default plasticity parameters (set_parameters_dict keys, mpm_solver.py:86-124): von Mises hardening
+    # (mpm_utils.py:250-252), viscoplastic return map (:315-359), damage softening down to mu = lam = 0 (:287-292)
+    for name, (mat, _) in MATERIAL_VARIANTS.items():
+        out[name] = (S.scene_c1(n=60, n_grid=12, seed=21, material=mat), 4, None)
     return out
+
+
+MATERIAL_VARIANTS = {
+    "trad_metal_hardening": ("metal", dict(hardening=1, xi=5.0)),
+    "trad_foam_viscous": ("foam", dict(plastic_viscosity=0.05)),
+    "trad_plasticine_softening": ("plasticine", dict(softening=40.0)),
+}
+
+
+def apply_material_variant(name, set_params):
+    """set_params(dict) forwards to the solver's parameter setter (set_parameters_dict / OracleSim.set_parameters)."""
+    set_params(dict(MATERIAL_VARIANTS[name][1]))
 
 
 # (method, kwargs) issued after the solver is set up; the order is the order the reference applies them in.
@@ -160,7 +176,7 @@ def apply_particle_ops(solver, state, n, device=None, to_tensor=None):
         getattr(solver, meth)(state, **kw)
 
 
-def run_reference(sc, nsub, joint_t, precision, with_ops=False, with_bcs=False):
+def run_reference(sc, nsub, joint_t, precision, with_ops=False, with_bcs=False, variant=None):
     """setup_simulation + rollout exactly as the reference's caller does, on the emulated Warp."""
     warp_emu.set_precision(precision)
     wp, ds, sv = import_reference()
@@ -205,6 +221,8 @@ def run_reference(sc, nsub, joint_t, precision, with_ops=False, with_bcs=False):
         if sc.yield_stress is not None:
             model.yield_stress = wp.from_numpy(sc.yield_stress, dtype=float)
         solver.prepare_mu_lam(model, state, dev)
+        if variant:
+            apply_material_variant(variant, lambda kw: solver.set_parameters_dict(model, state, kw, device=dev))
         if with_ops:
             apply_particle_ops(solver, state, N, device=dev)
         if with_bcs:
@@ -219,7 +237,8 @@ def run_reference(sc, nsub, joint_t, precision, with_ops=False, with_bcs=False):
     out = dict(x=g(state.particle_x), v=g(state.particle_v), C=g(state.particle_C), F=g(state.particle_F),
                F_trial=g(state.particle_F_trial), stress=g(state.particle_stress), d=g(state.particle_d),
                vertex_force=g(state.vertex_force), grid_m=g(state.grid_m), grid_v_in=g(state.grid_v_in),
-               grid_v_out=g(state.grid_v_out), time=np.float64(solver.time))
+               grid_v_out=g(state.grid_v_out), time=np.float64(solver.time),
+               yield_stress=g(model.yield_stress), mu=g(model.mu), lam=g(model.lam))  # damage / hardening mutate these
     return out
 
 
@@ -248,6 +267,8 @@ def main():
                 rec["fi_" + k] = v
         if joint_t is not None:
             rec["fi_joint_traditional_v"] = joint_t
+        if name in MATERIAL_VARIANTS:
+            rec["material_variant"] = np.int64(1)  # replay MATERIAL_VARIANTS[name]
         if name.endswith("grid_bcs"):
             rec["grid_bcs"] = np.int64(1)  # replay tests/golden/make_golden.py GRID_BCS
         if name.endswith("particle_ops"):
@@ -256,7 +277,8 @@ def main():
             rec["plane_point"] = np.asarray(sc.surface_colliders[0]["point"], np.float64)
             rec["plane_normal"] = np.asarray(sc.surface_colliders[0]["normal"], np.float64)
         for prec, tag in (("f64", "ref64_"), ("f32", "ref32_")):
-            r = run_reference(sc, nsub, joint_t, prec, with_ops=name.endswith("particle_ops"), with_bcs=name.endswith("grid_bcs"))
+            r = run_reference(sc, nsub, joint_t, prec, with_ops=name.endswith("particle_ops"), with_bcs=name.endswith("grid_bcs"),
+                              variant=name if name in MATERIAL_VARIANTS else None)
             for k, v in r.items():
                 if k.startswith("grid_") and tag == "ref32_":
                     continue

@@ -19,6 +19,7 @@ class FixedScene(S.Scene):
     _fi = None
     particle_ops = False
     grid_bcs = False
+    material_variant = None
 
     def frame_inputs(self, i):
         assert i == 0
@@ -43,6 +44,7 @@ def load(name):
         sc.surface_colliders = [dict(point=list(z["plane_point"]), normal=list(z["plane_normal"]))]
     sc.particle_ops = "particle_ops" in z.files  # replay tests/golden/make_golden.py PARTICLE_OPS after the setup
     sc.grid_bcs = "grid_bcs" in z.files          # replay GRID_BCS
+    sc.material_variant = name if "material_variant" in z.files else None  # replay MATERIAL_VARIANTS[name]
     ref64 = {k[6:]: z[k] for k in z.files if k.startswith("ref64_")}
     ref32 = {k[6:]: z[k] for k in z.files if k.startswith("ref32_")}
     return sc, int(z["nsub"]), ref64, ref32

@@ -15,6 +15,11 @@ import pytest
 from tests.golden_util import golden_names, load
 
 NAMES = golden_names()
+# Fixtures added after the round's GPU budget was spent: they pin the ORACLE to the reference source here; the CUDA
+# comparison is switched on once it has run on a B200 (the kernels read these parameters -- mpm_kernels.cuh
+# k_stress_traditional -- but an unrun test must not gate the suite).
+CUDA_NOT_YET_RUN = {"trad_metal_hardening", "trad_foam_viscous", "trad_plasticine_softening"}
+CUDA_NAMES = [n for n in NAMES if n not in CUDA_NOT_YET_RUN]
 
 
 def rel(a, b):
@@ -25,6 +30,9 @@ def rel(a, b):
 def run_oracle(sc, nsub, precision):
     from oracle.oracle import OracleSim
     o = OracleSim.from_scene(sc, precision, threads=1)
+    if sc.material_variant:
+        from tests.golden.make_golden import apply_material_variant
+        apply_material_variant(sc.material_variant, lambda kw: o.set_parameters(**kw))
     if sc.particle_ops:
         from tests.golden.make_golden import apply_particle_ops
         apply_particle_ops(o, None, sc.n_particles)
@@ -62,6 +70,9 @@ def test_oracle_f64_reproduces_reference_source(name):
         assert rel(o.F_trial[sl], ref["F_trial"][sl]) < 1e-9
         assert rel(o.F[sl], ref["F"][sl]) < 1e-8
         assert np.abs(o.stress[sl] - ref["stress"][sl]).max() < 1e-7 * max(np.abs(ref["stress"][sl]).max(), 1e-30)
+    if "yield_stress" in ref:  # fixtures that record the model arrays the return maps mutate (hardening, damage)
+        assert rel(o.yield_stress, ref["yield_stress"]) < 1e-9
+        assert rel(o.mu, ref["mu"]) < 1e-12 and rel(o.lam, ref["lam"]) < 1e-12
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -80,6 +91,9 @@ def _run_cuda(sc, nsub):
     from mpmavatar_b200.scene_setup import build_from_scene
     solver, model, state = build_from_scene(sc)
     solver.set_debug(True)
+    if sc.material_variant:
+        from tests.golden.make_golden import apply_material_variant
+        apply_material_variant(sc.material_variant, lambda kw: solver.set_parameters_dict(model, state, kw))
     if sc.particle_ops:
         from tests.golden.make_golden import apply_particle_ops
         apply_particle_ops(solver, state, sc.n_particles, to_tensor=lambda t: t.to("cuda"))
@@ -98,7 +112,7 @@ def _run_cuda(sc, nsub):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("name", CUDA_NAMES)
 def test_cuda_matches_reference_source(name):
     sc, nsub, ref, _ = load(name)
     solver, state = _run_cuda(sc, nsub)
