@@ -54,7 +54,7 @@ struct Recs {  // sorted sub-record arrays (see mpm_device.cuh)
     float* E12[2];  // ping-pong {d1,d2}
     float4* D3[2];  // ping-pong d3
     int* EF;
-    float4* VF;
+    float4* VF[2];  // ping-pong vertex-force accumulators (buffer `cur` is filled by the substep that reads directions `cur`)
     int *CE, *CV;  // packed stencil base cell per element / vertex (lets G2P start its node loads early)
 };
 __global__ void k_import_E(Grid g, int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R, int cur, const int* __restrict__ invV) {
@@ -97,7 +97,7 @@ __global__ void k_import_V(Grid g, int Nv, int Nnv, const uint32_t* __restrict__
     for (int k = 0; k < 3; k++) { p[V_X + k] = c.x[3 * s + k]; p[V_V + k] = c.v[3 * s + k]; }
     p[V_M] = c.mass[s];
     for (int k = 0; k < 9; k++) p[V_C + k] = c.C[9 * (size_t)s + k];
-    R.VF[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    R.VF[0][i] = R.VF[1][i] = make_float4(0.f, 0.f, 0.f, 0.f);
     R.CV[i] = pack_cell(base_of(p[0], g.inv_dx), base_of(p[1], g.inv_dx), base_of(p[2], g.inv_dx));
 }
 // d from direction buffer `cur`; the element stress of the LAST substep is re-evaluated from buffer
@@ -142,7 +142,9 @@ __global__ void k_export_T(int Nt, int Ne, const uint32_t* __restrict__ perm, Ca
     }
     c.mu[s] = t[T_MU]; c.lam[s] = t[T_LAM]; c.ys[s] = t[T_YS];  // damage / hardening mutate these
 }
-__global__ void k_export_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, Canon c, Recs R, const float* __restrict__ dbg_f) {
+// vertex_force of the LAST substep (the reference zeroes it at the start of p2g2p, so it holds the last substep's cloth
+// forces afterwards): buffer cur^1 once a substep has run since the import
+__global__ void k_export_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, Canon c, Recs R, int cur, int have_prev) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Nv) return;
     int s = Nnv + perm[i];
@@ -150,9 +152,9 @@ __global__ void k_export_V(int Nv, int Nnv, const uint32_t* __restrict__ perm, C
     const float* p = R.VP + (size_t)i * VP_F;
     for (int k = 0; k < 3; k++) { c.x[3 * s + k] = p[V_X + k]; c.v[3 * s + k] = p[V_V + k]; }
     for (int k = 0; k < 9; k++) c.C[9 * (size_t)s + k] = p[V_C + k];
-    const float4 f = R.VF[i];
+    const float4 f = have_prev ? R.VF[cur ^ 1][i] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float fr[3] = {f.x, f.y, f.z};
-    for (int k = 0; k < 3; k++) c.vforce[3 * vl + k] = dbg_f ? dbg_f[3 * i + k] : fr[k];
+    for (int k = 0; k < 3; k++) c.vforce[3 * vl + k] = fr[k];
 }
 __global__ void k_alloc_blocks(Grid g, int n, const float* __restrict__ rec, int F) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -459,7 +461,6 @@ struct MpmSolver {
     double host_time = 0.0;
     bool debug = false, profiling = false;
     bool pending_mover = false;  // mover flag of the scatter half, consumed by the gather half
-    float* dbg_f = nullptr;
     unsigned long long* node_mask = nullptr;
     // device block count mirrored (asynchronously) into pinned host memory after each re-sort
     int* h_nslots = nullptr;
@@ -500,7 +501,7 @@ static void export_to_canon(MpmSolver* s, cudaStream_t q) {
     if (!s->have_state || !s->canon_stale) return;
     if (s->Ne) k_export_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->permE, s->canon, s->R, s->cur, s->have_prev ? 1 : 0, s->md.friction_coeff);
     if (s->Nt) k_export_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->permT, s->canon, s->R);
-    if (s->Nv) k_export_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->Nnv, s->permV, s->canon, s->R, s->debug ? s->dbg_f : nullptr);
+    if (s->Nv) k_export_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->Nnv, s->permV, s->canon, s->R, s->cur, s->have_prev ? 1 : 0);
     s->launches += 3;
     s->canon_stale = false;
 }
@@ -601,7 +602,7 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
     if (ev) CK(cudaEventRecord(ev[1], q));
     const int ppb = 32 * P2G_NW;  // particles per P2G block
     if (s->Ne) {  // cloth stress fused in front of the element scatter; VF must be complete before the vertex scatter
-        P2GIn in{R.EP, nullptr, R.E12[cur], R.D3[cur], R.EF, R.EK, R.VF, s->md.friction_coeff};
+        P2GIn in{R.EP, nullptr, R.E12[cur], R.D3[cur], R.EF, R.EK, R.VF[cur], s->md.friction_coeff};
         launch_pdl(k_p2g<0>, cdiv(s->Ne, ppb), ppb, P2G_SMEM, q, pdl, s->g, in, s->Ne, a.dt, s->md.rpic);
         s->launches++;
     }
@@ -628,7 +629,7 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
         }
     };
     if (s->Nv) {
-        P2GIn in{R.VP, (const float*)R.VF, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
+        P2GIn in{R.VP, (const float*)R.VF[cur], nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
         launch_pdl(k_p2g<2>, cdiv(s->Nv, ppb), ppb, P2G_SMEM, q, pdl, s->g, in, s->Nv, a.dt, s->md.rpic);
         s->launches++;
     }
@@ -643,7 +644,7 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
     Advance none{nullptr, nullptr, 0}, adv{s->st, s->d_bcs, n_bc};
     const int last = s->Ne ? 2 : (s->Nt ? 1 : 0);  // the last kernel of the substep advances time
     const int gpb = 32 * G2P_NW;
-    if (s->Nv) { launch_pdl(k_g2p_vertices, cdiv(s->Nv, gpb), gpb, sm(G2P_NW, G2P_V_WB), q, pdl, s->g, s->Nv, R.VP, R.VF, R.CV, a.dt, s->debug ? s->dbg_f : nullptr, last == 0 ? adv : none); s->launches++; }
+    if (s->Nv) { launch_pdl(k_g2p_vertices, cdiv(s->Nv, gpb), gpb, sm(G2P_NW, G2P_V_WB), q, pdl, s->g, s->Nv, R.VP, R.VF[cur ^ 1], R.CV, a.dt, last == 0 ? adv : none); s->launches++; }
     if (s->Nt) { launch_pdl(k_g2p_traditional, cdiv(s->Nt, gpb), gpb, sm(G2P_NW, G2P_T_WB), q, pdl, s->g, s->Nt, R.TP, R.TF, a.dt, last == 1 ? adv : none); s->launches++; }
     if (ev) CK(cudaEventRecord(ev[6], q));
     if (s->Ne) {
@@ -706,6 +707,7 @@ static void destroy_graphs(MpmSolver* s) {
     s->graph_cache_ptr = nullptr;
 }
 static void destroy_sharded(MpmSolver* s);  // communicator + captured sharded windows (defined with the NCCL path)
+static void destroy_shard_graphs(MpmSolver* s);
 static void run_substeps(MpmSolver* s, SubstepArgs a, int count, cudaStream_t q) {
     const bool graphs = s->use_graphs && !s->profiling;
     while (count > 0) {
@@ -811,7 +813,7 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
             s->R.CE = s->dalloc<int>(ne); s->R.CV = s->dalloc<int>(nv);
             for (int b = 0; b < 2; b++) { s->R.E12[b] = s->dalloc<float>(ne * E12_F); s->R.D3[b] = s->dalloc<float4>(ne); }
             s->R.TP = s->dalloc<float>(nt * KP_F); s->R.TS = s->dalloc<float>(nt * S_F); s->R.TF = s->dalloc<float>(nt * TF_F);
-            s->R.VP = s->dalloc<float>(nv * VP_F); s->R.VF = s->dalloc<float4>(nv);
+            s->R.VP = s->dalloc<float>(nv * VP_F); s->R.VF[0] = s->dalloc<float4>(nv); s->R.VF[1] = s->dalloc<float4>(nv);
         }
         int nmax = std::max(s->Ne, std::max(s->Nt, s->Nv));
         s->permE = s->dalloc<uint32_t>(s->Ne); s->permT = s->dalloc<uint32_t>(s->Nt); s->permV = s->dalloc<uint32_t>(s->Nv);
@@ -879,11 +881,18 @@ const char* mpm_last_error(MpmSolver* s) { return s ? s->err.c_str() : g_create_
 
 int mpm_set_model(MpmSolver* s, const MpmModelParams* p) {
     API_BEGIN(s)
+    // the captured substep graphs carry the model scalars as by-value kernel arguments (gravity, material, damping,
+    // rpic, friction, ...): a change invalidates them, or a replay would silently step with the old parameters
+    const ModelDev old = s->md;
     s->md.material = p->material; s->md.hardening = p->hardening;
     s->md.friction_coeff = p->friction_coeff; s->md.alpha = p->alpha;
     s->md.gx = p->g[0]; s->md.gy = p->g[1]; s->md.gz = p->g[2];
     s->md.rpic = p->rpic_damping; s->md.damping = p->grid_v_damping_scale;
     s->md.xi = p->xi; s->md.plastic_viscosity = p->plastic_viscosity; s->md.softening = p->softening;
+    if (memcmp(&old, &s->md, sizeof(ModelDev)) != 0) {
+        destroy_graphs(s);
+        destroy_shard_graphs(s);
+    }
     API_END(s)
 }
 
@@ -941,6 +950,8 @@ int mpm_add_mesh_collider(MpmSolver* s, float friction) {
     if (s->has_collider) throw std::string("only one mesh collider is supported");
     s->has_collider = true;
     s->col_friction = friction;
+    destroy_graphs(s);  // the friction coefficient is a by-value argument of the captured grid update
+    destroy_shard_graphs(s);
     API_END(s)
 }
 
@@ -1377,15 +1388,18 @@ static void rebuild_shared_on_device(MpmSolver* s, int margin, cudaStream_t q) {
     s->n_rebuilds++;
 }
 
-static void destroy_sharded(MpmSolver* s) {
-    if (s->h_nshared) { cudaFreeHost(s->h_nshared); s->h_nshared = nullptr; }
-    close_peer_areas(s);
+static void destroy_shard_graphs(MpmSolver* s) {
     if (s->shard_graphs) {
         auto& v = shard_graphs(s);
         for (auto& e : v) cudaGraphExecDestroy(e.exec);
         delete &v;
         s->shard_graphs = nullptr;
     }
+}
+static void destroy_sharded(MpmSolver* s) {
+    if (s->h_nshared) { cudaFreeHost(s->h_nshared); s->h_nshared = nullptr; }
+    close_peer_areas(s);
+    destroy_shard_graphs(s);
     if (s->comm) {
         nccl_api()->CommDestroy(s->comm);
         s->comm = nullptr;
@@ -1648,7 +1662,6 @@ int mpm_set_debug(MpmSolver* s, int on) {
     s->debug = on != 0;
     if (s->debug && !s->g.dbg_acc) {
         s->g.dbg_acc = s->dalloc<float4>((size_t)s->g.cap * BN);
-        s->dbg_f = s->dalloc<float>(3 * (size_t)s->Nv + 3);
     }
     if (!s->debug) s->g.dbg_acc = nullptr;
     API_END(s)

@@ -29,7 +29,8 @@
 //   TS     stress      {S[9]}                              9 floats  written by the traditional stress kernel
 //   TF     trad state  {F[9], Ft[9], mu, lam, ys}         21 floats  written by stress (F,..) and G2P (Ft)
 //   VP     kinematics  {x,y,z,m, vx,vy,vz, C[9], pad[4]}  20 floats  written by G2P
-//   VF     force       float4 {fx,fy,fz,-}                           REDG.128 by stress, zeroed by G2P
+//   VF     force       float4 {fx,fy,fz,-}                           REDG.128 by stress; ping-pong with the directions: G2P
+//                                                                    clears the buffer of the NEXT substep, the last one stays readable
 // E12 / D3 are double buffered: G2P reads buffer `cur` and writes buffer `cur^1`, so the directions the
 // last stress evaluation saw stay available and the element stress (state.particle_stress) is
 // re-evaluated on export instead of being stored every substep.

@@ -1147,11 +1147,11 @@ constexpr int G2P_MINB = 16 / G2P_NW;  // unrolled contraction (traditional part
 #define MPM_G2P_E_WARPS 20
 #endif
 constexpr int G2P_V_MINB = MPM_G2P_V_WARPS / G2P_NW, G2P_E_MINB = MPM_G2P_E_WARPS / G2P_NW;  // lean contractions
-// g2p_v for cloth vertices (mpm_utils.py:716-786); also clears vertex_force for the next substep
-// (replaces set_vec3_to_zero, mpm_solver.py:251-256) and allocates grid blocks for the new position.
+// g2p_v for cloth vertices (mpm_utils.py:716-786); also clears the vertex_force accumulator of the next substep
+// and allocates grid blocks for the new position.
 constexpr int G2P_V_WB = VP_F * 32 * 4 + G2P_TILE_B;
-__global__ void __launch_bounds__(32 * G2P_NW, G2P_V_MINB) k_g2p_vertices(Grid g, int Nv, float* __restrict__ VP, float4* __restrict__ VF,
-                                                               int* __restrict__ CV, float dt, float* __restrict__ dbg_f, Advance adv) {
+__global__ void __launch_bounds__(32 * G2P_NW, G2P_V_MINB) k_g2p_vertices(Grid g, int Nv, float* __restrict__ VP, float4* __restrict__ VFnext,
+                                                               int* __restrict__ CV, float dt, Advance adv) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); advance_step(adv.st, dt, adv.bcs, adv.n_bc); }
     Warp w;
@@ -1193,8 +1193,9 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_V_MINB) k_g2p_vertices(Grid g
         r4[1] = make_float4(o.v[0], o.v[1], o.v[2], o.C[0]);
         r4[2] = make_float4(o.C[1], o.C[2], o.C[3], o.C[4]);
         r4[3] = make_float4(o.C[5], o.C[6], o.C[7], o.C[8]);
-        if (dbg_f) { float4 f = VF[p]; dbg_f[3 * p] = f.x; dbg_f[3 * p + 1] = f.y; dbg_f[3 * p + 2] = f.z; }
-        VF[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // vertex forces are double buffered: the NEXT substep's accumulator is cleared here (replaces set_vec3_to_zero,
+        // mpm_solver.py:251-256), this substep's forces stay readable as state.vertex_force
+        VFnext[p] = make_float4(0.f, 0.f, 0.f, 0.f);
         const int nb0 = base_of(xm.x, g.inv_dx), nb1 = base_of(xm.y, g.inv_dx), nb2 = base_of(xm.z, g.inv_dx);
         if (nb0 != G.b[0] || nb1 != G.b[1] || nb2 != G.b[2]) {  // the blocks under the new stencil exist unless the cell changed
             ensure_stencil_blocks(g, xm.x, xm.y, xm.z);

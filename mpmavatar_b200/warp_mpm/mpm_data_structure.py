@@ -32,6 +32,30 @@ def _lazy(name):
         return getattr(self, key)
 
     def set_(self, value):
+        # the solver may hold newer data than the canonical tensors: bring them up to date BEFORE the caller's value
+        # goes in, so that the next (lazy) export cannot overwrite it
+        self._pull()
+        setattr(self, key, value)
+        self._dirty = True
+
+    return property(get, set_)
+
+
+_MODEL_ARRAYS = ("E", "nu", "mu", "lam", "gamma", "kappa", "yield_stress")
+
+
+def _model_array(name):
+    """Per-particle model arrays.  The return maps mutate mu / lam / yield_stress in place in the reference
+    (mpm_utils.py:250-252, 287-292); here they live in the solver's sorted records between exports, so a read pulls
+    them first and a write pulls BEFORE the new tensor is bound (otherwise the next export would overwrite it)."""
+    key = "_" + name
+
+    def get(self):
+        self._pull()
+        return getattr(self, key)
+
+    def set_(self, value):
+        self._pull()
         setattr(self, key, value)
         self._dirty = True
 
@@ -193,9 +217,18 @@ class MPMStateStruct:
 
 class MPMModelStruct:
     """mpm_data_structure.py:610-733"""
+    for _n in _MODEL_ARRAYS:
+        locals()[_n] = _model_array(_n)
+    del _n
 
     def __init__(self):
         self._dirty = True
+        self._solver = None  # the MPMWARP this model was last bound to
+
+    def _pull(self):
+        sv = self._solver
+        if sv is not None and sv._bound_model is self and sv._bound_state is not None:
+            sv._bound_state._pull()
 
     def init(self, shape, device=None, requires_grad=False) -> None:
         dev = _dev(device)

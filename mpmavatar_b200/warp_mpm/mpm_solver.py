@@ -205,6 +205,7 @@ class MPMWARP(object):
         state._dirty = model._dirty = False
         state._stale = False
         state._solver = self
+        model._solver = self
         self._bound_state, self._bound_model = state, model
 
     def _export_into(self, state):
@@ -212,11 +213,13 @@ class MPMWARP(object):
         a.x, a.v, a.C = _ptr(state._particle_x), _ptr(state._particle_v), _ptr(state._particle_C)
         a.F, a.F_trial, a.stress = _ptr(state._particle_F), _ptr(state._particle_F_trial), _ptr(state._particle_stress)
         a.d, a.vertex_force = _ptr(state._particle_d), _ptr(state._vertex_force)
-        if self._bound_model is not None:  # damage / hardening mutate these (mpm_utils.py:250,287-292)
-            m = self._bound_model
-            a.mu, a.lam, a.yield_stress = _ptr(m.mu), _ptr(m.lam), _ptr(m.yield_stress)
+        m = self._bound_model
+        # damage / hardening mutate these (mpm_utils.py:250,287-292); a model the caller has touched since the last
+        # import (_dirty) keeps the caller's values
+        if m is not None and not m._dirty and state is self._bound_state:
+            a.mu, a.lam, a.yield_stress = _ptr(m._mu), _ptr(m._lam), _ptr(m._yield_stress)
+        state._stale = False  # before the call: the lazy properties used above must not recurse
         self._ck(self._libh.mpm_export_state(self._h, C.byref(a), self._stream()))
-        state._stale = False
 
     def _export_grid(self):
         n = self.n_grid

@@ -82,6 +82,29 @@ def tiny_scenes():
     # (mpm_utils.py:250-252), viscoplastic return map (:315-359), damage softening down to mu = lam = 0 (:287-292)
     for name, (mat, _) in MATERIAL_VARIANTS.items():
         out[name] = (S.scene_c1(n=60, n_grid=12, seed=21, material=mat), 4, None)
+    # grid sizes that are NOT multiples of the solver's 4^3 blocks -- the reference's real operating points are 200, 150
+    # (scripts/physics/actorshq_a2_lower.sh:36) and 250 (run_demo.py:142): 150 = 250 = 2 (mod 4).  Particles are driven into
+    # the upper walls so that the position clamp [2dx, lim - 2dx] (mpm_utils.py:767-778) acts in the last, partial block.
+    for n_grid, mat, seed in ((14, "jelly", 31), (15, "sand", 32)):
+        sw = S.scene_c1(n=90, n_grid=n_grid, seed=seed, material=mat)
+        rng = np.random.default_rng(seed)
+        dxw = 2.0 / n_grid
+        lo, hi = 2.0 - 4.5 * dxw, 2.0 - 2.0 * dxw  # a block of particles within 2.5 cells of the x, y upper walls
+        sw.x = np.stack([rng.uniform(lo, hi, 90), rng.uniform(lo, hi, 90), rng.uniform(0.9, 1.3, 90)], 1).astype(np.float32)
+        sw.x[:6] = np.float32(hi)  # some start exactly on the clamp value
+        sw.v = (np.array([6.0, 9.0, -1.0], np.float32) + 2.0 * rng.normal(size=(90, 3))).astype(np.float32)
+        sw.dt = 1e-3  # the fastest particles cross the clamp in the first substep, the rest within three
+        out[f"trad_{mat}_grid{n_grid}_walls"] = (sw, 3, None)
+    sc18 = S._cloth_scene("golden_cloth_body_grid18", 6, 12, 7, 18, with_body=True)
+    sc18.body_verts, sc18.body_faces = S.capsule_mesh(segs=12, rings_cyl=5, rings_cap=3, radius=0.22, cyl_len=0.7,
+                                                      center=(1.0, 1.0, 1.0))
+    sc18.v = (0.3 * np.random.default_rng(6).normal(size=sc18.x.shape)).astype(np.float32)
+    out["cloth_body_joints_grid18"] = (sc18, 3, None)
+    s50 = S.scene_demo_like(Nu=16, Nr=8, n_sand=120, n_grid=50, seed=9)
+    s50.body_verts, s50.body_faces = S.capsule_mesh(segs=16, rings_cyl=8, rings_cap=3, radius=0.22, cyl_len=0.7,
+                                                    center=(1.0, 1.0, 1.0))
+    s50.v = (0.2 * np.random.default_rng(10).normal(size=s50.x.shape)).astype(np.float32)
+    out["demo_sand_plane_pinned_grid50"] = (s50, 2, np.zeros((s50.num_joint_t, 3), np.float32))
     return out
 
 
@@ -249,8 +272,37 @@ SCENE_SCALARS = ("name", "n_grid", "grid_lim", "dt", "material", "n_elements", "
                  "num_joint_v", "num_joint_f", "num_joint_t")
 
 
+def make_cov_fixture():
+    """export_particle_cov_to_torch / compute_cov_from_F (mpm_solver.py:543-561, mpm_utils.py:1108-1132) run from the
+    reference source on random F_trial and covariances; stored as tests/golden/cov_export.npz."""
+    warp_emu.set_precision("f64")
+    wp, ds, sv = import_reference()
+    rng = np.random.default_rng(41)
+    N, Ne, Nv = 40, 12, 10
+    Nnv = N - Nv
+    Ft = np.eye(3)[None] + 0.3 * rng.normal(size=(Nnv, 3, 3))
+    a = rng.normal(size=(Nnv, 3, 3))
+    cov33 = a @ a.transpose(0, 2, 1)
+    cov6 = np.stack([cov33[:, 0, 0], cov33[:, 0, 1], cov33[:, 0, 2], cov33[:, 1, 1], cov33[:, 1, 2], cov33[:, 2, 2]], 1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        state = ds.MPMStateStruct()
+        state.init(N, Ne, Nv, device="cpu", requires_grad=False)
+        state.particle_F_trial = wp.from_numpy(Ft, dtype=wp.mat33)
+        state.particle_cov = wp.from_numpy(cov6.reshape(-1), dtype=float)
+        solver = sv.MPMWARP.__new__(sv.MPMWARP)
+        solver.n_no_vertices = Nnv
+        solver.time_profile = {}
+        out = solver.export_particle_cov_to_torch(state, device="cpu")
+    path = os.path.join(HERE, "cov_export.npz")
+    np.savez_compressed(path, F_trial=Ft.astype(np.float32), cov=cov6.astype(np.float32).reshape(-1),
+                        ref64_new_cov=np.asarray(out.numpy(), np.float64), counts=np.asarray([N, Ne, Nv]))
+    print(f"cov_export: Nnv={Nnv} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def main():
     only = set(sys.argv[1:])
+    if not only or "cov_export" in only:
+        make_cov_fixture()
     for name, (sc, nsub, joint_t) in tiny_scenes().items():
         if only and name not in only:
             continue
