@@ -49,32 +49,91 @@ __global__ void k_invert(int n, const uint32_t* __restrict__ perm, int* __restri
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) inv[perm[i]] = i;
 }
-struct Recs {  // sorted sub-record arrays (see mpm_device.cuh)
-    float *EP, *EK, *TP, *TS, *TF, *VP;
-    float* E12[2];  // ping-pong {d1,d2}
-    float4* D3[2];  // ping-pong d3
-    int* EF;
+// ---- direct re-sort: keys from the sorted records themselves, then one gather per class from copy A to copy B
+__global__ void k_keys_rec(Grid g, int n, const float* __restrict__ rec, int F, uint32_t* keys, uint32_t* vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = rec + (size_t)i * F;
+    keys[i] = sort_key(g, p[0], p[1], p[2]);
+    vals[i] = i;
+}
+struct Recs;
+struct Recs {  // sorted particle arrays (see mpm_device.cuh)
+    // cloth elements: float4 / int4 streams
+    int4* EFM;
+    float4 *K0, *K1, *XE, *C0, *C1, *SP3, *EV, *ED1, *ED2;
+    float4* D3[2];  // ping-pong d3 (+ C[8])
+    int* CE;
+    // traditional particles / vertices: sub-records
+    float *TP, *TS, *TF, *VP;
     float4* VF[2];  // ping-pong vertex-force accumulators (buffer `cur` is filled by the substep that reads directions `cur`)
-    int *CE, *CV;  // packed stencil base cell per element / vertex (lets G2P start its node loads early)
+    int* CV;        // packed stencil base cell per vertex (lets G2P start its node loads early)
+    // sorted slot -> canonical index within the class, and back
+    uint32_t *permE, *permT, *permV;
+    int *invE, *invT, *invV;
 };
+// ord[i] = old slot of the particle that moves to slot i
+__global__ void k_permute_V(int Nv, const uint32_t* __restrict__ ord, Recs A, Recs B, int* __restrict__ o2n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Nv) return;
+    const int s = (int)ord[i];
+    const float4* src = reinterpret_cast<const float4*>(A.VP + (size_t)s * VP_F);
+    float4* dst = reinterpret_cast<float4*>(B.VP + (size_t)i * VP_F);
+#pragma unroll
+    for (int k = 0; k < VP_F / 4; k++) dst[k] = src[k];
+    B.VF[0][i] = A.VF[0][s];
+    B.VF[1][i] = A.VF[1][s];
+    B.CV[i] = A.CV[s];
+    const uint32_t c = A.permV[s];
+    B.permV[i] = c;
+    B.invV[c] = i;
+    o2n[s] = i;
+}
+__global__ void k_permute_E(int Ne, const uint32_t* __restrict__ ord, Recs A, Recs B, const int* __restrict__ o2nV) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Ne) return;
+    const int s = (int)ord[i];
+    int4 efm = A.EFM[s];  // corner slots follow the vertices to their new slots
+    efm.x = o2nV[efm.x]; efm.y = o2nV[efm.y]; efm.z = o2nV[efm.z];
+    B.EFM[i] = efm;
+    B.K0[i] = A.K0[s]; B.K1[i] = A.K1[s]; B.XE[i] = A.XE[s]; B.EV[i] = A.EV[s]; B.ED1[i] = A.ED1[s]; B.ED2[i] = A.ED2[s];
+    B.C0[i] = A.C0[s]; B.C1[i] = A.C1[s]; B.SP3[i] = A.SP3[s]; B.D3[0][i] = A.D3[0][s]; B.D3[1][i] = A.D3[1][s];
+    B.CE[i] = A.CE[s];
+    const uint32_t c = A.permE[s];
+    B.permE[i] = c;
+    B.invE[c] = i;
+}
+__global__ void k_permute_T(int Nt, const uint32_t* __restrict__ ord, Recs A, Recs B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Nt) return;
+    const int s = (int)ord[i];
+    for (int k = 0; k < KP_F; k++) B.TP[(size_t)i * KP_F + k] = A.TP[(size_t)s * KP_F + k];
+    for (int k = 0; k < S_F; k++) B.TS[(size_t)i * S_F + k] = A.TS[(size_t)s * S_F + k];
+    for (int k = 0; k < TF_F; k++) B.TF[(size_t)i * TF_F + k] = A.TF[(size_t)s * TF_F + k];
+    const uint32_t c = A.permT[s];
+    B.permT[i] = c;
+    B.invT[c] = i;
+}
 __global__ void k_import_E(Grid g, int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R, int cur, const int* __restrict__ invV) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Ne) return;
     int s = perm[i];  // canonical element index == canonical particle index
-    float* p = R.EP + (size_t)i * KP_F;
-    for (int k = 0; k < 3; k++) { p[P_X + k] = c.x[3 * s + k]; p[P_V + k] = c.v[3 * s + k]; }
-    p[P_M] = c.mass[s];
-    p[P_VOL] = c.vol[s];
-    for (int k = 0; k < 9; k++) p[P_C + k] = c.C[9 * (size_t)s + k];
+    const float x = c.x[3 * s], y = c.x[3 * s + 1], z = c.x[3 * s + 2];
+    R.XE[i] = make_float4(x, y, z, 0.f);
+    R.EV[i] = make_float4(c.v[3 * s], c.v[3 * s + 1], c.v[3 * s + 2], 0.f);
+    const float* C = c.C + 9 * (size_t)s;
+    R.C0[i] = make_float4(C[0], C[1], C[2], C[3]);
+    R.C1[i] = make_float4(C[4], C[5], C[6], C[7]);
     const float* ds = c.d + 9 * (size_t)s;  // row-major 3x3 whose COLUMNS are d1,d2,d3
-    float* e = R.E12[cur] + (size_t)i * E12_F;
-    for (int row = 0; row < 3; row++) { e[row] = ds[3 * row]; e[3 + row] = ds[3 * row + 1]; }
-    R.D3[cur][i] = make_float4(ds[2], ds[5], ds[8], 0.f);
-    for (int k = 0; k < 3; k++) R.EF[(size_t)i * EF_F + k] = invV[(int)c.faces[3 * s + k]];  // int(face[k]), mpm_utils.py:172
-    R.CE[i] = pack_cell(base_of(p[0], g.inv_dx), base_of(p[1], g.inv_dx), base_of(p[2], g.inv_dx));
-    float* ek = R.EK + (size_t)i * EK_F;
-    for (int k = 0; k < 3; k++) ek[K_RINV + k] = c.Rinv[3 * s + k];
-    ek[K_MU] = c.mu[s]; ek[K_LAM] = c.lam[s]; ek[K_GAMMA] = c.gamma[s]; ek[K_KAPPA] = c.kappa[s]; ek[K_VOL] = c.vol[s];
+    R.ED1[i] = make_float4(ds[0], ds[3], ds[6], 0.f);
+    R.ED2[i] = make_float4(ds[1], ds[4], ds[7], 0.f);
+    R.D3[cur][i] = make_float4(ds[2], ds[5], ds[8], C[8]);
+    R.SP3[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // int(face[k]), mpm_utils.py:172; the mass rides in the fourth word
+    R.EFM[i] = make_int4(invV[(int)c.faces[3 * s]], invV[(int)c.faces[3 * s + 1]], invV[(int)c.faces[3 * s + 2]], __float_as_int(c.mass[s]));
+    R.CE[i] = pack_cell(base_of(x, g.inv_dx), base_of(y, g.inv_dx), base_of(z, g.inv_dx));
+    R.K0[i] = make_float4(c.Rinv[3 * s], c.Rinv[3 * s + 1], c.Rinv[3 * s + 2], c.mu[s]);
+    R.K1[i] = make_float4(c.lam[s], c.gamma[s], c.kappa[s], c.vol[s]);
 }
 __global__ void k_import_T(int Nt, int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,31 +159,26 @@ __global__ void k_import_V(Grid g, int Nv, int Nnv, const uint32_t* __restrict__
     R.VF[0][i] = R.VF[1][i] = make_float4(0.f, 0.f, 0.f, 0.f);
     R.CV[i] = pack_cell(base_of(p[0], g.inv_dx), base_of(p[1], g.inv_dx), base_of(p[2], g.inv_dx));
 }
-// d from direction buffer `cur`; the element stress of the LAST substep is re-evaluated from buffer
-// `cur^1`, which still holds the d1,d2 and the return-mapped d3 that substep's stress was computed from
-// (kirchoff_stress_Anisotropy is evaluated on exactly that d in the reference, mpm_utils.py:1043-1046)
-__global__ void k_export_E(int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R, int cur, int have_prev, float friction_coeff) {
+// Element state in canonical order.  stepped = a substep has run since the import: the stress of the LAST substep is
+// SP3 (x) the return-mapped d3 still held by direction buffer cur^1 (mpm_utils.py:177).
+__global__ void k_export_E(int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R, int cur, int stepped) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Ne) return;
     int s = perm[i];
-    const float* p = R.EP + (size_t)i * KP_F;
-    for (int k = 0; k < 3; k++) { c.x[3 * s + k] = p[P_X + k]; c.v[3 * s + k] = p[P_V + k]; }
-    for (int k = 0; k < 9; k++) c.C[9 * (size_t)s + k] = p[P_C + k];
-    const float* e = R.E12[cur] + (size_t)i * E12_F;
-    const float4 d3 = R.D3[cur][i];
+    const float4 xe = R.XE[i], ev = R.EV[i], e1 = R.ED1[i], e2 = R.ED2[i];
+    const float x[3] = {xe.x, xe.y, xe.z}, v[3] = {ev.x, ev.y, ev.z}, d1[3] = {e1.x, e1.y, e1.z}, d2[3] = {e2.x, e2.y, e2.z};
+    for (int k = 0; k < 3; k++) { c.x[3 * s + k] = x[k]; c.v[3 * s + k] = v[k]; }
+    const float4 c0 = R.C0[i], c1 = R.C1[i], d3 = R.D3[cur][i];
+    float* C = c.C + 9 * (size_t)s;
+    C[0] = c0.x; C[1] = c0.y; C[2] = c0.z; C[3] = c0.w; C[4] = c1.x; C[5] = c1.y; C[6] = c1.z; C[7] = c1.w; C[8] = d3.w;
     float* dd = c.d + 9 * (size_t)s;
-    for (int row = 0; row < 3; row++) { dd[3 * row] = e[row]; dd[3 * row + 1] = e[3 + row]; }
+    for (int row = 0; row < 3; row++) { dd[3 * row] = d1[row]; dd[3 * row + 1] = d2[row]; }
     dd[2] = d3.x; dd[5] = d3.y; dd[8] = d3.z;
-    if (have_prev) {
-        const float* q = R.E12[cur ^ 1] + (size_t)i * E12_F;
-        const float4 q3 = R.D3[cur ^ 1][i];
-        const float* ek = R.EK + (size_t)i * EK_F;
-        const float d1[3] = {q[0], q[1], q[2]}, d2[3] = {q[3], q[4], q[5]}, d3p[3] = {q3.x, q3.y, q3.z};
-        const ElemConst kc{ek[K_RINV], ek[K_RINV + 1], ek[K_RINV + 2], ek[K_MU], ek[K_LAM], ek[K_GAMMA], ek[K_KAPPA], ek[K_VOL]};
-        ElemStress es;
-        element_stress<false>(d1, d2, d3p, kc, friction_coeff, es);
+    if (stepped) {
+        const float4 sp = R.SP3[i], n3 = R.D3[cur ^ 1][i];
+        const float P3[3] = {sp.x, sp.y, sp.z}, nd3[3] = {n3.x, n3.y, n3.z};
         for (int rr = 0; rr < 3; rr++)
-            for (int cc = 0; cc < 3; cc++) c.stress[9 * (size_t)s + 3 * rr + cc] = kc.vol * (es.P3[rr] * es.nd3[cc]);
+            for (int cc = 0; cc < 3; cc++) c.stress[9 * (size_t)s + 3 * rr + cc] = P3[rr] * nd3[cc];
     }
 }
 __global__ void k_export_T(int Nt, int Ne, const uint32_t* __restrict__ perm, Canon c, Recs R) {
@@ -174,7 +228,7 @@ __global__ void k_export_grid(Grid g, float* gm, float* gvin, float* gvout) {
     int ix = ((co & 1023) << 2) + (l >> 4), iy = (((co >> 10) & 1023) << 2) + ((l >> 2) & 3), iz = (((co >> 20) & 1023) << 2) + (l & 3);
     if (ix >= g.n || iy >= g.n || iz >= g.n) return;
     size_t gi = ((size_t)ix * g.n + iy) * g.n + iz;
-    idx = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023) * BN + l;
+    idx = block_node(g, co, l);
     if (g.dbg_acc) {
         float4 a = g.dbg_acc[idx];
         if (gm) gm[gi] = a.w;
@@ -238,7 +292,8 @@ __global__ void k_shared_pack(Grid g, const int* __restrict__ shared, int n_shar
         const int co = shared[idx >> 6], l = idx & 63;
         const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), m = a;
-        if (g.table[blk] >= 0) { a = g.acc[blk * BN + l]; m = g.mov[blk * BN + l]; }
+        const int ni = block_node(g, co, l);
+        if (g.table[blk] >= 0) { a = g.acc[ni]; m = g.mov[ni]; }
         buf[2 * idx] = a;
         buf[2 * idx + 1] = m;
     }
@@ -248,7 +303,8 @@ __global__ void k_shared_unpack(Grid g, const int* __restrict__ shared, int n_sh
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_shared * BN; idx += gridDim.x * blockDim.x) {
         const int co = shared[idx >> 6], l = idx & 63;
         const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
-        if (g.table[blk] >= 0) { g.acc[blk * BN + l] = buf[2 * idx]; g.mov[blk * BN + l] = buf[2 * idx + 1]; }
+        const int ni = block_node(g, co, l);
+        if (g.table[blk] >= 0) { g.acc[ni] = buf[2 * idx]; g.mov[ni] = buf[2 * idx + 1]; }
     }
 }
 
@@ -277,7 +333,8 @@ __global__ void k_shared_pack2(Grid g, SharedLists L, float4* __restrict__ buf) 
         const int co = (mv ? L.M : L.A)[j >> 6], l = j & 63;
         const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.table[blk] >= 0) a = (mv ? g.mov : g.acc)[blk * BN + l];
+        const int ni = block_node(g, co, l);
+        if (g.table[blk] >= 0) a = (mv ? g.mov : g.acc)[ni];
         buf[mv ? (size_t)L.capA * BN + j : j] = a;
     }
 }
@@ -288,7 +345,8 @@ __global__ void k_shared_unpack2(Grid g, SharedLists L, const float4* __restrict
         const int j = mv ? idx - nA : idx;
         const int co = (mv ? L.M : L.A)[j >> 6], l = j & 63;
         const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
-        if (g.table[blk] >= 0) (mv ? g.mov : g.acc)[blk * BN + l] = buf[mv ? (size_t)L.capA * BN + j : j];
+        const int ni = block_node(g, co, l);
+        if (g.table[blk] >= 0) (mv ? g.mov : g.acc)[ni] = buf[mv ? (size_t)L.capA * BN + j : j];
     }
 }
 __global__ void k_shared_coords(Grid g, const int* __restrict__ lin, int* __restrict__ n_sel, int cap, int* __restrict__ coords,
@@ -339,7 +397,8 @@ __global__ void __launch_bounds__(256) k_shared_push(Grid g, SharedLists L, cons
         const int co = (mv ? L.M : L.A)[j >> 6], l = j & 63;
         const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.table[blk] >= 0) a = (mv ? g.mov : g.acc)[blk * BN + l];
+        const int ni = block_node(g, co, l);
+        if (g.table[blk] >= 0) a = (mv ? g.mov : g.acc)[ni];
         const size_t off = ((size_t)par * P.nranks + P.rank) * P.slot_bytes + ((mv ? (size_t)L.capA * BN + j : j) << 4);
         for (int r = 0; r < P.nranks; r++)
             if (r != P.rank && ((mem >> r) & 1)) *reinterpret_cast<float4*>(P.base[r] + off) = a;
@@ -375,8 +434,9 @@ __global__ void __launch_bounds__(256) k_shared_pull(Grid g, SharedLists L, cons
         if (!((mem >> P.rank) & 1)) continue;
         const int co = (mv ? L.M : L.A)[j >> 6], l = j & 63;
         const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
+        const int ni = block_node(g, co, l);
         if (g.table[blk] < 0) continue;  // not under any of my stencils: my G2P never reads it
-        float4* mine = (mv ? g.mov : g.acc) + blk * BN + l;
+        float4* mine = (mv ? g.mov : g.acc) + ni;
         const size_t off = (size_t)par * P.nranks * P.slot_bytes + ((mv ? (size_t)L.capA * BN + j : j) << 4);
         float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int r = 0; r < P.nranks; r++) {
@@ -409,8 +469,10 @@ struct MpmSolver {
     std::string err;
     // particles
     Recs R{};
-    uint32_t *permE = nullptr, *permT = nullptr, *permV = nullptr;
-    int *invE = nullptr, *invT = nullptr, *invV = nullptr;
+    Recs R2{};  // the other copy: a re-sort gathers R -> R2 and swaps them
+    int rbuf = 0;  // which copy R is (the captured graphs hold raw pointers: part of their keys)
+    uint32_t *ordE = nullptr, *ordT = nullptr, *ordV = nullptr;  // re-sort: old slot of every new slot
+    int* o2nV = nullptr;                                         // re-sort: new slot of every old vertex slot
     uint32_t *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr;
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0;
@@ -453,8 +515,9 @@ struct MpmSolver {
     unsigned char* peer_local = nullptr;     // this rank's receive area (cudaMalloc, exported over CUDA IPC)
     void* peer_open[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     PeerArea peer{};
-    int cur = 0;             // direction buffer (E12/D3) holding the current d
-    bool have_prev = false;  // buffer cur^1 holds the d of the last stress evaluation
+    int cur = 0;             // direction (D3) / vertex-force (VF) buffer of the coming substep
+    bool have_prev = false;  // a substep has run since the last import: buffer cur^1 holds the return-mapped d3 and the vertex
+                             // forces of the last substep
     int n_resorts = 0, n_rebuilds = 0;
     long long n_substeps = 0;
     int launches = 0;
@@ -485,42 +548,70 @@ struct MpmSolver {
 };
 
 // ---------------------------------------------------------------- internals
+static int sort_bits(MpmSolver* s) {
+    int bits = 6;
+    for (int nb = s->g.nb; nb > 1; nb = (nb + 1) / 2) bits += 3;
+    return std::min(bits + 3, 32);
+}
 static void sort_class(MpmSolver* s, int n, int offset, uint32_t* perm, int* inv, cudaStream_t q) {
     if (n == 0) return;
     k_keys<<<cdiv(n, 256), 256, 0, q>>>(s->g, n, s->canon.x, offset, s->keys_in, s->vals_in);
-    int bits = 6;
-    for (int nb = s->g.nb; nb > 1; nb = (nb + 1) / 2) bits += 3;
-    bits = std::min(bits + 3, 32);
     size_t tmp = s->cub_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(s->cub_tmp, tmp, s->keys_in, s->keys_out, s->vals_in, perm, n, 0, bits, q));
+    CK(cub::DeviceRadixSort::SortPairs(s->cub_tmp, tmp, s->keys_in, s->keys_out, s->vals_in, perm, n, 0, sort_bits(s), q));
     k_invert<<<cdiv(n, 256), 256, 0, q>>>(n, perm, inv);
     s->launches += 3;
 }
 
 static void export_to_canon(MpmSolver* s, cudaStream_t q) {
     if (!s->have_state || !s->canon_stale) return;
-    if (s->Ne) k_export_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->permE, s->canon, s->R, s->cur, s->have_prev ? 1 : 0, s->md.friction_coeff);
-    if (s->Nt) k_export_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->permT, s->canon, s->R);
-    if (s->Nv) k_export_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->Nnv, s->permV, s->canon, s->R, s->cur, s->have_prev ? 1 : 0);
+    if (s->Ne) k_export_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->R.permE, s->canon, s->R, s->cur, s->have_prev ? 1 : 0);
+    if (s->Nt) k_export_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->R.permT, s->canon, s->R);
+    if (s->Nv) k_export_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->Nnv, s->R.permV, s->canon, s->R, s->cur, s->have_prev ? 1 : 0);
     s->launches += 3;
     s->canon_stale = false;
 }
 
-// canonical mirror -> sorted records, and rebuild of the sparse grid
+// order of one class by the cell keys of its CURRENT sorted records: ord[i] = old slot of new slot i
+static void sort_records(MpmSolver* s, int n, const float* rec, int F, uint32_t* ord, cudaStream_t q) {
+    if (n == 0) return;
+    k_keys_rec<<<cdiv(n, 256), 256, 0, q>>>(s->g, n, rec, F, s->keys_in, s->vals_in);
+    size_t tmp = s->cub_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(s->cub_tmp, tmp, s->keys_in, s->keys_out, s->vals_in, ord, n, 0, sort_bits(s), q));
+    s->launches += 2;
+}
+
+// Re-sort.  After an import the canonical mirror is the source (sort, then import into the records); the periodic
+// re-sort of a running simulation never touches the mirror: the records are gathered straight from copy R into copy
+// R2 in the new order (one read and one write of the state instead of export -> mirror -> import), the elements'
+// corner slots and the slot <-> canonical maps are composed on the way, and the copies swap.  Both end with the rebuild
+// of the sparse grid.
 static void resort(MpmSolver* s, cudaStream_t q) {
+    if (!s->need_sort && s->have_state && getenv("MPM_B200_RESORT_VIA_MIRROR") == nullptr) {
+        const Recs &A = s->R, &B = s->R2;
+        sort_records(s, s->Nv, A.VP, VP_F, s->ordV, q);
+        if (s->Nv) k_permute_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->Nv, s->ordV, A, B, s->o2nV);
+        sort_records(s, s->Ne, (const float*)A.XE, 4, s->ordE, q);
+        if (s->Ne) k_permute_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->Ne, s->ordE, A, B, s->o2nV);
+        sort_records(s, s->Nt, A.TP, KP_F, s->ordT, q);
+        if (s->Nt) k_permute_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->ordT, A, B);
+        s->launches += 3;
+        std::swap(s->R, s->R2);
+        s->rbuf ^= 1;
+    } else {
     export_to_canon(s, q);
-    sort_class(s, s->Ne, 0, s->permE, s->invE, q);
-    sort_class(s, s->Nt, s->Ne, s->permT, s->invT, q);
-    sort_class(s, s->Nv, s->Nnv, s->permV, s->invV, q);
-    if (s->Ne) k_import_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->permE, s->canon, s->R, s->cur, s->invV);
+    sort_class(s, s->Ne, 0, s->R.permE, s->R.invE, q);
+    sort_class(s, s->Nt, s->Ne, s->R.permT, s->R.invT, q);
+    sort_class(s, s->Nv, s->Nnv, s->R.permV, s->R.invV, q);
+    if (s->Ne) k_import_E<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.permE, s->canon, s->R, s->cur, s->R.invV);
     s->have_prev = false;
-    if (s->Nt) k_import_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->permT, s->canon, s->R);
-    if (s->Nv) k_import_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->Nnv, s->permV, s->canon, s->R);
+    if (s->Nt) k_import_T<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->Nt, s->Ne, s->R.permT, s->canon, s->R);
+    if (s->Nv) k_import_V<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->Nnv, s->R.permV, s->canon, s->R);
+    }
     // all accumulators are zero between substeps, so rebuilding the table needs no pool sweep
     size_t nt = (size_t)s->g.nb * s->g.nb * s->g.nb;
     k_fill_int<<<std::min(cdiv((long long)nt, 256), 1184), 256, 0, q>>>(s->g.table, nt, -1);
     CK(cudaMemsetAsync(s->g.n_slots, 0, sizeof(int), q));
-    if (s->Ne) k_alloc_blocks<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.EP, KP_F);
+    if (s->Ne) k_alloc_blocks<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, (const float*)s->R.XE, 4);
     if (s->Nt) k_alloc_blocks<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F);
     if (s->Nv) k_alloc_blocks<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F);
     CK(cudaMemcpyAsync(s->h_nslots, s->g.n_slots, sizeof(int), cudaMemcpyDeviceToHost, q));
@@ -590,10 +681,13 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
     const bool pdl = s->use_pdl && !s->profiling;
     if (halves & HALF_SCATTER) {
     if (n_ops) {
-        if (s->Ne) k_particle_ops<<<cdiv(s->Ne, 256), 256, 0, q>>>(s->Ne, R.EP, KP_F, s->permE, 0, s->d_ops, n_ops, s->st, a.dt);
-        if (s->Nt) k_particle_ops<<<cdiv(s->Nt, 256), 256, 0, q>>>(s->Nt, R.TP, KP_F, s->permT, s->Ne, s->d_ops, n_ops, s->st, a.dt);
-        if (s->Nv) k_particle_ops<<<cdiv(s->Nv, 256), 256, 0, q>>>(s->Nv, R.VP, VP_F, s->permV, s->Nnv, s->d_ops, n_ops, s->st, a.dt);
-        s->launches += 3;
+        if (s->Ne) {
+            k_particle_ops<<<cdiv(s->Ne, 256), 256, 0, q>>>(s->Ne, (const float*)R.XE, 4, (float*)R.EV, 4, (const float*)R.EFM + 3, 4, s->R.permE, 0, s->d_ops, n_ops, s->st, a.dt);
+            s->launches++;
+        }
+        if (s->Nt) k_particle_ops<<<cdiv(s->Nt, 256), 256, 0, q>>>(s->Nt, R.TP + P_X, KP_F, R.TP + P_V, KP_F, R.TP + P_M, KP_F, s->R.permT, s->Ne, s->d_ops, n_ops, s->st, a.dt);
+        if (s->Nv) k_particle_ops<<<cdiv(s->Nv, 256), 256, 0, q>>>(s->Nv, R.VP + V_X, VP_F, R.VP + V_V, VP_F, R.VP + V_M, VP_F, s->R.permV, s->Nnv, s->d_ops, n_ops, s->st, a.dt);
+        s->launches += 2;
     }
     if (s->Nt) {
         k_stress_traditional<<<cdiv(s->Nt, 32 * STRESS_T_NW), 32 * STRESS_T_NW, sm(STRESS_T_NW, STRESS_T_WB), q>>>(s->Nt, R.TF, R.TS, s->md, a.dt);
@@ -601,13 +695,13 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
     }
     if (ev) CK(cudaEventRecord(ev[1], q));
     const int ppb = 32 * P2G_NW;  // particles per P2G block
-    if (s->Ne) {  // cloth stress fused in front of the element scatter; VF must be complete before the vertex scatter
-        P2GIn in{R.EP, nullptr, R.E12[cur], R.D3[cur], R.EF, R.EK, R.VF[cur], s->md.friction_coeff};
-        launch_pdl(k_p2g<0>, cdiv(s->Ne, ppb), ppb, P2G_SMEM, q, pdl, s->g, in, s->Ne, a.dt, s->md.rpic);
+    if (s->Ne) {  // cloth stress + scatter; VF must be complete before the vertex scatter
+        ElemIO io{R.EFM, R.K0, R.K1, R.XE, R.EV, R.ED1, R.ED2, R.C0, R.C1, R.D3[cur], R.SP3, R.VF[cur]};
+        launch_pdl(k_p2g_elements, cdiv(s->Ne, ppb), ppb, P2G_SMEM, q, pdl, s->g, io, s->Ne, a.dt, s->md.rpic, s->md.friction_coeff);
         s->launches++;
     }
     if (s->Nt) {
-        P2GIn in{R.TP, R.TS, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
+        P2GIn in{R.TP, R.TS};
         launch_pdl(k_p2g<1>, cdiv(s->Nt, ppb), ppb, P2G_SMEM, q, pdl, s->g, in, s->Nt, a.dt, s->md.rpic);
         s->launches++;
     }
@@ -617,7 +711,7 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
         const int tot = a.mover ? a.njt + s->cfg.num_joint_v + s->cfg.num_joint_f : 0;
         ColliderArgs ca{a.collider ? s->cfg.n_mesh_f : 0, s->mesh_faces, s->mesh_x, s->mesh_v, s->st, a.dt, a.advance_mesh ? 1 : 0};
         MoverArgs ma{a.mover ? a.njt : 0, a.mover ? s->cfg.num_joint_v : 0, a.mover ? s->cfg.num_joint_f : 0, s->Nt,
-                     s->joint_t, s->joint_v, s->joint_f, R.EP, R.TP, R.VP, s->invE, s->invT, s->invV};
+                     s->joint_t, s->joint_v, s->joint_f, R.TP, R.VP, R.XE, s->R.invE, s->R.invT, s->R.invV};
         if (ev) {  // profiling: separate launches so that the two phases are timed separately
             if (ca.Mf) { k_collider_scatter<<<cdiv(ca.Mf, 128), 128, 0, q>>>(s->g, ca); s->launches++; }
             CK(cudaEventRecord(ev[3], q));
@@ -629,8 +723,8 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
         }
     };
     if (s->Nv) {
-        P2GIn in{R.VP, (const float*)R.VF[cur], nullptr, nullptr, nullptr, nullptr, nullptr, 0.f};
-        launch_pdl(k_p2g<2>, cdiv(s->Nv, ppb), ppb, P2G_SMEM, q, pdl, s->g, in, s->Nv, a.dt, s->md.rpic);
+        P2GIn in{R.VP, (const float*)R.VF[cur]};
+        launch_pdl(k_p2g<2>, cdiv(s->Nv, 32 * P2G_V_NW), 32 * P2G_V_NW, 128 + P2G_V_NW * P2G_WB, q, pdl, s->g, in, s->Nv, a.dt, s->md.rpic);
         s->launches++;
     }
     if (ev) CK(cudaEventRecord(ev[2], q));
@@ -641,18 +735,27 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
     launch_pdl(k_grid_update, GRID_UPDATE_CTAS, 256, 0, q, pdl, s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, (const BCDesc*)s->d_bcs, n_bc, (const StepState*)s->st);
     s->launches++;
     if (ev) CK(cudaEventRecord(ev[5], q));
+    // gather side: the first kernel waits for the grid update, the others follow it; the last kernel advances time
     Advance none{nullptr, nullptr, 0}, adv{s->st, s->d_bcs, n_bc};
-    const int last = s->Ne ? 2 : (s->Nt ? 1 : 0);  // the last kernel of the substep advances time
     const int gpb = 32 * G2P_NW;
-    if (s->Nv) { launch_pdl(k_g2p_vertices, cdiv(s->Nv, gpb), gpb, sm(G2P_NW, G2P_V_WB), q, pdl, s->g, s->Nv, R.VP, R.VF[cur ^ 1], R.CV, a.dt, last == 0 ? adv : none); s->launches++; }
-    if (s->Nt) { launch_pdl(k_g2p_traditional, cdiv(s->Nt, gpb), gpb, sm(G2P_NW, G2P_T_WB), q, pdl, s->g, s->Nt, R.TP, R.TF, a.dt, last == 1 ? adv : none); s->launches++; }
+    int follower = 0;
+    if (s->Nv) {
+        launch_pdl(k_g2p_vertices, cdiv(s->Nv, gpb), gpb, sm(G2P_NW, G2P_V_WB), q, pdl, s->g, s->Nv, R.VP, R.VF[cur ^ 1], R.CV, a.dt, 1, (s->Nt || s->Ne) ? none : adv);
+        s->launches++;
+        follower = 1;
+    }
+    if (s->Nt) {
+        launch_pdl(k_g2p_traditional, cdiv(s->Nt, gpb), gpb, sm(G2P_NW, G2P_T_WB), q, pdl, s->g, s->Nt, R.TP, R.TF, a.dt, (follower && pdl) ? 0 : 1, s->Ne ? none : adv);
+        s->launches++;
+    }
     if (ev) CK(cudaEventRecord(ev[6], q));
     if (s->Ne) {
-        launch_pdl(k_g2p_elements, cdiv(s->Ne, gpb), gpb, sm(G2P_NW, G2P_E_WB), q, pdl, s->g, s->Ne, R.EP, (const int*)R.EF, (const float4*)R.D3[cur], R.E12[cur ^ 1], R.D3[cur ^ 1], R.CE, (const float*)R.VP, a.dt, last == 2 ? adv : none);
+        ElemG2P eg{R.EFM, R.XE, R.EV, R.ED1, R.ED2, R.C0, R.C1, R.D3[cur], R.D3[cur ^ 1], R.CE, R.VP};
+        launch_pdl(k_g2p_elements, cdiv(s->Ne, gpb), gpb, sm(G2P_NW, G2P_E_WB), q, pdl, s->g, s->Ne, eg, a.dt, adv);
         s->launches++;
-        s->cur ^= 1;
-        s->have_prev = true;
     }
+    if (s->Ne) s->cur ^= 1;
+    s->have_prev = true;
     if (ev) {
         CK(cudaEventRecord(ev[7], q));
         CK(cudaEventRecord(ev[8], q));
@@ -667,7 +770,7 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
 constexpr int GRAPH_U = 16;  // even: the direction ping-pong index is the same before and after a replay
 struct GraphKey {
     float dt;
-    int collider, mover, advance_mesh, njt, cur, n_bc, n_ops, debug;
+    int collider, mover, advance_mesh, njt, cur, n_bc, n_ops, debug, rbuf;
     bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 struct GraphEntry {
@@ -715,7 +818,7 @@ static void run_substeps(MpmSolver* s, SubstepArgs a, int count, cudaStream_t q)
             GraphKey key{};
             key.dt = a.dt; key.collider = a.collider; key.mover = a.mover; key.advance_mesh = a.advance_mesh;
             key.njt = a.njt; key.cur = s->cur; key.n_bc = (int)s->h_bcs.size();
-            key.n_ops = (int)s->h_ops.size(); key.debug = s->debug;
+            key.n_ops = (int)s->h_ops.size(); key.debug = s->debug; key.rbuf = s->rbuf;
             auto& cache = graph_cache(s);
             GraphEntry* hit = nullptr;
             for (auto& e : cache) if (e.key == key) hit = &e;
@@ -739,7 +842,7 @@ static void run_substeps(MpmSolver* s, SubstepArgs a, int count, cudaStream_t q)
                 hit = &cache.back();
             }
             CK(cudaGraphLaunch(hit->exec, q));
-            if (s->Ne) s->have_prev = true;
+            s->have_prev = true;
             s->launches += hit->launches_per_replay;
             count -= GRAPH_U;
         } else {
@@ -806,20 +909,28 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         g.clk = s->dalloc<unsigned long long>(64 * 64);
         g.ts = nullptr;
         k_fill_int<<<1184, 256>>>(g.table, nt, -1);
-        {   // sorted sub-records, each with 32 records of slack for the 16-byte bulk-copy granule
+        // sorted particle arrays (two copies, see resort), each with 32 records of slack: the 16-byte bulk-copy granule and the
+        // lanes past the end of the last slab read in bounds
+        auto alloc_recs = [&](Recs& R) {
             size_t ne = (size_t)s->Ne + 32, nt = (size_t)s->Nt + 32, nv = (size_t)s->Nv + 32;
-            s->R.EP = s->dalloc<float>(ne * KP_F); s->R.EK = s->dalloc<float>(ne * EK_F);
-            s->R.EF = s->dalloc<int>(ne * EF_F);
-            s->R.CE = s->dalloc<int>(ne); s->R.CV = s->dalloc<int>(nv);
-            for (int b = 0; b < 2; b++) { s->R.E12[b] = s->dalloc<float>(ne * E12_F); s->R.D3[b] = s->dalloc<float4>(ne); }
-            s->R.TP = s->dalloc<float>(nt * KP_F); s->R.TS = s->dalloc<float>(nt * S_F); s->R.TF = s->dalloc<float>(nt * TF_F);
-            s->R.VP = s->dalloc<float>(nv * VP_F); s->R.VF[0] = s->dalloc<float4>(nv); s->R.VF[1] = s->dalloc<float4>(nv);
-        }
+            R.EFM = s->dalloc<int4>(ne);
+            R.K0 = s->dalloc<float4>(ne); R.K1 = s->dalloc<float4>(ne); R.XE = s->dalloc<float4>(ne);
+            R.C0 = s->dalloc<float4>(ne); R.C1 = s->dalloc<float4>(ne); R.SP3 = s->dalloc<float4>(ne);
+            R.EV = s->dalloc<float4>(ne); R.ED1 = s->dalloc<float4>(ne); R.ED2 = s->dalloc<float4>(ne);
+            R.CE = s->dalloc<int>(ne); R.CV = s->dalloc<int>(nv);
+            for (int b = 0; b < 2; b++) R.D3[b] = s->dalloc<float4>(ne);
+            R.TP = s->dalloc<float>(nt * KP_F); R.TS = s->dalloc<float>(nt * S_F); R.TF = s->dalloc<float>(nt * TF_F);
+            R.VP = s->dalloc<float>(nv * VP_F); R.VF[0] = s->dalloc<float4>(nv); R.VF[1] = s->dalloc<float4>(nv);
+            R.permE = s->dalloc<uint32_t>(s->Ne); R.permT = s->dalloc<uint32_t>(s->Nt); R.permV = s->dalloc<uint32_t>(s->Nv);
+            R.invE = s->dalloc<int>(s->Ne); R.invT = s->dalloc<int>(s->Nt); R.invV = s->dalloc<int>(s->Nv);
+        };
+        alloc_recs(s->R);
+        alloc_recs(s->R2);
         int nmax = std::max(s->Ne, std::max(s->Nt, s->Nv));
-        s->permE = s->dalloc<uint32_t>(s->Ne); s->permT = s->dalloc<uint32_t>(s->Nt); s->permV = s->dalloc<uint32_t>(s->Nv);
-        s->invE = s->dalloc<int>(s->Ne); s->invT = s->dalloc<int>(s->Nt); s->invV = s->dalloc<int>(s->Nv);
+        s->ordE = s->dalloc<uint32_t>(s->Ne); s->ordT = s->dalloc<uint32_t>(s->Nt); s->ordV = s->dalloc<uint32_t>(s->Nv);
+        s->o2nV = s->dalloc<int>(s->Nv);
         s->keys_in = s->dalloc<uint32_t>(nmax); s->keys_out = s->dalloc<uint32_t>(nmax); s->vals_in = s->dalloc<uint32_t>(nmax);
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, s->cub_bytes, s->keys_in, s->keys_out, s->vals_in, s->permE, nmax, 0, 32));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, s->cub_bytes, s->keys_in, s->keys_out, s->vals_in, s->R.permE, nmax, 0, 32));
         s->cub_tmp = s->dalloc<char>(s->cub_bytes);
         Canon& c = s->canon;
         int N = s->N, Nnv = s->Nnv;
@@ -850,9 +961,9 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         s->md.material = 0; s->md.hardening = 0; s->md.friction_coeff = 0.f; s->md.alpha = 0.f;
         s->md.gx = s->md.gy = s->md.gz = 0.f; s->md.rpic = 0.f; s->md.damping = 1.1f;
         s->md.xi = 0.f; s->md.plastic_viscosity = 0.f; s->md.softening = 0.1f;
-        CK(cudaFuncSetAttribute(k_p2g<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
+        CK(cudaFuncSetAttribute(k_p2g_elements, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
         CK(cudaFuncSetAttribute(k_p2g<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
-        CK(cudaFuncSetAttribute(k_p2g<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
+        CK(cudaFuncSetAttribute(k_p2g<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + P2G_V_NW * P2G_WB));
         CK(cudaDeviceSynchronize());
         CK(cudaGetLastError());
     } catch (const std::string& e) {
@@ -1224,7 +1335,7 @@ NcclApi* nccl_api() {
 
 struct ShardGraphKey {
     float dt;
-    int collider, mover, advance_mesh, cur, n_bc, n_ops, xcap, len;
+    int collider, mover, advance_mesh, cur, n_bc, n_ops, xcap, len, rbuf;
     const void* shared_ptr;
     bool operator==(const ShardGraphKey& o) const { return memcmp(this, &o, sizeof(ShardGraphKey)) == 0; }
 };
@@ -1268,9 +1379,9 @@ static void mark_potential(MpmSolver* s, int margin, cudaStream_t q) {
     unsigned char* mj = s->d_mark + nt;
     CK(cudaMemsetAsync(s->d_mark, 0, 2 * nt, q));
     const int bit = (s->comm && s->comm_size <= 8) ? (1 << s->comm_rank) : 1;  // rank set for <= 8 ranks, else a count
-    if (s->Ne) k_mark_potential<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.EP, KP_F, margin, s->d_mark, mj, s->permE, s->cfg.num_joint_f, bit);
+    if (s->Ne) k_mark_potential<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, (const float*)s->R.XE, 4, margin, s->d_mark, mj, s->R.permE, s->cfg.num_joint_f, bit);
     if (s->Nt) k_mark_potential<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F, margin, s->d_mark, nullptr, nullptr, 0, bit);
-    if (s->Nv) k_mark_potential<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, margin, s->d_mark, mj, s->permV, s->cfg.num_joint_v, bit);
+    if (s->Nv) k_mark_potential<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, margin, s->d_mark, mj, s->R.permV, s->cfg.num_joint_v, bit);
     s->launches += 3;
 }
 // (Re)allocate this rank's receive area for the current capacities and map every peer's (CUDA IPC; the handles travel
@@ -1470,7 +1581,7 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
             ShardGraphKey key{};
             key.dt = a.dt; key.collider = a.collider; key.mover = a.mover; key.advance_mesh = a.advance_mesh; key.cur = s->cur;
             key.n_bc = (int)s->h_bcs.size(); key.n_ops = (int)s->h_ops.size(); key.xcap = s->xcap_blocks * 65536 + s->xcapM; key.len = W + (s->p2p_ready ? 1000 : 0);
-            key.shared_ptr = s->d_shared;
+            key.shared_ptr = s->d_shared; key.rbuf = s->rbuf;
             auto& cache = shard_graphs(s);
             ShardGraph* hit = nullptr;
             for (auto& e : cache) if (e.key == key) hit = &e;
@@ -1492,7 +1603,7 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
             }
             CK(cudaGraphLaunch(hit->exec, q));
             s->launches += hit->launches;
-            if (s->Ne) s->have_prev = true;
+            s->have_prev = true;
             done = W;
         } else {
             sharded_substep(s, a, q);
@@ -1717,7 +1828,7 @@ int mpm_get_stats(MpmSolver* s, MpmStats* out, void* stream) {
     CK(cudaMalloc(&cnt, sizeof(unsigned long long)));
     CK(cudaMemsetAsync(mask, 0, nmask * sizeof(unsigned long long), q));
     CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), q));
-    if (s->Ne) k_mark_nodes<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, s->R.EP, KP_F, mask);
+    if (s->Ne) k_mark_nodes<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, (const float*)s->R.XE, 4, mask);
     if (s->Nt) k_mark_nodes<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F, mask);
     if (s->Nv) k_mark_nodes<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, mask);
     k_popc<<<cdiv((long long)nmask, 256), 256, 0, q>>>(mask, (int)nmask, cnt);

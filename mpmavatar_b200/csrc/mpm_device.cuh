@@ -1,9 +1,13 @@
 // Device-side data layout and helpers of the B200 MPM substep solver.
 //
 // GRID: 4x4x4-node blocks, DIRECTLY ADDRESSED, SPARSELY VISITED.  Node (ix,iy,iz) lives at
-// ((bx*nb+by)*nb+bz)*64 + local in every per-node array -- pure arithmetic, no lookup on the P2G / G2P
-// path (256^3: 268 MB per array, 512^3: 2.1 GB; 180 GB of HBM makes dense ADDRESSING affordable) -- while
-// only the ACTIVE blocks (those under some particle stencil) are ever touched: a block table (nb^3
+// ((bx*nb+by)*nb+bz)*64 + local in every per-node array, which is SEPARABLE: index = X(ix) + Y(iy) + Z(iz) with one
+// small term per axis (axis_offset), so the three offsets per axis of a cell run's stencil are computed once by the
+// run's leader lane and every stencil node is a three-term sum (256^3: 268 MB per array, 512^3: 2.1 GB; 180 GB of
+// HBM makes dense ADDRESSING affordable).  A block's 64 nodes are 1 KB of contiguous memory -- neighbouring cells
+// share cache lines in all three directions (a plain x-major layout was measured: cheaper index arithmetic, but the
+// gather and the grid update lose more to the scattered 48-byte rows than the arithmetic saves).  Only the
+// ACTIVE blocks (those under some particle stencil) are ever touched: a block table (nb^3
 // ints, -1 = inactive, else position in the active list slot_coord[]) is maintained by the kernels that
 // move particles, and the grid update walks that list.  Nothing ever sweeps the dense arrays.
 // Every per-node quantity is a float4 so that one P2G contribution is ONE 16-byte REDG.E.ADD.F32x4
@@ -18,25 +22,26 @@
 // zero_grid sweep.
 //
 // PARTICLES: three classes (elements, traditional, vertices), each sorted by
-// (Morton(block), cell-in-block).  Per class the state is split into small AoS sub-records
-// GROUPED BY THE KERNEL THAT WRITES THEM, so that every kernel reads and writes whole records:
-//   EP/TP  kinematics  {x,y,z,m, vx,vy,vz,vol, C[9]}      17 floats  written by G2P
-//   E12    directions  {d1[3], d2[3]}                      6 floats  written by G2P        (ping-pong)
-//   D3     direction   float4 {d3[3], -}                             return-mapped in place by the fused
-//                                                                    stress+P2G kernel, advanced by G2P (ping-pong)
-//   EF     corners     int[3] sorted vertex slots          3 ints    read-only
-//   EK     constants   {Rinv[3], mu, lam, gamma, kappa, vol} 8 floats read-only
+// (Morton(block), cell-in-block).  A warp owns 32 consecutive particles of a class.
+// Cloth ELEMENTS are a handful of float4 / int4 streams (lane = particle: every load / store is one fully coalesced
+// LDG.128 / STG.128, no shared-memory staging):
+//   EFM    int4   {corner vertex slots (sorted order) x3, mass as float bits}     read-only
+//   K0,K1  float4 {Rinv[3], mu}, {lam, gamma, kappa, vol}                         read-only
+//   XE,EV  float4 centroid / velocity = mean of the corner vertices               written by the element G2P
+//   ED1,ED2 float4 in-plane directions d1, d2 = two edges                          written by the element G2P
+//   CE     int    packed stencil base cell of XE               (lets G2P start its node loads early)
+//   C0,C1  float4 {C[0..3]}, {C[4..7]}; C[8] rides in D3.w     written by the element G2P
+//   D3     float4 {d3[3], C[8]}   ping-pong: return-mapped in place by the stress + P2G kernel (buffer `cur`),
+//                                 advanced by G2P into buffer `cur^1`
+//   SP3    float4 {vol * P3}      third stress column of the last substep (state.particle_stress = SP3 (x) d3)
+// Traditional particles and vertices keep small AoS sub-records GROUPED BY THE KERNEL THAT WRITES THEM, moved
+// with a single cp.async.bulk (TMA, SASS UBLKCP) per slab into / out of shared memory:
+//   TP     kinematics  {x,y,z,m, vx,vy,vz,vol, C[9]}      17 floats  written by G2P
 //   TS     stress      {S[9]}                              9 floats  written by the traditional stress kernel
 //   TF     trad state  {F[9], Ft[9], mu, lam, ys}         21 floats  written by stress (F,..) and G2P (Ft)
 //   VP     kinematics  {x,y,z,m, vx,vy,vz, C[9], pad[4]}  20 floats  written by G2P
-//   VF     force       float4 {fx,fy,fz,-}                           REDG.128 by stress; ping-pong with the directions: G2P
-//                                                                    clears the buffer of the NEXT substep, the last one stays readable
-// E12 / D3 are double buffered: G2P reads buffer `cur` and writes buffer `cur^1`, so the directions the
-// last stress evaluation saw stay available and the element stress (state.particle_stress) is
-// re-evaluated on export instead of being stored every substep.
-// A warp owns 32 consecutive records: the slab of each sub-record is one contiguous chunk that
-// is moved with a single cp.async.bulk (TMA, SASS UBLKCP) into / out of shared memory, where
-// lane = particle accesses are bank-conflict free.
+//   VF     force       float4 {fx,fy,fz,-}   REDG.128 by stress; ping-pong like D3: G2P clears the buffer of the
+//                                            NEXT substep, the last one stays readable (state.vertex_force)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -49,25 +54,21 @@ constexpr int MAX_BC = 16;
 constexpr int MAX_OPS = 64;
 
 // sub-record sizes in floats
-constexpr int KP_F = 17;  // EP / TP
+constexpr int KP_F = 17;  // TP
 constexpr int S_F = 9;    // TS
-constexpr int E12_F = 6;
-constexpr int EF_F = 3;
-constexpr int EK_F = 8;
 constexpr int TF_F = 21;
 constexpr int VP_F = 20;  // 16 used + 4 pad: an 80-byte stride makes lane = particle LDS.128 / STS.128 bank-conflict free
                           // (at 64 bytes they were 4-way conflicted: 64 of the ~290 shared-memory wavefronts of a G2P warp)
 constexpr int VF_F = 4;
 // field offsets
-constexpr int P_X = 0, P_M = 3, P_V = 4, P_VOL = 7, P_C = 8;  // EP / TP
+constexpr int P_X = 0, P_M = 3, P_V = 4, P_VOL = 7, P_C = 8;  // TP
 constexpr int V_X = 0, V_M = 3, V_V = 4, V_C = 7;              // VP
-constexpr int K_RINV = 0, K_MU = 3, K_LAM = 4, K_GAMMA = 5, K_KAPPA = 6, K_VOL = 7;
 constexpr int T_F = 0, T_FT = 9, T_MU = 18, T_LAM = 19, T_YS = 20;
 
 struct Grid {
     int n, nb;
     float dx, inv_dx, lim;
-    int cap;
+    int cap;          // nb^3 blocks
     int* table;       // [nb^3] -1 = inactive, else index into slot_coord
     int* n_slots;     // device counter: number of active blocks
     int* slot_coord;  // [cap] active list: bx | by<<10 | bz<<20
@@ -318,34 +319,72 @@ __device__ __forceinline__ void ensure_stencil_blocks(const Grid& g, float x, fl
         for (int b = y0; b <= y1; b++)
             for (int c = z0; c <= z1; c++) ensure_block(g, a, b, c);
 }
+// per-axis terms of the node index: index(ix,iy,iz) = axis_offset<0>(ix) + axis_offset<1>(iy) + axis_offset<2>(iz)
+template <int AXIS>
+__device__ __forceinline__ int axis_offset(const Grid& g, int i) {
+    const int blk = i >> 2, loc = i & 3;
+    if (AXIS == 0) return blk * (g.nb * g.nb * BN) + (loc << 4);
+    if (AXIS == 1) return blk * (g.nb * BN) + (loc << 2);
+    return blk * BN + loc;
+}
 // index of node (ix,iy,iz) in the per-node arrays, -1 outside the grid
 __device__ __forceinline__ int node_index(const Grid& g, int ix, int iy, int iz) {
     if ((unsigned)ix >= (unsigned)g.n || (unsigned)iy >= (unsigned)g.n || (unsigned)iz >= (unsigned)g.n) return -1;
     return table_index(g, ix >> 2, iy >> 2, iz >> 2) * BN + ((ix & 3) << 4) + ((iy & 3) << 2) + (iz & 3);
 }
-// activity of the (up to) 2x2x2 blocks under a 3^3 stencil whose base node is (bx,by,bz) >= 0:
-// eight independent table loads issued together (used by the body / joint scatters, which must not
+// node l (0..63: x = l>>4, y = (l>>2)&3, z = l&3) of the block with packed coordinates co
+__device__ __forceinline__ int block_node(const Grid& g, int co, int l) {
+    return table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023) * BN + l;
+}
+// ---- stencil addressing for a cell run.  The run's leader lane stores the nine per-axis offsets of the stencil whose
+// packed cell is c (pack_cell: base + 2 per axis) -- o[0..2] x, o[3..5] y, o[6..8] z -- and every lane then adds the
+// three that belong to its node (li,lj,lk) = (lane/9, lane/3%3, lane%3); lanes 27..31 alias node 26 (their loads hit
+// the same shared-memory words as lane 26: no extra bank conflict; their results are discarded).  o[0] = -1: the
+// stencil leaves the grid (nothing is loaded / scattered).
+__device__ __forceinline__ void stencil_offsets(const Grid& g, int c, int* o) {
+    const int bx = (c & 1023) - 2, by = ((c >> 10) & 1023) - 2, bz = (int)((unsigned)c >> 20) - 2;
+    const bool ok = c >= 0 && (unsigned)bx <= (unsigned)(g.n - 3) && (unsigned)by <= (unsigned)(g.n - 3) && (unsigned)bz <= (unsigned)(g.n - 3);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        o[i] = ok ? axis_offset<0>(g, bx + i) : -1;
+        o[3 + i] = axis_offset<1>(g, by + i);
+        o[6 + i] = axis_offset<2>(g, bz + i);
+    }
+}
+struct LaneNode {
+    int li, lj, lk;
+    __device__ __forceinline__ explicit LaneNode(int lane) {
+        const int l = min(lane, 26);
+        li = l / 9; lj = 3 + (l / 3) % 3; lk = 6 + l % 3;
+    }
+    // node index from a run's nine offsets; negative if the run's stencil leaves the grid
+    __device__ __forceinline__ int node(const int* o, bool& ok) const {
+        const int x = o[li];
+        ok = x >= 0;
+        return x + o[lj] + o[lk];
+    }
+};
+// activity of the (up to) 2x2x2 blocks under a 3^3 stencil whose base node is (bx,by,bz) >= 0, as an 8-bit mask
+// (bit (cx<<2 | cy<<1 | cz)): eight independent table loads issued together (body / joint scatters, which must not
 // touch inactive blocks)
-__device__ __forceinline__ void load_slots8(const Grid& g, int bx, int by, int bz, int* sl) {
+__device__ __forceinline__ unsigned load_active8(const Grid& g, int bx, int by, int bz) {
     const int X0 = bx >> 2, Y0 = by >> 2, Z0 = bz >> 2;
+    int sl[8];
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         int X = X0 + (c >> 2), Y = Y0 + ((c >> 1) & 1), Z = Z0 + (c & 1);
         bool ok = bx >= 0 && by >= 0 && bz >= 0 && X < g.nb && Y < g.nb && Z < g.nb;
         sl[c] = ok ? lookup_slot(g, X, Y, Z) : -1;
     }
-}
-__device__ __forceinline__ int sel8(const int* sl, int c) {
-    int s = sl[0];
+    unsigned m = 0;
 #pragma unroll
-    for (int q = 1; q < 8; q++) s = (c == q) ? sl[q] : s;
-    return s;
+    for (int c = 0; c < 8; c++) m |= (sl[c] >= 0 ? 1u : 0u) << c;
+    return m;
 }
-// index of stencil node (i,j,k) given the 8 activity words, -1 if its block is not active
-__device__ __forceinline__ int stencil_node(const Grid& g, const int* sl, int bx, int by, int bz, int i, int j, int k) {
-    const int ix = bx + i, iy = by + j, iz = bz + k;
-    const int c = (((ix >> 2) - (bx >> 2)) << 2) | (((iy >> 2) - (by >> 2)) << 1) | ((iz >> 2) - (bz >> 2));
-    return sel8(sl, c) < 0 ? -1 : node_index(g, ix, iy, iz);
+// per axis: does stencil offset i (0..2) from base b fall into the second block?  bit i of the result
+__device__ __forceinline__ unsigned axis_cross(int b) {
+    const int r = b & 3;  // offsets i with r + i >= 4
+    return r == 3 ? 6u : (r == 2 ? 4u : 0u);
 }
 
 // quadratic B-spline factor of stencil offset i at fractional position f (mpm_utils.py:506-514):

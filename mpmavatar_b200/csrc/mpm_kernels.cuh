@@ -278,17 +278,19 @@ __global__ void __launch_bounds__(32 * STRESS_T_NW) k_stress_traditional(int Nt,
     slab_store(w, {Slab{sT, TF, TF_F}, Slab{sS, TS, S_F}});
 }
 
-// pre-P2G particle operations on one class (mpm_solver.py:260-279); v and mass sit at the same
-// offsets in EP/TP and VP records
-__global__ void k_particle_ops(int n, float* __restrict__ rec, int F, const uint32_t* __restrict__ perm, int canon_offset,
-                               const ParticleOp* __restrict__ ops, int n_ops, const StepState* __restrict__ st, float dt) {
+// pre-P2G particle operations on one class (mpm_solver.py:260-279).  Position, velocity and mass of particle p sit at
+// xr + p*xF, vr + p*vF and mr + p*mF (TP / VP records, or the element streams XE / EV / EFM.w).
+__global__ void k_particle_ops(int n, const float* __restrict__ xr, int xF, float* __restrict__ vr, int vF, const float* __restrict__ mr,
+                               int mF, const uint32_t* __restrict__ perm, int canon_offset, const ParticleOp* __restrict__ ops, int n_ops,
+                               const StepState* __restrict__ st, float dt) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     float time = (float)st->time;
     int ci = canon_offset + (int)perm[p];
-    float* r = rec + (size_t)p * F;
-    float vx = r[P_V], vy = r[P_V + 1], vz = r[P_V + 2];
-    float m = r[P_M];
+    float* r = vr + (size_t)p * vF;
+    const float* xp = xr + (size_t)p * xF;
+    float vx = r[0], vy = r[1], vz = r[2];
+    float m = mr[(size_t)p * mF];
     bool ch = false;
     for (int k = 0; k < n_ops; k++) {
         ParticleOp op = ops[k];
@@ -298,7 +300,7 @@ __global__ void k_particle_ops(int n, float* __restrict__ rec, int F, const uint
         if (op.kind == 1 && mk >= 1) { vx += op.vec[0] * dt; vy += op.vec[1] * dt; vz += op.vec[2] * dt; ch = true; }
         if (op.kind == 2 && mk == 1) { vx = op.vec[0]; vy = op.vec[1]; vz = op.vec[2]; ch = true; }
         if (op.kind == 3 && mk == 1) {  // mpm_solver.py:1216-1254
-            const float ox = r[P_X] - op.point[0], oy = r[P_X + 1] - op.point[1], oz = r[P_X + 2] - op.point[2];
+            const float ox = xp[0] - op.point[0], oy = xp[1] - op.point[1], oz = xp[2] - op.point[2];
             const float dn = ox * op.n[0] + oy * op.n[1] + oz * op.n[2];
             const float hd = len3(ox - dn * op.n[0], oy - dn * op.n[1], oz - dn * op.n[2]);
             float theta = acosf((ox * op.h1[0] + oy * op.h1[1] + oz * op.h1[2]) / hd);
@@ -310,16 +312,15 @@ __global__ void k_particle_ops(int n, float* __restrict__ rec, int F, const uint
             ch = true;
         }
     }
-    if (ch) { r[P_V] = vx; r[P_V + 1] = vy; r[P_V + 2] = vz; }
+    if (ch) { r[0] = vx; r[1] = vy; r[2] = vz; }
 }
 
 // ============================================================ P2G (+ fused cloth stress)
 // p2g_apic_with_stress (mpm_utils.py:484-557), restructured for cell-sorted particles; for cloth
 // elements compute_stress_from_F_trial (mpm_utils.py:1017-1046) is fused in front of it, so the
 // stress never round-trips through HBM.
-//  stage 0  cp.async.bulk brings the warp's sub-record slabs into smem.
-//  stage 1  lane = particle.  (elements: return mapping + stress; the three corner forces leave as
-//           REDG.128 into VF, the return-mapped d3 as one coalesced STG.128.)  The contribution of a
+//  stage 1  lane = particle.  (elements: corner gather, return mapping + stress; the three corner forces leave as
+//           REDG.128 into VF.)  The contribution of a
 //           particle to stencil node (i,j,k), {dt*f + w m (v + C dpos), w m}, is separable:
 //             out(i,j,k) = w2k T_ij + (w0i w1j) Uz_k,      T_ij = w1j Ux_i + w0i Uy_j,
 //             Ux_i = w0i (A + i Bx) + dw0i S0,  Uy_j = w1j j By + dw1j S1,  Uz_k = w2k k Bz + dw2k S2
@@ -328,220 +329,162 @@ __global__ void k_particle_ops(int n, float* __restrict__ rec, int F, const uint
 //           of 27 float4; w0i w1j is recovered from the mass component of T_ij, see below).
 //  stage 2  lane = stencil node (27 of 32 lanes): particles of one cell form a run; the lane expands and
 //           accumulates its node along the run (2 broadcast LDS.128 + 3 FFMA2 + 1 FFMA per particle) and
-//           flushes with ONE REDG.E.ADD.F32x4 per node per run (the node address of the next run is
-//           looked up while the current run is summed).  No intra-warp reduction, no shared-memory
+//           flushes with ONE REDG.E.ADD.F32x4 per node per run; the node address is the run's base node plus a
+//           per-lane constant (linear node layout).  No intra-warp reduction, no shared-memory
 //           atomics; global atomics drop from 27*4 per particle to 27 per cell run.
-// KIND 0: cloth element, 1: traditional (stress*vol, :496), 2: cloth vertex.
 #ifndef MPM_P2G_NW
 #define MPM_P2G_NW 1
 #endif
 constexpr int P2G_NW = MPM_P2G_NW;  // warps (= slabs) per CTA
-constexpr int P2G_T_B = 32 * 9 * 16, P2G_U_B = 32 * 3 * 16;
-constexpr int P2G_WB = P2G_T_B + P2G_U_B;  // 6144 B; the raw slabs (<= 4864 B) are overlaid on it
-constexpr int P2G_SMEM = 128 + P2G_NW * P2G_WB + 64;  // + slack for the stage-2 look-ahead loads
+#ifndef MPM_P2G_V_NW
+#define MPM_P2G_V_NW 1
+#endif
+#ifndef MPM_P2G_V_WARPS
+#define MPM_P2G_V_WARPS 32
+#endif
+constexpr int P2G_V_NW = MPM_P2G_V_NW, P2G_V_MINB = MPM_P2G_V_WARPS / MPM_P2G_V_NW;  // the vertex scatter
+// Stage 2 can take a run's node offsets from its leader lane (as the gather does) instead of decoding the packed cell in
+// every lane: 20 instructions less per flush, but the 1152 bytes of offsets per warp cost resident warps (31 instead of 35
+// by shared memory) -- measured on C3: 88.4 us per substep with, 86.8 without.
+#ifndef MPM_P2G_LEADER_OFFSETS
+#define MPM_P2G_LEADER_OFFSETS 0
+#endif
+// T tiles | U tiles | per-run node offsets (or 64 bytes of slack for the stage-2 look-ahead loads)
+constexpr int P2G_T_B = 32 * 9 * 16, P2G_U_B = 32 * 3 * 16, P2G_O_B = MPM_P2G_LEADER_OFFSETS ? 32 * 9 * 4 : 64;
+constexpr int P2G_WB = P2G_T_B + P2G_U_B + P2G_O_B;  // 7296 B; the raw slabs of the record kernels (<= 3328 B) are overlaid on the tiles
+constexpr int P2G_SMEM = 128 + P2G_NW * P2G_WB;  // the stage-2 look-ahead reads a few bytes past the U tiles: into the offsets
 
-struct P2GIn {
-    const float* KP;   // EP / TP / VP
-    const float* SF;   // TS (KIND 1) or VF (KIND 2)
-    const float* E12;  // KIND 0 only from here
-    float4* D3;
-    const int* EF;
-    const float* EK;
-    float4* VF;
-    float friction_coeff;
+struct P2GPart {  // what stage 1 hands to the tile writer, lane = particle
+    float x[3], m, v[3], C[9];
+    float Sp[9];  // -dt/dx * (vol *) stress, row-major; unused when STRESS = false
 };
 
-template <int KIND>
-__global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, float dt, float rpic) {
-    constexpr int F0 = (KIND == 2) ? VP_F : KP_F;  // kinematics record
-    extern __shared__ __align__(128) unsigned char smem[];
-    Warp w;
-    if (!warp_begin<P2G_NW, P2G_WB>(w, n, smem)) return;
-    ts_begin(g, TS_P2G_E + KIND);
-    PHASE_BEGIN();
-    float* buf = reinterpret_cast<float*>(w.buf);
-    // PDL invariants of this file: (1) every kernel executes griddepcontrol.wait before it exits, so completion is
-    // transitive along the stream; (2) a kernel whose successor runs code in front of its own wait triggers
-    // only AFTER its wait, so "my grid has started" implies "my predecessor's predecessor has completed" -- that
-    // is what the code in front of a wait may rely on.
-    // The vertex scatter only needs its predecessor (the element kernel) for the vertex forces: the VP slab is
-    // loaded and unpacked while the element kernel drains, griddepcontrol.wait sits in front of the VF read.
-    if (KIND != 2) {
-        pdl_wait();
-        pdl_trigger();  // let the successor's CTAs be scheduled into the slots this grid frees
+// weights + contribution tiles of this lane's particle; returns its packed stencil base cell (a distinct negative
+// value for lanes without a particle).  fetch_force(fv) is called after the weights are done: the vertex scatter
+// waits for its predecessor there (the vertex forces are the only input the element kernel produces).
+template <bool STRESS, typename FV>
+__device__ __forceinline__ int p2g_write_tiles(const Grid& g, const Warp& w, bool valid, P2GPart& P, float dt, float rpic,
+                                               FV&& fetch_force) {
+    float* C = P.C;
+    if (rpic != 0.0f) {  // mpm_utils.py:528-542
+        float Cn[9];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+                Cn[3 * a + b] = (1.0f - rpic) * C[3 * a + b] + rpic / 2.0f * (C[3 * a + b] - C[3 * b + a]);
+#pragma unroll
+        for (int i = 0; i < 9; i++) C[i] = (rpic < -0.001f) ? 0.0f : Cn[i];
     }
-    // ---- stage 0
-    float* raw1 = buf + 32 * F0;
-    float* s12 = buf + 32 * KP_F;
-    float* sD3 = s12 + 32 * E12_F;
-    float* sEF = sD3 + 32 * 4;
-    float* sEK = sEF + 32 * EF_F;
-    if (KIND == 0) slab_load(w, {Slab{buf, in.KP, KP_F}, Slab{s12, in.E12, E12_F}, Slab{sD3, in.D3, 4}, Slab{sEF, in.EF, EF_F}, Slab{sEK, in.EK, EK_F}});
-    if (KIND == 1) slab_load(w, {Slab{buf, in.KP, KP_F}, Slab{raw1, in.SF, S_F}});
-    if (KIND == 2) slab_load(w, {Slab{buf, in.KP, VP_F}});
-    PHASE(g, KIND, 0);  // slab load
-    // ---- stage 1
-    const bool valid = w.lane < w.cnt;
-    float x[3] = {0.f, 0.f, 0.f}, m = 0.f, v[3] = {0.f, 0.f, 0.f}, C[9], Sp[9], fv[3] = {0.f, 0.f, 0.f};
+    int b[3];
+    float f[3], wgt[3][3], dwg[3][3];
 #pragma unroll
-    for (int i = 0; i < 9; i++) { C[i] = 0.f; Sp[i] = 0.f; }
-    if (valid) {
-        const float* r = buf + w.lane * F0;
-        if (KIND == 2) {
-            const float4* r4 = reinterpret_cast<const float4*>(r);
-            const float4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
-            x[0] = a.x; x[1] = a.y; x[2] = a.z; m = a.w;
-            v[0] = b.x; v[1] = b.y; v[2] = b.z;
-            C[0] = b.w; C[1] = c.x; C[2] = c.y; C[3] = c.z; C[4] = c.w; C[5] = d.x; C[6] = d.y; C[7] = d.z; C[8] = d.w;
-        } else {
-            x[0] = r[0]; x[1] = r[1]; x[2] = r[2]; m = r[P_M];
-            v[0] = r[P_V]; v[1] = r[P_V + 1]; v[2] = r[P_V + 2];
+    for (int a = 0; a < 3; a++) {
+        const float gp = P.x[a] * g.inv_dx;
+        b[a] = (int)(gp - 0.5f);
+        f[a] = gp - (float)b[a];
 #pragma unroll
-            for (int i = 0; i < 9; i++) C[i] = r[P_C + i];
-            if (KIND == 1) {
-                const float sc = -dt * g.inv_dx * r[P_VOL];
-                const float* s = raw1 + w.lane * S_F;
+        for (int i = 0; i < 3; i++) bspline(f[a], i, wgt[a][i], dwg[a][i]);
+    }
+    float fv[3] = {0.f, 0.f, 0.f};
+    fetch_force(fv);
+    const float m = P.m;
+    // w m (v + C dpos) + dt w f_vertex = w (A + B_x i + B_y j + B_z k), dpos = (ijk - f) dx
+    const float mdx = m * g.dx;
+    float A[3];
 #pragma unroll
-                for (int i = 0; i < 9; i++) Sp[i] = sc * s[i];
-            }
-        }
-        if (KIND == 0) {
-            const float2* e2 = reinterpret_cast<const float2*>(s12 + w.lane * E12_F);
-            const float2 da = e2[0], db = e2[1], dc = e2[2];
-            const float4 d3v = reinterpret_cast<const float4*>(sD3)[w.lane];
-            const float d1[3] = {da.x, da.y, db.x}, d2[3] = {db.y, dc.x, dc.y}, d3[3] = {d3v.x, d3v.y, d3v.z};
-            const int* fc = reinterpret_cast<const int*>(sEF) + w.lane * EF_F;
-            const int face0 = fc[0], face1 = fc[1], face2 = fc[2];
-            const float4 k0 = reinterpret_cast<const float4*>(sEK + w.lane * EK_F)[0], k1 = reinterpret_cast<const float4*>(sEK + w.lane * EK_F)[1];
-            const ElemConst ek{k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-            ElemStress es;
-            element_stress(d1, d2, d3, ek, in.friction_coeff, es);
-            // vertex_force scatter (mpm_utils.py:172-175): one 16-byte vector atomic per corner
-            atomicAdd(&in.VF[face0], make_float4(es.f1[0], es.f1[1], es.f1[2], 0.f));
-            atomicAdd(&in.VF[face1], make_float4(es.f2[0], es.f2[1], es.f2[2], 0.f));
-            atomicAdd(&in.VF[face2], make_float4(es.f3[0], es.f3[1], es.f3[2], 0.f));
-            in.D3[w.p0 + w.lane] = make_float4(es.nd3[0], es.nd3[1], es.nd3[2], 0.f);
-            // stress = vol * P3 (x) nd3 already carries the volume (mpm_utils.py:177, :494)
-            const float sc = -dt * g.inv_dx * ek.vol;
+    for (int c = 0; c < 3; c++)
+        A[c] = m * (P.v[c] - g.dx * (C[3 * c] * f[0] + C[3 * c + 1] * f[1] + C[3 * c + 2] * f[2])) + dt * fv[c];
+    const V4 A4 = v4(A[0], A[1], A[2], m);
+    const V4 Bx = v4(mdx * C[0], mdx * C[3], mdx * C[6], 0.f), By = v4(mdx * C[1], mdx * C[4], mdx * C[7], 0.f),
+             Bz = v4(mdx * C[2], mdx * C[5], mdx * C[8], 0.f);
+    V4 Ux[3], Uy[3], Uz[3];
+    Ux[0] = mul4(wgt[0][0], A4);
+    Ux[1] = mul4(wgt[0][1], add4(A4, Bx));
+    Ux[2] = mul4(wgt[0][2], fma4(2.0f, Bx, A4));
+    Uy[0] = v4(0.f, 0.f, 0.f, 0.f);
+    Uy[1] = mul4(wgt[1][1], By);
+    Uy[2] = mul4(2.0f * wgt[1][2], By);
+    Uz[0] = v4(0.f, 0.f, 0.f, 0.f);
+    Uz[1] = mul4(wgt[2][1], Bz);
+    Uz[2] = mul4(2.0f * wgt[2][2], Bz);
+    if (STRESS) {  // dt * (-stress grad w), stress pre-scaled in Sp
+        const float* Sp = P.Sp;
+        const V4 S0 = v4(Sp[0], Sp[3], Sp[6], 0.f), S1 = v4(Sp[1], Sp[4], Sp[7], 0.f), S2 = v4(Sp[2], Sp[5], Sp[8], 0.f);
 #pragma unroll
-            for (int rr = 0; rr < 3; rr++)
-#pragma unroll
-                for (int cc = 0; cc < 3; cc++) Sp[3 * rr + cc] = sc * (es.P3[rr] * es.nd3[cc]);
+        for (int i = 0; i < 3; i++) {
+            Ux[i] = fma4(dwg[0][i], S0, Ux[i]);
+            Uy[i] = fma4(dwg[1][i], S1, Uy[i]);
+            Uz[i] = fma4(dwg[2][i], S2, Uz[i]);
         }
     }
-    __syncwarp();  // the contributions overwrite the raw slabs
-    PHASE(g, KIND, 1);  // unpack (+ stress)
-    int mycell;
-    {
-        if (rpic != 0.0f) {  // mpm_utils.py:528-542
-            float Cn[9];
-#pragma unroll
-            for (int a = 0; a < 3; a++)
-#pragma unroll
-                for (int b = 0; b < 3; b++)
-                    Cn[3 * a + b] = (1.0f - rpic) * C[3 * a + b] + rpic / 2.0f * (C[3 * a + b] - C[3 * b + a]);
-#pragma unroll
-            for (int i = 0; i < 9; i++) C[i] = (rpic < -0.001f) ? 0.0f : Cn[i];
-        }
-        int b[3];
-        float f[3], wgt[3][3], dwg[3][3];
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            const float gp = x[a] * g.inv_dx;
-            b[a] = (int)(gp - 0.5f);
-            f[a] = gp - (float)b[a];
-#pragma unroll
-            for (int i = 0; i < 3; i++) bspline(f[a], i, wgt[a][i], dwg[a][i]);
-        }
-        if (KIND == 2) {  // the weights above were computed while the element kernel drained
-            pdl_wait();
-            pdl_trigger();
-            if (valid) {
-                const float4 f4 = __ldcg(reinterpret_cast<const float4*>(in.SF) + w.p0 + w.lane);  // written by L2 atomics
-                fv[0] = f4.x; fv[1] = f4.y; fv[2] = f4.z;
-            }
-        }
-        // w m (v + C dpos) + dt w f_vertex = w (A + B_x i + B_y j + B_z k), dpos = (ijk - f) dx
-        const float mdx = m * g.dx;
-        float A[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-            A[c] = m * (v[c] - g.dx * (C[3 * c] * f[0] + C[3 * c + 1] * f[1] + C[3 * c + 2] * f[2])) + dt * fv[c];
-        const V4 A4 = v4(A[0], A[1], A[2], m);
-        const V4 Bx = v4(mdx * C[0], mdx * C[3], mdx * C[6], 0.f), By = v4(mdx * C[1], mdx * C[4], mdx * C[7], 0.f),
-                 Bz = v4(mdx * C[2], mdx * C[5], mdx * C[8], 0.f);
-        V4 Ux[3], Uy[3], Uz[3];
-        Ux[0] = mul4(wgt[0][0], A4);
-        Ux[1] = mul4(wgt[0][1], add4(A4, Bx));
-        Ux[2] = mul4(wgt[0][2], fma4(2.0f, Bx, A4));
-        Uy[0] = v4(0.f, 0.f, 0.f, 0.f);
-        Uy[1] = mul4(wgt[1][1], By);
-        Uy[2] = mul4(2.0f * wgt[1][2], By);
-        Uz[0] = v4(0.f, 0.f, 0.f, 0.f);
-        Uz[1] = mul4(wgt[2][1], Bz);
-        Uz[2] = mul4(2.0f * wgt[2][2], Bz);
-        if (KIND != 2) {  // dt * (-stress grad w), stress pre-scaled in Sp
-            const V4 S0 = v4(Sp[0], Sp[3], Sp[6], 0.f), S1 = v4(Sp[1], Sp[4], Sp[7], 0.f), S2 = v4(Sp[2], Sp[5], Sp[8], 0.f);
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                Ux[i] = fma4(dwg[0][i], S0, Ux[i]);
-                Uy[i] = fma4(dwg[1][i], S1, Uy[i]);
-                Uz[i] = fma4(dwg[2][i], S2, Uz[i]);
-            }
-        }
-        // The second term of out(i,j,k) needs w0i w1j, and the mass component of T_ij IS m w0i w1j: with Uz_k stored
-        // as Uz_k / m the term becomes T_ij.w * (Uz_k / m) and stage 2 reads 8 words per particle instead of 9 (no
-        // separate weight tile).  m = 0 (ghost vertices of a sharded run): Uz_k = 0 for vertices, exact.  A massless
-        // element / traditional particle (volume > 0, density 0) still exerts its stress force: rare slow path below.
-        const float inv_m = (m != 0.0f) ? 1.0f / m : 0.0f;
-        if (KIND != 2 && valid && m == 0.0f) {
+    // The second term of out(i,j,k) needs w0i w1j, and the mass component of T_ij IS m w0i w1j: with Uz_k stored
+    // as Uz_k / m the term becomes T_ij.w * (Uz_k / m) and stage 2 reads 8 words per particle instead of 9 (no
+    // separate weight tile).  m = 0 (ghost vertices of a sharded run): Uz_k = 0 for vertices, exact.  A massless
+    // element / traditional particle (volume > 0, density 0) still exerts its stress force: rare slow path below.
+    const float inv_m = (m != 0.0f) ? 1.0f / m : 0.0f;
+    if (STRESS && valid && m == 0.0f) {
 #pragma unroll  // static indices: a rolled loop would push wgt / Uz into local memory for the whole kernel
-            for (int n = 0; n < 27; n++) {
-                const int i = n / 9, j = (n / 3) % 3, k = n % 3;
-                const float wij = wgt[0][i] * wgt[1][j];
-                const int ni = node_index(g, b[0] + i, b[1] + j, b[2] + k);
-                if (ni >= 0) atomicAdd(&g.acc[ni], make_float4(wij * Uz[k].lo.x, wij * Uz[k].lo.y, wij * Uz[k].hi.x, 0.f));
-            }
+        for (int n = 0; n < 27; n++) {
+            const int i = n / 9, j = (n / 3) % 3, k = n % 3;
+            const float wij = wgt[0][i] * wgt[1][j];
+            const int ni = node_index(g, b[0] + i, b[1] + j, b[2] + k);
+            if (ni >= 0) atomicAdd(&g.acc[ni], make_float4(wij * Uz[k].lo.x, wij * Uz[k].lo.y, wij * Uz[k].hi.x, 0.f));
         }
-        float4* tT = reinterpret_cast<float4*>(w.buf) + w.lane * 9;
-        float4* tU = reinterpret_cast<float4*>(w.buf + P2G_T_B) + w.lane * 3;
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const V4 T = fma4(wgt[1][j], Ux[i], mul4(wgt[0][i], Uy[j]));
-                tT[i * 3 + j] = make_float4(T.lo.x, T.lo.y, T.hi.x, T.hi.y);
-            }
-#pragma unroll
-        for (int k = 0; k < 3; k++) tU[k] = make_float4(Uz[k].lo.x * inv_m, Uz[k].lo.y * inv_m, Uz[k].hi.x * inv_m, wgt[2][k]);
-        mycell = valid ? pack_cell(b[0], b[1], b[2]) : -1 - w.lane;
     }
+    float4* tT = reinterpret_cast<float4*>(w.buf) + w.lane * 9;
+    float4* tU = reinterpret_cast<float4*>(w.buf + P2G_T_B) + w.lane * 3;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const V4 T = fma4(wgt[1][j], Ux[i], mul4(wgt[0][i], Uy[j]));
+            tT[i * 3 + j] = make_float4(T.lo.x, T.lo.y, T.hi.x, T.hi.y);
+        }
+#pragma unroll
+    for (int k = 0; k < 3; k++) tU[k] = make_float4(Uz[k].lo.x * inv_m, Uz[k].lo.y * inv_m, Uz[k].hi.x * inv_m, wgt[2][k]);
+    // particles whose stencil leaves the grid are flagged (the reference has no bounds check there, mpm_utils.py:516-557)
+    const bool inside = (unsigned)b[0] <= (unsigned)(g.n - 3) && (unsigned)b[1] <= (unsigned)(g.n - 3) && (unsigned)b[2] <= (unsigned)(g.n - 3);
+    if (valid && !inside) g.flags[1] = 1;
+    return valid ? pack_cell(b[0], b[1], b[2]) : -1 - w.lane;
+}
+
+// stage 2: lane = stencil node, one pass over the slab's 32 tile records, one REDG.128 per node per cell run
+__device__ __forceinline__ void p2g_stage2(const Grid& g, const Warp& w, int mycell) {
     const Runs R = find_runs(w.lane, w.cnt, mycell);
+#if MPM_P2G_LEADER_OFFSETS
+    int* ro = reinterpret_cast<int*>(w.buf + P2G_T_B + P2G_U_B);
+    if ((R.starts >> w.lane) & 1u) stencil_offsets(g, mycell, ro + R.mine * 9);  // the run's leader: nine per-axis node offsets
+#endif
     __syncwarp();
-    PHASE(g, KIND, 2);  // stage 1
-    // ---- stage 2
     const bool act = w.lane < 27;
-    const int li = act ? w.lane / 9 : 0, lj = act ? (w.lane / 3) % 3 : 0, lk = act ? w.lane % 3 : 0;
-    const float4* pT = reinterpret_cast<const float4*>(w.buf) + (li * 3 + lj);
-    const float4* pU = reinterpret_cast<const float4*>(w.buf + P2G_T_B) + lk;
-    // one pass over the slab with a fixed trip count (loads of later particles are in flight while earlier
-    // ones are accumulated); a warp-uniform test of `starts` closes a run: one REDG.128 per node
-    auto flush = [&](int c, float2 lo, float2 hi) {
+    const LaneNode ln(w.lane);  // lanes 27..31 shadow lane 26 (same shared-memory words: no extra wavefront)
+    const float4* pT = reinterpret_cast<const float4*>(w.buf) + (ln.li * 3 + (ln.lj - 3));
+    const float4* pU = reinterpret_cast<const float4*>(w.buf + P2G_T_B) + (ln.lk - 6);
+    int run = 0;
+    int c = __shfl_sync(0xffffffffu, mycell, 0);  // packed cell of the current run (used without leader offsets)
+    auto flush = [&](float2 lo, float2 hi) {
         if (act && (hi.y != 0.0f || lo.x != 0.0f || lo.y != 0.0f || hi.x != 0.0f)) {
-            const int ni = node_index(g, (c & 1023) - 2 + li, ((c >> 10) & 1023) - 2 + lj, ((c >> 20) & 1023) - 2 + lk);
+#if MPM_P2G_LEADER_OFFSETS
+            bool ok;
+            const int ni = ln.node(ro + run * 9, ok);
+#else  // every lane decodes the run's packed cell itself
+            const int ni = node_index(g, (c & 1023) - 2 + ln.li, ((c >> 10) & 1023) - 2 + (ln.lj - 3), ((c >> 20) & 1023) - 2 + (ln.lk - 6));
+            const bool ok = ni >= 0;
+#endif
 #ifdef MPM_NO_RED  // analysis build: everything but the atomics (results are wrong)
-            if (ni == -12345) atomicAdd(&g.acc[0], make_float4(lo.x, lo.y, hi.x, hi.y));
+            if (ni == 0x7fffffff) atomicAdd(&g.acc[0], make_float4(lo.x, lo.y, hi.x, hi.y));
 #else
-            if (ni >= 0) atomicAdd(&g.acc[ni], make_float4(lo.x, lo.y, hi.x, hi.y));
-            else g.flags[1] = 1;
+            if (ok) atomicAdd(&g.acc[ni], make_float4(lo.x, lo.y, hi.x, hi.y));
 #endif
         }
+        run++;
     };
     float2 alo = make_float2(0.f, 0.f), ahi = alo;
-    int c = __shfl_sync(0xffffffffu, mycell, 0);
-    // one pass over the slab; the shared-memory loads of particle q+1 are in flight while particle q is accumulated
-    // (deeper prefetch was measured: no gain, more address arithmetic).  The loads of "particle 32" read a few bytes
-    // past the tiles, inside the CTA's allocation (P2G_SMEM carries the slack), and are never used.
+    // one pass over the slab with a fixed trip count; the shared-memory loads of particle q+1 are in flight while
+    // particle q is accumulated (deeper prefetch was measured: no gain, more address arithmetic).  The loads of
+    // "particle 32" read a few bytes past the tiles, inside the warp's region, and are never used.  A warp-uniform
+    // test of `starts` closes a run.
     float4 Tn = pT[0], Un = pU[0];
 #pragma unroll 8
     for (int q = 0; q < 32; q++) {  // records past cnt contribute zeros
@@ -549,19 +492,158 @@ __global__ void __launch_bounds__(32 * P2G_NW) k_p2g(Grid g, P2GIn in, int n, fl
         Tn = pT[(q + 1) * 9];
         Un = pU[(q + 1) * 3];
         if (q > 0 && ((R.starts >> q) & 1u)) {
-            flush(c, alo, ahi);
+            flush(alo, ahi);
             alo = ahi = make_float2(0.f, 0.f);
+#if !MPM_P2G_LEADER_OFFSETS
             c = __shfl_sync(0xffffffffu, mycell, q);
+#endif
         }
         alo = fma2(U.w, make_float2(T.x, T.y), alo);
         ahi = fma2(U.w, make_float2(T.z, T.w), ahi);
         alo = fma2(T.w, make_float2(U.x, U.y), alo);  // (m w0i w1j) (Uz_k / m)
         ahi.x = fmaf(T.w, U.z, ahi.x);
     }
-    flush(c, alo, ahi);
+    flush(alo, ahi);
+}
+
+struct P2GIn {
+    const float* KP;  // TP / VP records
+    const float* SF;  // TS (KIND 1) or the vertex forces VF (KIND 2)
+};
+
+// KIND 1: traditional (stress*vol, :496), 2: cloth vertex.  PDL invariants of this file: (1) every kernel executes
+// griddepcontrol.wait before it exits, so completion is transitive along the stream; (2) a kernel whose successor
+// runs code in front of its own wait that READS what this kernel's predecessors wrote triggers only AFTER its
+// own wait, so "my grid has started" implies "my predecessor's predecessor has completed".
+template <int KIND>
+__global__ void __launch_bounds__(32 * (KIND == 2 ? P2G_V_NW : P2G_NW), KIND == 2 ? P2G_V_MINB : 1) k_p2g(Grid g, P2GIn in, int n, float dt, float rpic) {
+    static_assert(KIND == 1 || KIND == 2, "elements have their own kernel");
+    constexpr int F0 = (KIND == 2) ? VP_F : KP_F;  // kinematics record
+    constexpr int NW = (KIND == 2) ? P2G_V_NW : P2G_NW;
+    extern __shared__ __align__(128) unsigned char smem[];
+    Warp w;
+    if (!warp_begin<NW, P2G_WB>(w, n, smem)) return;
+    ts_begin(g, TS_P2G_E + KIND);
+    PHASE_BEGIN();
+    float* buf = reinterpret_cast<float*>(w.buf);
+    // The vertex scatter only needs its predecessor (the element kernel) for the vertex forces: the VP slab is
+    // loaded and unpacked while the element kernel drains, griddepcontrol.wait sits in front of the VF read.
+    if (KIND != 2) {
+        pdl_wait();
+        pdl_trigger();  // let the successor's CTAs be scheduled into the slots this grid frees
+    }
+    float* raw1 = buf + 32 * F0;
+    if (KIND == 1) slab_load(w, {Slab{buf, in.KP, KP_F}, Slab{raw1, in.SF, S_F}});
+    if (KIND == 2) slab_load(w, {Slab{buf, in.KP, VP_F}});
+    PHASE(g, KIND, 0);  // slab load
+    const bool valid = w.lane < w.cnt;
+    P2GPart P;
+    P.m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { P.x[i] = 0.f; P.v[i] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 9; i++) { P.C[i] = 0.f; P.Sp[i] = 0.f; }
+    if (valid) {
+        const float* r = buf + w.lane * F0;
+        if (KIND == 2) {
+            const float4* r4 = reinterpret_cast<const float4*>(r);
+            const float4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
+            P.x[0] = a.x; P.x[1] = a.y; P.x[2] = a.z; P.m = a.w;
+            P.v[0] = b.x; P.v[1] = b.y; P.v[2] = b.z;
+            P.C[0] = b.w; P.C[1] = c.x; P.C[2] = c.y; P.C[3] = c.z; P.C[4] = c.w; P.C[5] = d.x; P.C[6] = d.y; P.C[7] = d.z; P.C[8] = d.w;
+        } else {
+            P.x[0] = r[0]; P.x[1] = r[1]; P.x[2] = r[2]; P.m = r[P_M];
+            P.v[0] = r[P_V]; P.v[1] = r[P_V + 1]; P.v[2] = r[P_V + 2];
+#pragma unroll
+            for (int i = 0; i < 9; i++) P.C[i] = r[P_C + i];
+            const float sc = -dt * g.inv_dx * r[P_VOL];
+            const float* s = raw1 + w.lane * S_F;
+#pragma unroll
+            for (int i = 0; i < 9; i++) P.Sp[i] = sc * s[i];
+        }
+    }
+    __syncwarp();  // the contributions overwrite the raw slabs
+    PHASE(g, KIND, 1);  // unpack
+    const int mycell = p2g_write_tiles<KIND == 1>(g, w, valid, P, dt, rpic, [&](float (&fv)[3]) {
+        if (KIND == 2) {  // the weights were computed while the element kernel drained
+            pdl_wait();
+            pdl_trigger();
+            if (valid) {
+                const float4 f4 = __ldcg(reinterpret_cast<const float4*>(in.SF) + w.p0 + w.lane);  // written by L2 atomics
+                fv[0] = f4.x; fv[1] = f4.y; fv[2] = f4.z;
+            }
+        }
+    });
+    PHASE(g, KIND, 2);  // stage 1
+    p2g_stage2(g, w, mycell);
     PHASE(g, KIND, 3);  // stage 2
     PHASE_END(g, KIND);
     ts_end(g, TS_P2G_E + KIND);
+}
+
+// ---- cloth elements: constitutive update + scatter in one kernel.  The element state arrives as coalesced float4
+// streams (lane = particle, one LDG.128 each; see mpm_device.cuh) -- no shared-memory staging, the tiles of stage 1
+// are the only shared-memory traffic.
+struct ElemIO {
+    const int4* EFM;
+    const float4 *K0, *K1;
+    const float4 *XE, *EV, *ED1, *ED2, *C0, *C1;
+    float4* D3;   // buffer `cur`: read, return-mapped in place
+    float4* SP3;
+    float4* VF;   // buffer `cur`
+};
+__global__ void __launch_bounds__(32 * P2G_NW, 28 / P2G_NW) k_p2g_elements(Grid g, ElemIO A, int n, float dt, float rpic, float friction_coeff) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Warp w;
+    if (!warp_begin<P2G_NW, P2G_WB>(w, n, smem)) return;
+    ts_begin(g, TS_P2G_E);
+    PHASE_BEGIN();
+    const bool valid = w.lane < w.cnt;
+    const int p = w.p0 + w.lane;  // the arrays carry 32 records of slack: lanes past cnt read (and discard) in bounds
+    // constants: nobody writes them between imports
+    const int4 efm = __ldg(&A.EFM[p]);
+    const float4 k0 = __ldg(&A.K0[p]), k1 = __ldg(&A.K1[p]);
+    pdl_wait();     // the element G2P of the previous substep (the last kernel of a substep) is complete
+    pdl_trigger();
+    const float4 xe = A.XE[p], ev = A.EV[p], e1 = A.ED1[p], e2 = A.ED2[p], c0 = A.C0[p], c1 = A.C1[p], d3v = A.D3[p];
+    P2GPart P;
+    P.x[0] = xe.x; P.x[1] = xe.y; P.x[2] = xe.z;
+    P.v[0] = ev.x; P.v[1] = ev.y; P.v[2] = ev.z;
+    P.m = __int_as_float(efm.w);
+    P.C[0] = c0.x; P.C[1] = c0.y; P.C[2] = c0.z; P.C[3] = c0.w; P.C[4] = c1.x; P.C[5] = c1.y; P.C[6] = c1.z; P.C[7] = c1.w; P.C[8] = d3v.w;
+    if (!valid) {  // a harmless stand-in: zero contribution, finite arithmetic
+        P.m = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { P.x[i] = 0.f; P.v[i] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < 9; i++) { P.C[i] = 0.f; P.Sp[i] = 0.f; }
+    }
+    PHASE(g, 0, 0);  // loads
+    if (valid) {
+        const float d1[3] = {e1.x, e1.y, e1.z}, d2[3] = {e2.x, e2.y, e2.z}, d3[3] = {d3v.x, d3v.y, d3v.z};
+        const ElemConst ek{k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+        ElemStress es;
+        element_stress(d1, d2, d3, ek, friction_coeff, es);
+        // vertex_force scatter (mpm_utils.py:172-175): one 16-byte vector atomic per corner
+        atomicAdd(&A.VF[efm.x], make_float4(es.f1[0], es.f1[1], es.f1[2], 0.f));
+        atomicAdd(&A.VF[efm.y], make_float4(es.f2[0], es.f2[1], es.f2[2], 0.f));
+        atomicAdd(&A.VF[efm.z], make_float4(es.f3[0], es.f3[1], es.f3[2], 0.f));
+        A.D3[p] = make_float4(es.nd3[0], es.nd3[1], es.nd3[2], d3v.w);
+        // stress = vol * P3 (x) nd3 already carries the volume (mpm_utils.py:177, :494); kept for state.particle_stress
+        A.SP3[p] = make_float4(ek.vol * es.P3[0], ek.vol * es.P3[1], ek.vol * es.P3[2], 0.f);
+        const float sc = -dt * g.inv_dx * ek.vol;
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++)
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++) P.Sp[3 * rr + cc] = sc * (es.P3[rr] * es.nd3[cc]);
+    }
+    PHASE(g, 0, 1);  // stress
+    const int mycell = p2g_write_tiles<true>(g, w, valid, P, dt, rpic, [](float (&)[3]) {});
+    PHASE(g, 0, 2);  // stage 1
+    p2g_stage2(g, w, mycell);
+    PHASE(g, 0, 3);  // stage 2
+    PHASE_END(g, 0);
+    ts_end(g, TS_P2G_E);
 }
 
 // ============================================================ collider / mover scatter
@@ -597,6 +679,32 @@ struct ColliderArgs {
     float dt;
     int advance;
 };
+// one scatter of a 3^3 stencil into the ACTIVE blocks only: node = X(ix) + Y(iy) + Z(iz) (axis_offset); the activity of
+// the (up to) eight blocks under the stencil is an 8-bit mask, a node's block is picked by three per-axis crossing bits
+template <typename F>
+__device__ __forceinline__ void scatter_active_nodes(const Grid& g, const Stencil& sp, unsigned act8, bool flag_inactive, F&& add) {
+    int ox[3], oy[3], oz[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        ox[i] = axis_offset<0>(g, sp.b[0] + i);
+        oy[i] = axis_offset<1>(g, sp.b[1] + i);
+        oz[i] = axis_offset<2>(g, sp.b[2] + i);
+    }
+    const unsigned cx = axis_cross(sp.b[0]), cy = axis_cross(sp.b[1]), cz = axis_cross(sp.b[2]);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const unsigned c = (((cx >> i) & 1u) << 2) | (((cy >> j) & 1u) << 1) | ((cz >> k) & 1u);
+                if (!((act8 >> c) & 1u)) {
+                    if (flag_inactive) g.flags[1] = 1;
+                    continue;
+                }
+                add(ox[i] + oy[j] + oz[k], sp.w[0][i] * sp.w[1][j] * sp.w[2][k]);
+            }
+}
 __device__ __forceinline__ void collider_scatter_face(const Grid& g, const ColliderArgs& ca, int f) {
     const int* __restrict__ faces = ca.faces;
     const float* __restrict__ px = ca.px;
@@ -621,29 +729,17 @@ __device__ __forceinline__ void collider_scatter_face(const Grid& g, const Colli
     Stencil sp;
     make_stencil(g, fp[0], fp[1], fp[2], sp);
     if (!scatter_ok(g, sp)) return;
-    int sl[8];
-    load_slots8(g, sp.b[0], sp.b[1], sp.b[2], sl);
-    bool any = false;
-#pragma unroll
-    for (int c = 0; c < 8; c++) any = any || sl[c] >= 0;
-    if (!any) return;
+    const unsigned act8 = load_active8(g, sp.b[0], sp.b[1], sp.b[2]);
+    if (!act8) return;
     float e1[3] = {P[1][0] - P[0][0], P[1][1] - P[0][1], P[1][2] - P[0][2]};
     float e2[3] = {P[2][0] - P[0][0], P[2][1] - P[0][1], P[2][2] - P[0][2]};
     float nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
     float nl = len3(nx, ny, nz);
     if (nl > 0.0f) { nx /= nl; ny /= nl; nz /= nl; } else { nx = ny = nz = 0.0f; }
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                int ni = stencil_node(g, sl, sp.b[0], sp.b[1], sp.b[2], i, j, k);
-                if (ni < 0) continue;
-                float ww = sp.w[0][i] * sp.w[1][j] * sp.w[2][k];
-                atomicAdd(&g.colv[ni], make_float4(ww * fv[0], ww * fv[1], ww * fv[2], ww));
-                atomicAdd(&g.coln[ni], make_float4(ww * nx, ww * ny, ww * nz, 0.0f));
-            }
+    scatter_active_nodes(g, sp, act8, false, [&](int ni, float ww) {
+        atomicAdd(&g.colv[ni], make_float4(ww * fv[0], ww * fv[1], ww * fv[2], ww));
+        atomicAdd(&g.coln[ni], make_float4(ww * nx, ww * ny, ww * nz, 0.0f));
+    });
 }
 __global__ void __launch_bounds__(128) k_collider_scatter(Grid g, ColliderArgs ca) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -654,36 +750,28 @@ __global__ void __launch_bounds__(128) k_collider_scatter(Grid g, ColliderArgs c
 // threads [0,njt) pinned traditional tail, [njt, njt+njv) joint vertices, then joint faces.
 struct MoverArgs {
     int njt, njv, njf, Nt;
-    const float *vt, *vvv, *vf, *EP, *TP, *VP;
+    const float *vt, *vvv, *vf, *TP, *VP;
+    const float4* XE;
     const int *invE, *invT, *invV;
 };
 __device__ __forceinline__ void mover_scatter_one(const Grid& g, const MoverArgs& ma, int t) {
     const int njt = ma.njt, njv = ma.njv, Nt = ma.Nt;
     const float *__restrict__ vt = ma.vt, *__restrict__ vvv = ma.vvv, *__restrict__ vf = ma.vf;
-    const float *__restrict__ EP = ma.EP, *__restrict__ TP = ma.TP, *__restrict__ VP = ma.VP;
+    const float *__restrict__ TP = ma.TP, *__restrict__ VP = ma.VP;
     const int *__restrict__ invE = ma.invE, *__restrict__ invT = ma.invT, *__restrict__ invV = ma.invV;
     const float* xr;
     const float* vel;
     if (t < njt) { xr = TP + (size_t)invT[Nt - njt + t] * KP_F; vel = vt + 3 * t; }
     else if (t < njt + njv) { xr = VP + (size_t)invV[t - njt] * VP_F; vel = vvv + 3 * (t - njt); }
-    else { xr = EP + (size_t)invE[t - njt - njv] * KP_F; vel = vf + 3 * (t - njt - njv); }
+    else { xr = reinterpret_cast<const float*>(ma.XE + invE[t - njt - njv]); vel = vf + 3 * (t - njt - njv); }
     Stencil sp;
     make_stencil(g, xr[0], xr[1], xr[2], sp);
     if (!scatter_ok(g, sp)) return;
-    int sl[8];
-    load_slots8(g, sp.b[0], sp.b[1], sp.b[2], sl);
-    float v0 = vel[0], v1 = vel[1], v2 = vel[2];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                int ni = stencil_node(g, sl, sp.b[0], sp.b[1], sp.b[2], i, j, k);
-                if (ni < 0) { g.flags[1] = 1; continue; }
-                float ww = sp.w[0][i] * sp.w[1][j] * sp.w[2][k];
-                atomicAdd(&g.mov[ni], make_float4(ww * v0, ww * v1, ww * v2, ww));
-            }
+    const unsigned act8 = load_active8(g, sp.b[0], sp.b[1], sp.b[2]);
+    const float v0 = vel[0], v1 = vel[1], v2 = vel[2];
+    scatter_active_nodes(g, sp, act8, true, [&](int ni, float ww) {
+        atomicAdd(&g.mov[ni], make_float4(ww * v0, ww * v1, ww * v2, ww));
+    });
 }
 __global__ void __launch_bounds__(128) k_mover_scatter(Grid g, MoverArgs ma) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -730,7 +818,7 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
             const int nidx = idx + gridDim.x * blockDim.x;
             if (nidx < total) co_next = g.slot_coord[nidx >> 6];
         }
-        const int ni = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023) * BN + l;
+        const int ni = block_node(g, co, l);
         // all four accumulator loads are issued before any use (memory-level parallelism)
         const float4 a = g.acc[ni];
         const float4 mv = g.mov[ni];
@@ -1016,24 +1104,25 @@ __device__ __forceinline__ void g2p_contract_lean(const float4* __restrict__ T, 
 // in flight) into a shared-memory tile, then lane = particle contracts its run's tile with broadcast
 // reads.  Replaces 8 table lookups + 27 dependent gathers per particle.
 constexpr int G2P_RMAX = 8;  // runs per contraction pass (tile capacity)
-constexpr int G2P_TILE_B = 128 + G2P_RMAX * 27 * 16;  // run cells | tiles
+constexpr int G2P_OFF_B = 32 * 9 * 4;                        // nine per-axis node offsets for each of up to 32 runs
+constexpr int G2P_TILE_B = G2P_OFF_B + G2P_RMAX * 27 * 16;  // run offsets | tiles
 struct Gather {
     const Grid& g;
     const Warp& w;
-    int* runcell;
+    int* runoff;  // nine per-axis node offsets of every run (set by the run's leader lane)
     float4* tile;
     Runs R;
     bool valid;
     float f[3];
     int b[3];
     __device__ __forceinline__ Gather(const Grid& g_, const Warp& w_, unsigned char* tile_mem, bool valid_)
-        : g(g_), w(w_), runcell(reinterpret_cast<int*>(tile_mem)), tile(reinterpret_cast<float4*>(tile_mem + 128)), valid(valid_) {}
+        : g(g_), w(w_), runoff(reinterpret_cast<int*>(tile_mem)), tile(reinterpret_cast<float4*>(tile_mem + G2P_OFF_B)), valid(valid_) {}
     // the packed stencil base of every lane's particle is all the staging needs: with the per-particle cell
     // arrays (CV / CE) the node loads are issued before the particle slab has arrived
     __device__ __forceinline__ void begin(int cell) {
         if (!valid) cell = -1 - w.lane;
         R = find_runs(w.lane, w.cnt, cell);
-        if ((R.starts >> w.lane) & 1u) runcell[R.mine] = cell;
+        if ((R.starts >> w.lane) & 1u) stencil_offsets(g, cell, runoff + R.mine * 9);  // the run's leader decodes its cell once
         __syncwarp();
     }
     __device__ __forceinline__ int set_position(float x, float y, float z) {
@@ -1046,24 +1135,21 @@ struct Gather {
         return pack_cell(b[0], b[1], b[2]);
     }
     // lanes 0..26 copy the nodes of runs [r0, r0 + G2P_RMAX) into the tile with cp.async (LDGSTS): global ->
-    // shared without staging registers, every run of the pass in flight at once.  Four runs are addressed per
-    // trip so that their (dependent, integer) index chains interleave; a node outside the grid and the unused
-    // slots of the last trip are zero-filled by a cp.async of source size 0 instead of a branch.
+    // shared without staging registers, every run of the pass in flight at once.  A node's address is the sum of
+    // the three per-axis offsets its run's leader has stored; a stencil that leaves the grid and the unused slots of the
+    // last trip are zero-filled by a cp.async of source size 0 instead of a branch.
     __device__ __forceinline__ void stage_issue(int r0) const {
         const int nrp = min(G2P_RMAX, R.nr - r0);
         if (w.lane < 27) {
-            const int li = w.lane / 9 - 2, lj = (w.lane / 3) % 3 - 2, lk = w.lane % 3 - 2;
+            const LaneNode ln(w.lane);
             float4* dst = tile + w.lane;
             for (int rb = 0; rb < nrp; rb += 4) {
-                int c[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) c[u] = runcell[r0 + min(rb + u, nrp - 1)];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const unsigned ix = (c[u] & 1023) + li, iy = ((c[u] >> 10) & 1023) + lj, iz = ((unsigned)c[u] >> 20) + lk;
-                    const bool ok = max(max(ix, iy), iz) < (unsigned)g.n && rb + u < nrp;
-                    const unsigned ni = ((((ix >> 2) * g.nb + (iy >> 2)) * g.nb + (iz >> 2)) << 6) + (((ix & 3) << 4) | ((iy & 3) << 2) | (iz & 3));
-                    cp_async16_zfill(dst + (rb + u) * 27, g.vout + (ok ? ni : 0u), ok ? 16 : 0);
+                    bool ok;
+                    const int ni = ln.node(runoff + (r0 + min(rb + u, nrp - 1)) * 9, ok);
+                    ok = ok && rb + u < nrp;
+                    cp_async16_zfill(dst + (rb + u) * 27, g.vout + (ok ? ni : 0), ok ? 16 : 0);
                 }
             }
         }
@@ -1147,27 +1233,33 @@ constexpr int G2P_MINB = 16 / G2P_NW;  // unrolled contraction (traditional part
 #define MPM_G2P_E_WARPS 20
 #endif
 constexpr int G2P_V_MINB = MPM_G2P_V_WARPS / G2P_NW, G2P_E_MINB = MPM_G2P_E_WARPS / G2P_NW;  // lean contractions
+// The gather-side kernels run in the order  grid update -> vertex G2P -> [traditional G2P] -> element G2P.
+// Only the FIRST of them waits for the grid update (wait_first); a follower starts when every CTA of its predecessor
+// has passed that wait (PDL invariant 2), so the grid velocities are final for it too: it works while its predecessor
+// drains, lets its successor in when its own gather is done, and waits before it exits (invariant 1) -- the element
+// kernel earlier: in front of its corner reads, which need the moved vertices.
 // g2p_v for cloth vertices (mpm_utils.py:716-786); also clears the vertex_force accumulator of the next substep
 // and allocates grid blocks for the new position.
 constexpr int G2P_V_WB = VP_F * 32 * 4 + G2P_TILE_B;
 __global__ void __launch_bounds__(32 * G2P_NW, G2P_V_MINB) k_g2p_vertices(Grid g, int Nv, float* __restrict__ VP, float4* __restrict__ VFnext,
-                                                               int* __restrict__ CV, float dt, Advance adv) {
+                                                               int* __restrict__ CV, float dt, int wait_first, Advance adv) {
     extern __shared__ __align__(128) unsigned char smem[];
-    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); advance_step(adv.st, dt, adv.bcs, adv.n_bc); }
     Warp w;
     if (!warp_begin<G2P_NW, G2P_V_WB>(w, Nv, smem)) return;
     ts_begin(g, TS_G2P_V);
     PHASE_BEGIN();
     float* sP = reinterpret_cast<float*>(w.buf);
     // VP and CV were last written by the previous substep's G2P: the slab load and the run search overlap the
-    // tail of the grid update; only the node velocities need the predecessor
+    // tail of the grid update; only the node velocities need it
     slab_issue(w, {Slab{sP, VP, VP_F}});
     const bool valid = w.lane < w.cnt;
     const int p = w.p0 + w.lane;
     Gather G(g, w, w.buf + VP_F * 32 * 4, valid);
     G.begin(valid ? CV[p] : 0);
-    pdl_wait();
-    pdl_trigger();
+    if (wait_first) {
+        pdl_wait();
+        pdl_trigger();
+    }
     G.stage_issue(0);  // node loads are in flight before the slab lands
     PHASE(g, 3, 1);
     slab_wait(w);
@@ -1184,6 +1276,7 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_V_MINB) k_g2p_vertices(Grid g
         G.remaining_passes_lean<0>(no_d3, o);
     }
     PHASE(g, 3, 3);
+    if (!wait_first) pdl_trigger();
     if (valid) {
         const float dxc = 1.0f / g.inv_dx, a_min = dxc * 2.0f, a_max = g.lim - dxc * 2.0f;
         xm.x = clampf(xm.x + dt * o.v[0], a_min, a_max);
@@ -1207,21 +1300,24 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_V_MINB) k_g2p_vertices(Grid g
     PHASE(g, 3, 5);
     PHASE_END(g, 3);
     ts_end(g, TS_G2P_V);
+    if (!wait_first) pdl_wait();
+    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);  // every predecessor has completed
 }
 
 // g2p_v for traditional particles: additionally F_trial = (I + dt grad v) F (mpm_utils.py:783-786)
 constexpr int G2P_T_WB = (KP_F + TF_F) * 32 * 4 + G2P_TILE_B;
 __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_traditional(Grid g, int Nt, float* __restrict__ TP, float* __restrict__ TF,
-                                                                  float dt, Advance adv) {
+                                                                  float dt, int wait_first, Advance adv) {
     extern __shared__ __align__(128) unsigned char smem[];
-    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); advance_step(adv.st, dt, adv.bcs, adv.n_bc); }
     Warp w;
     if (!warp_begin<G2P_NW, G2P_T_WB>(w, Nt, smem)) return;
     ts_begin(g, TS_G2P_T);
     float* sP = reinterpret_cast<float*>(w.buf);
     float* sT = sP + 32 * KP_F;
-    pdl_wait();
-    pdl_trigger();
+    if (wait_first) {
+        pdl_wait();
+        pdl_trigger();
+    }
     slab_load(w, {Slab{sP, TP, KP_F}, Slab{sT, TF, TF_F}});
     const bool valid = w.lane < w.cnt;
     float* r = sP + w.lane * KP_F;
@@ -1233,6 +1329,7 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_traditional(Grid 
     G.stage_wait();
     G.contract(0, o);
     G.remaining_passes(o);
+    if (!wait_first) pdl_trigger();
     if (valid) {
         float* t = sT + w.lane * TF_F;
         const float dxc = 1.0f / g.inv_dx, a_min = dxc * 2.0f, a_max = g.lim - dxc * 2.0f;
@@ -1254,100 +1351,82 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_MINB) k_g2p_traditional(Grid 
     }
     slab_store(w, {Slab{sP, TP, KP_F}, Slab{sT, TF, TF_F}});
     ts_end(g, TS_G2P_T);
+    if (!wait_first) pdl_wait();
+    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);
 }
 
 // g2p_e (mpm_utils.py:788-857): C and grad v at the OLD centroid, x/v = mean of the three
-// already-updated corner vertices, d = [x2-x1, x3-x1, (I + dt grad v) d3].  Reads the return-mapped d3
-// of direction buffer `cur`, writes d1,d2,d3 of buffer `cur^1` (see mpm_device.cuh).
-constexpr int G2P_E_WB = (KP_F + E12_F) * 32 * 4 + G2P_TILE_B;
-__global__ void __launch_bounds__(32 * G2P_NW, G2P_E_MINB) k_g2p_elements(Grid g, int Ne, float* __restrict__ EP, const int* __restrict__ EF,
-                                                               const float4* __restrict__ D3in, float* __restrict__ E12out,
-                                                               float4* __restrict__ D3out, int* __restrict__ CE,
-                                                               const float* __restrict__ VP, float dt, Advance adv) {
+// already-updated corner vertices, d = [x2-x1, x3-x1, (I + dt grad v) d3].  All element state moves as coalesced
+// float4 streams; the only shared memory is the node tile of the gather.  Reads the return-mapped d3 of direction
+// buffer `cur`, writes buffer `cur^1`.  A follower of the vertex G2P: gather + contraction need the grid update only,
+// griddepcontrol.wait sits in front of the corner reads.
+struct ElemG2P {
+    const int4* EFM;
+    float4 *XE, *EV, *ED1, *ED2, *C0, *C1;
+    const float4* D3in;
+    float4* D3out;
+    int* CE;
+    const float* VP;
+};
+constexpr int G2P_E_WB = G2P_TILE_B;
+__global__ void __launch_bounds__(32 * G2P_NW, G2P_E_MINB) k_g2p_elements(Grid g, int Ne, ElemG2P A, float dt, Advance adv) {
     extern __shared__ __align__(128) unsigned char smem[];
-    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); advance_step(adv.st, dt, adv.bcs, adv.n_bc); }
     Warp w;
     if (!warp_begin<G2P_NW, G2P_E_WB>(w, Ne, smem)) return;
     ts_begin(g, TS_G2P_E);
-    float* sP = reinterpret_cast<float*>(w.buf);
-    float* s12 = sP + 32 * KP_F;
     PHASE_BEGIN();
-    // Everything up to the corner reads is independent of the predecessor (the vertex G2P): EP / CE / EF / D3 were
-    // last written by earlier kernels and the grid velocities by the grid update, whose completion every CTA
-    // of the predecessor has waited for before this grid could start.  So the gather and the contraction
-    // of this kernel fill the predecessor's tail; griddepcontrol.wait sits in front of the corner reads.
-    slab_issue(w, {Slab{sP, EP, KP_F}});
     const bool valid = w.lane < w.cnt;
-    float* r = sP + w.lane * KP_F;
     const int p = w.p0 + w.lane;
-    int cell = 0;
-    {   // corner slots and d3 are not needed before the contraction is done: park them in the (still unused)
-        // E12 staging area of this lane to keep them out of the register-hungry contraction
-        int f0 = 0, f1 = 0, f2 = 0;
-        float4 d3v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-            cell = CE[p];
-            f0 = EF[(size_t)p * EF_F]; f1 = EF[(size_t)p * EF_F + 1]; f2 = EF[(size_t)p * EF_F + 2];
-            d3v = D3in[p];
-        }
-        float4* park = reinterpret_cast<float4*>(s12 + w.lane * E12_F);  // 24 bytes per lane, 8-byte aligned
-        reinterpret_cast<int2*>(park)[0] = make_int2(f0, f1);
-        reinterpret_cast<float2*>(park)[1] = make_float2(__int_as_float(f2), d3v.x);
-        reinterpret_cast<float2*>(park)[2] = make_float2(d3v.y, d3v.z);
-    }
-    Gather G(g, w, w.buf + (KP_F + E12_F) * 32 * 4, valid);
+    const int cell = valid ? A.CE[p] : 0;
+    const float4 xe = A.XE[p], d3v4 = A.D3in[p];
+#ifdef MPM_G2P_E_EFM_EARLY
+    const int4 efm = __ldg(&A.EFM[p]);
+#endif
+    Gather G(g, w, w.buf, valid);
     G.begin(cell);
     G.stage_issue(0);
     PHASE(g, 5, 1);
-    slab_wait(w);
-    PHASE(g, 5, 0);
-    G.set_position(valid ? r[0] : 0.f, valid ? r[1] : 0.f, valid ? r[2] : 0.f);
+    G.set_position(valid ? xe.x : 0.f, valid ? xe.y : 0.f, valid ? xe.z : 0.f);
     G.stage_wait();
     PHASE(g, 5, 2);
     {
         Gathered o;
-        const float2* park = reinterpret_cast<const float2*>(s12 + w.lane * E12_F);
-        const float2 pk1 = park[1], pk2 = park[2];
-        const float d3v[3] = {pk1.y, pk2.x, pk2.y};
+        const float d3v[3] = {d3v4.x, d3v4.y, d3v4.z};
         G.contract_lean<1>(0, d3v, o);
         G.remaining_passes_lean<1>(d3v, o);
         if (valid) {
-#pragma unroll
-            for (int i = 0; i < 9; i++) r[P_C + i] = o.C[i];
-            // d3 <- (I + dt grad v) d3 (mpm_utils.py:850-855), with (grad v) d3 accumulated directly
-            D3out[p] = make_float4(fmaf(dt, o.G[0], d3v[0]), fmaf(dt, o.G[1], d3v[1]), fmaf(dt, o.G[2], d3v[2]), 0.f);
+            A.C0[p] = make_float4(o.C[0], o.C[1], o.C[2], o.C[3]);
+            A.C1[p] = make_float4(o.C[4], o.C[5], o.C[6], o.C[7]);
+            // d3 <- (I + dt grad v) d3 (mpm_utils.py:850-855), with (grad v) d3 accumulated directly; C[8] rides along
+            A.D3out[p] = make_float4(fmaf(dt, o.G[0], d3v[0]), fmaf(dt, o.G[1], d3v[1]), fmaf(dt, o.G[2], d3v[2]), o.C[8]);
         }
     }
     PHASE(g, 5, 4);  // contraction
+#ifndef MPM_G2P_E_EFM_EARLY
+    const int4 efm = __ldg(&A.EFM[p]);
+#endif
     pdl_wait();      // the corner vertices must have been moved by the vertex G2P
     pdl_trigger();
     if (valid) {
-        const int2 pk0 = reinterpret_cast<const int2*>(s12 + w.lane * E12_F)[0];
-        const int f0 = pk0.x, f1 = pk0.y, f2 = __float_as_int(reinterpret_cast<const float2*>(s12 + w.lane * E12_F)[1].x);
-        const float4* c0 = reinterpret_cast<const float4*>(VP + (size_t)f0 * VP_F);
-        const float4* c1 = reinterpret_cast<const float4*>(VP + (size_t)f1 * VP_F);
-        const float4* c2 = reinterpret_cast<const float4*>(VP + (size_t)f2 * VP_F);
-        const float4 x1 = c0[0], v1 = c0[1], x2 = c1[0], v2 = c1[1], x3 = c2[0], v3 = c2[1];
+        const float4* q0 = reinterpret_cast<const float4*>(A.VP + (size_t)efm.x * VP_F);
+        const float4* q1 = reinterpret_cast<const float4*>(A.VP + (size_t)efm.y * VP_F);
+        const float4* q2 = reinterpret_cast<const float4*>(A.VP + (size_t)efm.z * VP_F);
+        const float4 x1 = q0[0], v1 = q0[1], x2 = q1[0], v2 = q1[1], x3 = q2[0], v3 = q2[1];
         const float nx = (x1.x + x2.x + x3.x) / 3.0f, ny = (x1.y + x2.y + x3.y) / 3.0f, nz = (x1.z + x2.z + x3.z) / 3.0f;
-        r[0] = nx; r[1] = ny; r[2] = nz;
-        r[P_V] = (v1.x + v2.x + v3.x) / 3.0f;
-        r[P_V + 1] = (v1.y + v2.y + v3.y) / 3.0f;
-        r[P_V + 2] = (v1.z + v2.z + v3.z) / 3.0f;
-        float2* e2 = reinterpret_cast<float2*>(s12 + w.lane * E12_F);
-        e2[0] = make_float2(x2.x - x1.x, x2.y - x1.y);
-        e2[1] = make_float2(x2.z - x1.z, x3.x - x1.x);
-        e2[2] = make_float2(x3.y - x1.y, x3.z - x1.z);
+        A.XE[p] = make_float4(nx, ny, nz, 0.f);
+        A.EV[p] = make_float4((v1.x + v2.x + v3.x) / 3.0f, (v1.y + v2.y + v3.y) / 3.0f, (v1.z + v2.z + v3.z) / 3.0f, 0.f);
+        A.ED1[p] = make_float4(x2.x - x1.x, x2.y - x1.y, x2.z - x1.z, 0.f);
+        A.ED2[p] = make_float4(x3.x - x1.x, x3.y - x1.y, x3.z - x1.z, 0.f);
         const int nb0 = base_of(nx, g.inv_dx), nb1 = base_of(ny, g.inv_dx), nb2 = base_of(nz, g.inv_dx);
         if (nb0 != G.b[0] || nb1 != G.b[1] || nb2 != G.b[2]) {
             ensure_stencil_blocks(g, nx, ny, nz);
-            CE[p] = pack_cell(nb0, nb1, nb2);
+            A.CE[p] = pack_cell(nb0, nb1, nb2);
         }
     }
     PHASE(g, 5, 3);  // corner reads
-    slab_store(w, {Slab{sP, EP, KP_F}, Slab{s12, E12out, E12_F}});
-    PHASE(g, 5, 5);  // epilogue + store
     PHASE_END(g, 5);
     ts_end(g, TS_G2P_E);
+    if (adv.st && blockIdx.x == 0 && threadIdx.x == 0) advance_step(adv.st, dt, adv.bcs, adv.n_bc);  // every predecessor has completed
 }
 
 }  // namespace mpm
