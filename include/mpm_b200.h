@@ -168,10 +168,18 @@ int mpm_step_sharded(MpmSolver *s, float dt, int nsub, const MpmFrameInputs *in,
  * compacted in ascending order); only buffer growth synchronises.  mpm_shared_info synchronises. */
 int mpm_comm_unique_id(char *out128);
 int mpm_attach_comm(MpmSolver *s, const char *id128, int rank, int nranks);
+/* The same stepping over a transport the CALLER owns instead of NCCL: `allgather` must gather `nbytes` host bytes from
+ * every rank into recv[nranks * nbytes] in rank order and block until done (torch.distributed / gloo, MPI, ...).  Only
+ * the set-up traffic uses it -- the CUDA-IPC handles of the receive areas and the block marks of a shared-list rebuild;
+ * the per-substep exchange stays the peer-to-peer push / pull kernels (mode 2), also between ranks that share one GPU
+ * (which NCCL refuses), so the kernels can be verified on a single-GPU box.  Where no peer mapping is possible the exchange
+ * falls back to pack -> host all-gather -> rank-ordered sum -> unpack (mode 3; synchronises every substep). */
+typedef int (*MpmHostAllGatherFn)(void *ctx, const void *send, void *recv, int nbytes);
+int mpm_attach_host_comm(MpmSolver *s, int rank, int nranks, MpmHostAllGatherFn allgather, void *ctx);
 int mpm_step_sharded_nccl(MpmSolver *s, float dt, int nsub, const MpmFrameInputs *in, int refresh, int margin, void *stream);
 int mpm_shared_info(MpmSolver *s, int *n_shared, int *cap_blocks, int *n_rebuilds, void *stream);
 /* how the shared blocks travel: 0 caller's collective (callbacks), 1 ncclAllReduce inside the captured windows,
- * 2 peer-to-peer: with <= 8 ranks on one NVLink domain every rank maps every peer's receive area (CUDA IPC) and the
+ * 3 all-reduce through the caller's host all-gather, 2 peer-to-peer: with <= 8 ranks on one NVLink domain every rank maps every peer's receive area (CUDA IPC) and the
  * push / pull kernels move the parts directly (MPM_B200_P2P=0 forces 1) */
 int mpm_shared_mode(MpmSolver *s);
 int mpm_step_gather(MpmSolver *s, float dt, void *stream);

@@ -48,6 +48,7 @@ class MpmProfile(C.Structure):
 
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)
 REBUILD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+HOST_ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int)
 
 # every symbol include/mpm_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
@@ -74,6 +75,7 @@ SYMBOLS = {
     "mpm_step_sharded": (C.c_int, [_P, C.c_float, C.c_int, C.POINTER(MpmFrameInputs), _P, C.c_int, EXCHANGE_FN, REBUILD_FN, _P, _P]),
     "mpm_comm_unique_id": (C.c_int, [_P]),
     "mpm_attach_comm": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "mpm_attach_host_comm": (C.c_int, [_P, C.c_int, C.c_int, HOST_ALLGATHER_FN, _P]),
     "mpm_step_sharded_nccl": (C.c_int, [_P, C.c_float, C.c_int, C.POINTER(MpmFrameInputs), C.c_int, C.c_int, _P]),
     "mpm_shared_mode": (C.c_int, [_P]),
     "mpm_shared_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),

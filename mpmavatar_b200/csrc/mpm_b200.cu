@@ -500,6 +500,9 @@ struct MpmSolver {
     int n_shared = 0, shared_cap = 0, shared_age = -1;
     int* d_n_shared = nullptr;     // device copy of n_shared (read by the captured pack / unpack launches)
     ncclComm_t comm = nullptr;     // mpm_attach_comm: this solver's own communicator
+    MpmHostAllGatherFn host_ag = nullptr;  // mpm_attach_host_comm: the caller's blocking host all-gather (gloo, MPI, ...)
+    void* host_ctx = nullptr;
+    std::vector<unsigned char> host_stage;
     int comm_rank = 0, comm_size = 1;
     float* xbuf = nullptr;         // exchange buffer of the in-graph path, xcap_blocks * 512 floats
     int xcap_blocks = 0;
@@ -1348,6 +1351,50 @@ std::vector<ShardGraph>& shard_graphs(MpmSolver* s) {
     if (!s->shard_graphs) s->shard_graphs = new std::vector<ShardGraph>();
     return *static_cast<std::vector<ShardGraph>*>(s->shard_graphs);
 }
+// ---- the few collectives the sharded path needs, over either transport: the solver's own NCCL communicator
+// (mpm_attach_comm), or a blocking HOST all-gather supplied by the caller (mpm_attach_host_comm: gloo / MPI ranks, also
+// ranks that share one GPU, which NCCL refuses).  The host transport synchronises the stream.
+bool have_comm(const MpmSolver* s) { return s->comm != nullptr || s->host_ag != nullptr; }
+void host_allgather(MpmSolver* s, const void* send, void* recv, size_t nbytes) {
+    if (s->host_ag(s->host_ctx, send, recv, (int)nbytes) != 0) throw std::string("host all-gather callback failed");
+}
+// every rank's `nbytes` host bytes, in rank order
+void allgather_host_bytes(MpmSolver* s, const void* send, void* recv, size_t nbytes, cudaStream_t q) {
+    if (s->host_ag) { host_allgather(s, send, recv, nbytes); return; }
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) =
+        (decltype(AllGather))dlsym(nccl_api()->lib, "ncclAllGather");
+    if (!AllGather) throw std::string("libnccl.so.2 lacks ncclAllGather");
+    unsigned char* d = s->dalloc<unsigned char>((size_t)(s->comm_size + 1) * nbytes);
+    CK(cudaMemcpyAsync(d + (size_t)s->comm_size * nbytes, send, nbytes, cudaMemcpyHostToDevice, q));
+    NCK(AllGather(d + (size_t)s->comm_size * nbytes, d, nbytes, ncclUint8, s->comm, q));
+    CK(cudaMemcpyAsync(recv, d, (size_t)s->comm_size * nbytes, cudaMemcpyDeviceToHost, q));
+    CK(cudaStreamSynchronize(q));
+}
+// in-place sum over the ranks of a DEVICE buffer: bytes (the block marks) or floats (the packed shared blocks; the host
+// transport adds the ranks' parts in rank order, so every rank gets bit-identical sums)
+template <typename T>
+void allreduce_sum_device(MpmSolver* s, T* d, size_t n, cudaStream_t q) {
+    if (s->comm) {
+        NCK(nccl_api()->AllReduce(d, d, n, sizeof(T) == 1 ? ncclUint8 : ncclFloat, ncclSum, s->comm, q));
+        return;
+    }
+    const size_t bytes = n * sizeof(T);
+    s->host_stage.resize((size_t)(s->comm_size + 1) * bytes);
+    unsigned char* mine = s->host_stage.data() + (size_t)s->comm_size * bytes;
+    CK(cudaMemcpyAsync(mine, d, bytes, cudaMemcpyDeviceToHost, q));
+    CK(cudaStreamSynchronize(q));
+    host_allgather(s, mine, s->host_stage.data(), bytes);
+    T* acc = reinterpret_cast<T*>(mine);
+    const T* all = reinterpret_cast<const T*>(s->host_stage.data());
+    for (size_t i = 0; i < n; i++) {
+        T v = all[i];
+        for (int r = 1; r < s->comm_size; r++) v = (T)(v + all[(size_t)r * n + i]);
+        acc[i] = v;
+    }
+    CK(cudaMemcpyAsync(d, mine, bytes, cudaMemcpyHostToDevice, q));
+    CK(cudaStreamSynchronize(q));
+}
+
 // one sharded substep on stream q: scatter half, pack, all-reduce, unpack, gather half
 void sharded_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
     launch_substep(s, a, q, HALF_SCATTER);
@@ -1360,7 +1407,7 @@ void sharded_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
         s->launches += 2;
     } else {
         k_shared_pack2<<<ctas, 256, 0, q>>>(s->g, L, (float4*)s->xbuf);
-        NCK(nccl_api()->AllReduce(s->xbuf, s->xbuf, (size_t)(s->xcap_blocks + s->xcapM) * BN * 4, ncclFloat, ncclSum, s->comm, q));
+        allreduce_sum_device(s, s->xbuf, (size_t)(s->xcap_blocks + s->xcapM) * BN * 4, q);
         k_shared_unpack2<<<ctas, 256, 0, q>>>(s->g, L, (const float4*)s->xbuf);
         s->launches += 3;
     }
@@ -1378,7 +1425,7 @@ static void mark_potential(MpmSolver* s, int margin, cudaStream_t q) {
     }
     unsigned char* mj = s->d_mark + nt;
     CK(cudaMemsetAsync(s->d_mark, 0, 2 * nt, q));
-    const int bit = (s->comm && s->comm_size <= 8) ? (1 << s->comm_rank) : 1;  // rank set for <= 8 ranks, else a count
+    const int bit = (have_comm(s) && s->comm_size <= 8) ? (1 << s->comm_rank) : 1;  // rank set for <= 8 ranks, else a count
     if (s->Ne) k_mark_potential<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, (const float*)s->R.XE, 4, margin, s->d_mark, mj, s->R.permE, s->cfg.num_joint_f, bit);
     if (s->Nt) k_mark_potential<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F, margin, s->d_mark, nullptr, nullptr, 0, bit);
     if (s->Nv) k_mark_potential<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, margin, s->d_mark, mj, s->R.permV, s->cfg.num_joint_v, bit);
@@ -1395,10 +1442,7 @@ static void close_peer_areas(MpmSolver* s) {
 }
 static void setup_peer_areas(MpmSolver* s, cudaStream_t q) {
     const int n = s->comm_size;
-    if (!s->use_p2p || !s->comm || n < 2 || n > 8) return;
-    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) =
-        (decltype(AllGather))dlsym(nccl_api()->lib, "ncclAllGather");
-    if (!AllGather) return;
+    if (!s->use_p2p || !have_comm(s) || n < 2 || n > 8) return;
     CK(cudaStreamSynchronize(q));
     // every rank has finished every exchange that used the old areas (it is inside this collective).  Imported
     // mappings are closed first; the old local area is freed only after the all-gather below, i.e. after every peer
@@ -1416,12 +1460,9 @@ static void setup_peer_areas(MpmSolver* s, cudaStream_t q) {
     mine.ok = cudaMalloc(&s->peer_local, total) == cudaSuccess && cudaMemset(s->peer_local, 0, total) == cudaSuccess &&
               cudaDeviceSynchronize() == cudaSuccess && cudaIpcGetMemHandle(&mine.h, s->peer_local) == cudaSuccess;
     cudaGetLastError();
-    Msg* d_msgs = s->dalloc<Msg>(n + 1);
-    CK(cudaMemcpyAsync(d_msgs + n, &mine, sizeof(Msg), cudaMemcpyHostToDevice, q));
-    NCK(AllGather(d_msgs + n, d_msgs, sizeof(Msg), ncclUint8, s->comm, q));
+    // the handles travel over whichever transport the solver has (NCCL all-gather or the caller's host all-gather)
     std::vector<Msg> all(n);
-    CK(cudaMemcpyAsync(all.data(), d_msgs, n * sizeof(Msg), cudaMemcpyDeviceToHost, q));
-    CK(cudaStreamSynchronize(q));
+    allgather_host_bytes(s, &mine, all.data(), sizeof(Msg), q);
     if (old_local) cudaFree(old_local);
     bool ok = true;
     for (int r = 0; r < n; r++) ok = ok && all[r].ok;
@@ -1433,13 +1474,11 @@ static void setup_peer_areas(MpmSolver* s, cudaStream_t q) {
         s->peer_open[r] = ptr;
         P.base[r] = (unsigned char*)ptr;
     }
-    // agree on the outcome: one rank failing to map a peer must switch every rank to the NCCL exchange
-    int* d_ok = s->dalloc<int>(1);
+    // agree on the outcome: one rank failing to map a peer must switch every rank to the all-reduce exchange
     int h_ok = ok ? 1 : 0;
-    CK(cudaMemcpyAsync(d_ok, &h_ok, sizeof(int), cudaMemcpyHostToDevice, q));
-    NCK(nccl_api()->AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, s->comm, q));
-    CK(cudaMemcpyAsync(&h_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, q));
-    CK(cudaStreamSynchronize(q));
+    std::vector<int> oks(n);
+    allgather_host_bytes(s, &h_ok, oks.data(), sizeof(int), q);
+    for (int r = 0; r < n; r++) h_ok = std::min(h_ok, oks[r]);
     if (!h_ok) { close_peer_areas(s); return; }
     P.slot_bytes = slot;
     P.flags_off = flags_off;
@@ -1468,7 +1507,7 @@ static void rebuild_shared_on_device(MpmSolver* s, int margin, cudaStream_t q) {
     // the lists (as of the previous rebuild) near their capacities: re-size from the actual counts below
     bool resize = first || s->h_nshared[0] * 10 > s->xcap_blocks * 9 || s->h_nshared[1] * 10 > s->xcapM * 9;
     mark_potential(s, margin, q);
-    NCK(nccl_api()->AllReduce(s->d_mark, s->d_mark, 2 * nt, ncclUint8, ncclSum, s->comm, q));
+    allreduce_sum_device(s, s->d_mark, 2 * nt, q);  // a sum of distinct rank bits is the member set
     const int bits = s->comm_size <= 8 ? 1 : 0;
     size_t tmp = s->sel_bytes;
     CK(cub::DeviceSelect::If(s->sel_tmp, tmp, it, s->d_sel, s->d_n_shared, (int)nt, SharedPred{s->d_mark, nullptr, bits}, q));
@@ -1547,10 +1586,21 @@ int mpm_attach_comm(MpmSolver* s, const char* id128, int rank, int nranks) {
     API_END(s)
 }
 
+int mpm_attach_host_comm(MpmSolver* s, int rank, int nranks, MpmHostAllGatherFn allgather, void* ctx) {
+    API_BEGIN(s)
+    if (!allgather || nranks < 1 || rank < 0 || rank >= nranks) throw std::string("mpm_attach_host_comm: bad arguments");
+    if (s->comm) { nccl_api()->CommDestroy(s->comm); s->comm = nullptr; }
+    s->host_ag = allgather;
+    s->host_ctx = ctx;
+    s->comm_rank = rank;
+    s->comm_size = nranks;
+    API_END(s)
+}
+
 int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs* in, int refresh, int margin, void* stream) {
     API_BEGIN(s)
     cudaStream_t q = (cudaStream_t)stream;
-    if (!s->comm) throw std::string("mpm_step_sharded_nccl before mpm_attach_comm");
+    if (!have_comm(s)) throw std::string("mpm_step_sharded_nccl before mpm_attach_comm / mpm_attach_host_comm");
     MpmFrameInputs none{};
     if (!in) in = &none;
     SubstepArgs a{};
@@ -1577,7 +1627,7 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
         }
         const int room = std::min({left, refresh - s->shared_age, s->resort_interval - s->since_sort});
         int done = 1;
-        if (s->use_graphs && room >= W) {
+        if (s->use_graphs && room >= W && (s->comm || s->p2p_ready)) {  // a host-transport all-reduce cannot be captured
             ShardGraphKey key{};
             key.dt = a.dt; key.collider = a.collider; key.mover = a.mover; key.advance_mesh = a.advance_mesh; key.cur = s->cur;
             key.n_bc = (int)s->h_bcs.size(); key.n_ops = (int)s->h_ops.size(); key.xcap = s->xcap_blocks * 65536 + s->xcapM; key.len = W + (s->p2p_ready ? 1000 : 0);
@@ -1619,7 +1669,7 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
     API_END(s)
 }
 
-int mpm_shared_mode(MpmSolver* s) { return !s ? -1 : (s->p2p_ready ? 2 : (s->comm ? 1 : 0)); }
+int mpm_shared_mode(MpmSolver* s) { return !s ? -1 : (s->p2p_ready ? 2 : (s->comm ? 1 : (s->host_ag ? 3 : 0))); }
 
 int mpm_shared_info(MpmSolver* s, int* n_shared, int* cap_blocks, int* n_rebuilds, void* stream) {
     API_BEGIN(s)

@@ -33,10 +33,14 @@ class ShardedMPM:
         self.n_shared = 0
         self.k = 0  # substeps since the last shared-list rebuild
         self.stats = {"rebuilds": 0, "shared_blocks": 0, "exchange_bytes": 0}
-        # NCCL backend: the solver gets its own communicator and replays captured windows (kernels + the
-        # all-reduce in one CUDA graph); gloo (CPU rendezvous, ranks sharing a GPU) keeps the callback path
-        self.in_graph = dist.get_backend(group) == "nccl" and os.environ.get("MPM_B200_SHARD_GRAPH", "1") != "0"
-        if self.in_graph:
+        # The substep loop runs inside the library (mpm_step_sharded_nccl: captured windows, the shared blocks move with
+        # the peer-to-peer push / pull kernels).  NCCL backend: the solver gets its own communicator (the unique id travels
+        # through torch.distributed).  Any other backend (gloo: CPU rendezvous, also two ranks SHARING one GPU, which NCCL
+        # refuses): the library's set-up traffic goes through a host all-gather callback on this group.
+        # MPM_B200_SHARD_GRAPH=0 keeps the older per-substep callback path (mpm_step_sharded).
+        nccl = dist.get_backend(group) == "nccl"
+        self.in_graph = os.environ.get("MPM_B200_SHARD_GRAPH", "1") != "0"
+        if self.in_graph and nccl:
             uid = torch.zeros(128, dtype=torch.uint8)
             if self.rank == 0:
                 raw = (C.c_char * 128)()
@@ -47,6 +51,22 @@ class ShardedMPM:
             dist.broadcast(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
             self._uid = bytes(uid.cpu().numpy().tobytes())
             self._ck(self.lib.mpm_attach_comm(self.h, self._uid, self.rank, self.world))
+        elif self.in_graph:
+            self._cb_err = []
+
+            def host_allgather(ctx, send, recv, nbytes):
+                try:
+                    mine = torch.frombuffer((C.c_ubyte * nbytes).from_address(send), dtype=torch.uint8).clone()
+                    out = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(self.world)]
+                    dist.all_gather(out, mine, group=self.group)
+                    dst = torch.frombuffer((C.c_ubyte * (nbytes * self.world)).from_address(recv), dtype=torch.uint8)
+                    dst.copy_(torch.cat(out))
+                    return 0
+                except Exception as e:  # noqa: BLE001 -- must not unwind through C
+                    self._cb_err.append(e)
+                    return 1
+            self._host_ag = _lib.HOST_ALLGATHER_FN(host_allgather)  # keep the trampoline alive
+            self._ck(self.lib.mpm_attach_host_comm(self.h, self.rank, self.world, self._host_ag, None))
 
     # collectives: NCCL works on device tensors; with gloo (CPU tests, or two ranks sharing one GPU) they are
     # staged through host memory
@@ -150,8 +170,8 @@ class ShardedMPM:
         else:
             rc = self.lib.mpm_step_sharded(self.h, C.c_float(dt), int(nsub), C.byref(fin), C.c_void_p(self.buf.data_ptr()),
                                            self.refresh, ex, rb, None, self._stream())
-        if err:
-            raise err[0]
+        if err or getattr(self, "_cb_err", None):
+            raise (err or self._cb_err)[0]
         self._ck(rc)
         if self.in_graph:
             self.refresh_stats()
@@ -164,7 +184,8 @@ class ShardedMPM:
         n, cap, rb = C.c_int(0), C.c_int(0), C.c_int(0)
         self._ck(self.lib.mpm_shared_info(self.h, C.byref(n), C.byref(cap), C.byref(rb), self._stream()))
         self.n_shared = n.value
-        mode = {0: "callback", 1: "nccl all-reduce in graph", 2: "peer-to-peer push/pull in graph"}.get(self.lib.mpm_shared_mode(self.h), "?")
+        mode = {0: "callback", 1: "nccl all-reduce in graph", 2: "peer-to-peer push/pull in graph",
+                3: "host all-gather per substep"}.get(self.lib.mpm_shared_mode(self.h), "?")
         self.stats.update(rebuilds=rb.value, shared_blocks=n.value, exchange_bytes=cap.value * 64 * 8 * 4, exchange=mode)
 
     def gather_positions(self):
