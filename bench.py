@@ -37,6 +37,7 @@ SUBSTEPS_PER_STEP = 400
 # profiles/r1_v17_ncu_full_summary.txt): 55.29 + 17.86 + 16.12 + 49.81 MB for k_p2g<0>, k_p2g<2>, k_g2p_vertices,
 # k_g2p_elements (the vertex records carry 16 bytes of padding, see VP_F)
 TRAFFIC_NCU = 139.08e6
+TRAFFIC_SOURCE = "constant: ncu --set full capture of one substep's P2G/G2P launches, cold caches (profiles/), not measured in this run"
 METRIC = "mpm_substeps_per_sec_500k_particles_256grid"
 
 
@@ -101,6 +102,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(sc, parallelism):
+    """The `config` object of both arms (ours and --impl reference): the same workload, so the driver's same_config holds.
+    The reference arm times a bounded SAMPLE of it (cpu_baseline.sample says which)."""
+    return {"workload": f"C3: {sc.n_particles} cloth particles ({sc.n_elements} elements + {sc.n_vertices} "
+                        f"vertices), {sc.n_grid}^3 grid, capsule body collider ({sc.body_verts.shape[0]} verts / "
+                        f"{sc.body_faces.shape[0]} faces) + {sc.num_joint_v} joint vertices/faces, dt=1e-4",
+            "substeps_per_step": SUBSTEPS_PER_STEP, "l2": "256 MiB L2 flush between timed steps",
+            "parallelism": parallelism}
+
+
 def algorithmic_bytes(sc, A):
     """304*Ne + 248*Nt + 148*Nv + 28*A bytes per substep for P2G+G2P."""
     return 304 * sc.n_elements + 248 * sc.n_traditional + 148 * sc.n_vertices + 28 * A
@@ -136,12 +147,10 @@ def run_reference(args, rank, world):
     val = args.steps * sample / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "substeps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3: 499968 cloth particles (332928 elements + 167040 vertices), 256^3 grid, "
-                                   "capsule body collider (10466 verts / 20928 faces) + 1152 joint vertices/faces, "
-                                   "dt=1e-4", "substeps_per_step": sample, "dense_grid": True},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(sc, "1 GPU"),
             "cpu_baseline": {"value": val, "unit": "substeps/s", "cores": threads, "kind": "port",
-                             "sample": f"{sample} substeps per step x {args.steps} steps of the C3 workload, "
+                             "sample": f"{sample} substeps (of the workload's {SUBSTEPS_PER_STEP}) per step x {args.steps} steps of the C3 workload, "
                                        f"dense 256^3 grid, OpenMP {threads} threads (reference Warp runtime is not "
                                        f"installable offline; oracle/ is its line-faithful C port)"},
             "e2e": {"value": val, "unit": "substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -188,6 +197,25 @@ def run_sharded(args, sc, rank, local_rank, world, dev, barrier):
             f = {k: v.to(dev, non_blocking=True) for k, v in f.items()}
         sm.step(sc.dt, S_PER, f["mesh_x"], f["mesh_v"], f["joint_verts_v"], f["joint_faces_v"])
 
+    # parity of the sharded path against the single-GPU solver over the first substeps of this very rollout (outside every
+    # timed region): all ranks step, the owned particles are gathered, rank 0 steps an unsharded solver and compares
+    n_par = 48
+    f0 = dev_frames[0]
+    sm.step(sc.dt, n_par, f0["mesh_x"], f0["mesh_v"], f0["joint_verts_v"], f0["joint_faces_v"])
+    Xs, Vs = sm.gather_positions()
+    parity = None
+    if rank == 0:
+        from mpmavatar_b200.scene_setup import build_from_scene
+        ref_solver, ref_model, ref_state = build_from_scene(sc, device=dev)
+        ref_solver.step(ref_model, ref_state, sc.dt, n_par, f0["mesh_x"], f0["mesh_v"], None, f0["joint_verts_v"], f0["joint_faces_v"])
+        x1, v1 = ref_state.particle_x, ref_state.particle_v
+        parity = {"substeps": n_par, "x": float((Xs - x1).abs().max() / x1.abs().max()),
+                  "v": float((Vs - v1).abs().max() / v1.abs().max()),
+                  "note": "max |sharded - single GPU| / max |single GPU| over all particles; differences: order of the float atomics"}
+        del ref_solver, ref_model, ref_state, x1, v1
+        torch.cuda.empty_cache()
+    del Xs, Vs
+    barrier()
     fi = 0
     clocks = ClockSampler(local_rank, enabled=(rank == 0))
     clocks.start()  # sampled through warm-up and the timed region (the same load)
@@ -250,13 +278,11 @@ def run_sharded(args, sc, rank, local_rank, world, dev, barrier):
         line = {"metric": METRIC, "value": value, "unit": "substeps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"C3: {sc.n_particles} cloth particles ({sc.n_elements} elements + {sc.n_vertices} "
-                                       f"vertices), {sc.n_grid}^3 grid, capsule body collider ({sc.body_verts.shape[0]} verts / "
-                                       f"{sc.body_faces.shape[0]} faces) + {sc.num_joint_v} joint vertices/faces, dt=1e-4",
-                           "substeps_per_step": S_PER, "l2": "256 MiB L2 flush between timed steps",
-                           "parallelism": f"one simulation sharded into {world} spatial tiles (particle-count balanced slabs), "
-                                          f"mass-0 ghost vertices, ONE all-reduce of the shared grid blocks per substep "
-                                          f"({sm.stats['shared_blocks']} blocks, {sm.stats['exchange_bytes']} bytes)"},
+                "config": workload_config(sc, f"one simulation sharded into {world} spatial tiles (particle-count balanced slabs), "
+                                              f"mass-0 ghost vertices, ONE exchange of the shared grid blocks per substep "
+                                              f"({sm.stats['shared_blocks']} blocks, {sm.stats['exchange_bytes']} bytes, "
+                                              f"{sm.stats.get('exchange', '?')})"),
+                "parity_vs_single_gpu": parity,
                 "clocks": clk, "e2e": {"value": e2e_value, "unit": "substeps/s", "h2d_bytes_per_step": h2d,
                                        "d2h_bytes_per_step": n_own * 12},
                 "gpu_launches": int(launches.item()),
@@ -386,6 +412,39 @@ def main():
     state._stale = True
     finite = finite and bool(torch.isfinite(host_x).all())
 
+    # ---------------- e2e_p2g2p_loop: the UNCHANGED caller's inner loop (train_material_params.py:616-628): one p2g2p call per
+    # substep through the Python mirror, a fresh mesh_x tensor computed by the caller for every call, positions read back
+    # with wp.to_torch(...).clone() once per frame
+    import mpmavatar_b200
+    mpmavatar_b200.install()
+    import warp as wp
+    reset_rollout(sc, solver, model, state, dev)
+
+    def frame_loop(i):
+        f = dev_frames[i]
+        mesh_x, mesh_v, jv, jf = f["mesh_x"], f["mesh_v"], f["joint_verts_v"], f["joint_faces_v"]
+        for k in range(S_PER):
+            mesh_x_curr = mesh_x + sc.dt * k * mesh_v
+            solver.p2g2p(model, state, sc.dt, mesh_x=mesh_x_curr, mesh_v=mesh_v, joint_traditional_v=None,
+                         joint_verts_v=jv, joint_faces_v=jf, device=dev)
+        return wp.to_torch(state.particle_x).clone()
+    frame_loop(0)
+    barrier()
+    n_loop = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    e0.record()
+    for k in range(n_loop):
+        pos = frame_loop(1 + k)
+    e1.record()
+    barrier()
+    loop_wall = time.perf_counter() - t0
+    loop_value = n_loop * S_PER / (e0.elapsed_time(e1) * 1e-3)
+    finite = finite and bool(torch.isfinite(pos).all())
+    e2e_loop = {"value": loop_value, "unit": "substeps/s", "frames": n_loop, "calls_per_frame": S_PER,
+                "host_us_per_call": loop_wall / (n_loop * S_PER) * 1e6,
+                "what": "400 x MPMWARP.p2g2p(model, state, dt, mesh_x + k*dt*mesh_v, ...) per frame through the Python mirror, "
+                        "wp.to_torch(state.particle_x).clone() per frame: the reference caller's loop, unedited"}
+
     # ---------------- roofline: per-phase events in a separate profiling pass
     stats = solver.stats()
     A = int(stats["n_active_nodes"])
@@ -410,7 +469,7 @@ def main():
     achieved = bytes_pg / t_pg / 1e9
     roofline = {"bound": "hbm", "kernel": "p2g + g2p (k_p2g<0,1,2>, k_g2p_vertices, k_g2p_traditional, k_g2p_elements)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": TRAFFIC_NCU, "algorithmic_bytes_per_substep": bytes_pg, "active_nodes": A,
+                "traffic": TRAFFIC_NCU, "traffic_source": TRAFFIC_SOURCE, "algorithmic_bytes_per_substep": bytes_pg, "active_nodes": A,
                 "timing": "P2G phase + G2P phase per substep = first CTA start to last CTA end of their kernels on the GPU "
                           "global timer (mpm_measure_timeline), median over 28 graph-replayed substeps",
                 "timeline_us": tl,
@@ -418,15 +477,14 @@ def main():
                 "phase_us_per_substep_events_serialised": {k[:-3]: round(v * 1e3, 2) for k, v in per.items()}}
 
     line = {"metric": METRIC, "value": value, "unit": "substeps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak" if world > 1 else "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C3: {sc.n_particles} cloth particles ({sc.n_elements} elements + {sc.n_vertices} "
-                                   f"vertices), {sc.n_grid}^3 grid, capsule body collider ({sc.body_verts.shape[0]} verts / "
-                                   f"{sc.body_faces.shape[0]} faces) + {sc.num_joint_v} joint vertices/faces, dt=1e-4",
-                       "substeps_per_step": S_PER, "l2": "256 MiB L2 flush between timed steps",
-                       "parallelism": "1 rollout per GPU (independent finite-difference probes), no collective"},
+            "config": workload_config(sc, "1 GPU" if world == 1 else f"{world} independent rollouts, one per GPU (--replicas: the "
+                                                                      f"reference's finite-difference probes), no collective"),
             "clocks": clk, "e2e": {"value": e2e_value, "unit": "substeps/s", "h2d_bytes_per_step": h2d,
                                    "d2h_bytes_per_step": d2h},
+            "e2e_p2g2p_loop": e2e_loop,
             "gpu_launches": int(launches), "roofline": roofline, "finite": finite,
             "active_blocks": int(stats["n_active_blocks"]), "resorts": int(stats["n_resorts"])}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

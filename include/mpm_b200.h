@@ -75,6 +75,9 @@ typedef struct {
     const float *joint_traditional_v;         /* [n_joint_t,3]: pins the LAST n_joint_t traditional particles */
     int n_joint_t;
     const float *joint_verts_v, *joint_faces_v; /* [num_joint_v,3], [num_joint_f,3] */
+    int device_inputs; /* 1: every non-NULL pointer above is a DEVICE pointer -- the inputs are then staged by ONE kernel
+                        * instead of one cudaMemcpyAsync each, and a single substep replays a captured graph: two driver
+                        * calls per p2g2p (the unchanged callers make one call per substep, train_material_params.py:622-626) */
 } MpmFrameInputs;
 
 typedef struct {

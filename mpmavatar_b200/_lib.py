@@ -32,7 +32,8 @@ class MpmParticleArrays(C.Structure):
 
 class MpmFrameInputs(C.Structure):
     _fields_ = [("mesh_x", C.c_void_p), ("mesh_v", C.c_void_p), ("joint_traditional_v", C.c_void_p),
-                ("n_joint_t", C.c_int), ("joint_verts_v", C.c_void_p), ("joint_faces_v", C.c_void_p)]
+                ("n_joint_t", C.c_int), ("joint_verts_v", C.c_void_p), ("joint_faces_v", C.c_void_p),
+                ("device_inputs", C.c_int)]
 
 
 class MpmStats(C.Structure):

@@ -773,7 +773,7 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
 constexpr int GRAPH_U = 16;  // even: the direction ping-pong index is the same before and after a replay
 struct GraphKey {
     float dt;
-    int collider, mover, advance_mesh, njt, cur, n_bc, n_ops, debug, rbuf;
+    int collider, mover, advance_mesh, njt, cur, n_bc, n_ops, debug, rbuf, len;
     bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 struct GraphEntry {
@@ -814,14 +814,16 @@ static void destroy_graphs(MpmSolver* s) {
 }
 static void destroy_sharded(MpmSolver* s);  // communicator + captured sharded windows (defined with the NCCL path)
 static void destroy_shard_graphs(MpmSolver* s);
-static void run_substeps(MpmSolver* s, SubstepArgs a, int count, cudaStream_t q) {
+// single = the call is ONE substep (the unchanged callers' p2g2p loop): it replays a one-substep graph
+static void run_substeps(MpmSolver* s, SubstepArgs a, int count, cudaStream_t q, bool single = false) {
     const bool graphs = s->use_graphs && !s->profiling;
     while (count > 0) {
-        if (graphs && count >= GRAPH_U) {
+        const int len = (graphs && count >= GRAPH_U) ? GRAPH_U : ((graphs && single && count == 1 && !s->debug) ? 1 : 0);
+        if (len) {
             GraphKey key{};
             key.dt = a.dt; key.collider = a.collider; key.mover = a.mover; key.advance_mesh = a.advance_mesh;
             key.njt = a.njt; key.cur = s->cur; key.n_bc = (int)s->h_bcs.size();
-            key.n_ops = (int)s->h_ops.size(); key.debug = s->debug; key.rbuf = s->rbuf;
+            key.n_ops = (int)s->h_ops.size(); key.debug = s->debug; key.rbuf = s->rbuf; key.len = len;
             auto& cache = graph_cache(s);
             GraphEntry* hit = nullptr;
             for (auto& e : cache) if (e.key == key) hit = &e;
@@ -832,7 +834,11 @@ static void run_substeps(MpmSolver* s, SubstepArgs a, int count, cudaStream_t q)
                 // which cannot be captured); the instantiated graph is launched on the caller's stream
                 if (!s->cap_stream) CK(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
                 CK(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
-                for (int i = 0; i < GRAPH_U; i++) launch_substep(s, a, s->cap_stream);
+                const int cur0 = s->cur;
+                const bool prev0 = s->have_prev;
+                for (int i = 0; i < len; i++) launch_substep(s, a, s->cap_stream);
+                s->cur = cur0;  // the capture only recorded launches: the replay below does the stepping
+                s->have_prev = prev0;
                 CK(cudaStreamEndCapture(s->cap_stream, &graph));
                 GraphEntry e;
                 e.key = key;
@@ -846,8 +852,9 @@ static void run_substeps(MpmSolver* s, SubstepArgs a, int count, cudaStream_t q)
             }
             CK(cudaGraphLaunch(hit->exec, q));
             s->have_prev = true;
+            if (s->Ne && (len & 1)) s->cur ^= 1;
             s->launches += hit->launches_per_replay;
-            count -= GRAPH_U;
+            count -= len;
         } else {
             launch_substep(s, a, q);
             count -= 1;
@@ -1170,31 +1177,36 @@ int mpm_step(MpmSolver* s, float dt, int nsub, const MpmFrameInputs* in, void* s
     if (!in) in = &none;
     if (in->n_joint_t > s->Nt) throw std::string("n_joint_t exceeds the number of traditional particles");
     upload_lists(s, q);
-    size_t mv3 = 3 * (size_t)s->cfg.n_mesh_v * sizeof(float);
-    if (in->mesh_x && mv3) CK(cudaMemcpyAsync(s->mesh_x, in->mesh_x, mv3, cudaMemcpyDefault, q));
-    if (in->mesh_v && mv3) CK(cudaMemcpyAsync(s->mesh_v, in->mesh_v, mv3, cudaMemcpyDefault, q));
     SubstepArgs a{};
     a.dt = dt;
     a.collider = s->has_collider;
     a.advance_mesh = in->mesh_x != nullptr && nsub > 1;
     // the mover runs only when BOTH joint_verts_v and joint_faces_v are given (mpm_solver.py:421)
     a.mover = s->has_mover && in->joint_verts_v && in->joint_faces_v;
-    a.njt = 0;
+    a.njt = (a.mover && in->joint_traditional_v && in->n_joint_t > 0) ? in->n_joint_t : 0;
+    const int mv3 = 3 * s->cfg.n_mesh_v;
+    StageInputs si{};
+    int nsi = 0, most = 0;
+    auto stage = [&](float* dst, const float* src, int n) {
+        if (!src || n <= 0) return;
+        if (in->device_inputs) { si.src[nsi] = src; si.dst[nsi] = dst; si.n[nsi] = n; nsi++; most = std::max(most, n); }
+        else CK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(float), cudaMemcpyDefault, q));
+    };
+    stage(s->mesh_x, in->mesh_x, mv3);
+    stage(s->mesh_v, in->mesh_v, mv3);
     if (a.mover) {
-        if (s->cfg.num_joint_v) CK(cudaMemcpyAsync(s->joint_v, in->joint_verts_v, 3 * (size_t)s->cfg.num_joint_v * sizeof(float), cudaMemcpyDefault, q));
-        if (s->cfg.num_joint_f) CK(cudaMemcpyAsync(s->joint_f, in->joint_faces_v, 3 * (size_t)s->cfg.num_joint_f * sizeof(float), cudaMemcpyDefault, q));
-        if (in->joint_traditional_v && in->n_joint_t > 0) {
-            a.njt = in->n_joint_t;
-            CK(cudaMemcpyAsync(s->joint_t, in->joint_traditional_v, 3 * (size_t)a.njt * sizeof(float), cudaMemcpyDefault, q));
-        }
+        stage(s->joint_v, in->joint_verts_v, 3 * s->cfg.num_joint_v);
+        stage(s->joint_f, in->joint_faces_v, 3 * s->cfg.num_joint_f);
+        stage(s->joint_t, in->joint_traditional_v, 3 * a.njt);
     }
-    k_reset_k<<<1, 1, 0, q>>>(s->st);
+    if (in->device_inputs) k_stage_inputs<<<std::max(1, std::min(cdiv(most, 256), 148)), 256, 0, q>>>(si, s->st);  // + substep counter reset
+    else k_reset_k<<<1, 1, 0, q>>>(s->st);
     s->launches++;
     int left = nsub;
     while (left > 0) {
         if (s->need_sort || s->since_sort >= s->resort_interval) resort(s, q);
         int chunk = std::min(left, s->resort_interval - s->since_sort);
-        run_substeps(s, a, chunk, q);
+        run_substeps(s, a, chunk, q, nsub == 1);
         s->since_sort += chunk;
         s->n_substeps += chunk;
         s->canon_stale = true;

@@ -920,6 +920,20 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
     ts_end(g, TS_GRID);
 }
 __global__ void k_reset_k(StepState* st) { st->k = 0; }
+// per-call inputs of p2g2p (body points / velocities, joint velocities) from DEVICE pointers into the solver's own
+// buffers, and the substep counter reset, in one launch
+struct StageInputs {
+    const float* src[5];
+    float* dst[5];
+    int n[5];  // floats; 0 = not given
+};
+__global__ void k_stage_inputs(StageInputs a, StepState* st) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->k = 0;
+    const int stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 5; j++)
+        for (int i = t; i < a.n[j]; i += stride) a.dst[j][i] = a.src[j][i];
+}
 
 // ============================================================ G2P
 struct Gathered {

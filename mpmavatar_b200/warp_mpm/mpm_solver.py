@@ -241,7 +241,13 @@ class MPMWARP(object):
         self._bind(mpm_model, mpm_state)
         dev = self.device
         fi = _lib.MpmFrameInputs()
-        keep = [_f32(q, dev) for q in (mesh_x, mesh_v, joint_traditional_v, joint_verts_v, joint_faces_v)]
+
+        def ready(t):  # the common case costs three attribute reads: an fp32 CUDA tensor of this device, dense
+            if t is None or (type(t) is torch.Tensor and t.dtype is torch.float32 and t.device == dev and t.is_contiguous()):
+                return t
+            return _f32(t, dev)
+        keep = [ready(q) for q in (mesh_x, mesh_v, joint_traditional_v, joint_verts_v, joint_faces_v)]
+        fi.device_inputs = 1 if all(k is None or k.is_cuda for k in keep) else 0
         if keep[0] is not None and keep[0].shape[0] != self.num_mesh_v:
             raise ValueError("mesh_x does not match the body mesh given at construction")
         fi.mesh_x, fi.mesh_v = _ptr(keep[0]), _ptr(keep[1])

@@ -27,7 +27,7 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_lib.MpmConfig) == 11 * 4
     assert ctypes.sizeof(_lib.MpmModelParams) == 12 * 4
     assert ctypes.sizeof(_lib.MpmParticleArrays) == 17 * 8
-    assert ctypes.sizeof(_lib.MpmFrameInputs) == 6 * 8
+    assert ctypes.sizeof(_lib.MpmFrameInputs) == 7 * 8
 
 
 def test_reference_names_and_signatures():
