@@ -184,7 +184,7 @@ def run_sharded(args, sc, rank, local_rank, world, dev, barrier):
     import torch.distributed as dist
     from mpmavatar_b200.sharded_solver import ShardedMPM
     S_PER = SUBSTEPS_PER_STEP
-    sm = ShardedMPM(sc, dev, refresh=16, margin=1)
+    sm = ShardedMPM(sc, dev, refresh=32, margin=2)
     frames = [sc.frame_inputs(i) for i in range(2 * (args.warmup + args.steps) + 2)]
     keys = ("mesh_x", "mesh_v", "joint_verts_v", "joint_faces_v")
     dev_frames = [{k: torch.as_tensor(f[k], device=dev) for k in keys} for f in frames]

@@ -721,7 +721,7 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
             if (tot) { k_mover_scatter<<<cdiv(tot, 128), 128, 0, q>>>(s->g, ma); s->launches++; }
             CK(cudaEventRecord(ev[4], q));
         } else if (ca.Mf + tot) {
-            launch_pdl(k_body_scatter, cdiv(ca.Mf + tot, 128), 128, 0, q, pdl, s->g, ca, ma);
+            launch_pdl(k_body_scatter, cdiv(3LL * (ca.Mf + tot), 128), 128, 0, q, pdl, s->g, ca, ma);
             s->launches++;
         }
     };
@@ -1629,7 +1629,7 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
     a.advance_mesh = in->mesh_x != nullptr && nsub > 1;
     k_reset_k<<<1, 1, 0, q>>>(s->st);
     s->launches++;
-    constexpr int W = 8;  // substeps per captured window (even: the direction ping-pong returns to its start)
+    constexpr int W = 16;  // substeps per captured window (even: the direction ping-pong returns to its start)
     int left = nsub;
     while (left > 0) {
         if (s->need_sort || s->since_sort >= s->resort_interval) resort(s, q);

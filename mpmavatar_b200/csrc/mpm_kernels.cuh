@@ -681,8 +681,10 @@ struct ColliderArgs {
 };
 // one scatter of a 3^3 stencil into the ACTIVE blocks only: node = X(ix) + Y(iy) + Z(iz) (axis_offset); the activity of
 // the (up to) eight blocks under the stencil is an 8-bit mask, a node's block is picked by three per-axis crossing bits
+// (i_only >= 0: only the nodes of stencil plane i = i_only -- the scatter kernels give every face / joint particle three
+// threads, one per plane, which shortens the chain of dependent atomics of a thread from 27 (x2) to 9 (x2))
 template <typename F>
-__device__ __forceinline__ void scatter_active_nodes(const Grid& g, const Stencil& sp, unsigned act8, bool flag_inactive, F&& add) {
+__device__ __forceinline__ void scatter_active_nodes(const Grid& g, const Stencil& sp, unsigned act8, bool flag_inactive, int i_only, F&& add) {
     int ox[3], oy[3], oz[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -692,7 +694,8 @@ __device__ __forceinline__ void scatter_active_nodes(const Grid& g, const Stenci
     }
     const unsigned cx = axis_cross(sp.b[0]), cy = axis_cross(sp.b[1]), cz = axis_cross(sp.b[2]);
 #pragma unroll
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 3; i++) {
+        if (i_only >= 0 && i != i_only) continue;
 #pragma unroll
         for (int j = 0; j < 3; j++)
 #pragma unroll
@@ -704,8 +707,9 @@ __device__ __forceinline__ void scatter_active_nodes(const Grid& g, const Stenci
                 }
                 add(ox[i] + oy[j] + oz[k], sp.w[0][i] * sp.w[1][j] * sp.w[2][k]);
             }
+    }
 }
-__device__ __forceinline__ void collider_scatter_face(const Grid& g, const ColliderArgs& ca, int f) {
+__device__ __forceinline__ void collider_scatter_face(const Grid& g, const ColliderArgs& ca, int f, int i_only = -1) {
     const int* __restrict__ faces = ca.faces;
     const float* __restrict__ px = ca.px;
     const float* __restrict__ pv = ca.pv;
@@ -736,7 +740,7 @@ __device__ __forceinline__ void collider_scatter_face(const Grid& g, const Colli
     float nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
     float nl = len3(nx, ny, nz);
     if (nl > 0.0f) { nx /= nl; ny /= nl; nz /= nl; } else { nx = ny = nz = 0.0f; }
-    scatter_active_nodes(g, sp, act8, false, [&](int ni, float ww) {
+    scatter_active_nodes(g, sp, act8, false, i_only, [&](int ni, float ww) {
         atomicAdd(&g.colv[ni], make_float4(ww * fv[0], ww * fv[1], ww * fv[2], ww));
         atomicAdd(&g.coln[ni], make_float4(ww * nx, ww * ny, ww * nz, 0.0f));
     });
@@ -754,7 +758,7 @@ struct MoverArgs {
     const float4* XE;
     const int *invE, *invT, *invV;
 };
-__device__ __forceinline__ void mover_scatter_one(const Grid& g, const MoverArgs& ma, int t) {
+__device__ __forceinline__ void mover_scatter_one(const Grid& g, const MoverArgs& ma, int t, int i_only = -1) {
     const int njt = ma.njt, njv = ma.njv, Nt = ma.Nt;
     const float *__restrict__ vt = ma.vt, *__restrict__ vvv = ma.vvv, *__restrict__ vf = ma.vf;
     const float *__restrict__ TP = ma.TP, *__restrict__ VP = ma.VP;
@@ -769,7 +773,7 @@ __device__ __forceinline__ void mover_scatter_one(const Grid& g, const MoverArgs
     if (!scatter_ok(g, sp)) return;
     const unsigned act8 = load_active8(g, sp.b[0], sp.b[1], sp.b[2]);
     const float v0 = vel[0], v1 = vel[1], v2 = vel[2];
-    scatter_active_nodes(g, sp, act8, true, [&](int ni, float ww) {
+    scatter_active_nodes(g, sp, act8, true, i_only, [&](int ni, float ww) {
         atomicAdd(&g.mov[ni], make_float4(ww * v0, ww * v1, ww * v2, ww));
     });
 }
@@ -781,13 +785,14 @@ __global__ void __launch_bounds__(128) k_mover_scatter(Grid g, MoverArgs ma) {
 // (different accumulators; the block table and the positions are those of the previous substep), so its CTAs fill
 // the tail of the vertex P2G; the wait before exit keeps completion transitive.  (Placing it between the two P2G
 // kernels was measured: its ~1.1 M vector atomics then collide with the element kernel's and slow that kernel by
-// more than the scatter's own exposed time.)  Threads [0, Mf) faces, then the movers.
+// more than the scatter's own exposed time.)  Thread triples [0, Mf) faces, then the movers.
 __global__ void __launch_bounds__(128) k_body_scatter(Grid g, ColliderArgs ca, MoverArgs ma) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = tt / 3, i_only = tt - 3 * t;  // three threads per face / joint particle: one stencil plane each
     pdl_trigger();
     ts_begin(g, TS_SCATTER);
-    if (t < ca.Mf) collider_scatter_face(g, ca, t);
-    else if (t - ca.Mf < ma.njt + ma.njv + ma.njf) mover_scatter_one(g, ma, t - ca.Mf);
+    if (t < ca.Mf) collider_scatter_face(g, ca, t, i_only);
+    else if (t - ca.Mf < ma.njt + ma.njv + ma.njf) mover_scatter_one(g, ma, t - ca.Mf, i_only);
     ts_end(g, TS_SCATTER);  // before the wait: the stamp is the end of this kernel's own work
     pdl_wait();
 }
