@@ -213,6 +213,43 @@ int mpm_measure_timeline(MpmSolver *s, float dt, int n, const MpmFrameInputs *in
 /* latency analysis (builds with -DMPM_CLK only fill it): 8 kernels x 8 per-warp phase cycle sums; synchronises */
 int mpm_debug_phase_clocks(MpmSolver *s, unsigned long long *out64, int reset);
 
+/* ---- caller-side glue around the hot path, on the device.  The first, second, fourth and
+ * fifth are stateless (no solver handle; errors through mpm_last_error(NULL)); device pointers unless said otherwise. */
+
+/* wld2sim normalisation of setup_simulation (train_material_params.py:365-373): scale_shift4 (HOST) = {scale, shift[3]} with
+ * scale = 1 / max extent of verts_wld, shift = (1,1,1) - box centre * scale.  Synchronises. */
+int mpm_cloth_normalisation(const float *verts_wld, int n_verts, float *scale_shift4, void *stream);
+
+/* Particle construction from the tracked garment mesh: verts_sim = verts_wld * scale + shift, then compute_dir_vol and
+ * compute_rest_dir_inv (train_material_params.py:508-515, 533-553) per face, element centroids (:379).  NULL outputs
+ * (except x) are skipped. */
+typedef struct {
+    float *x;            /* [n_faces + n_verts, 3] canonical positions: element centroids, then the sim-space vertices */
+    float *vol;          /* [n_faces + n_verts] element_vol = 0.25 * thickness * area, then vertex_vol = sum over incident faces */
+    float *init_dir;     /* [n_faces, 9] row-major d = [d1 d2 normalize(d1 x d2)] as columns */
+    float *rest_dir;     /* [n_faces, 3] R11 R12 R22 of the QR of [d1 d2] */
+    float *rest_dir_inv; /* [n_faces, 3] 1/R11, -R12/(R11 R22), 1/R22 */
+} MpmClothParticles;
+int mpm_build_cloth_particles(const float *verts_wld, const int *faces, int n_verts, int n_faces, float thickness, float scale,
+                              const float shift[3], const MpmClothParticles *out, void *stream);
+
+/* Cloth vertex positions straight from the solver's sorted records: original vertex order, world coordinates
+ * ((p - shift) / scale: sim2wld, train_material_params.py:373,630,812).  Optional: out_wld [n_vertices,3]; scatter into a
+ * full-body vertex array full_verts at scatter_idx [n_vertices] (int64, reordered_cloth_v_idx, :814); sum of squared
+ * differences to target [n_vertices,3] into *sse (device double; F.mse_loss = sse / (3 n_vertices), :631). */
+int mpm_export_cloth_verts(MpmSolver *s, float scale, const float shift[3], float *out_wld, const long long *scatter_idx,
+                           float *full_verts, const float *target, double *sse, void *stream);
+
+/* Per-frame OBJ (train_material_params.py:819-821): "v x y z" lines from HOST float32 vertices -- every number the shortest
+ * decimal that reads back as the same float32 -- followed by `tail` (the vt / f lines) verbatim. */
+int mpm_write_obj(const char *path, const float *verts_host, int n_verts, const char *tail, long long tail_len);
+
+/* Hand-off to the renderer without the OBJ detour: what MeshGaussianModel.set_mesh_by_verts computes from the simulated
+ * vertices (scene/mesh_gaussian_model.py:137-146, utils/graphics_utils.py:88-107): face centre [F,3], orientation matrix
+ * [F,9] (columns a0 a1 a2), unit quaternion wxyz [F,4] (defined up to sign), scale [F].  NULL outputs are skipped. */
+int mpm_face_frames(const float *verts, const int *faces, int n_faces, float *center, float *orien, float *quat, float *scale,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,10 @@ class MpmProfile(C.Structure):
                                          "g2p_v_ms", "g2p_e_ms", "resort_ms")] + [("n_substeps", C.c_longlong)]
 
 
+class MpmClothParticles(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("x", "vol", "init_dir", "rest_dir", "rest_dir_inv")]
+
+
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)
 REBUILD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
 HOST_ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int)
@@ -94,6 +98,11 @@ SYMBOLS = {
     "mpm_get_stats": (C.c_int, [_P, C.POINTER(MpmStats), _P]),
     "mpm_force_resort": (C.c_int, [_P]),
     "mpm_debug_phase_clocks": (C.c_int, [_P, _P, C.c_int]),
+    "mpm_cloth_normalisation": (C.c_int, [_P, C.c_int, _F3, _P]),
+    "mpm_build_cloth_particles": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_float, _F3, C.POINTER(MpmClothParticles), _P]),
+    "mpm_export_cloth_verts": (C.c_int, [_P, C.c_float, _F3, _P, _P, _P, _P, _P, _P]),
+    "mpm_write_obj": (C.c_int, [C.c_char_p, _P, C.c_int, C.c_char_p, C.c_longlong]),
+    "mpm_face_frames": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _P]),
 }
 
 

@@ -8,7 +8,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libmpm_b200.so")
-SOURCES = ["mpm_b200.cu", "mpm_kernels.cuh", "mpm_device.cuh"]
+SOURCES = ["mpm_b200.cu", "mpm_kernels.cuh", "mpm_device.cuh", "mpm_mesh.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-Wno-deprecated-declarations"]
 

@@ -1931,3 +1931,109 @@ int mpm_force_resort(MpmSolver* s) {
 }
 
 }  // extern "C"
+
+// ================================================================ caller-side glue on the device
+#include "mpm_mesh.cuh"
+
+#define STATELESS_BEGIN try {
+#define STATELESS_END             \
+    }                             \
+    catch (const std::string& e) { \
+        g_create_error = e;       \
+        return -2;                \
+    }                             \
+    return 0;
+
+extern "C" {
+
+int mpm_cloth_normalisation(const float* verts_wld, int n_verts, float* scale_shift4, void* stream) {
+    STATELESS_BEGIN
+    cudaStream_t q = (cudaStream_t)stream;
+    if (!verts_wld || n_verts <= 0 || !scale_shift4) throw std::string("mpm_cloth_normalisation: bad arguments");
+    float* d = nullptr;
+    CK(cudaMalloc(&d, 6 * sizeof(float)));
+    const float init[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    CK(cudaMemcpyAsync(d, init, sizeof init, cudaMemcpyHostToDevice, q));
+    k_minmax<<<std::min(cdiv(n_verts, 256), 592), 256, 0, q>>>(verts_wld, n_verts, d);
+    float h[6];
+    CK(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, q));
+    CK(cudaStreamSynchronize(q));
+    cudaFree(d);
+    // train_material_params.py:365-370 in fp32, as torch evaluates it
+    float max_diff = 0.f;
+    for (int a = 0; a < 3; a++) max_diff = std::max(max_diff, h[3 + a] - h[a]);
+    const float scale = 1.0f / max_diff;
+    scale_shift4[0] = scale;
+    for (int a = 0; a < 3; a++) scale_shift4[1 + a] = 1.0f - ((h[a] + h[3 + a]) / 2.0f) * scale;
+    STATELESS_END
+}
+
+int mpm_build_cloth_particles(const float* verts_wld, const int* faces, int n_verts, int n_faces, float thickness, float scale,
+                              const float shift[3], const MpmClothParticles* out, void* stream) {
+    STATELESS_BEGIN
+    cudaStream_t q = (cudaStream_t)stream;
+    if (!verts_wld || !faces || !out || n_verts <= 0 || n_faces <= 0) throw std::string("mpm_build_cloth_particles: bad arguments");
+    if (!out->x) throw std::string("mpm_build_cloth_particles: out->x is required (the sim-space vertices live in its tail)");
+    float* verts_sim = out->x + 3 * (size_t)n_faces;  // canonical order [elements | vertices] (train_material_params.py:387)
+    k_wld2sim<<<cdiv(n_verts, 256), 256, 0, q>>>(verts_wld, n_verts, scale, shift[0], shift[1], shift[2], verts_sim);
+    if (out->vol) CK(cudaMemsetAsync(out->vol + n_faces, 0, (size_t)n_verts * sizeof(float), q));
+    ClothOut o{out->x, out->init_dir, out->rest_dir, out->rest_dir_inv, out->vol, out->vol ? out->vol + n_faces : nullptr};
+    k_cloth_faces<<<cdiv(n_faces, 128), 128, 0, q>>>(verts_sim, faces, n_faces, thickness, o);
+    CK(cudaGetLastError());
+    STATELESS_END
+}
+
+int mpm_export_cloth_verts(MpmSolver* s, float scale, const float shift[3], float* out_wld, const long long* scatter_idx,
+                           float* full_verts, const float* target, double* sse, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    if (!s->have_state) throw std::string("mpm_export_cloth_verts before mpm_import_state");
+    if (s->need_sort) resort(s, q);
+    if (sse) CK(cudaMemsetAsync(sse, 0, sizeof(double), q));
+    if (s->Nv)
+        k_export_verts<<<cdiv(s->Nv, 256), 256, 0, q>>>(s->Nv, s->R.VP, s->R.permV, scale, shift[0], shift[1], shift[2], out_wld, scatter_idx,
+                                                       full_verts, target, sse);
+    s->launches++;
+    CK(cudaGetLastError());
+    API_END(s)
+}
+
+int mpm_face_frames(const float* verts, const int* faces, int n_faces, float* center, float* orien, float* quat, float* scale, void* stream) {
+    STATELESS_BEGIN
+    if (!verts || !faces || n_faces <= 0) throw std::string("mpm_face_frames: bad arguments");
+    k_face_frames<<<cdiv(n_faces, 128), 128, 0, (cudaStream_t)stream>>>(verts, faces, n_faces, FaceFrames{center, orien, quat, scale});
+    CK(cudaGetLastError());
+    STATELESS_END
+}
+
+// "v x y z\n" per vertex with the shortest decimal that reads back as the same float32 (what the reference's f-string of a
+// numpy float32 prints), then `tail` (the texture-coordinate / face lines) verbatim; one buffered write
+int mpm_write_obj(const char* path, const float* verts_host, int n_verts, const char* tail, long long tail_len) {
+    STATELESS_BEGIN
+    if (!path || (!verts_host && n_verts > 0)) throw std::string("mpm_write_obj: bad arguments");
+    std::string buf;
+    buf.resize((size_t)n_verts * 52 + 16);
+    char* p = &buf[0];
+    auto put = [&](float v) {
+        char* b = p;
+        auto r = std::to_chars(p, p + 24, v);
+        p = r.ptr;
+        bool plain = true;  // "1" -> "1.0" as Python prints floats
+        for (char* c = b; c < p; c++) if (*c == '.' || *c == 'e' || *c == 'n' || *c == 'i') plain = false;
+        if (plain) { *p++ = '.'; *p++ = '0'; }
+    };
+    for (int i = 0; i < n_verts; i++) {
+        *p++ = 'v';
+        for (int a = 0; a < 3; a++) { *p++ = ' '; put(verts_host[3 * (size_t)i + a]); }
+        *p++ = '\n';
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) throw std::string("mpm_write_obj: cannot open ") + path;
+    bool ok = fwrite(buf.data(), 1, (size_t)(p - buf.data()), f) == (size_t)(p - buf.data());
+    if (ok && tail && tail_len > 0) ok = fwrite(tail, 1, (size_t)tail_len, f) == (size_t)tail_len;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) throw std::string("mpm_write_obj: write failed for ") + path;
+    STATELESS_END
+}
+
+}  // extern "C"
