@@ -415,20 +415,46 @@ __device__ __forceinline__ V4 mul4(float s, V4 a) { return V4{mul2(s, a.lo), mul
 __device__ __forceinline__ V4 fma4(float s, V4 a, V4 c) { return V4{fma2(s, a.lo, c.lo), fma2(s, a.hi, c.hi)}; }
 __device__ __forceinline__ V4 add4(V4 a, V4 b) { return V4{add2(a.lo, b.lo), add2(a.hi, b.hi)}; }
 
-// ------------------------------------------------------------------ cell runs of a sorted slab
-// Particles are sorted by cell, so the 32 particles of a warp form a few runs that share one 27-node
-// stencil.  `cell` packs the clamped stencil base; lanes >= cnt must pass distinct negative values.
+// ------------------------------------------------------------------ cell groups of a slab
+// Particles are sorted by cell every few dozen substeps; in between they drift (a falling garment moves a cell or two
+// between two re-sorts), and the particles of one OLD cell end up interleaved over two or more new cells.  The 32
+// particles of a warp are therefore grouped by their CURRENT cell with one MATCH.ANY: every distinct cell is exactly one
+// group ("run"), however its members are scattered over the lanes.  `cell` packs the clamped stencil base; lanes >= cnt
+// must pass distinct negative values (they form trailing groups of their own).
 struct Runs {
-    unsigned starts;  // bit l set: lane l is the first particle of a run
-    int nr;           // number of runs
+    unsigned starts;  // find_runs: bit l set = slot l is the first of a run.  group_runs: bit l set = lane l leads a group
+    int nr;           // number of runs among the lanes < cnt
     int mine;         // run index of this lane
+    int slot;         // group_runs: position of this lane's particle when the slab is ordered group by group
 };
+// adjacency version: the slab is already ordered run by run
 __device__ __forceinline__ Runs find_runs(int lane, int cnt, int cell) {
     const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
     Runs r;
     r.starts = __ballot_sync(0xffffffffu, lane < cnt && (lane == 0 || cell != prev));
     r.nr = __popc(r.starts);
     r.mine = __popc(r.starts & (0xffffffffu >> (31 - lane))) - 1;
+    r.slot = lane;
+    return r;
+}
+// grouping version: runs are numbered by their leader (lowest) lane; slot = members of earlier groups + my rank in mine
+__device__ __forceinline__ Runs group_runs(int lane, int cnt, int cell) {
+    const unsigned peers = __match_any_sync(0xffffffffu, cell);
+    const int leader = __ffs(peers) - 1;
+    const unsigned lt = (1u << lane) - 1u;
+    Runs r;
+    r.starts = __ballot_sync(0xffffffffu, leader == lane && lane < cnt);
+    r.nr = __popc(r.starts);
+    r.mine = __popc(r.starts & ((1u << leader) - 1u));
+    // exclusive prefix sum of the group sizes over the leader lanes, fetched from my leader
+    int scan = (leader == lane) ? __popc(peers) : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, scan, o);
+        if (lane >= o) scan += up;
+    }
+    const int excl = scan - ((leader == lane) ? __popc(peers) : 0);
+    r.slot = __shfl_sync(0xffffffffu, excl, leader) + __popc(peers & lt);
     return r;
 }
 __device__ __forceinline__ int pack_cell(int bx, int by, int bz) {

@@ -349,8 +349,9 @@ constexpr int P2G_V_NW = MPM_P2G_V_NW, P2G_V_MINB = MPM_P2G_V_WARPS / MPM_P2G_V_
 #ifndef MPM_P2G_LEADER_OFFSETS
 #define MPM_P2G_LEADER_OFFSETS 0
 #endif
-// T tiles | U tiles | per-run node offsets (or 64 bytes of slack for the stage-2 look-ahead loads)
-constexpr int P2G_T_B = 32 * 9 * 16, P2G_U_B = 32 * 3 * 16, P2G_O_B = MPM_P2G_LEADER_OFFSETS ? 32 * 9 * 4 : 64;
+// T tiles | U tiles | per-run node offsets (or the 32 cells of the slab in grouped order, which is also the slack the
+// stage-2 look-ahead loads run into)
+constexpr int P2G_T_B = 32 * 9 * 16, P2G_U_B = 32 * 3 * 16, P2G_O_B = MPM_P2G_LEADER_OFFSETS ? 32 * 9 * 4 : 128;
 constexpr int P2G_WB = P2G_T_B + P2G_U_B + P2G_O_B;  // 7296 B; the raw slabs of the record kernels (<= 3328 B) are overlaid on the tiles
 constexpr int P2G_SMEM = 128 + P2G_NW * P2G_WB;  // the stage-2 look-ahead reads a few bytes past the U tiles: into the offsets
 
@@ -359,8 +360,8 @@ struct P2GPart {  // what stage 1 hands to the tile writer, lane = particle
     float Sp[9];  // -dt/dx * (vol *) stress, row-major; unused when STRESS = false
 };
 
-// weights + contribution tiles of this lane's particle; returns its packed stencil base cell (a distinct negative
-// value for lanes without a particle).  fetch_force(fv) is called after the weights are done: the vertex scatter
+// weights + contribution tiles of this lane's particle, written in cell-grouped order; returns the packed stencil base
+// cell of SLOT `lane` of that order (a distinct negative value for the trailing slots without a particle).  fetch_force(fv) is called after the weights are done: the vertex scatter
 // waits for its predecessor there (the vertex forces are the only input the element kernel produces).
 template <bool STRESS, typename FV>
 __device__ __forceinline__ int p2g_write_tiles(const Grid& g, const Warp& w, bool valid, P2GPart& P, float dt, float rpic,
@@ -432,8 +433,12 @@ __device__ __forceinline__ int p2g_write_tiles(const Grid& g, const Warp& w, boo
             if (ni >= 0) atomicAdd(&g.acc[ni], make_float4(wij * Uz[k].lo.x, wij * Uz[k].lo.y, wij * Uz[k].hi.x, 0.f));
         }
     }
-    float4* tT = reinterpret_cast<float4*>(w.buf) + w.lane * 9;
-    float4* tU = reinterpret_cast<float4*>(w.buf + P2G_T_B) + w.lane * 3;
+    // the slab is re-grouped by CURRENT cell on the way into the tiles: this particle's record goes to slot G.slot, so
+    // that stage 2 meets every distinct cell as ONE contiguous run however far the particles have drifted since the sort
+    const int mycell = valid ? pack_cell(b[0], b[1], b[2]) : -1 - w.lane;
+    const Runs G = group_runs(w.lane, w.cnt, mycell);
+    float4* tT = reinterpret_cast<float4*>(w.buf) + G.slot * 9;
+    float4* tU = reinterpret_cast<float4*>(w.buf + P2G_T_B) + G.slot * 3;
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -446,7 +451,11 @@ __device__ __forceinline__ int p2g_write_tiles(const Grid& g, const Warp& w, boo
     // particles whose stencil leaves the grid are flagged (the reference has no bounds check there, mpm_utils.py:516-557)
     const bool inside = (unsigned)b[0] <= (unsigned)(g.n - 3) && (unsigned)b[1] <= (unsigned)(g.n - 3) && (unsigned)b[2] <= (unsigned)(g.n - 3);
     if (valid && !inside) g.flags[1] = 1;
-    return valid ? pack_cell(b[0], b[1], b[2]) : -1 - w.lane;
+    // the cell of every SLOT, for stage 2
+    int* cs = reinterpret_cast<int*>(w.buf + P2G_T_B + P2G_U_B);
+    cs[G.slot] = mycell;
+    __syncwarp();
+    return cs[w.lane];
 }
 
 // stage 2: lane = stencil node, one pass over the slab's 32 tile records, one REDG.128 per node per cell run
@@ -454,6 +463,7 @@ __device__ __forceinline__ void p2g_stage2(const Grid& g, const Warp& w, int myc
     const Runs R = find_runs(w.lane, w.cnt, mycell);
 #if MPM_P2G_LEADER_OFFSETS
     int* ro = reinterpret_cast<int*>(w.buf + P2G_T_B + P2G_U_B);
+    __syncwarp();  // the slot cells in this region have been read
     if ((R.starts >> w.lane) & 1u) stencil_offsets(g, mycell, ro + R.mine * 9);  // the run's leader: nine per-axis node offsets
 #endif
     __syncwarp();
@@ -1140,8 +1150,8 @@ struct Gather {
     // arrays (CV / CE) the node loads are issued before the particle slab has arrived
     __device__ __forceinline__ void begin(int cell) {
         if (!valid) cell = -1 - w.lane;
-        R = find_runs(w.lane, w.cnt, cell);
-        if ((R.starts >> w.lane) & 1u) stencil_offsets(g, cell, runoff + R.mine * 9);  // the run's leader decodes its cell once
+        R = group_runs(w.lane, w.cnt, cell);  // one tile per DISTINCT cell, wherever its particles sit in the slab
+        if ((R.starts >> w.lane) & 1u) stencil_offsets(g, cell, runoff + R.mine * 9);  // the group's leader decodes its cell once
         __syncwarp();
     }
     __device__ __forceinline__ int set_position(float x, float y, float z) {

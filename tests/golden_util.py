@@ -12,7 +12,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def golden_names():
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith("cov_")]  # cov_export.npz is not a scene (tests/test_cov_export.py)
+    # cov_export.npz (tests/test_cov_export.py) and cloth_particles.npz (tests/test_cloth_io.py) are not scenes
+    return [n for n in names if not n.startswith("cov_") and n != "cloth_particles"]
 
 
 class FixedScene(S.Scene):

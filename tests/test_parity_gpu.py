@@ -301,6 +301,31 @@ def test_c3_full_size_properties():
     assert solver.stats()["overflow"] == 0
 
 
+def test_c5_full_size_properties():
+    """BASELINE.json config 5 (2 002 176 particles / 512^3 / body collider + joints): the dense oracle grid would be 11 GB,
+    so size-independent properties instead: mass conservation on the grid, free fall of the unconstrained cloth in the
+    first substep, the joint ring driven at the body velocity, finiteness and no overflow over 100 substeps."""
+    from mpmavatar_b200.scene_setup import frame_tensors
+    sc = S.scene_c5()
+    solver, model, state = run_cuda(sc, 1, per_call=False, debug=True)
+    gm, gvi, gvo = state.export_grid()
+    total_mass = float(state.particle_mass.double().sum())
+    assert abs(float(gm.double().sum()) - total_mass) < 1e-4 * total_mass
+    del gm, gvi, gvo
+    v = state.particle_v
+    assert float(v[:, 1].median()) == pytest.approx(-9.8 * sc.dt, rel=1e-2)
+    ft = frame_tensors(sc, 0)
+    Nnv = sc.n_no_vertices
+    jv = v[Nnv:Nnv + sc.num_joint_v // 2]  # the top ring is surrounded by prescribed nodes only
+    assert float((jv - ft["joint_verts_v"][: sc.num_joint_v // 2]).abs().max()) < 0.05 * float(ft["joint_verts_v"].abs().max())
+    st = solver.stats()
+    assert st["overflow"] == 0 and st["n_active_nodes"] > 300_000
+    solver.set_debug(False)
+    solver.step(model, state, sc.dt, 100, ft["mesh_x"], ft["mesh_v"], None, ft["joint_verts_v"], ft["joint_faces_v"])
+    assert torch.isfinite(state.particle_x).all() and torch.isfinite(state.particle_v).all()
+    assert solver.stats()["overflow"] == 0
+
+
 def test_kats_on_gpu_free_fall_and_clamp():
     sc = S.scene_c1(n=500, n_grid=16, seed=5, material="snow")  # no stress branch -> zero stress
     sc.v[:] = np.array([0.3, -0.2, 0.1], np.float32)
