@@ -1132,7 +1132,10 @@ __device__ __forceinline__ void g2p_contract_lean(const float4* __restrict__ T, 
 // fetch the run's 27 node velocities ONCE (one table lookup + one LDG.128 per lane, up to G2P_RMAX runs
 // in flight) into a shared-memory tile, then lane = particle contracts its run's tile with broadcast
 // reads.  Replaces 8 table lookups + 27 dependent gathers per particle.
-constexpr int G2P_RMAX = 8;  // runs per contraction pass (tile capacity)
+#ifndef MPM_G2P_RMAX
+#define MPM_G2P_RMAX 16
+#endif
+constexpr int G2P_RMAX = MPM_G2P_RMAX;  // runs per contraction pass (tile capacity)
 constexpr int G2P_OFF_B = 32 * 9 * 4;                        // nine per-axis node offsets for each of up to 32 runs
 constexpr int G2P_TILE_B = G2P_OFF_B + G2P_RMAX * 27 * 16;  // run offsets | tiles
 struct Gather {
@@ -1397,7 +1400,7 @@ struct ElemG2P {
     int* CE;
     const float* VP;
 };
-constexpr int G2P_E_WB = G2P_TILE_B;
+constexpr int G2P_E_WB = G2P_TILE_B + 512;  // + the corner slots of the 32 elements, parked by cp.async until the contraction is done
 __global__ void __launch_bounds__(32 * G2P_NW, G2P_E_MINB) k_g2p_elements(Grid g, int Ne, ElemG2P A, float dt, Advance adv) {
     extern __shared__ __align__(128) unsigned char smem[];
     Warp w;
@@ -1408,11 +1411,12 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_E_MINB) k_g2p_elements(Grid g
     const int p = w.p0 + w.lane;
     const int cell = valid ? A.CE[p] : 0;
     const float4 xe = A.XE[p], d3v4 = A.D3in[p];
-#ifdef MPM_G2P_E_EFM_EARLY
-    const int4 efm = __ldg(&A.EFM[p]);
-#endif
     Gather G(g, w, w.buf, valid);
     G.begin(cell);
+    // the corner slots are needed after the contraction only: global -> shared without a register (LDGSTS), in flight
+    // together with the node tiles, so that no load sits between the contraction and the corner reads
+    int4* park = reinterpret_cast<int4*>(w.buf + G2P_TILE_B) + w.lane;
+    cp_async16(park, &A.EFM[p]);
     G.stage_issue(0);
     PHASE(g, 5, 1);
     G.set_position(valid ? xe.x : 0.f, valid ? xe.y : 0.f, valid ? xe.z : 0.f);
@@ -1431,9 +1435,7 @@ __global__ void __launch_bounds__(32 * G2P_NW, G2P_E_MINB) k_g2p_elements(Grid g
         }
     }
     PHASE(g, 5, 4);  // contraction
-#ifndef MPM_G2P_E_EFM_EARLY
-    const int4 efm = __ldg(&A.EFM[p]);
-#endif
+    const int4 efm = *park;
     pdl_wait();      // the corner vertices must have been moved by the vertex G2P
     pdl_trigger();
     if (valid) {
