@@ -602,7 +602,10 @@ struct ElemIO {
     float4* SP3;
     float4* VF;   // buffer `cur`
 };
-__global__ void __launch_bounds__(32 * P2G_NW, 28 / P2G_NW) k_p2g_elements(Grid g, ElemIO A, int n, float dt, float rpic, float friction_coeff) {
+#ifndef MPM_P2G_E_WARPS
+#define MPM_P2G_E_WARPS 28
+#endif
+__global__ void __launch_bounds__(32 * P2G_NW, MPM_P2G_E_WARPS / P2G_NW) k_p2g_elements(Grid g, ElemIO A, int n, float dt, float rpic, float friction_coeff) {
     extern __shared__ __align__(128) unsigned char smem[];
     Warp w;
     if (!warp_begin<P2G_NW, P2G_WB>(w, n, smem)) return;
