@@ -527,6 +527,7 @@ struct MpmSolver {
     double host_time = 0.0;
     bool debug = false, profiling = false;
     bool pending_mover = false;  // mover flag of the scatter half, consumed by the gather half
+    int pending_njt = 0;
     unsigned long long* node_mask = nullptr;
     // device block count mirrored (asynchronously) into pinned host memory after each re-sort
     int* h_nslots = nullptr;
@@ -1234,7 +1235,7 @@ int mpm_step_scatter(MpmSolver* s, float dt, const MpmFrameInputs* in, void* str
     if (!in) in = &none;
     SubstepArgs a{};
     begin_half_step(s, in, a, dt, q);
-    if (in->n_joint_t > 0) throw std::string("sharded stepping does not support pinned traditional particles yet");
+    if (in->n_joint_t > s->Nt) throw std::string("n_joint_t exceeds the number of traditional particles");
     upload_lists(s, q);
     size_t mv3 = 3 * (size_t)s->cfg.n_mesh_v * sizeof(float);
     if (in->mesh_x && mv3) CK(cudaMemcpyAsync(s->mesh_x, in->mesh_x, mv3, cudaMemcpyDefault, q));
@@ -1242,9 +1243,14 @@ int mpm_step_scatter(MpmSolver* s, float dt, const MpmFrameInputs* in, void* str
     if (a.mover) {
         if (s->cfg.num_joint_v) CK(cudaMemcpyAsync(s->joint_v, in->joint_verts_v, 3 * (size_t)s->cfg.num_joint_v * sizeof(float), cudaMemcpyDefault, q));
         if (s->cfg.num_joint_f) CK(cudaMemcpyAsync(s->joint_f, in->joint_faces_v, 3 * (size_t)s->cfg.num_joint_f * sizeof(float), cudaMemcpyDefault, q));
+        if (in->joint_traditional_v && in->n_joint_t > 0) {  // this rank's share of the pinned tail (sharding.local_joint_traditional)
+            a.njt = in->n_joint_t;
+            CK(cudaMemcpyAsync(s->joint_t, in->joint_traditional_v, 3 * (size_t)a.njt * sizeof(float), cudaMemcpyDefault, q));
+        }
     }
     if (s->need_sort || s->since_sort >= s->resort_interval) resort(s, q);
     s->pending_mover = a.mover;
+    s->pending_njt = a.njt;
     launch_substep(s, a, q, HALF_SCATTER);
     CK(cudaGetLastError());
     API_END(s)
@@ -1256,6 +1262,7 @@ int mpm_step_gather(MpmSolver* s, float dt, void* stream) {
     SubstepArgs a{};
     begin_half_step(s, nullptr, a, dt, q);
     a.mover = s->pending_mover;
+    a.njt = s->pending_njt;
     launch_substep(s, a, q, HALF_GATHER);
     s->since_sort++;
     s->n_substeps++;
@@ -1275,7 +1282,7 @@ int mpm_step_sharded(MpmSolver* s, float dt, int nsub, const MpmFrameInputs* in,
     if (!in) in = &none;
     SubstepArgs a{};
     begin_half_step(s, in, a, dt, q);
-    if (in->n_joint_t > 0) throw std::string("sharded stepping does not support pinned traditional particles yet");
+    if (in->n_joint_t > s->Nt) throw std::string("n_joint_t exceeds the number of traditional particles");
     upload_lists(s, q);
     size_t mv3 = 3 * (size_t)s->cfg.n_mesh_v * sizeof(float);
     if (in->mesh_x && mv3) CK(cudaMemcpyAsync(s->mesh_x, in->mesh_x, mv3, cudaMemcpyDefault, q));
@@ -1283,6 +1290,10 @@ int mpm_step_sharded(MpmSolver* s, float dt, int nsub, const MpmFrameInputs* in,
     if (a.mover) {
         if (s->cfg.num_joint_v) CK(cudaMemcpyAsync(s->joint_v, in->joint_verts_v, 3 * (size_t)s->cfg.num_joint_v * sizeof(float), cudaMemcpyDefault, q));
         if (s->cfg.num_joint_f) CK(cudaMemcpyAsync(s->joint_f, in->joint_faces_v, 3 * (size_t)s->cfg.num_joint_f * sizeof(float), cudaMemcpyDefault, q));
+        if (in->joint_traditional_v && in->n_joint_t > 0) {  // this rank's share of the pinned tail (sharding.local_joint_traditional)
+            a.njt = in->n_joint_t;
+            CK(cudaMemcpyAsync(s->joint_t, in->joint_traditional_v, 3 * (size_t)a.njt * sizeof(float), cudaMemcpyDefault, q));
+        }
     }
     a.advance_mesh = in->mesh_x != nullptr && nsub > 1;  // substep k sees mesh_x + dt*k*mesh_v (device-side counter)
     k_reset_k<<<1, 1, 0, q>>>(s->st);
@@ -1350,7 +1361,7 @@ NcclApi* nccl_api() {
 
 struct ShardGraphKey {
     float dt;
-    int collider, mover, advance_mesh, cur, n_bc, n_ops, xcap, len, rbuf;
+    int collider, mover, advance_mesh, cur, n_bc, n_ops, xcap, len, rbuf, njt;
     const void* shared_ptr;
     bool operator==(const ShardGraphKey& o) const { return memcmp(this, &o, sizeof(ShardGraphKey)) == 0; }
 };
@@ -1439,7 +1450,8 @@ static void mark_potential(MpmSolver* s, int margin, cudaStream_t q) {
     CK(cudaMemsetAsync(s->d_mark, 0, 2 * nt, q));
     const int bit = (have_comm(s) && s->comm_size <= 8) ? (1 << s->comm_rank) : 1;  // rank set for <= 8 ranks, else a count
     if (s->Ne) k_mark_potential<<<cdiv(s->Ne, 128), 128, 0, q>>>(s->g, s->Ne, (const float*)s->R.XE, 4, margin, s->d_mark, mj, s->R.permE, s->cfg.num_joint_f, bit);
-    if (s->Nt) k_mark_potential<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F, margin, s->d_mark, nullptr, nullptr, 0, bit);
+    // any traditional particle may belong to the pinned tail (its length changes from call to call, run_demo.py:524)
+    if (s->Nt) k_mark_potential<<<cdiv(s->Nt, 128), 128, 0, q>>>(s->g, s->Nt, s->R.TP, KP_F, margin, s->d_mark, mj, s->R.permT, s->Nt, bit);
     if (s->Nv) k_mark_potential<<<cdiv(s->Nv, 128), 128, 0, q>>>(s->g, s->Nv, s->R.VP, VP_F, margin, s->d_mark, mj, s->R.permV, s->cfg.num_joint_v, bit);
     s->launches += 3;
 }
@@ -1617,7 +1629,7 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
     if (!in) in = &none;
     SubstepArgs a{};
     begin_half_step(s, in, a, dt, q);
-    if (in->n_joint_t > 0) throw std::string("sharded stepping does not support pinned traditional particles yet");
+    if (in->n_joint_t > s->Nt) throw std::string("n_joint_t exceeds the number of traditional particles");
     upload_lists(s, q);
     size_t mv3 = 3 * (size_t)s->cfg.n_mesh_v * sizeof(float);
     if (in->mesh_x && mv3) CK(cudaMemcpyAsync(s->mesh_x, in->mesh_x, mv3, cudaMemcpyDefault, q));
@@ -1625,6 +1637,10 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
     if (a.mover) {
         if (s->cfg.num_joint_v) CK(cudaMemcpyAsync(s->joint_v, in->joint_verts_v, 3 * (size_t)s->cfg.num_joint_v * sizeof(float), cudaMemcpyDefault, q));
         if (s->cfg.num_joint_f) CK(cudaMemcpyAsync(s->joint_f, in->joint_faces_v, 3 * (size_t)s->cfg.num_joint_f * sizeof(float), cudaMemcpyDefault, q));
+        if (in->joint_traditional_v && in->n_joint_t > 0) {  // this rank's share of the pinned tail (sharding.local_joint_traditional)
+            a.njt = in->n_joint_t;
+            CK(cudaMemcpyAsync(s->joint_t, in->joint_traditional_v, 3 * (size_t)a.njt * sizeof(float), cudaMemcpyDefault, q));
+        }
     }
     a.advance_mesh = in->mesh_x != nullptr && nsub > 1;
     k_reset_k<<<1, 1, 0, q>>>(s->st);
@@ -1643,7 +1659,7 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
             ShardGraphKey key{};
             key.dt = a.dt; key.collider = a.collider; key.mover = a.mover; key.advance_mesh = a.advance_mesh; key.cur = s->cur;
             key.n_bc = (int)s->h_bcs.size(); key.n_ops = (int)s->h_ops.size(); key.xcap = s->xcap_blocks * 65536 + s->xcapM; key.len = W + (s->p2p_ready ? 1000 : 0);
-            key.shared_ptr = s->d_shared; key.rbuf = s->rbuf;
+            key.shared_ptr = s->d_shared; key.rbuf = s->rbuf; key.njt = a.njt;
             auto& cache = shard_graphs(s);
             ShardGraph* hit = nullptr;
             for (auto& e : cache) if (e.key == key) hit = &e;

@@ -42,7 +42,9 @@ def build_from_scene(sc, device="cuda:0", resort_interval=0):
         solver.add_surface_collider(**b)
     if sc.body_verts is not None:
         solver.add_mesh_collider(solver.mesh.id, n_grid=sc.n_grid, friction=sc.mesh_friction)
-    if sc.num_joint_v or sc.num_joint_f:
+    # (a rank of a sharded run needs the mover even without joint particles of its own: its grid blocks receive the
+    # prescribed-velocity sums of the other ranks)
+    if sc.num_joint_v or sc.num_joint_f or sc.num_joint_t or getattr(sc, "force_mover", False):
         solver.add_particle_mover(n_grid=sc.n_grid)
     reset_rollout(sc, solver, model, state, device)
     return solver, model, state

@@ -125,7 +125,7 @@ class ShardedMPM:
         self.stats["shared_blocks"] = self.n_shared
         self.stats["exchange_bytes"] = self.n_shared * 64 * 8 * 4
 
-    def step(self, dt, nsub, mesh_x=None, mesh_v=None, joint_verts_v=None, joint_faces_v=None):
+    def step(self, dt, nsub, mesh_x=None, mesh_v=None, joint_verts_v=None, joint_faces_v=None, joint_traditional_v=None):
         """nsub substeps; substep k sees body points mesh_x + dt*k*mesh_v (the callers' inner loop,
         train_material_params.py:622-626).  Joint velocity arrays are the GLOBAL ones.  The substep loop
         runs in C (mpm_step_sharded); per substep it calls back once for the all-reduce."""
@@ -140,6 +140,12 @@ class ShardedMPM:
                               torch.as_tensor(p.elems[:p.num_joint_f], device=dev, dtype=torch.long))
             jv = T(joint_verts_v)[self._jidx[0]].contiguous() if p.num_joint_v else torch.zeros(1, 3, device=dev)
             jf = T(joint_faces_v)[self._jidx[1]].contiguous() if p.num_joint_f else torch.zeros(1, 3, device=dev)
+        jt, njt = None, 0
+        if jv is not None and joint_traditional_v is not None and len(joint_traditional_v):
+            # the caller pins the LAST len(joint_traditional_v) traditional particles (mpm_solver.py:283,446): this rank's share
+            njt, rows = sh.local_joint_traditional(self.part, len(joint_traditional_v))
+            if njt:
+                jt = T(joint_traditional_v)[torch.as_tensor(rows, device=dev)].contiguous()
         if self.buf is None and not self.in_graph:
             self.rebuild_shared()
         fin = _lib.MpmFrameInputs()
@@ -147,6 +153,8 @@ class ShardedMPM:
         fin.mesh_v = None if mesh_v is None else C.c_void_p(mesh_v.data_ptr())
         if jv is not None:
             fin.joint_verts_v, fin.joint_faces_v = C.c_void_p(jv.data_ptr()), C.c_void_p(jf.data_ptr())
+        if jt is not None:
+            fin.joint_traditional_v, fin.n_joint_t = C.c_void_p(jt.data_ptr()), njt
         err = []
 
         def exchange(ctx, buf, n):
@@ -175,7 +183,7 @@ class ShardedMPM:
         self._ck(rc)
         if self.in_graph:
             self.refresh_stats()
-        self._keep = (mesh_x, mesh_v, jv, jf)
+        self._keep = (mesh_x, mesh_v, jv, jf, jt)
         self.state._stale = True
         self.state._solver = self.solver
 
@@ -191,10 +199,11 @@ class ShardedMPM:
     def gather_positions(self):
         """Full canonical particle_x / particle_v on every rank (original particle order)."""
         p, sc, dev = self.part, self.sc, self.device
-        Ne_l = len(p.elems)
+        n_own = len(p.elems) + len(p.trads) + p.n_owned_v  # local order: [elements | traditional | owned vertices | ghosts]
         x, v = self.state.particle_x, self.state.particle_v
-        ids = torch.as_tensor(np.concatenate([p.elems, sc.n_elements + p.verts[:p.n_owned_v]]), device=dev, dtype=torch.long)
-        own = torch.cat([x[: Ne_l + p.n_owned_v], v[: Ne_l + p.n_owned_v]], 1).contiguous()
+        ids = torch.as_tensor(np.concatenate([p.elems, sc.n_elements + p.trads,
+                                              sc.n_elements + sc.n_traditional + p.verts[:p.n_owned_v]]), device=dev, dtype=torch.long)
+        own = torch.cat([x[:n_own], v[:n_own]], 1).contiguous()
         sizes = [int(s.item()) for s in self._all_gather(torch.tensor([own.shape[0]], dtype=torch.int64, device=dev))]
         pad = max(sizes)
         send = torch.zeros(pad, 7, device=dev)

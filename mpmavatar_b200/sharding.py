@@ -22,6 +22,10 @@ Scheme
     rebuild (CFL: <= 0.05 cell per substep, a block is 4 cells).
   * Prescribed-velocity (joint) particles are scattered by their owner only; they stay first in the local
     element / vertex order as the reference's mover kernels require (mpm_solver.py:450-472).
+  * TRADITIONAL particles (the demo's sand, run_demo.py:309-379) have no mesh coupling: they are cut into equally
+    sized runs along the same axis and need no ghosts.  A rank keeps its share in ascending global order, so the
+    pinned TAIL of the global order (joint_traditional_v pins the last n particles, mpm_solver.py:283,446) is the tail
+    of every rank's local order too: rank-local count = owned ids >= Nt - n (local_joint_traditional).
 """
 from __future__ import annotations
 
@@ -67,6 +71,8 @@ class Part:
     faces_local: np.ndarray  # [len(elems),3] indices into `verts`
     num_joint_v: int         # owned joint vertices (a prefix of `verts`)
     num_joint_f: int         # owned joint faces (a prefix of `elems`)
+    trads: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0, np.int64))  # owned traditional ids, ascending
+    n_traditional_global: int = 0
 
     @property
     def n_ghost_v(self):
@@ -74,13 +80,17 @@ class Part:
 
 
 def partition(x, faces, n_elements, n_vertices, n_grid, grid_lim, world, num_joint_v=0, num_joint_f=0):
-    """x: canonical positions [elements | vertices]; faces: [Ne,3] vertex-local ints."""
+    """x: canonical positions [elements | traditional | vertices]; faces: [Ne,3] vertex-local ints."""
     Ne, Nv = n_elements, n_vertices
-    if x.shape[0] != Ne + Nv:
-        raise NotImplementedError("sharding supports cloth scenes (elements + vertices) only")
-    axis = int(np.argmax(x.max(0) - x.min(0)))  # slabs across the longest extent
-    e_owner = _equal_cuts(morton_block_keys(x[:Ne], n_grid, grid_lim), world, x[:Ne, axis])
-    v_owner = _equal_cuts(morton_block_keys(x[Ne:], n_grid, grid_lim), world, x[Ne:, axis])
+    Nt = x.shape[0] - Ne - Nv
+    if Nt < 0:
+        raise ValueError("x is shorter than n_elements + n_vertices")
+    xe, xt, xv = x[:Ne], x[Ne:Ne + Nt], x[Ne + Nt:]
+    cloth = np.concatenate([xe, xv]) if Ne + Nv else xt
+    axis = int(np.argmax(cloth.max(0) - cloth.min(0)))  # slabs across the longest extent of the garment
+    e_owner = _equal_cuts(morton_block_keys(xe, n_grid, grid_lim), world, xe[:, axis]) if Ne else np.zeros(0, np.int32)
+    v_owner = _equal_cuts(morton_block_keys(xv, n_grid, grid_lim), world, xv[:, axis]) if Nv else np.zeros(0, np.int32)
+    t_owner = _equal_cuts(morton_block_keys(xt, n_grid, grid_lim), world, xt[:, axis]) if Nt else np.zeros(0, np.int32)
     parts = []
     for r in range(world):
         elems = np.nonzero(e_owner == r)[0]
@@ -92,30 +102,47 @@ def partition(x, faces, n_elements, n_vertices, n_grid, grid_lim, world, num_joi
         g2l[verts] = np.arange(len(verts))
         parts.append(Part(rank=r, world=world, elems=elems, verts=verts, n_owned_v=len(owned),
                           faces_local=g2l[faces[elems]].astype(np.int64),
-                          num_joint_v=int((owned < num_joint_v).sum()), num_joint_f=int((elems < num_joint_f).sum())))
+                          num_joint_v=int((owned < num_joint_v).sum()), num_joint_f=int((elems < num_joint_f).sum()),
+                          trads=np.nonzero(t_owner == r)[0], n_traditional_global=Nt))
     return parts
 
 
 def local_scene(sc, part: Part):
     """The rank's sub-scene in the canonical layout [owned elements | owned vertices, ghost vertices];
     ghosts get volume 0, hence mass 0 (mass = density * vol, mpm_data_structure.py:434-467)."""
-    Ne = sc.n_elements
-    ids = np.concatenate([part.elems, Ne + part.verts])
+    Ne, Nt = sc.n_elements, sc.n_traditional
+    ids = np.concatenate([part.elems, Ne + part.trads, Ne + Nt + part.verts]).astype(np.int64)
     vol = sc.vol[ids].copy()
-    vol[len(part.elems) + part.n_owned_v:] = 0.0
+    vol[len(part.elems) + len(part.trads) + part.n_owned_v:] = 0.0
     pick = lambda a: None if a is None else np.ascontiguousarray(a[ids])
+    nnv_ids = np.concatenate([part.elems, Ne + part.trads]).astype(np.int64)  # rows of the [Nnv, ...] arrays
     loc = dataclasses.replace(
-        sc, name=f"{sc.name}_r{part.rank}of{part.world}", n_elements=len(part.elems), n_traditional=0,
+        sc, name=f"{sc.name}_r{part.rank}of{part.world}", n_elements=len(part.elems), n_traditional=len(part.trads),
         n_vertices=len(part.verts), x=pick(sc.x), v=pick(sc.v), vol=vol, density=pick(sc.density), E=pick(sc.E),
         nu=pick(sc.nu), gamma=pick(sc.gamma), kappa=pick(sc.kappa), faces=part.faces_local,
-        d=np.ascontiguousarray(sc.d[part.elems]), R_inv=np.ascontiguousarray(sc.R_inv[part.elems]), F_trial=None,
-        yield_stress=pick(sc.yield_stress), num_joint_v=part.num_joint_v, num_joint_f=part.num_joint_f, num_joint_t=0)
+        d=np.ascontiguousarray(sc.d[part.elems]), R_inv=np.ascontiguousarray(sc.R_inv[part.elems]),
+        F_trial=None if sc.F_trial is None else np.ascontiguousarray(sc.F_trial[nnv_ids]),
+        yield_stress=pick(sc.yield_stress), num_joint_v=part.num_joint_v, num_joint_f=part.num_joint_f,
+        num_joint_t=local_joint_traditional(part, sc.num_joint_t)[0])
+    # the mover must exist on every rank as soon as ANY rank has prescribed-velocity particles (scene_setup.build_from_scene)
+    loc.force_mover = bool(sc.num_joint_v or sc.num_joint_f or sc.num_joint_t)
     return loc
+
+
+def local_joint_traditional(part: Part, n_pinned: int):
+    """(count, rows): how many of this rank's traditional particles lie in the pinned tail of the GLOBAL order (the last
+    n_pinned traditional particles, mpm_solver.py:283,446) and which rows of the caller's joint_traditional_v they take.
+    They are the tail of the rank's local order because `trads` is ascending."""
+    first = part.n_traditional_global - int(n_pinned)
+    mine = part.trads[part.trads >= first]
+    return len(mine), (mine - first).astype(np.int64)
 
 
 def local_frame_inputs(fi, part: Part):
     """Restrict the per-frame solver inputs to the rank's owned joints; the body mesh is replicated."""
     out = dict(fi)
+    if fi.get("joint_traditional_v") is not None:
+        out["joint_traditional_v"] = np.ascontiguousarray(fi["joint_traditional_v"][local_joint_traditional(part, len(fi["joint_traditional_v"]))[1]])
     if fi.get("joint_verts_v") is not None:
         out["joint_verts_v"] = np.ascontiguousarray(fi["joint_verts_v"][part.verts[:part.num_joint_v]])
         out["joint_faces_v"] = np.ascontiguousarray(fi["joint_faces_v"][part.elems[:part.num_joint_f]])

@@ -54,6 +54,33 @@ def test_partition_covers_everything_once():
             assert p.n_ghost_v < 0.5 * p.n_owned_v + 64
 
 
+def test_partition_with_traditional_particles_and_pinned_tail():
+    """The run_demo.py scene shape: cloth + sand, the tail of the sand pinned by joint_traditional_v."""
+    sc = S.scene_demo_like()
+    Ne, Nt = sc.n_elements, sc.n_traditional
+    for world in (2, 3):
+        parts = sh.partition(sc.x, sc.faces, Ne, sc.n_vertices, sc.n_grid, sc.grid_lim, world, sc.num_joint_v, sc.num_joint_f)
+        assert sorted(np.concatenate([p.trads for p in parts]).tolist()) == list(range(Nt))
+        for n_pinned in (sc.num_joint_t, 37, 0):
+            jt = np.arange(3 * n_pinned, dtype=np.float32).reshape(n_pinned, 3)
+            tot, seen = 0, []
+            for p in parts:
+                k, rows = sh.local_joint_traditional(p, n_pinned)
+                tot += k
+                assert (np.diff(p.trads) > 0).all()
+                assert (p.trads[len(p.trads) - k:] >= Nt - n_pinned).all() and (p.trads[: len(p.trads) - k] < Nt - n_pinned).all()
+                seen.append(Nt - n_pinned + rows)  # global ids of the rows this rank takes
+                if n_pinned:
+                    lfi = sh.local_frame_inputs(dict(joint_traditional_v=jt), p)
+                    assert (lfi["joint_traditional_v"] == jt[rows]).all()
+            assert tot == n_pinned and sorted(np.concatenate(seen).tolist()) == list(range(Nt - n_pinned, Nt))
+        loc = sh.local_scene(sc, parts[0])
+        p = parts[0]
+        assert loc.n_traditional == len(p.trads) and loc.n_particles == len(p.elems) + len(p.trads) + len(p.verts)
+        assert (loc.x[loc.n_elements:loc.n_elements + loc.n_traditional] == sc.x[Ne + p.trads]).all()
+        assert loc.num_joint_t == sh.local_joint_traditional(p, sc.num_joint_t)[0]
+
+
 def test_morton_key_matches_block_order():
     x = np.array([[1.0, 1.0, 1.0], [1.0, 1.0, 1.01], [0.2, 1.9, 0.3]], np.float32)
     k = sh.morton_block_keys(x, 64, 2.0)
