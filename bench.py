@@ -34,10 +34,10 @@ sys.path.insert(0, ROOT)
 
 SUBSTEPS_PER_STEP = 400
 # dram__bytes_read.sum + dram__bytes_write.sum of the P2G / G2P launches of one substep (ncu --set full, cold caches;
-# profiles/r1_v17_ncu_full_summary.txt): 55.29 + 17.86 + 16.12 + 49.81 MB for k_p2g<0>, k_p2g<2>, k_g2p_vertices,
-# k_g2p_elements (the vertex records carry 16 bytes of padding, see VP_F)
-TRAFFIC_NCU = 139.08e6
-TRAFFIC_SOURCE = "constant: ncu --set full capture of one substep's P2G/G2P launches, cold caches (profiles/), not measured in this run"
+# profiles/r2_v5_ncu_full_summary.txt): 58.55 + 17.88 + 16.15 + 33.68 MB for k_p2g_elements, k_p2g<2>, k_g2p_vertices,
+# k_g2p_elements.  A CONSTANT from that capture, not measured in the bench run (roofline.traffic_source says so).
+TRAFFIC_NCU = 126.25e6
+TRAFFIC_SOURCE = "constant: ncu --set full capture of one substep's P2G/G2P launches, cold caches (profiles/r2_v5_ncu_full_summary.txt), not measured in this run"
 METRIC = "mpm_substeps_per_sec_500k_particles_256grid"
 
 
