@@ -503,6 +503,8 @@ struct MpmSolver {
     MpmHostAllGatherFn host_ag = nullptr;  // mpm_attach_host_comm: the caller's blocking host all-gather (gloo, MPI, ...)
     void* host_ctx = nullptr;
     std::vector<unsigned char> host_stage;
+    unsigned char* ag_dev = nullptr;  // device staging of the NCCL all-gather of host bytes
+    size_t ag_bytes = 0;
     int comm_rank = 0, comm_size = 1;
     float* xbuf = nullptr;         // exchange buffer of the in-graph path, xcap_blocks * 512 floats
     int xcap_blocks = 0;
@@ -535,6 +537,7 @@ struct MpmSolver {
     void* graph_cache_ptr = nullptr;
     bool use_graphs = true;
     bool use_pdl = true;  // MPM_B200_PDL=0 disables programmatic dependent launch
+    bool scatter_early = false;  // MPM_B200_SCATTER_EARLY=1
     cudaStream_t cap_stream = nullptr;
     // profiling
     cudaEvent_t ev[10]{};
@@ -726,13 +729,15 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
             s->launches++;
         }
     };
+    const bool scatter_early = s->scatter_early && !ev;  // A/B: body scatter between the element and the vertex P2G
+    if (scatter_early) scatter_launch();
     if (s->Nv) {
         P2GIn in{R.VP, (const float*)R.VF[cur]};
         launch_pdl(k_p2g<2>, cdiv(s->Nv, 32 * P2G_V_NW), 32 * P2G_V_NW, 128 + P2G_V_NW * P2G_WB, q, pdl, s->g, in, s->Nv, a.dt, s->md.rpic);
         s->launches++;
     }
     if (ev) CK(cudaEventRecord(ev[2], q));
-    scatter_launch();
+    if (!scatter_early) scatter_launch();
     }  // HALF_SCATTER
     if (!(halves & HALF_GATHER)) return;
     // one thread per node of the active blocks, grid-strided over the device-side block count
@@ -894,6 +899,7 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         if (cfg->resort_interval > 0) s->resort_interval = cfg->resort_interval;
         if (const char* e = getenv("MPM_B200_RESORT")) { if (cfg->resort_interval <= 0 && atoi(e) > 0) s->resort_interval = atoi(e); }
         if (const char* e = getenv("MPM_B200_PDL")) s->use_pdl = atoi(e) != 0;
+        if (const char* e = getenv("MPM_B200_SCATTER_EARLY")) s->scatter_early = atoi(e) != 0;
         if (const char* e = getenv("MPM_B200_GRAPHS")) s->use_graphs = atoi(e) != 0;
         if (const char* e = getenv("MPM_B200_P2P")) s->use_p2p = atoi(e) != 0;
         Grid& g = s->g;
@@ -1387,7 +1393,12 @@ void allgather_host_bytes(MpmSolver* s, const void* send, void* recv, size_t nby
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) =
         (decltype(AllGather))dlsym(nccl_api()->lib, "ncclAllGather");
     if (!AllGather) throw std::string("libnccl.so.2 lacks ncclAllGather");
-    unsigned char* d = s->dalloc<unsigned char>((size_t)(s->comm_size + 1) * nbytes);
+    const size_t need = (size_t)(s->comm_size + 1) * nbytes;
+    if (need > s->ag_bytes) {  // small, rarely used (set-up traffic): grown, never shrunk
+        s->ag_dev = s->dalloc<unsigned char>(need);
+        s->ag_bytes = need;
+    }
+    unsigned char* d = s->ag_dev;
     CK(cudaMemcpyAsync(d + (size_t)s->comm_size * nbytes, send, nbytes, cudaMemcpyHostToDevice, q));
     NCK(AllGather(d + (size_t)s->comm_size * nbytes, d, nbytes, ncclUint8, s->comm, q));
     CK(cudaMemcpyAsync(recv, d, (size_t)s->comm_size * nbytes, cudaMemcpyDeviceToHost, q));
