@@ -274,6 +274,11 @@ def run_sharded(args, sc, rank, local_rank, world, dev, barrier):
     peak, peak_src = measured_peaks()
     bytes_pg = algorithmic_bytes(lsc, A)
     achieved = bytes_pg / t_pg / 1e9
+    # the sharded chain as it runs (PDL, peer-to-peer exchange): per-kernel stamps incl. k_shared_push / k_shared_pull
+    tl = None
+    if sm.lib.mpm_shared_mode(sm.h) == 2:
+        from mpmavatar_b200.timeline import measure_sharded, summarise
+        tl = summarise(measure_sharded(sm, sc.dt, dev_frames[-1], 24))
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "substeps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -289,7 +294,8 @@ def run_sharded(args, sc, rank, local_rank, world, dev, barrier):
                 "roofline": {"bound": "hbm", "kernel": "p2g + g2p of rank 0's tile", "achieved": achieved, "peak": peak,
                              "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "algorithmic_bytes_per_substep": bytes_pg, "active_nodes": A,
-                             "phase_us_per_substep": {k[:-3]: round(v * 1e3, 2) for k, v in per.items()}},
+                             "phase_us_per_substep": {k[:-3]: round(v * 1e3, 2) for k, v in per.items()},
+                             "timeline_us": tl},
                 "finite": bool(fin.item() > 0), "shard": {"owned_elements": len(p.elems), "owned_vertices": p.n_owned_v,
                                                           "ghost_vertices": p.n_ghost_v, **sm.stats}}
         print(json.dumps(line), flush=True)

@@ -210,6 +210,10 @@ int mpm_force_resort(MpmSolver *s);
  * 1 P2G traditional, 2 P2G vertices, 3 body/joint scatter, 4 grid update, 5 G2P vertices, 6 G2P traditional,
  * 7 G2P elements.  The kernels overlap under programmatic dependent launch, which CUDA events cannot resolve. */
 int mpm_measure_timeline(MpmSolver *s, float dt, int n, const MpmFrameInputs *in, long long *out, void *stream);
+/* the same for the SHARDED chain (collective; needs the peer-to-peer exchange, i.e. at least one mpm_step_sharded_nccl call
+ * before): n <= 32, out[n][10][2]; ids 0-7 as above, 8 = k_shared_push (from the end of its wait for this rank's scatters to
+ * its last flag store), 9 = k_shared_pull (including the wait for the slowest peer's flag: the ranks' skew). */
+int mpm_measure_timeline_sharded(MpmSolver *s, float dt, int n, const MpmFrameInputs *in, long long *out, void *stream);
 /* latency analysis (builds with -DMPM_CLK only fill it): 8 kernels x 8 per-warp phase cycle sums; synchronises */
 int mpm_debug_phase_clocks(MpmSolver *s, unsigned long long *out64, int reset);
 

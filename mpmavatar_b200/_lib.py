@@ -90,6 +90,7 @@ SYMBOLS = {
     "mpm_shared_pack": (C.c_int, [_P, _P, _P]),
     "mpm_shared_unpack": (C.c_int, [_P, _P, _P]),
     "mpm_measure_timeline": (C.c_int, [_P, C.c_float, C.c_int, C.POINTER(MpmFrameInputs), _P, _P]),
+    "mpm_measure_timeline_sharded": (C.c_int, [_P, C.c_float, C.c_int, C.POINTER(MpmFrameInputs), _P, _P]),
     "mpm_set_time": (C.c_int, [_P, C.c_double]),
     "mpm_export_grid": (C.c_int, [_P, _P, _P, _P, _P]),
     "mpm_set_debug": (C.c_int, [_P, C.c_int]),

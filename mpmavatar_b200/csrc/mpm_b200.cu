@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(256) k_shared_push(Grid g, SharedLists L, cons
     const int nA = min(*L.nA, L.capA) * BN, nM = min(*L.nM, L.capM) * BN;
     pdl_wait();     // every scatter into acc / mov of this substep is complete
     pdl_trigger();  // the pull may start polling the peers' flags while this rank still sends
+    ts_begin(g, TS_PUSH);  // stamped behind the wait: the time this rank spends SENDING
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nA + nM; idx += gridDim.x * blockDim.x) {
         const bool mv = idx >= nA;
         const int j = mv ? idx - nA : idx;
@@ -414,11 +415,13 @@ __global__ void __launch_bounds__(256) k_shared_push(Grid g, SharedLists L, cons
                 if (r != P.rank) st_release_sys(reinterpret_cast<unsigned*>(P.base[r] + P.flags_off) + par * P.nranks + P.rank, E + 1);
         }
     }
+    ts_end(g, TS_PUSH);
 }
 __global__ void __launch_bounds__(256) k_shared_pull(Grid g, SharedLists L, const unsigned char* __restrict__ memA,
                                                      const unsigned char* __restrict__ memM, PeerArea P) {
     const unsigned E = *P.epoch;
     const int par = E & 1;
+    ts_begin(g, TS_PULL);  // includes the wait for the slowest peer's flag: the ranks' skew shows up here
     if (threadIdx.x < P.nranks && threadIdx.x != P.rank) {
         const unsigned* f = reinterpret_cast<const unsigned*>(P.base[P.rank] + P.flags_off) + par * P.nranks + threadIdx.x;
         while (ld_acquire_sys(f) < E + 1) __nanosleep(64);
@@ -455,6 +458,7 @@ __global__ void __launch_bounds__(256) k_shared_pull(Grid g, SharedLists L, cons
             *P.epoch = E + 1;
         }
     }
+    ts_end(g, TS_PULL);
 }
 
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
@@ -1705,6 +1709,47 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
     }
     s->canon_stale = true;
     CK(cudaGetLastError());
+    API_END(s)
+}
+
+// Timeline probe of the SHARDED chain (collective: every rank calls it with the same n): n <= 32 sharded substeps launched
+// eagerly with the stamps on; out[n][10][2] as mpm_measure_timeline plus ids 8 (k_shared_push, from the end of its wait to
+// its last flag) and 9 (k_shared_pull, including the wait for the slowest peer).  Requires the peer-to-peer exchange.
+int mpm_measure_timeline_sharded(MpmSolver* s, float dt, int n, const MpmFrameInputs* in, long long* out, void* stream) {
+    API_BEGIN(s)
+    cudaStream_t q = (cudaStream_t)stream;
+    if (n < 1 || n > 32) throw std::string("mpm_measure_timeline_sharded: 1 <= n <= 32");
+    if (!s->p2p_ready) throw std::string("mpm_measure_timeline_sharded needs the peer-to-peer exchange (step once first)");
+    MpmFrameInputs none{};
+    if (!in) in = &none;
+    SubstepArgs a{};
+    begin_half_step(s, in, a, dt, q);
+    const size_t per = 2 * TS_KERNELS_SHARDED;
+    std::vector<unsigned long long> h((size_t)n * per);
+    for (size_t i = 0; i < h.size(); i++) h[i] = (i & 1) ? 0ull : ~0ull;
+    unsigned long long* d = s->dalloc<unsigned long long>(h.size());
+    CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, q));
+    // no re-sort, no shared-list rebuild inside the probe: n stays far below both intervals' slack (the caller steps
+    // normally before and after)
+    for (int i = 0; i < n; i++) {
+        s->g.ts = d + (size_t)i * per;
+        sharded_substep(s, a, q);
+    }
+    s->g.ts = nullptr;
+    s->shared_age += n;
+    s->since_sort += n;
+    s->n_substeps += n;
+    s->canon_stale = true;
+    for (int k = 0; k < n; k++) s->host_time += (double)dt;
+    CK(cudaMemcpyAsync(h.data(), d, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, q));
+    CK(cudaStreamSynchronize(q));
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < h.size(); i += 2) t0 = std::min(t0, h[i]);
+    for (size_t i = 0; i < h.size(); i += 2) {
+        const bool ran = h[i] != ~0ull;
+        out[i] = ran ? (long long)(h[i] - t0) : -1;
+        out[i + 1] = ran ? (long long)(h[i + 1] - t0) : -1;
+    }
     API_END(s)
 }
 

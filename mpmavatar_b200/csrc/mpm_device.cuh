@@ -81,7 +81,8 @@ struct Grid {
 // Timeline probe: first CTA start / last CTA end of a kernel on the GPU's global timer.  CUDA events cannot
 // time kernels that overlap under programmatic dependent launch; these stamps can.  One 64-bit atomic per warp
 // at each end, only when g.ts is set.
-enum { TS_P2G_E = 0, TS_P2G_T, TS_P2G_V, TS_SCATTER, TS_GRID, TS_G2P_V, TS_G2P_T, TS_G2P_E, TS_KERNELS };
+enum { TS_P2G_E = 0, TS_P2G_T, TS_P2G_V, TS_SCATTER, TS_GRID, TS_G2P_V, TS_G2P_T, TS_G2P_E, TS_KERNELS,
+       TS_PUSH = TS_KERNELS, TS_PULL, TS_KERNELS_SHARDED };  // the two exchange kernels of a sharded substep
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

@@ -8,7 +8,7 @@ import torch
 
 from . import _lib
 
-NAMES = ["p2g_E", "p2g_T", "p2g_V", "scatter", "grid", "g2p_V", "g2p_T", "g2p_E"]
+NAMES = ["p2g_E", "p2g_T", "p2g_V", "scatter", "grid", "g2p_V", "g2p_T", "g2p_E", "push", "pull"]
 
 
 def measure(solver, dt, ft, n=32):
@@ -22,6 +22,32 @@ def measure(solver, dt, ft, n=32):
                                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0:
         raise RuntimeError("libmpm_b200: " + solver._libh.mpm_last_error(solver._h).decode())
+    return out
+
+
+def measure_sharded(sm, dt, ft, n=24):
+    """Collective (every rank calls it): per-kernel stamps of n sharded substeps of a ShardedMPM, incl. the two exchange
+    kernels.  ft: GLOBAL frame tensors (the rank's joint rows are picked as ShardedMPM.step does)."""
+    p = sm.part
+    fin = _lib.MpmFrameInputs()
+    keep = []
+    for k in ("mesh_x", "mesh_v"):
+        if ft.get(k) is not None:
+            setattr(fin, k, ft[k].data_ptr())
+    if ft.get("joint_verts_v") is not None and ft.get("joint_faces_v") is not None:
+        dev = sm.device
+        iv = torch.as_tensor(p.verts[:p.num_joint_v], device=dev, dtype=torch.long)
+        jf_i = torch.as_tensor(p.elems[:p.num_joint_f], device=dev, dtype=torch.long)
+        jv = ft["joint_verts_v"][iv].contiguous() if p.num_joint_v else torch.zeros(1, 3, device=dev)
+        jf = ft["joint_faces_v"][jf_i].contiguous() if p.num_joint_f else torch.zeros(1, 3, device=dev)
+        keep += [jv, jf]
+        fin.joint_verts_v, fin.joint_faces_v = jv.data_ptr(), jf.data_ptr()
+    out = np.zeros((n, 10, 2), np.int64)
+    rc = sm.lib.mpm_measure_timeline_sharded(sm.h, C.c_float(dt), n, C.byref(fin), out.ctypes.data_as(C.c_void_p),
+                                             C.c_void_p(torch.cuda.current_stream(sm.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError("libmpm_b200: " + sm.lib.mpm_last_error(sm.h).decode())
+    sm.state._stale = True
     return out
 
 

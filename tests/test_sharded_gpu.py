@@ -40,8 +40,13 @@ def _worker(rank, world, port, nccl, q, env):
     sm.step(sc.dt, NSUB, fi["mesh_x"], fi["mesh_v"], fi["joint_verts_v"], fi["joint_faces_v"])
     X, V = sm.gather_positions()
     st = sm.solver.stats()
+    tl = None
+    if env.get("MPM_TEST_TIMELINE") == "1" and sm.lib.mpm_shared_mode(sm.h) == 2:  # after the parity data has been taken
+        from mpmavatar_b200.scene_setup import frame_tensors
+        from mpmavatar_b200.timeline import measure_sharded, summarise
+        tl = summarise(measure_sharded(sm, sc.dt, frame_tensors(sc, 0, dev), 12))
     if rank == 0:
-        q.put((X.cpu().numpy(), V.cpu().numpy(), dict(sm.stats), st["overflow"], sm.part.n_ghost_v,
+        q.put((X.cpu().numpy(), V.cpu().numpy(), dict(sm.stats, timeline=tl), st["overflow"], sm.part.n_ghost_v,
                sm.lib.mpm_shared_mode(sm.h)))
     dist.barrier()
     dist.destroy_process_group()
@@ -85,9 +90,12 @@ def test_two_rank_peer_to_peer_exchange_matches_single_gpu():
     a single-GPU box the two ranks share cuda:0 (gloo rendezvous, host all-gather for the set-up traffic) -- the SAME
     kernels exchange the blocks, so this is the driver-visible parity evidence for them."""
     nccl = torch.cuda.device_count() >= 2
-    X, V, stats, overflow, n_ghost, mode = _run(nccl, {"MPM_B200_SHARD_GRAPH": "1"})
+    X, V, stats, overflow, n_ghost, mode = _run(nccl, {"MPM_B200_SHARD_GRAPH": "1", "MPM_TEST_TIMELINE": "1"})
     assert mode == 2, f"expected the peer-to-peer exchange, got mode {mode} ({stats.get('exchange')})"
     _check(X, V, stats, overflow, n_ghost)
+    tl = stats["timeline"]  # the sharded timeline probe stamps the two exchange kernels
+    assert tl is not None and {"push", "pull", "p2g_E", "grid", "g2p_E"} <= set(tl["kernels"])
+    assert tl["kernels"]["pull"]["start_us"] >= tl["kernels"]["p2g_E"]["start_us"] and tl["substep_us"] > 0
 
 
 @pytest.mark.timeout(900)
