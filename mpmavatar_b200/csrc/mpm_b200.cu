@@ -350,7 +350,7 @@ __global__ void k_shared_unpack2(Grid g, SharedLists L, const float4* __restrict
     }
 }
 __global__ void k_shared_coords(Grid g, const int* __restrict__ lin, int* __restrict__ n_sel, int cap, int* __restrict__ coords,
-                                const unsigned char* __restrict__ mark, unsigned char* __restrict__ members) {
+                                const unsigned char* __restrict__ mark, unsigned char* __restrict__ members, int* __restrict__ map) {
     const int n = *n_sel;
     if (n > cap && blockIdx.x == 0 && threadIdx.x == 0) g.flags[0] = 1;  // reported as overflow
     const int m = min(n, cap);
@@ -359,106 +359,46 @@ __global__ void k_shared_coords(Grid g, const int* __restrict__ lin, int* __rest
         const int bz = t % g.nb, by = (t / g.nb) % g.nb, bx = t / (g.nb * g.nb);
         coords[i] = bx | (by << 10) | (bz << 20);
         members[i] = mark[t];  // the ranks that can touch the block (peer-to-peer exchange)
+        map[t] = i;            // block -> position in this list (the grid update's fused pull), -1 elsewhere
     }
 }
 
 // ---- peer-to-peer exchange of the shared blocks over NVLink (replaces pack -> ncclAllReduce -> unpack)
-// Every rank owns a receive area [2 epochs parity][nranks senders][capA + capM blocks][64 float4] and flags
-// [2][nranks], both mapped into every peer (CUDA IPC).  k_shared_push writes this rank's partial sums of every block
-// it is a member of straight into the receive areas of the block's other members and then raises its flag there;
-// k_shared_pull waits for the flags of all peers and adds the members' parts IN RANK ORDER (own part included at its
-// position), so every member computes bit-identical sums.  Two parities suffice: a rank can only push epoch e+2 after
-// its pull of e+1, which needed every peer's push of e+1, which follows that peer's pull of e.
-struct PeerArea {
-    unsigned char* base[8];  // receive area of every rank as mapped here (base[rank] is the local one)
-    unsigned long long slot_bytes, flags_off;
-    int rank, nranks;
-    unsigned* epoch;    // completed exchanges (device)
-    unsigned* counter;  // last-CTA detection: [0] push, [1] pull
-};
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__global__ void __launch_bounds__(256) k_shared_push(Grid g, SharedLists L, const unsigned char* __restrict__ memA,
-                                                     const unsigned char* __restrict__ memM, PeerArea P) {
-    const unsigned E = *P.epoch;  // written by the previous pull, which completed before the scatter half started
+// Every rank owns a receive area [2 epoch parities][nranks senders][capA + capM blocks][64 float4] and arrival counters
+// [2][nranks] (64-bit, monotonic), both mapped into every peer (CUDA IPC; PeerArea in mpm_device.cuh).  k_shared_push
+// writes this rank's partial sums of every block it is a member of straight into the receive areas of the block's other
+// members; every CTA then fences and adds 1 to its counter in EVERY peer (red.release.sys).  The PULL is fused into the
+// grid update (k_grid_update): it waits until every peer's counter says "all CTAs of this epoch's push have arrived" and,
+// at the nodes of shared blocks, adds the members' parts IN RANK ORDER (own part included at its position), so every member
+// computes bit-identical sums; its last CTA advances the epoch.  Two parities suffice: a rank can only push epoch e+2
+// after its grid update of e+1, which needed every peer's push of e+1, which follows that peer's grid update of e.
+// (Round 1 / early round 2 had a separate pull kernel and a last-CTA flag per sender: the sharded timeline probe showed the
+// exchange at 16-30 us of a 64 us substep; the fused form removes one kernel, the local counter and the flag hop.)
+__global__ void __launch_bounds__(256) k_shared_push(Grid g, SharedLists L, PeerArea P) {
+    const unsigned E = *P.epoch;  // advanced by the previous grid update, which completed before the scatter half started
     const int par = E & 1;
     const int nA = min(*L.nA, L.capA) * BN, nM = min(*L.nM, L.capM) * BN;
     pdl_wait();     // every scatter into acc / mov of this substep is complete
-    pdl_trigger();  // the pull may start polling the peers' flags while this rank still sends
+    pdl_trigger();  // the grid update may start (it polls the peers' counters while this rank still sends)
     ts_begin(g, TS_PUSH);  // stamped behind the wait: the time this rank spends SENDING
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nA + nM; idx += gridDim.x * blockDim.x) {
         const bool mv = idx >= nA;
         const int j = mv ? idx - nA : idx;
-        const int mem = (mv ? memM : memA)[j >> 6];
+        const int mem = (mv ? P.memM : P.memA)[j >> 6];
         if (!((mem >> P.rank) & 1)) continue;  // not a member: nothing to send, nobody reads this slot
         const int co = (mv ? L.M : L.A)[j >> 6], l = j & 63;
-        const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int ni = block_node(g, co, l);
-        if (g.table[blk] >= 0) a = (mv ? g.mov : g.acc)[ni];
+        // no activity test: the accumulators of a block this rank has not activated are zero (invariant 2), and zero is
+        // what its part must be
+        const float4 a = (mv ? g.mov : g.acc)[block_node(g, co, l)];
         const size_t off = ((size_t)par * P.nranks + P.rank) * P.slot_bytes + ((mv ? (size_t)L.capA * BN + j : j) << 4);
         for (int r = 0; r < P.nranks; r++)
             if (r != P.rank && ((mem >> r) & 1)) *reinterpret_cast<float4*>(P.base[r] + off) = a;
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned done = atomicAdd(&P.counter[0], 1u);
-        if (done == gridDim.x - 1) {  // the last CTA: every part is written and fenced
-            P.counter[0] = 0;
-            __threadfence_system();
-            for (int r = 0; r < P.nranks; r++)
-                if (r != P.rank) st_release_sys(reinterpret_cast<unsigned*>(P.base[r] + P.flags_off) + par * P.nranks + P.rank, E + 1);
-        }
-    }
+    if (threadIdx.x < P.nranks && threadIdx.x != P.rank)
+        red_release_sys_add(reinterpret_cast<unsigned long long*>(P.base[threadIdx.x] + P.flags_off) + par * P.nranks + P.rank, 1ull);
     ts_end(g, TS_PUSH);
-}
-__global__ void __launch_bounds__(256) k_shared_pull(Grid g, SharedLists L, const unsigned char* __restrict__ memA,
-                                                     const unsigned char* __restrict__ memM, PeerArea P) {
-    const unsigned E = *P.epoch;
-    const int par = E & 1;
-    ts_begin(g, TS_PULL);  // includes the wait for the slowest peer's flag: the ranks' skew shows up here
-    if (threadIdx.x < P.nranks && threadIdx.x != P.rank) {
-        const unsigned* f = reinterpret_cast<const unsigned*>(P.base[P.rank] + P.flags_off) + par * P.nranks + threadIdx.x;
-        while (ld_acquire_sys(f) < E + 1) __nanosleep(64);
-    }
-    __syncthreads();
-    pdl_wait();  // this rank's push has completed: it reads the very accumulators (and the epoch) that are updated below
-    pdl_trigger();
-    const int nA = min(*L.nA, L.capA) * BN, nM = min(*L.nM, L.capM) * BN;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nA + nM; idx += gridDim.x * blockDim.x) {
-        const bool mv = idx >= nA;
-        const int j = mv ? idx - nA : idx;
-        const int mem = (mv ? memM : memA)[j >> 6];
-        if (!((mem >> P.rank) & 1)) continue;
-        const int co = (mv ? L.M : L.A)[j >> 6], l = j & 63;
-        const int blk = table_index(g, co & 1023, (co >> 10) & 1023, (co >> 20) & 1023);
-        const int ni = block_node(g, co, l);
-        if (g.table[blk] < 0) continue;  // not under any of my stencils: my G2P never reads it
-        float4* mine = (mv ? g.mov : g.acc) + ni;
-        const size_t off = (size_t)par * P.nranks * P.slot_bytes + ((mv ? (size_t)L.capA * BN + j : j) << 4);
-        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < P.nranks; r++) {
-            if (!((mem >> r) & 1)) continue;
-            const float4 v = (r == P.rank) ? *mine : __ldcv(reinterpret_cast<const float4*>(P.base[P.rank] + off + (size_t)r * P.slot_bytes));
-            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-        }
-        *mine = sum;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned done = atomicAdd(&P.counter[1], 1u);
-        if (done == gridDim.x - 1) {
-            P.counter[1] = 0;
-            *P.epoch = E + 1;
-        }
-    }
-    ts_end(g, TS_PULL);
 }
 
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
@@ -524,6 +464,8 @@ struct MpmSolver {
     unsigned char* peer_local = nullptr;     // this rank's receive area (cudaMalloc, exported over CUDA IPC)
     void* peer_open[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     PeerArea peer{};
+    PeerArea gu_peer{};  // what the grid update of the substep being launched pulls from (nranks = 0: nothing)
+    int *d_mapA = nullptr, *d_mapM = nullptr;  // block -> position in the shared lists
     int cur = 0;             // direction (D3) / vertex-force (VF) buffer of the coming substep
     bool have_prev = false;  // a substep has run since the last import: buffer cur^1 holds the return-mapped d3 and the vertex
                              // forces of the last substep
@@ -745,7 +687,7 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
     }  // HALF_SCATTER
     if (!(halves & HALF_GATHER)) return;
     // one thread per node of the active blocks, grid-strided over the device-side block count
-    launch_pdl(k_grid_update, GRID_UPDATE_CTAS, 256, 0, q, pdl, s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, (const BCDesc*)s->d_bcs, n_bc, (const StepState*)s->st);
+    launch_pdl(k_grid_update, GRID_UPDATE_CTAS, 256, 0, q, pdl, s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, (const BCDesc*)s->d_bcs, n_bc, (const StepState*)s->st, s->gu_peer);
     s->launches++;
     if (ev) CK(cudaEventRecord(ev[5], q));
     // gather side: the first kernel waits for the grid update, the others follow it; the last kernel advances time
@@ -1439,10 +1381,12 @@ void sharded_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
     const int ctas = std::max(1, std::min(cdiv((long long)(s->xcap_blocks + s->xcapM) * BN, 256), 148 * 4));
     const SharedLists L{s->d_shared, s->d_n_shared, s->d_sharedM, s->d_nM, s->xcap_blocks, s->xcapM};
     if (s->p2p_ready) {
-        const bool pdl = s->use_pdl;
-        launch_pdl(k_shared_push, ctas, 256, 0, q, pdl, s->g, L, (const unsigned char*)s->d_memA, (const unsigned char*)s->d_memM, s->peer);
-        launch_pdl(k_shared_pull, ctas, 256, 0, q, pdl, s->g, L, (const unsigned char*)s->d_memA, (const unsigned char*)s->d_memM, s->peer);
-        s->launches += 2;
+        PeerArea P = s->peer;
+        P.mapA = s->d_mapA; P.mapM = s->d_mapM; P.memA = s->d_memA; P.memM = s->d_memM;
+        P.capA = s->xcap_blocks; P.push_ctas = ctas;
+        launch_pdl(k_shared_push, ctas, 256, 0, q, s->use_pdl, s->g, L, P);
+        s->launches++;
+        s->gu_peer = P;  // the pull half runs inside the grid update
     } else {
         k_shared_pack2<<<ctas, 256, 0, q>>>(s->g, L, (float4*)s->xbuf);
         allreduce_sum_device(s, s->xbuf, (size_t)(s->xcap_blocks + s->xcapM) * BN * 4, q);
@@ -1450,6 +1394,7 @@ void sharded_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
         s->launches += 3;
     }
     launch_substep(s, a, q, HALF_GATHER);
+    s->gu_peer = PeerArea{};
 }
 }  // namespace
 
@@ -1493,7 +1438,7 @@ static void setup_peer_areas(MpmSolver* s, cudaStream_t q) {
     s->p2p_ready = false;
     const size_t slot = (size_t)(s->xcap_blocks + s->xcapM) * BN * sizeof(float4);
     const size_t flags_off = 2 * (size_t)n * slot;
-    const size_t total = flags_off + 2 * (size_t)n * sizeof(unsigned);
+    const size_t total = flags_off + 2 * (size_t)n * sizeof(unsigned long long);  // + arrival counters [parity][sender]
     struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
     Msg mine{};
     mine.ok = cudaMalloc(&s->peer_local, total) == cudaSuccess && cudaMemset(s->peer_local, 0, total) == cudaSuccess &&
@@ -1569,8 +1514,11 @@ static void rebuild_shared_on_device(MpmSolver* s, int margin, cudaStream_t q) {
         s->d_memM = s->dalloc<unsigned char>(s->xcapM);
         setup_peer_areas(s, q);
     }
-    k_shared_coords<<<std::max(1, std::min(cdiv(s->xcap_blocks, 256), 64)), 256, 0, q>>>(s->g, s->d_sel, s->d_n_shared, s->xcap_blocks, s->d_shared, s->d_mark, s->d_memA);
-    k_shared_coords<<<std::max(1, std::min(cdiv(s->xcapM, 256), 64)), 256, 0, q>>>(s->g, s->d_sel + nt, s->d_nM, s->xcapM, s->d_sharedM, s->d_mark, s->d_memM);
+    if (!s->d_mapA) { s->d_mapA = s->dalloc<int>(nt); s->d_mapM = s->dalloc<int>(nt); }
+    k_fill_int<<<std::min(cdiv((long long)nt, 256), 1184), 256, 0, q>>>(s->d_mapA, nt, -1);
+    k_fill_int<<<std::min(cdiv((long long)nt, 256), 1184), 256, 0, q>>>(s->d_mapM, nt, -1);
+    k_shared_coords<<<std::max(1, std::min(cdiv(s->xcap_blocks, 256), 64)), 256, 0, q>>>(s->g, s->d_sel, s->d_n_shared, s->xcap_blocks, s->d_shared, s->d_mark, s->d_memA, s->d_mapA);
+    k_shared_coords<<<std::max(1, std::min(cdiv(s->xcapM, 256), 64)), 256, 0, q>>>(s->g, s->d_sel + nt, s->d_nM, s->xcapM, s->d_sharedM, s->d_mark, s->d_memM, s->d_mapM);
     CK(cudaMemcpyAsync(&s->h_nshared[0], s->d_n_shared, sizeof(int), cudaMemcpyDeviceToHost, q));
     CK(cudaMemcpyAsync(&s->h_nshared[1], s->d_nM, sizeof(int), cudaMemcpyDeviceToHost, q));
     s->launches += 2;
@@ -1714,7 +1662,7 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
 
 // Timeline probe of the SHARDED chain (collective: every rank calls it with the same n): n <= 32 sharded substeps launched
 // eagerly with the stamps on; out[n][10][2] as mpm_measure_timeline plus ids 8 (k_shared_push, from the end of its wait to
-// its last flag) and 9 (k_shared_pull, including the wait for the slowest peer).  Requires the peer-to-peer exchange.
+// its last counter add) and 9 (the wait for the slowest peer's push at the head of k_grid_update, whose pull is fused).  Requires the peer-to-peer exchange.
 int mpm_measure_timeline_sharded(MpmSolver* s, float dt, int n, const MpmFrameInputs* in, long long* out, void* stream) {
     API_BEGIN(s)
     cudaStream_t q = (cudaStream_t)stream;

@@ -124,6 +124,28 @@ __device__ __forceinline__ void ts_end(const Grid& g, int k) {
 #define PHASE_END(gr, k) do {} while (0)
 #endif
 
+// Peer-to-peer exchange of the grid blocks shared with other ranks (sharded runs; mpm_b200.cu k_shared_push, the fused pull of
+// k_grid_update).  nranks == 0: not a peer-to-peer sharded step.
+struct PeerArea {
+    unsigned char* base[8];  // receive area of every rank as mapped here (base[rank] is the local one)
+    unsigned long long slot_bytes, flags_off;
+    int rank, nranks;
+    unsigned* epoch;    // completed exchanges (device)
+    unsigned* counter;  // last-CTA detection of the grid update
+    const int *mapA, *mapM;            // block (table index) -> position in the shared lists A (acc) / M (mov), -1 if not listed
+    const unsigned char *memA, *memM;  // member ranks of every listed block (bit r = rank r can touch it)
+    int capA;                          // capacity of list A: list M's slots follow it in the receive areas
+    int push_ctas;                     // CTAs of k_shared_push: what a peer's arrival counter grows by per exchange
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 struct StepState {
     double time;  // MPMWARP.time (mpm_solver.py:28,536)
     int k;        // substep index inside the current mpm_step call

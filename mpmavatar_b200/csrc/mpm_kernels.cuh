@@ -816,9 +816,12 @@ __global__ void __launch_bounds__(128) k_body_scatter(Grid g, ColliderArgs ca, M
 //   mesh collider normalize_grid + collide (mpm_solver.py:882-917),
 //   particle mover normalize_grid (:790-799), and every grid_postprocess BC in order (:487-501),
 // then re-zeroes the accumulators it consumed (replaces the three dense zero_grid sweeps).
+// Sharded runs with the peer-to-peer exchange (P.nranks > 1): the PULL half of the exchange is fused in -- the kernel waits
+// for every peer's push of this epoch and, at the nodes of blocks shared with other ranks, sums the members' parts in rank
+// order (its own part at its position) before the update.
 __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float dt, int use_collider, float col_friction,
                                                      int use_mover, const BCDesc* __restrict__ bcs, int n_bc,
-                                                     const StepState* __restrict__ st) {
+                                                     const StepState* __restrict__ st, PeerArea P) {
     // the active list was last changed by the previous substep's G2P: the node address is computed while the
     // scatter kernels in front of this one drain (PDL invariant: wait, then trigger)
     ts_begin(g, TS_GRID);
@@ -826,8 +829,21 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
     const int total = n_slots * BN;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int co_next = idx < total ? g.slot_coord[idx >> 6] : 0;
-    pdl_wait();
+    pdl_wait();     // single GPU: the scatters; sharded: this rank's push (it reads the accumulators zeroed below)
     pdl_trigger();  // the G2P kernels behind this one may take the slots it frees (they wait for its completion)
+    const bool pull = P.nranks > 1;
+    unsigned E = 0;
+    if (pull) {  // every peer's push of this epoch has arrived in full: each of its CTAs added 1 to its counter here
+        E = *P.epoch;
+        ts_begin(g, TS_PULL);  // slot 9 of the sharded timeline: the wait for the slowest peer (the ranks' skew)
+        if (threadIdx.x < P.nranks && threadIdx.x != P.rank) {
+            const unsigned long long* c = reinterpret_cast<const unsigned long long*>(P.base[P.rank] + P.flags_off) + (E & 1) * P.nranks + threadIdx.x;
+            const unsigned long long want = (unsigned long long)P.push_ctas * ((E >> 1) + 1);
+            while (ld_acquire_sys(c) < want) __nanosleep(32);
+        }
+        __syncthreads();
+        ts_end(g, TS_PULL);
+    }
     const float time = (float)st->time;
     for (; idx < total; idx += gridDim.x * blockDim.x) {
         const int l = idx & 63;
@@ -838,8 +854,40 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
         }
         const int ni = block_node(g, co, l);
         // all four accumulator loads are issued before any use (memory-level parallelism)
-        const float4 a = g.acc[ni];
-        const float4 mv = g.mov[ni];
+        float4 a = g.acc[ni];
+        float4 mv = g.mov[ni];
+        const float4 a_own = a, mv_own = mv;  // what THIS rank accumulated: decides what has to be re-zeroed
+        if (pull) {
+            const int blk = ni >> 6;
+            const int ja = P.mapA[blk], jm = P.mapM[blk];
+            const size_t par_off = (size_t)(E & 1) * P.nranks * P.slot_bytes;
+            if (ja >= 0) {
+                const int mem = P.memA[ja];
+                if ((mem >> P.rank) & 1) {
+                    const unsigned char* src = P.base[P.rank] + par_off + (((size_t)ja * BN + l) << 4);
+                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int r = 0; r < P.nranks; r++) {
+                        if (!((mem >> r) & 1)) continue;
+                        const float4 v = (r == P.rank) ? a : __ldcv(reinterpret_cast<const float4*>(src + (size_t)r * P.slot_bytes));
+                        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                    }
+                    a = sum;
+                }
+            }
+            if (jm >= 0) {
+                const int mem = P.memM[jm];
+                if ((mem >> P.rank) & 1) {
+                    const unsigned char* src = P.base[P.rank] + par_off + ((((size_t)P.capA + jm) * BN + l) << 4);
+                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int r = 0; r < P.nranks; r++) {
+                        if (!((mem >> r) & 1)) continue;
+                        const float4 v = (r == P.rank) ? mv : __ldcv(reinterpret_cast<const float4*>(src + (size_t)r * P.slot_bytes));
+                        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                    }
+                    mv = sum;
+                }
+            }
+        }
         float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), cn = cv;
         if (use_collider) { cv = g.colv[ni]; cn = g.coln[ni]; }
         float vx = 0.f, vy = 0.f, vz = 0.f;
@@ -851,7 +899,7 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
             vz = a.z * inv + dt * md.gz;
         }
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.w != 0.0f || a.x != 0.0f || a.y != 0.0f || a.z != 0.0f) g.acc[ni] = zero4;
+        if (a_own.w != 0.0f || a_own.x != 0.0f || a_own.y != 0.0f || a_own.z != 0.0f) g.acc[ni] = zero4;
         if (md.damping < 1.0f) {
             vx -= (1.0f - md.damping) * vx;
             vy -= (1.0f - md.damping) * vy;
@@ -879,8 +927,8 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
             }
         }
         // the mover accumulators are consumed (and cleared) even on steps without joint inputs
+        if (mv_own.w != 0.0f || mv_own.x != 0.0f || mv_own.y != 0.0f || mv_own.z != 0.0f) g.mov[ni] = zero4;
         if (mv.w != 0.0f || mv.x != 0.0f || mv.y != 0.0f || mv.z != 0.0f) {
-            g.mov[ni] = zero4;
             if (use_mover && mv.w > 1e-15f) {
                 float inv = 1.0f / mv.w;
                 vx = mv.x * inv; vy = mv.y * inv; vz = mv.z * inv;
@@ -936,6 +984,17 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
         g.vout[ni] = make_float4(vx, vy, vz, 0.0f);
     }
     ts_end(g, TS_GRID);
+    if (pull) {  // the last CTA closes the exchange
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned done = atomicAdd(&P.counter[1], 1u);
+            if (done == gridDim.x - 1) {
+                P.counter[1] = 0;
+                *P.epoch = E + 1;
+            }
+        }
+    }
 }
 __global__ void k_reset_k(StepState* st) { st->k = 0; }
 // per-call inputs of p2g2p (body points / velocities, joint velocities) from DEVICE pointers into the solver's own
