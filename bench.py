@@ -274,7 +274,7 @@ def run_sharded(args, sc, rank, local_rank, world, dev, barrier):
     peak, peak_src = measured_peaks()
     bytes_pg = algorithmic_bytes(lsc, A)
     achieved = bytes_pg / t_pg / 1e9
-    # the sharded chain as it runs (PDL, peer-to-peer exchange): per-kernel stamps incl. k_shared_push / k_shared_pull
+    # the sharded chain as it runs (PDL, peer-to-peer exchange): per-kernel stamps incl. the grid update's push phase and its wait for the peers
     tl = None
     if sm.lib.mpm_shared_mode(sm.h) == 2:
         from mpmavatar_b200.timeline import measure_sharded, summarise

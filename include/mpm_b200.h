@@ -174,7 +174,7 @@ int mpm_attach_comm(MpmSolver *s, const char *id128, int rank, int nranks);
 /* The same stepping over a transport the CALLER owns instead of NCCL: `allgather` must gather `nbytes` host bytes from
  * every rank into recv[nranks * nbytes] in rank order and block until done (torch.distributed / gloo, MPI, ...).  Only
  * the set-up traffic uses it -- the CUDA-IPC handles of the receive areas and the block marks of a shared-list rebuild;
- * the per-substep exchange stays the peer-to-peer push kernel + the pull fused into the grid update (mode 2), also
+ * the per-substep exchange stays peer-to-peer, fused into the grid update (mode 2), also
  * between ranks that share one GPU (which NCCL refuses), so the kernels can be verified on a single-GPU box.  Where no peer mapping is possible the exchange
  * falls back to pack -> host all-gather -> rank-ordered sum -> unpack (mode 3; synchronises every substep). */
 typedef int (*MpmHostAllGatherFn)(void *ctx, const void *send, void *recv, int nbytes);
@@ -183,7 +183,7 @@ int mpm_step_sharded_nccl(MpmSolver *s, float dt, int nsub, const MpmFrameInputs
 int mpm_shared_info(MpmSolver *s, int *n_shared, int *cap_blocks, int *n_rebuilds, void *stream);
 /* how the shared blocks travel: 0 caller's collective (callbacks), 1 ncclAllReduce inside the captured windows,
  * 3 all-reduce through the caller's host all-gather, 2 peer-to-peer: with <= 8 ranks on one NVLink domain every rank
- * maps every peer's receive area (CUDA IPC) and the push kernel and the grid update's fused pull move the parts directly (MPM_B200_P2P=0 forces 1) */
+ * maps every peer's receive area (CUDA IPC) and the grid update pushes / pulls the parts itself (MPM_B200_P2P=0 forces 1) */
 int mpm_shared_mode(MpmSolver *s);
 int mpm_step_gather(MpmSolver *s, float dt, void *stream);
 int mpm_get_active_blocks(MpmSolver *s, int *coords, int cap, int *n, void *stream);
@@ -211,9 +211,9 @@ int mpm_force_resort(MpmSolver *s);
  * 7 G2P elements.  The kernels overlap under programmatic dependent launch, which CUDA events cannot resolve. */
 int mpm_measure_timeline(MpmSolver *s, float dt, int n, const MpmFrameInputs *in, long long *out, void *stream);
 /* the same for the SHARDED chain (collective; needs the peer-to-peer exchange, i.e. at least one mpm_step_sharded_nccl call
- * before): n <= 32, out[n][10][2]; ids 0-7 as above, 8 = k_shared_push (from the end of its wait for this rank's scatters to
- * its last counter add), 9 = the wait for the slowest peer's push at the head of k_grid_update (the ranks' skew; the
- * pull itself is fused into the grid update). */
+ * before): n <= 32, out[n][10][2]; ids 0-7 as above; 8 = the push phase at the head of the grid update (first store into a
+ * peer's receive area to the last arrival-counter add), 9 = its wait for the slowest peer's push (the ranks' skew).  The
+ * whole exchange is fused into k_grid_update<true>. */
 int mpm_measure_timeline_sharded(MpmSolver *s, float dt, int n, const MpmFrameInputs *in, long long *out, void *stream);
 /* latency analysis (builds with -DMPM_CLK only fill it): 8 kernels x 8 per-warp phase cycle sums; synchronises */
 int mpm_debug_phase_clocks(MpmSolver *s, unsigned long long *out64, int reset);

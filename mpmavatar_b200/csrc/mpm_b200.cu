@@ -363,44 +363,6 @@ __global__ void k_shared_coords(Grid g, const int* __restrict__ lin, int* __rest
     }
 }
 
-// ---- peer-to-peer exchange of the shared blocks over NVLink (replaces pack -> ncclAllReduce -> unpack)
-// Every rank owns a receive area [2 epoch parities][nranks senders][capA + capM blocks][64 float4] and arrival counters
-// [2][nranks] (64-bit, monotonic), both mapped into every peer (CUDA IPC; PeerArea in mpm_device.cuh).  k_shared_push
-// writes this rank's partial sums of every block it is a member of straight into the receive areas of the block's other
-// members; every CTA then fences and adds 1 to its counter in EVERY peer (red.release.sys).  The PULL is fused into the
-// grid update (k_grid_update): it waits until every peer's counter says "all CTAs of this epoch's push have arrived" and,
-// at the nodes of shared blocks, adds the members' parts IN RANK ORDER (own part included at its position), so every member
-// computes bit-identical sums; its last CTA advances the epoch.  Two parities suffice: a rank can only push epoch e+2
-// after its grid update of e+1, which needed every peer's push of e+1, which follows that peer's grid update of e.
-// (Round 1 / early round 2 had a separate pull kernel and a last-CTA flag per sender: the sharded timeline probe showed the
-// exchange at 16-30 us of a 64 us substep; the fused form removes one kernel, the local counter and the flag hop.)
-__global__ void __launch_bounds__(256) k_shared_push(Grid g, SharedLists L, PeerArea P) {
-    const unsigned E = *P.epoch;  // advanced by the previous grid update, which completed before the scatter half started
-    const int par = E & 1;
-    const int nA = min(*L.nA, L.capA) * BN, nM = min(*L.nM, L.capM) * BN;
-    pdl_wait();     // every scatter into acc / mov of this substep is complete
-    pdl_trigger();  // the grid update may start (it polls the peers' counters while this rank still sends)
-    ts_begin(g, TS_PUSH);  // stamped behind the wait: the time this rank spends SENDING
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nA + nM; idx += gridDim.x * blockDim.x) {
-        const bool mv = idx >= nA;
-        const int j = mv ? idx - nA : idx;
-        const int mem = (mv ? P.memM : P.memA)[j >> 6];
-        if (!((mem >> P.rank) & 1)) continue;  // not a member: nothing to send, nobody reads this slot
-        const int co = (mv ? L.M : L.A)[j >> 6], l = j & 63;
-        // no activity test: the accumulators of a block this rank has not activated are zero (invariant 2), and zero is
-        // what its part must be
-        const float4 a = (mv ? g.mov : g.acc)[block_node(g, co, l)];
-        const size_t off = ((size_t)par * P.nranks + P.rank) * P.slot_bytes + ((mv ? (size_t)L.capA * BN + j : j) << 4);
-        for (int r = 0; r < P.nranks; r++)
-            if (r != P.rank && ((mem >> r) & 1)) *reinterpret_cast<float4*>(P.base[r] + off) = a;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < P.nranks && threadIdx.x != P.rank)
-        red_release_sys_add(reinterpret_cast<unsigned long long*>(P.base[threadIdx.x] + P.flags_off) + par * P.nranks + P.rank, 1ull);
-    ts_end(g, TS_PUSH);
-}
-
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
@@ -613,6 +575,7 @@ static void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem,
 
 // the grid update grid-strides over the allocated blocks (count on the device): 8 CTAs of 256 threads per SM
 constexpr int GRID_UPDATE_CTAS = 148 * 5;  // one wave at 48 registers x 256 threads
+constexpr int GRID_UPDATE_CTAS_PEER = 148 * 4;  // k_grid_update<true>: every CTA resident at once (launch bounds 256 x 4)
 
 // A substep has two halves around the grid: everything that SCATTERS to it (constitutive update, P2G,
 // body-mesh and joint scatters) and everything that reads it back (grid update, G2P).  Single-GPU
@@ -687,7 +650,10 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
     }  // HALF_SCATTER
     if (!(halves & HALF_GATHER)) return;
     // one thread per node of the active blocks, grid-strided over the device-side block count
-    launch_pdl(k_grid_update, GRID_UPDATE_CTAS, 256, 0, q, pdl, s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, (const BCDesc*)s->d_bcs, n_bc, (const StepState*)s->st, s->gu_peer);
+    if (s->gu_peer.nranks > 1)  // sharded, peer-to-peer: the exchange is fused in; all CTAs must be resident (4 per SM)
+        launch_pdl(k_grid_update<true>, GRID_UPDATE_CTAS_PEER, 256, 0, q, pdl, s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, (const BCDesc*)s->d_bcs, n_bc, (const StepState*)s->st, s->gu_peer);
+    else
+        launch_pdl(k_grid_update<false>, GRID_UPDATE_CTAS, 256, 0, q, pdl, s->g, s->md, a.dt, a.collider ? 1 : 0, s->col_friction, a.mover ? 1 : 0, (const BCDesc*)s->d_bcs, n_bc, (const StepState*)s->st, PeerArea{});
     s->launches++;
     if (ev) CK(cudaEventRecord(ev[5], q));
     // gather side: the first kernel waits for the grid update, the others follow it; the last kernel advances time
@@ -1375,26 +1341,26 @@ void allreduce_sum_device(MpmSolver* s, T* d, size_t n, cudaStream_t q) {
     CK(cudaStreamSynchronize(q));
 }
 
-// one sharded substep on stream q: scatter half, pack, all-reduce, unpack, gather half
+// one sharded substep on stream q.  Peer-to-peer: the plain chain with the exchange fused into the grid update;
+// otherwise scatter half, pack, all-reduce, unpack, gather half
 void sharded_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
-    launch_substep(s, a, q, HALF_SCATTER);
-    const int ctas = std::max(1, std::min(cdiv((long long)(s->xcap_blocks + s->xcapM) * BN, 256), 148 * 4));
-    const SharedLists L{s->d_shared, s->d_n_shared, s->d_sharedM, s->d_nM, s->xcap_blocks, s->xcapM};
     if (s->p2p_ready) {
         PeerArea P = s->peer;
         P.mapA = s->d_mapA; P.mapM = s->d_mapM; P.memA = s->d_memA; P.memM = s->d_memM;
-        P.capA = s->xcap_blocks; P.push_ctas = ctas;
-        launch_pdl(k_shared_push, ctas, 256, 0, q, s->use_pdl, s->g, L, P);
-        s->launches++;
-        s->gu_peer = P;  // the pull half runs inside the grid update
-    } else {
-        k_shared_pack2<<<ctas, 256, 0, q>>>(s->g, L, (float4*)s->xbuf);
-        allreduce_sum_device(s, s->xbuf, (size_t)(s->xcap_blocks + s->xcapM) * BN * 4, q);
-        k_shared_unpack2<<<ctas, 256, 0, q>>>(s->g, L, (const float4*)s->xbuf);
-        s->launches += 3;
+        P.capA = s->xcap_blocks;
+        s->gu_peer = P;
+        launch_substep(s, a, q, HALF_SCATTER | HALF_GATHER);
+        s->gu_peer = PeerArea{};
+        return;
     }
+    launch_substep(s, a, q, HALF_SCATTER);
+    const int ctas = std::max(1, std::min(cdiv((long long)(s->xcap_blocks + s->xcapM) * BN, 256), 148 * 4));
+    const SharedLists L{s->d_shared, s->d_n_shared, s->d_sharedM, s->d_nM, s->xcap_blocks, s->xcapM};
+    k_shared_pack2<<<ctas, 256, 0, q>>>(s->g, L, (float4*)s->xbuf);
+    allreduce_sum_device(s, s->xbuf, (size_t)(s->xcap_blocks + s->xcapM) * BN * 4, q);
+    k_shared_unpack2<<<ctas, 256, 0, q>>>(s->g, L, (const float4*)s->xbuf);
+    s->launches += 3;
     launch_substep(s, a, q, HALF_GATHER);
-    s->gu_peer = PeerArea{};
 }
 }  // namespace
 
@@ -1438,7 +1404,8 @@ static void setup_peer_areas(MpmSolver* s, cudaStream_t q) {
     s->p2p_ready = false;
     const size_t slot = (size_t)(s->xcap_blocks + s->xcapM) * BN * sizeof(float4);
     const size_t flags_off = 2 * (size_t)n * slot;
-    const size_t total = flags_off + 2 * (size_t)n * sizeof(unsigned long long);  // + arrival counters [parity][sender]
+    const size_t stamp_off = flags_off + 2 * (size_t)n * sizeof(unsigned long long);  // arrival counters [parity][sender]
+    const size_t total = stamp_off + 2 * (size_t)n * (s->xcap_blocks + s->xcapM) * sizeof(unsigned);  // stamps [parity][sender][block]
     struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
     Msg mine{};
     mine.ok = cudaMalloc(&s->peer_local, total) == cudaSuccess && cudaMemset(s->peer_local, 0, total) == cudaSuccess &&
@@ -1466,6 +1433,7 @@ static void setup_peer_areas(MpmSolver* s, cudaStream_t q) {
     if (!h_ok) { close_peer_areas(s); return; }
     P.slot_bytes = slot;
     P.flags_off = flags_off;
+    P.stamp_off = stamp_off;
     P.rank = s->comm_rank;
     P.nranks = n;
     unsigned* ctr = s->dalloc<unsigned>(4);  // zeroed: epoch, push counter, pull counter
@@ -1661,8 +1629,8 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
 }
 
 // Timeline probe of the SHARDED chain (collective: every rank calls it with the same n): n <= 32 sharded substeps launched
-// eagerly with the stamps on; out[n][10][2] as mpm_measure_timeline plus ids 8 (k_shared_push, from the end of its wait to
-// its last counter add) and 9 (the wait for the slowest peer's push at the head of k_grid_update, whose pull is fused).  Requires the peer-to-peer exchange.
+// eagerly with the stamps on; out[n][10][2] as mpm_measure_timeline plus ids 8 (the push phase at the head of
+// k_grid_update<true>) and 9 (its wait for the slowest peer's push).  Requires the peer-to-peer exchange.
 int mpm_measure_timeline_sharded(MpmSolver* s, float dt, int n, const MpmFrameInputs* in, long long* out, void* stream) {
     API_BEGIN(s)
     cudaStream_t q = (cudaStream_t)stream;

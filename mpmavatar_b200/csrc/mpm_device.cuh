@@ -124,18 +124,20 @@ __device__ __forceinline__ void ts_end(const Grid& g, int k) {
 #define PHASE_END(gr, k) do {} while (0)
 #endif
 
-// Peer-to-peer exchange of the grid blocks shared with other ranks (sharded runs; mpm_b200.cu k_shared_push, the fused pull of
-// k_grid_update).  nranks == 0: not a peer-to-peer sharded step.
+// Peer-to-peer exchange of the grid blocks shared with other ranks (sharded runs; fused into k_grid_update<true>).
+// Every rank owns a receive area, mapped into every peer (CUDA IPC):
+//   parts    [2 epoch parities][nranks senders][capA + capM blocks][64] float4    at 0
+//   arrivals [2][nranks] u64, monotonic: + (CTAs of the grid update) per exchange  at flags_off
+//   stamps   [2][nranks][capA + capM] u32: epoch + 1 of the sender's last VALID part of the block   at stamp_off
 struct PeerArea {
     unsigned char* base[8];  // receive area of every rank as mapped here (base[rank] is the local one)
-    unsigned long long slot_bytes, flags_off;
-    int rank, nranks;
+    unsigned long long slot_bytes, flags_off, stamp_off;
+    int rank, nranks;  // nranks == 0: not a peer-to-peer sharded step
     unsigned* epoch;    // completed exchanges (device)
     unsigned* counter;  // last-CTA detection of the grid update
     const int *mapA, *mapM;            // block (table index) -> position in the shared lists A (acc) / M (mov), -1 if not listed
     const unsigned char *memA, *memM;  // member ranks of every listed block (bit r = rank r can touch it)
     int capA;                          // capacity of list A: list M's slots follow it in the receive areas
-    int push_ctas;                     // CTAs of k_shared_push: what a peer's arrival counter grows by per exchange
 };
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
     unsigned long long v;

@@ -816,10 +816,19 @@ __global__ void __launch_bounds__(128) k_body_scatter(Grid g, ColliderArgs ca, M
 //   mesh collider normalize_grid + collide (mpm_solver.py:882-917),
 //   particle mover normalize_grid (:790-799), and every grid_postprocess BC in order (:487-501),
 // then re-zeroes the accumulators it consumed (replaces the three dense zero_grid sweeps).
-// Sharded runs with the peer-to-peer exchange (P.nranks > 1): the PULL half of the exchange is fused in -- the kernel waits
-// for every peer's push of this epoch and, at the nodes of blocks shared with other ranks, sums the members' parts in rank
-// order (its own part at its position) before the update.
-__global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float dt, int use_collider, float col_friction,
+// PEER (sharded runs with the peer-to-peer exchange): the WHOLE exchange of the blocks shared with other ranks is fused in.
+//   1. push: every thread sends its own nodes' partial sums (acc, mov) of shared blocks straight into the receive areas of
+//      the blocks' other members, plus a per-block stamp "valid in epoch E" (a member that has NOT activated the block sends
+//      nothing: its part is zero, which a stale stamp says); the CTA then fences and adds 1 to its arrival counter in every
+//      peer (red.release.sys);
+//   2. the nodes of blocks that are not shared are updated while those stores are in flight;
+//   3. the CTA waits until every peer's counter says "all CTAs of epoch E have pushed", then updates the shared nodes from
+//      the sum of the members' parts IN RANK ORDER (own part at its position; every member computes identical bits).
+// Step 3 waits on ALL CTAs of the peers, so every CTA of this grid must be resident at once: the host launches 4 x 148 CTAs
+// and the launch bounds pin 4 CTAs per SM.  Two epoch parities of receive area suffice: a rank can only push epoch e+2 after
+// its grid update of e+1, which needed every peer's push of e+1, which follows that peer's grid update of e.
+template <bool PEER>
+__global__ void __launch_bounds__(256, PEER ? 4 : 5) k_grid_update(Grid g, ModelDev md, float dt, int use_collider, float col_friction,
                                                      int use_mover, const BCDesc* __restrict__ bcs, int n_bc,
                                                      const StepState* __restrict__ st, PeerArea P) {
     // the active list was last changed by the previous substep's G2P: the node address is computed while the
@@ -827,65 +836,101 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
     ts_begin(g, TS_GRID);
     const int n_slots = min(*g.n_slots, g.cap);
     const int total = n_slots * BN;
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    int co_next = idx < total ? g.slot_coord[idx >> 6] : 0;
-    pdl_wait();     // single GPU: the scatters; sharded: this rank's push (it reads the accumulators zeroed below)
+    const int idx0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    int co_next = idx0 < total ? g.slot_coord[idx0 >> 6] : 0;
+    pdl_wait();     // the scatters of this substep
     pdl_trigger();  // the G2P kernels behind this one may take the slots it frees (they wait for its completion)
-    const bool pull = P.nranks > 1;
     unsigned E = 0;
-    if (pull) {  // every peer's push of this epoch has arrived in full: each of its CTAs added 1 to its counter here
-        E = *P.epoch;
+    size_t par_off = 0;
+    const unsigned* stamps = nullptr;  // [sender][capA + capM] of this epoch's parity, local receive area
+    if (PEER) {
+        E = *P.epoch;  // advanced by the previous grid update, which completed long before this one started
+        par_off = (size_t)(E & 1) * P.nranks * P.slot_bytes;
+        const size_t nblk = P.slot_bytes / (BN * sizeof(float4));
+        const size_t stamp_off = P.stamp_off + (size_t)(E & 1) * P.nranks * nblk * sizeof(unsigned);
+        stamps = reinterpret_cast<const unsigned*>(P.base[P.rank] + stamp_off);
+        ts_begin(g, TS_PUSH);
+        for (int i = idx0; i < total; i += stride) {
+            const int co = g.slot_coord[i >> 6], l = i & 63;
+            const int ni = block_node(g, co, l), blk = ni >> 6;
+            const int ja = P.mapA[blk], jm = P.mapM[blk];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int j = h ? jm : ja;
+                if (j < 0) continue;
+                const int mem = (h ? P.memM : P.memA)[j];
+                if (!((mem >> P.rank) & 1)) continue;
+                const float4 v = (h ? g.mov : g.acc)[ni];
+                const size_t slot = (size_t)(h ? P.capA + j : j);
+                const size_t off = par_off + (size_t)P.rank * P.slot_bytes + ((slot * BN + l) << 4);
+                const size_t soff = stamp_off + ((size_t)P.rank * nblk + slot) * sizeof(unsigned);
+                for (int r = 0; r < P.nranks; r++) {
+                    if (r == P.rank || !((mem >> r) & 1)) continue;
+                    *reinterpret_cast<float4*>(P.base[r] + off) = v;
+                    if (l == 0) *reinterpret_cast<unsigned*>(P.base[r] + soff) = E + 1;
+                }
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < P.nranks && threadIdx.x != P.rank)
+            red_release_sys_add(reinterpret_cast<unsigned long long*>(P.base[threadIdx.x] + P.flags_off) + (E & 1) * P.nranks + P.rank, 1ull);
+        ts_end(g, TS_PUSH);
+    }
+    const float time = (float)st->time;
+    for (int pass = 0; pass < (PEER ? 2 : 1); pass++) {
+    if (PEER && pass == 1) {  // every peer's push of this epoch has arrived in full: each of its CTAs added 1 to its counter here
         ts_begin(g, TS_PULL);  // slot 9 of the sharded timeline: the wait for the slowest peer (the ranks' skew)
         if (threadIdx.x < P.nranks && threadIdx.x != P.rank) {
             const unsigned long long* c = reinterpret_cast<const unsigned long long*>(P.base[P.rank] + P.flags_off) + (E & 1) * P.nranks + threadIdx.x;
-            const unsigned long long want = (unsigned long long)P.push_ctas * ((E >> 1) + 1);
+            const unsigned long long want = (unsigned long long)gridDim.x * ((E >> 1) + 1);
             while (ld_acquire_sys(c) < want) __nanosleep(32);
         }
         __syncthreads();
         ts_end(g, TS_PULL);
+        co_next = idx0 < total ? g.slot_coord[idx0 >> 6] : 0;
     }
-    const float time = (float)st->time;
-    for (; idx < total; idx += gridDim.x * blockDim.x) {
+    for (int idx = idx0; idx < total; idx += stride) {
         const int l = idx & 63;
         const int co = co_next;
         {
-            const int nidx = idx + gridDim.x * blockDim.x;
+            const int nidx = idx + stride;
             if (nidx < total) co_next = g.slot_coord[nidx >> 6];
         }
         const int ni = block_node(g, co, l);
+        int ja = -1, jm = -1, memA = 0, memM = 0;
+        if (PEER) {
+            const int blk = ni >> 6;
+            ja = P.mapA[blk]; jm = P.mapM[blk];
+            if (ja >= 0) { memA = P.memA[ja]; if (!((memA >> P.rank) & 1)) ja = -1; }
+            if (jm >= 0) { memM = P.memM[jm]; if (!((memM >> P.rank) & 1)) jm = -1; }
+            if ((ja >= 0 || jm >= 0) != (pass == 1)) continue;
+        }
         // all four accumulator loads are issued before any use (memory-level parallelism)
         float4 a = g.acc[ni];
         float4 mv = g.mov[ni];
         const float4 a_own = a, mv_own = mv;  // what THIS rank accumulated: decides what has to be re-zeroed
-        if (pull) {
-            const int blk = ni >> 6;
-            const int ja = P.mapA[blk], jm = P.mapM[blk];
-            const size_t par_off = (size_t)(E & 1) * P.nranks * P.slot_bytes;
-            if (ja >= 0) {
-                const int mem = P.memA[ja];
-                if ((mem >> P.rank) & 1) {
-                    const unsigned char* src = P.base[P.rank] + par_off + (((size_t)ja * BN + l) << 4);
-                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int r = 0; r < P.nranks; r++) {
-                        if (!((mem >> r) & 1)) continue;
-                        const float4 v = (r == P.rank) ? a : __ldcv(reinterpret_cast<const float4*>(src + (size_t)r * P.slot_bytes));
-                        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        if (PEER) {
+            const size_t nblk = P.slot_bytes / (BN * sizeof(float4));
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int j = h ? jm : ja;
+                if (j < 0) continue;
+                const int mem = h ? memM : memA;
+                const size_t slot = (size_t)(h ? P.capA + j : j);
+                const unsigned char* src = P.base[P.rank] + par_off + ((slot * BN + l) << 4);
+                const float4 own = h ? mv : a;
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int r = 0; r < P.nranks; r++) {
+                    if (!((mem >> r) & 1)) continue;
+                    float4 v = own;
+                    if (r != P.rank) {
+                        v = __ldcv(reinterpret_cast<const float4*>(src + (size_t)r * P.slot_bytes));
+                        if (__ldcv(stamps + (size_t)r * nblk + slot) != E + 1) v = make_float4(0.f, 0.f, 0.f, 0.f);  // not active there
                     }
-                    a = sum;
+                    sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
                 }
-            }
-            if (jm >= 0) {
-                const int mem = P.memM[jm];
-                if ((mem >> P.rank) & 1) {
-                    const unsigned char* src = P.base[P.rank] + par_off + ((((size_t)P.capA + jm) * BN + l) << 4);
-                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int r = 0; r < P.nranks; r++) {
-                        if (!((mem >> r) & 1)) continue;
-                        const float4 v = (r == P.rank) ? mv : __ldcv(reinterpret_cast<const float4*>(src + (size_t)r * P.slot_bytes));
-                        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-                    }
-                    mv = sum;
-                }
+                if (h) mv = sum; else a = sum;
             }
         }
         float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), cn = cv;
@@ -983,8 +1028,9 @@ __global__ void __launch_bounds__(256) k_grid_update(Grid g, ModelDev md, float 
         }
         g.vout[ni] = make_float4(vx, vy, vz, 0.0f);
     }
+    }  // pass
     ts_end(g, TS_GRID);
-    if (pull) {  // the last CTA closes the exchange
+    if (PEER) {  // the last CTA closes the exchange
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();

@@ -34,7 +34,7 @@ class ShardedMPM:
         self.k = 0  # substeps since the last shared-list rebuild
         self.stats = {"rebuilds": 0, "shared_blocks": 0, "exchange_bytes": 0}
         # The substep loop runs inside the library (mpm_step_sharded_nccl: captured windows, the shared blocks move with
-        # the peer-to-peer push / pull kernels).  NCCL backend: the solver gets its own communicator (the unique id travels
+        # the peer-to-peer exchange fused into the grid update).  NCCL backend: the solver gets its own communicator (the unique id travels
         # through torch.distributed).  Any other backend (gloo: CPU rendezvous, also two ranks SHARING one GPU, which NCCL
         # refuses): the library's set-up traffic goes through a host all-gather callback on this group.
         # MPM_B200_SHARD_GRAPH=0 keeps the older per-substep callback path (mpm_step_sharded).
@@ -192,7 +192,7 @@ class ShardedMPM:
         n, cap, rb = C.c_int(0), C.c_int(0), C.c_int(0)
         self._ck(self.lib.mpm_shared_info(self.h, C.byref(n), C.byref(cap), C.byref(rb), self._stream()))
         self.n_shared = n.value
-        mode = {0: "callback", 1: "nccl all-reduce in graph", 2: "peer-to-peer push/pull in graph",
+        mode = {0: "callback", 1: "nccl all-reduce in graph", 2: "peer-to-peer, fused into the grid update, in graph",
                 3: "host all-gather per substep"}.get(self.lib.mpm_shared_mode(self.h), "?")
         self.stats.update(rebuilds=rb.value, shared_blocks=n.value, exchange_bytes=cap.value * 64 * 8 * 4, exchange=mode)
 

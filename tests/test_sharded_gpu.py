@@ -85,15 +85,15 @@ def _check(X, V, stats, overflow, n_ghost):
 
 @pytest.mark.timeout(900)
 def test_two_rank_peer_to_peer_exchange_matches_single_gpu():
-    """The path the multi-GPU bench runs: captured windows with the peer-to-peer exchange (k_shared_push + the pull fused
-    into k_grid_update: CUDA-IPC receive areas, system-scope arrival counters, rank-ordered sums).  On a box with two GPUs over NCCL; on
+    """The path the multi-GPU bench runs: captured windows with the peer-to-peer exchange fused into the grid update
+    (k_grid_update<true>: CUDA-IPC receive areas, system-scope arrival counters, rank-ordered sums).  On a box with two GPUs over NCCL; on
     a single-GPU box the two ranks share cuda:0 (gloo rendezvous, host all-gather for the set-up traffic) -- the SAME
     kernels exchange the blocks, so this is the driver-visible parity evidence for them."""
     nccl = torch.cuda.device_count() >= 2
     X, V, stats, overflow, n_ghost, mode = _run(nccl, {"MPM_B200_SHARD_GRAPH": "1", "MPM_TEST_TIMELINE": "1"})
     assert mode == 2, f"expected the peer-to-peer exchange, got mode {mode} ({stats.get('exchange')})"
     _check(X, V, stats, overflow, n_ghost)
-    tl = stats["timeline"]  # the sharded timeline probe stamps the push kernel and the grid update's wait for the peers
+    tl = stats["timeline"]  # the sharded timeline probe stamps the grid update's push phase and its wait for the peers
     assert tl is not None and {"push", "pull", "p2g_E", "grid", "g2p_E"} <= set(tl["kernels"])
     assert tl["kernels"]["pull"]["start_us"] >= tl["kernels"]["p2g_E"]["start_us"] and tl["substep_us"] > 0
 
