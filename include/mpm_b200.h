@@ -211,9 +211,9 @@ int mpm_force_resort(MpmSolver *s);
  * 7 G2P elements.  The kernels overlap under programmatic dependent launch, which CUDA events cannot resolve. */
 int mpm_measure_timeline(MpmSolver *s, float dt, int n, const MpmFrameInputs *in, long long *out, void *stream);
 /* the same for the SHARDED chain (collective; needs the peer-to-peer exchange, i.e. at least one mpm_step_sharded_nccl call
- * before): n <= 32, out[n][10][2]; ids 0-7 as above; 8 = the push phase at the head of the grid update (first store into a
- * peer's receive area to the last arrival-counter add), 9 = its wait for the slowest peer's push (the ranks' skew).  The
- * whole exchange is fused into k_grid_update<true>. */
+ * before): n <= 32, out[n][10][2]; ids 0-7 as above; 8 = the push phase at the head of the grid update (flagged stores of
+ * this rank's parts into the members' receive areas), 9 = its second pass: the nodes of shared blocks, including the wait
+ * for their members' parts (the neighbours' skew).  The whole exchange is fused into k_grid_update<true>. */
 int mpm_measure_timeline_sharded(MpmSolver *s, float dt, int n, const MpmFrameInputs *in, long long *out, void *stream);
 /* latency analysis (builds with -DMPM_CLK only fill it): 8 kernels x 8 per-warp phase cycle sums; synchronises */
 int mpm_debug_phase_clocks(MpmSolver *s, unsigned long long *out64, int reset);

@@ -1347,7 +1347,8 @@ void sharded_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q) {
     if (s->p2p_ready) {
         PeerArea P = s->peer;
         P.mapA = s->d_mapA; P.mapM = s->d_mapM; P.memA = s->d_memA; P.memM = s->d_memM;
-        P.capA = s->xcap_blocks;
+        P.listA = s->d_shared; P.listM = s->d_sharedM; P.nA = s->d_n_shared; P.nM = s->d_nM;
+        P.capA = s->xcap_blocks; P.capM = s->xcapM;
         s->gu_peer = P;
         launch_substep(s, a, q, HALF_SCATTER | HALF_GATHER);
         s->gu_peer = PeerArea{};
@@ -1402,10 +1403,8 @@ static void setup_peer_areas(MpmSolver* s, cudaStream_t q) {
     unsigned char* old_local = s->peer_local;
     s->peer_local = nullptr;
     s->p2p_ready = false;
-    const size_t slot = (size_t)(s->xcap_blocks + s->xcapM) * BN * sizeof(float4);
-    const size_t flags_off = 2 * (size_t)n * slot;
-    const size_t stamp_off = flags_off + 2 * (size_t)n * sizeof(unsigned long long);  // arrival counters [parity][sender]
-    const size_t total = stamp_off + 2 * (size_t)n * (s->xcap_blocks + s->xcapM) * sizeof(unsigned);  // stamps [parity][sender][block]
+    const size_t slot = (size_t)(s->xcap_blocks + s->xcapM) * BN * 32;  // flagged parts: 32 bytes per node
+    const size_t total = 2 * (size_t)n * slot;                            // [parity][sender]
     struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
     Msg mine{};
     mine.ok = cudaMalloc(&s->peer_local, total) == cudaSuccess && cudaMemset(s->peer_local, 0, total) == cudaSuccess &&
@@ -1432,8 +1431,6 @@ static void setup_peer_areas(MpmSolver* s, cudaStream_t q) {
     for (int r = 0; r < n; r++) h_ok = std::min(h_ok, oks[r]);
     if (!h_ok) { close_peer_areas(s); return; }
     P.slot_bytes = slot;
-    P.flags_off = flags_off;
-    P.stamp_off = stamp_off;
     P.rank = s->comm_rank;
     P.nranks = n;
     unsigned* ctr = s->dalloc<unsigned>(4);  // zeroed: epoch, push counter, pull counter
@@ -1630,7 +1627,7 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
 
 // Timeline probe of the SHARDED chain (collective: every rank calls it with the same n): n <= 32 sharded substeps launched
 // eagerly with the stamps on; out[n][10][2] as mpm_measure_timeline plus ids 8 (the push phase at the head of
-// k_grid_update<true>) and 9 (its wait for the slowest peer's push).  Requires the peer-to-peer exchange.
+// k_grid_update<true>) and 9 (its pass over the shared nodes, incl. the wait for the members' parts).  Requires the peer-to-peer exchange.
 int mpm_measure_timeline_sharded(MpmSolver* s, float dt, int n, const MpmFrameInputs* in, long long* out, void* stream) {
     API_BEGIN(s)
     cudaStream_t q = (cudaStream_t)stream;

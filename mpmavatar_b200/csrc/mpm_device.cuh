@@ -126,26 +126,33 @@ __device__ __forceinline__ void ts_end(const Grid& g, int k) {
 
 // Peer-to-peer exchange of the grid blocks shared with other ranks (sharded runs; fused into k_grid_update<true>).
 // Every rank owns a receive area, mapped into every peer (CUDA IPC):
-//   parts    [2 epoch parities][nranks senders][capA + capM blocks][64] float4    at 0
-//   arrivals [2][nranks] u64, monotonic: + (CTAs of the grid update) per exchange  at flags_off
-//   stamps   [2][nranks][capA + capM] u32: epoch + 1 of the sender's last VALID part of the block   at stamp_off
+//   [2 epoch parities][nranks senders][capA + capM blocks][64 nodes] x 32 bytes {x, flag, y, flag | z, flag, w, flag}
+// A part is valid in epoch E when all four flags read E + 1 (the area starts zeroed; epochs only grow).  Every 8-byte
+// {float, flag} pair is written by one store and read by one load, which the memory system never splits -- the "LL"
+// protocol of NCCL: data and its arrival flag travel together, so there is no fence and no separate signal.
 struct PeerArea {
     unsigned char* base[8];  // receive area of every rank as mapped here (base[rank] is the local one)
-    unsigned long long slot_bytes, flags_off, stamp_off;
+    unsigned long long slot_bytes;  // one sender's part of one parity: (capA + capM) * 64 * 32
     int rank, nranks;  // nranks == 0: not a peer-to-peer sharded step
     unsigned* epoch;    // completed exchanges (device)
     unsigned* counter;  // last-CTA detection of the grid update
-    const int *mapA, *mapM;            // block (table index) -> position in the shared lists A (acc) / M (mov), -1 if not listed
-    const unsigned char *memA, *memM;  // member ranks of every listed block (bit r = rank r can touch it)
-    int capA;                          // capacity of list A: list M's slots follow it in the receive areas
+    const int *listA, *listM;          // packed coordinates of the shared blocks: list A (acc) / M (mov)
+    const int *nA, *nM;                // their lengths (device)
+    const unsigned char *memA, *memM;  // member ranks of every listed block (bit r = rank r can reach it)
+    const int *mapA, *mapM;            // block (table index) -> position in list A / M, -1 if not listed
+    int capA, capM;                    // list capacities: list M's slots follow list A's in the receive areas
 };
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void ll_store(unsigned char* p, const float4& v, unsigned flag) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(p), "r"(__float_as_uint(v.x)), "r"(flag), "r"(__float_as_uint(v.y)) : "memory");
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(p + 16), "r"(__float_as_uint(v.z)), "r"(flag), "r"(__float_as_uint(v.w)) : "memory");
 }
-__device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsigned long long v) {
-    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ float4 ll_load(const unsigned char* p, unsigned flag) {
+    unsigned x, fx, y, fy, z, fz, w, fw;
+    do {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(fx), "=r"(y), "=r"(fy) : "l"(p) : "memory");
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(z), "=r"(fz), "=r"(w), "=r"(fw) : "l"(p + 16) : "memory");
+    } while (fx != flag || fy != flag || fz != flag || fw != flag);
+    return make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z), __uint_as_float(w));
 }
 
 struct StepState {

@@ -816,17 +816,18 @@ __global__ void __launch_bounds__(128) k_body_scatter(Grid g, ColliderArgs ca, M
 //   mesh collider normalize_grid + collide (mpm_solver.py:882-917),
 //   particle mover normalize_grid (:790-799), and every grid_postprocess BC in order (:487-501),
 // then re-zeroes the accumulators it consumed (replaces the three dense zero_grid sweeps).
-// PEER (sharded runs with the peer-to-peer exchange): the WHOLE exchange of the blocks shared with other ranks is fused in.
-//   1. push: every thread sends its own nodes' partial sums (acc, mov) of shared blocks straight into the receive areas of
-//      the blocks' other members, plus a per-block stamp "valid in epoch E" (a member that has NOT activated the block sends
-//      nothing: its part is zero, which a stale stamp says); the CTA then fences and adds 1 to its arrival counter in every
-//      peer (red.release.sys);
+// PEER (sharded runs with the peer-to-peer exchange): the WHOLE exchange of the blocks shared with other ranks is fused in,
+// as a flagged-data ("LL") protocol -- no fence, no counter, no separate kernel:
+//   1. push: the threads sweep the shared-block lists; for every block this rank is a member of they take its partial sums
+//      (acc, mov) out of the grid (re-zeroing them) and store them, each 8 bytes as {float, epoch flag}, straight into the
+//      receive areas of ALL members of the block, this rank's own included (PeerArea in mpm_device.cuh);
 //   2. the nodes of blocks that are not shared are updated while those stores are in flight;
-//   3. the CTA waits until every peer's counter says "all CTAs of epoch E have pushed", then updates the shared nodes from
-//      the sum of the members' parts IN RANK ORDER (own part at its position; every member computes identical bits).
-// Step 3 waits on ALL CTAs of the peers, so every CTA of this grid must be resident at once: the host launches 4 x 148 CTAs
-// and the launch bounds pin 4 CTAs per SM.  Two epoch parities of receive area suffice: a rank can only push epoch e+2 after
-// its grid update of e+1, which needed every peer's push of e+1, which follows that peer's grid update of e.
+//   3. the nodes of shared blocks are updated from the sum of the members' parts IN RANK ORDER (every member computes
+//      identical bits); each part is polled until both of its flags carry this epoch, so a rank waits for exactly the
+//      neighbours it shares the node with, not for a global barrier.
+// Step 3 waits on CTAs of the peers' grid updates, so every CTA of this grid must be resident at once: the host launches
+// 4 x 148 CTAs and the launch bounds pin 4 CTAs per SM.  Two epoch parities of receive area suffice: a rank can only push
+// epoch e+2 after its grid update of e+1, which needed its neighbours' pushes of e+1, which follow their grid updates of e.
 template <bool PEER>
 __global__ void __launch_bounds__(256, PEER ? 4 : 5) k_grid_update(Grid g, ModelDev md, float dt, int use_collider, float col_friction,
                                                      int use_mover, const BCDesc* __restrict__ bcs, int n_bc,
@@ -838,56 +839,39 @@ __global__ void __launch_bounds__(256, PEER ? 4 : 5) k_grid_update(Grid g, Model
     const int total = n_slots * BN;
     const int idx0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     int co_next = idx0 < total ? g.slot_coord[idx0 >> 6] : 0;
-    pdl_wait();     // the scatters of this substep
-    pdl_trigger();  // the G2P kernels behind this one may take the slots it frees (they wait for its completion)
     unsigned E = 0;
     size_t par_off = 0;
-    const unsigned* stamps = nullptr;  // [sender][capA + capM] of this epoch's parity, local receive area
+    int n_push_a = 0, n_push = 0;
     if (PEER) {
-        E = *P.epoch;  // advanced by the previous grid update, which completed long before this one started
+        E = *P.epoch;  // advanced by the previous grid update, which completed long before this one was launched
         par_off = (size_t)(E & 1) * P.nranks * P.slot_bytes;
-        const size_t nblk = P.slot_bytes / (BN * sizeof(float4));
-        const size_t stamp_off = P.stamp_off + (size_t)(E & 1) * P.nranks * nblk * sizeof(unsigned);
-        stamps = reinterpret_cast<const unsigned*>(P.base[P.rank] + stamp_off);
+        n_push_a = min(*P.nA, P.capA) * BN;
+        n_push = n_push_a + min(*P.nM, P.capM) * BN;
+    }
+    pdl_wait();     // the scatters of this substep
+    pdl_trigger();  // the G2P kernels behind this one may take the slots it frees (they wait for its completion)
+    if (PEER) {
         ts_begin(g, TS_PUSH);
-        for (int i = idx0; i < total; i += stride) {
-            const int co = g.slot_coord[i >> 6], l = i & 63;
-            const int ni = block_node(g, co, l), blk = ni >> 6;
-            const int ja = P.mapA[blk], jm = P.mapM[blk];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int j = h ? jm : ja;
-                if (j < 0) continue;
-                const int mem = (h ? P.memM : P.memA)[j];
-                if (!((mem >> P.rank) & 1)) continue;
-                const float4 v = (h ? g.mov : g.acc)[ni];
-                const size_t slot = (size_t)(h ? P.capA + j : j);
-                const size_t off = par_off + (size_t)P.rank * P.slot_bytes + ((slot * BN + l) << 4);
-                const size_t soff = stamp_off + ((size_t)P.rank * nblk + slot) * sizeof(unsigned);
-                for (int r = 0; r < P.nranks; r++) {
-                    if (r == P.rank || !((mem >> r) & 1)) continue;
-                    *reinterpret_cast<float4*>(P.base[r] + off) = v;
-                    if (l == 0) *reinterpret_cast<unsigned*>(P.base[r] + soff) = E + 1;
-                }
-            }
+        const unsigned flag = E + 1;
+        for (int i = idx0; i < n_push; i += stride) {
+            const bool m = i >= n_push_a;
+            const int e = m ? i - n_push_a : i, j = e >> 6, l = e & 63;
+            const int mem = (m ? P.memM : P.memA)[j];
+            if (!((mem >> P.rank) & 1)) continue;  // not a member: this rank cannot reach the block
+            const int co = (m ? P.listM : P.listA)[j];
+            float4* src = (m ? g.mov : g.acc) + block_node(g, co, l);
+            const float4 v = *src;  // zero if the block is not active here (invariant 2)
+            if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) *src = make_float4(0.f, 0.f, 0.f, 0.f);
+            const size_t off = par_off + (size_t)P.rank * P.slot_bytes + ((((size_t)(m ? P.capA + j : j)) * BN + l) << 5);
+            for (int r = 0; r < P.nranks; r++)
+                if ((mem >> r) & 1) ll_store(P.base[r] + off, v, flag);
         }
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x < P.nranks && threadIdx.x != P.rank)
-            red_release_sys_add(reinterpret_cast<unsigned long long*>(P.base[threadIdx.x] + P.flags_off) + (E & 1) * P.nranks + P.rank, 1ull);
         ts_end(g, TS_PUSH);
     }
     const float time = (float)st->time;
     for (int pass = 0; pass < (PEER ? 2 : 1); pass++) {
-    if (PEER && pass == 1) {  // every peer's push of this epoch has arrived in full: each of its CTAs added 1 to its counter here
-        ts_begin(g, TS_PULL);  // slot 9 of the sharded timeline: the wait for the slowest peer (the ranks' skew)
-        if (threadIdx.x < P.nranks && threadIdx.x != P.rank) {
-            const unsigned long long* c = reinterpret_cast<const unsigned long long*>(P.base[P.rank] + P.flags_off) + (E & 1) * P.nranks + threadIdx.x;
-            const unsigned long long want = (unsigned long long)gridDim.x * ((E >> 1) + 1);
-            while (ld_acquire_sys(c) < want) __nanosleep(32);
-        }
-        __syncthreads();
-        ts_end(g, TS_PULL);
+    if (PEER && pass == 1) {
+        ts_begin(g, TS_PULL);  // slot 9 of the sharded timeline: the shared nodes, incl. the wait for their members' parts
         co_next = idx0 < total ? g.slot_coord[idx0 >> 6] : 0;
     }
     for (int idx = idx0; idx < total; idx += stride) {
@@ -906,28 +890,23 @@ __global__ void __launch_bounds__(256, PEER ? 4 : 5) k_grid_update(Grid g, Model
             if (jm >= 0) { memM = P.memM[jm]; if (!((memM >> P.rank) & 1)) jm = -1; }
             if ((ja >= 0 || jm >= 0) != (pass == 1)) continue;
         }
-        // all four accumulator loads are issued before any use (memory-level parallelism)
-        float4 a = g.acc[ni];
-        float4 mv = g.mov[ni];
-        const float4 a_own = a, mv_own = mv;  // what THIS rank accumulated: decides what has to be re-zeroed
+        // all four accumulator loads are issued before any use (memory-level parallelism).  A quantity of a shared block was
+        // taken out of the grid by the push: it comes from the receive area instead
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), mv = a;
+        if (ja < 0) a = g.acc[ni];
+        if (jm < 0) mv = g.mov[ni];
+        const float4 a_own = a, mv_own = mv;  // what is still in the grid and has to be re-zeroed
         if (PEER) {
-            const size_t nblk = P.slot_bytes / (BN * sizeof(float4));
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int j = h ? jm : ja;
                 if (j < 0) continue;
                 const int mem = h ? memM : memA;
-                const size_t slot = (size_t)(h ? P.capA + j : j);
-                const unsigned char* src = P.base[P.rank] + par_off + ((slot * BN + l) << 4);
-                const float4 own = h ? mv : a;
+                const unsigned char* src = P.base[P.rank] + par_off + ((((size_t)(h ? P.capA + j : j)) * BN + l) << 5);
                 float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int r = 0; r < P.nranks; r++) {
                     if (!((mem >> r) & 1)) continue;
-                    float4 v = own;
-                    if (r != P.rank) {
-                        v = __ldcv(reinterpret_cast<const float4*>(src + (size_t)r * P.slot_bytes));
-                        if (__ldcv(stamps + (size_t)r * nblk + slot) != E + 1) v = make_float4(0.f, 0.f, 0.f, 0.f);  // not active there
-                    }
+                    const float4 v = ll_load(src + (size_t)r * P.slot_bytes, E + 1);
                     sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
                 }
                 if (h) mv = sum; else a = sum;
@@ -1029,6 +1008,7 @@ __global__ void __launch_bounds__(256, PEER ? 4 : 5) k_grid_update(Grid g, Model
         g.vout[ni] = make_float4(vx, vy, vz, 0.0f);
     }
     }  // pass
+    if (PEER) ts_end(g, TS_PULL);
     ts_end(g, TS_GRID);
     if (PEER) {  // the last CTA closes the exchange
         __syncthreads();

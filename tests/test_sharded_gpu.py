@@ -86,7 +86,7 @@ def _check(X, V, stats, overflow, n_ghost):
 @pytest.mark.timeout(900)
 def test_two_rank_peer_to_peer_exchange_matches_single_gpu():
     """The path the multi-GPU bench runs: captured windows with the peer-to-peer exchange fused into the grid update
-    (k_grid_update<true>: CUDA-IPC receive areas, system-scope arrival counters, rank-ordered sums).  On a box with two GPUs over NCCL; on
+    (k_grid_update<true>: CUDA-IPC receive areas, flagged-data stores, rank-ordered sums).  On a box with two GPUs over NCCL; on
     a single-GPU box the two ranks share cuda:0 (gloo rendezvous, host all-gather for the set-up traffic) -- the SAME
     kernels exchange the blocks, so this is the driver-visible parity evidence for them."""
     nccl = torch.cuda.device_count() >= 2
