@@ -1468,7 +1468,10 @@ static void rebuild_shared_on_device(MpmSolver* s, int margin, cudaStream_t q) {
         CK(cudaMemcpyAsync(&n[0], s->d_n_shared, sizeof(int), cudaMemcpyDeviceToHost, q));
         CK(cudaMemcpyAsync(&n[1], s->d_nM, sizeof(int), cudaMemcpyDeviceToHost, q));
         CK(cudaStreamSynchronize(q));
-        auto room = [](int k) { return (k + k / 4 + 32 + 31) / 32 * 32; };
+        // 100 % head-room: a re-size synchronises, re-maps the receive areas and re-captures the windows (2-8 ms), and the
+        // lists of a garment that is still settling grow by a quarter within a few hundred substeps
+        auto room = [](int k) { return (2 * k + 32 + 31) / 32 * 32; };
+        if (getenv("MPM_B200_TRACE")) fprintf(stderr, "[mpm_b200 rank %d] substep %lld: shared lists resized (%d, %d blocks; capacities were %d, %d)\n", s->comm_rank, (long long)s->n_substeps, n[0], n[1], s->xcap_blocks, s->xcapM);
         s->xcap_blocks = room(n[0]);
         s->xcapM = room(n[1]);
         s->xbuf = s->dalloc<float>((size_t)(s->xcap_blocks + s->xcapM) * BN * 4);
@@ -1595,6 +1598,7 @@ int mpm_step_sharded_nccl(MpmSolver* s, float dt, int nsub, const MpmFrameInputs
                 if (!s->cap_stream) CK(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
                 const int before = s->launches;
                 cudaGraph_t graph;
+                if (getenv("MPM_B200_TRACE")) fprintf(stderr, "[mpm_b200 rank %d] substep %lld: capturing a sharded window (graph %zu)\n", s->comm_rank, (long long)s->n_substeps, cache.size());
                 CK(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
                 for (int i = 0; i < W; i++) sharded_substep(s, a, s->cap_stream);
                 CK(cudaStreamEndCapture(s->cap_stream, &graph));
