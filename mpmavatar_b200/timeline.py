@@ -27,7 +27,8 @@ def measure(solver, dt, ft, n=32):
 
 def measure_sharded(sm, dt, ft, n=24):
     """Collective (every rank calls it): per-kernel stamps of n sharded substeps of a ShardedMPM, incl. the two exchange
-    kernels.  ft: GLOBAL frame tensors (the rank's joint rows are picked as ShardedMPM.step does)."""
+    phases of the grid update ("push": its flagged stores into the members' receive areas; "pull": its pass over the
+    nodes of shared blocks, which waits for the members' parts).  ft: GLOBAL frame tensors (the rank's joint rows are picked as ShardedMPM.step does)."""
     p = sm.part
     fin = _lib.MpmFrameInputs()
     keep = []
