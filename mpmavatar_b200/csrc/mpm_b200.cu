@@ -446,6 +446,8 @@ struct MpmSolver {
     bool use_graphs = true;
     bool use_pdl = true;  // MPM_B200_PDL=0 disables programmatic dependent launch
     bool scatter_early = false;  // MPM_B200_SCATTER_EARLY=1
+    float scatter_at = 0.3f;     // MPM_B200_SCATTER_AT: position of the body-scatter CTAs in the vertex P2G grid (fraction; < 0: own launch).
+                                 // C3, us per substep: own launch 78.7; at 0.0 / 0.3 / 0.5 / 0.7 / 0.9 of the grid 76.5 / 75.9 / 76.6 / 77.5 / 77.3
     cudaStream_t cap_stream = nullptr;
     // profiling
     cudaEvent_t ev[10]{};
@@ -618,16 +620,16 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
     }
     if (s->Nt) {
         P2GIn in{R.TP, R.TS};
-        launch_pdl(k_p2g<1>, cdiv(s->Nt, ppb), ppb, P2G_SMEM, q, pdl, s->g, in, s->Nt, a.dt, s->md.rpic);
+        launch_pdl(k_p2g<1>, cdiv(s->Nt, ppb), ppb, P2G_SMEM, q, pdl, s->g, in, s->Nt, a.dt, s->md.rpic, BodyScatter{});
         s->launches++;
     }
     // body-mesh collider and joint movers (mpm_solver.py:382-472): one launch behind the P2G kernels
     // (profiling: two launches, so that the two phases are timed separately)
+    const int tot = a.mover ? a.njt + s->cfg.num_joint_v + s->cfg.num_joint_f : 0;
+    const ColliderArgs ca{a.collider ? s->cfg.n_mesh_f : 0, s->mesh_faces, s->mesh_x, s->mesh_v, s->st, a.dt, a.advance_mesh ? 1 : 0};
+    const MoverArgs ma{a.mover ? a.njt : 0, a.mover ? s->cfg.num_joint_v : 0, a.mover ? s->cfg.num_joint_f : 0, s->Nt,
+                       s->joint_t, s->joint_v, s->joint_f, R.TP, R.VP, R.XE, s->R.invE, s->R.invT, s->R.invV};
     auto scatter_launch = [&]() {
-        const int tot = a.mover ? a.njt + s->cfg.num_joint_v + s->cfg.num_joint_f : 0;
-        ColliderArgs ca{a.collider ? s->cfg.n_mesh_f : 0, s->mesh_faces, s->mesh_x, s->mesh_v, s->st, a.dt, a.advance_mesh ? 1 : 0};
-        MoverArgs ma{a.mover ? a.njt : 0, a.mover ? s->cfg.num_joint_v : 0, a.mover ? s->cfg.num_joint_f : 0, s->Nt,
-                     s->joint_t, s->joint_v, s->joint_f, R.TP, R.VP, R.XE, s->R.invE, s->R.invT, s->R.invV};
         if (ev) {  // profiling: separate launches so that the two phases are timed separately
             if (ca.Mf) { k_collider_scatter<<<cdiv(ca.Mf, 128), 128, 0, q>>>(s->g, ca); s->launches++; }
             CK(cudaEventRecord(ev[3], q));
@@ -638,15 +640,25 @@ static void launch_substep(MpmSolver* s, const SubstepArgs& a, cudaStream_t q, i
             s->launches++;
         }
     };
-    const bool scatter_early = s->scatter_early && !ev;  // A/B: body scatter between the element and the vertex P2G
+    // where the body scatter runs: as CTAs in the middle of the vertex P2G grid (default), or as its own launch in front of
+    // (MPM_B200_SCATTER_EARLY=1) / behind (MPM_B200_SCATTER_AT < 0, profiling, no cloth vertices) that kernel
+    const bool fused = s->Nv && !ev && !s->scatter_early && s->scatter_at >= 0.0f && ca.Mf + tot > 0;
+    const bool scatter_early = s->scatter_early && !ev;
     if (scatter_early) scatter_launch();
     if (s->Nv) {
         P2GIn in{R.VP, (const float*)R.VF[cur]};
-        launch_pdl(k_p2g<2>, cdiv(s->Nv, 32 * P2G_V_NW), 32 * P2G_V_NW, 128 + P2G_V_NW * P2G_WB, q, pdl, s->g, in, s->Nv, a.dt, s->md.rpic);
+        const int slabs = cdiv(s->Nv, 32 * P2G_V_NW);
+        BodyScatter bs{};
+        if (fused) {
+            bs.ca = ca; bs.ma = ma;
+            bs.n_ctas = cdiv(3LL * (ca.Mf + tot), 32 * P2G_V_NW);
+            bs.first = std::min(slabs, (int)(s->scatter_at * slabs));
+        }
+        launch_pdl(k_p2g<2>, slabs + bs.n_ctas, 32 * P2G_V_NW, 128 + P2G_V_NW * P2G_WB, q, pdl, s->g, in, s->Nv, a.dt, s->md.rpic, bs);
         s->launches++;
     }
     if (ev) CK(cudaEventRecord(ev[2], q));
-    if (!scatter_early) scatter_launch();
+    if (!scatter_early && !fused) scatter_launch();
     }  // HALF_SCATTER
     if (!(halves & HALF_GATHER)) return;
     // one thread per node of the active blocks, grid-strided over the device-side block count
@@ -812,6 +824,7 @@ int mpm_create(const MpmConfig* cfg, MpmSolver** out) {
         if (const char* e = getenv("MPM_B200_RESORT")) { if (cfg->resort_interval <= 0 && atoi(e) > 0) s->resort_interval = atoi(e); }
         if (const char* e = getenv("MPM_B200_PDL")) s->use_pdl = atoi(e) != 0;
         if (const char* e = getenv("MPM_B200_SCATTER_EARLY")) s->scatter_early = atoi(e) != 0;
+        if (const char* e = getenv("MPM_B200_SCATTER_AT")) s->scatter_at = (float)atof(e);
         if (const char* e = getenv("MPM_B200_GRAPHS")) s->use_graphs = atoi(e) != 0;
         if (const char* e = getenv("MPM_B200_P2P")) s->use_p2p = atoi(e) != 0;
         Grid& g = s->g;

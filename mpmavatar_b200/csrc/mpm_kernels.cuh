@@ -19,10 +19,10 @@ struct Warp {
 };
 // NW warps per CTA, WB bytes of shared memory per warp (after a 128-byte barrier header)
 template <int NW, int WB>
-__device__ __forceinline__ bool warp_begin(Warp& w, int n, unsigned char* smem) {
+__device__ __forceinline__ bool warp_begin(Warp& w, int n, unsigned char* smem, int blk = -1) {
     const int warp = threadIdx.x >> 5;
     w.lane = threadIdx.x & 31;
-    w.p0 = (blockIdx.x * NW + warp) * 32;
+    w.p0 = ((blk < 0 ? (int)blockIdx.x : blk) * NW + warp) * 32;
     if (w.p0 >= n) return false;
     w.cnt = min(32, n - w.p0);
     w.bar = reinterpret_cast<uint64_t*>(smem) + warp;
@@ -521,76 +521,6 @@ struct P2GIn {
     const float* SF;  // TS (KIND 1) or the vertex forces VF (KIND 2)
 };
 
-// KIND 1: traditional (stress*vol, :496), 2: cloth vertex.  PDL invariants of this file: (1) every kernel executes
-// griddepcontrol.wait before it exits, so completion is transitive along the stream; (2) a kernel whose successor
-// runs code in front of its own wait that READS what this kernel's predecessors wrote triggers only AFTER its
-// own wait, so "my grid has started" implies "my predecessor's predecessor has completed".
-template <int KIND>
-__global__ void __launch_bounds__(32 * (KIND == 2 ? P2G_V_NW : P2G_NW), KIND == 2 ? P2G_V_MINB : 1) k_p2g(Grid g, P2GIn in, int n, float dt, float rpic) {
-    static_assert(KIND == 1 || KIND == 2, "elements have their own kernel");
-    constexpr int F0 = (KIND == 2) ? VP_F : KP_F;  // kinematics record
-    constexpr int NW = (KIND == 2) ? P2G_V_NW : P2G_NW;
-    extern __shared__ __align__(128) unsigned char smem[];
-    Warp w;
-    if (!warp_begin<NW, P2G_WB>(w, n, smem)) return;
-    ts_begin(g, TS_P2G_E + KIND);
-    PHASE_BEGIN();
-    float* buf = reinterpret_cast<float*>(w.buf);
-    // The vertex scatter only needs its predecessor (the element kernel) for the vertex forces: the VP slab is
-    // loaded and unpacked while the element kernel drains, griddepcontrol.wait sits in front of the VF read.
-    if (KIND != 2) {
-        pdl_wait();
-        pdl_trigger();  // let the successor's CTAs be scheduled into the slots this grid frees
-    }
-    float* raw1 = buf + 32 * F0;
-    if (KIND == 1) slab_load(w, {Slab{buf, in.KP, KP_F}, Slab{raw1, in.SF, S_F}});
-    if (KIND == 2) slab_load(w, {Slab{buf, in.KP, VP_F}});
-    PHASE(g, KIND, 0);  // slab load
-    const bool valid = w.lane < w.cnt;
-    P2GPart P;
-    P.m = 0.f;
-#pragma unroll
-    for (int i = 0; i < 3; i++) { P.x[i] = 0.f; P.v[i] = 0.f; }
-#pragma unroll
-    for (int i = 0; i < 9; i++) { P.C[i] = 0.f; P.Sp[i] = 0.f; }
-    if (valid) {
-        const float* r = buf + w.lane * F0;
-        if (KIND == 2) {
-            const float4* r4 = reinterpret_cast<const float4*>(r);
-            const float4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
-            P.x[0] = a.x; P.x[1] = a.y; P.x[2] = a.z; P.m = a.w;
-            P.v[0] = b.x; P.v[1] = b.y; P.v[2] = b.z;
-            P.C[0] = b.w; P.C[1] = c.x; P.C[2] = c.y; P.C[3] = c.z; P.C[4] = c.w; P.C[5] = d.x; P.C[6] = d.y; P.C[7] = d.z; P.C[8] = d.w;
-        } else {
-            P.x[0] = r[0]; P.x[1] = r[1]; P.x[2] = r[2]; P.m = r[P_M];
-            P.v[0] = r[P_V]; P.v[1] = r[P_V + 1]; P.v[2] = r[P_V + 2];
-#pragma unroll
-            for (int i = 0; i < 9; i++) P.C[i] = r[P_C + i];
-            const float sc = -dt * g.inv_dx * r[P_VOL];
-            const float* s = raw1 + w.lane * S_F;
-#pragma unroll
-            for (int i = 0; i < 9; i++) P.Sp[i] = sc * s[i];
-        }
-    }
-    __syncwarp();  // the contributions overwrite the raw slabs
-    PHASE(g, KIND, 1);  // unpack
-    const int mycell = p2g_write_tiles<KIND == 1>(g, w, valid, P, dt, rpic, [&](float (&fv)[3]) {
-        if (KIND == 2) {  // the weights were computed while the element kernel drained
-            pdl_wait();
-            pdl_trigger();
-            if (valid) {
-                const float4 f4 = __ldcg(reinterpret_cast<const float4*>(in.SF) + w.p0 + w.lane);  // written by L2 atomics
-                fv[0] = f4.x; fv[1] = f4.y; fv[2] = f4.z;
-            }
-        }
-    });
-    PHASE(g, KIND, 2);  // stage 1
-    p2g_stage2(g, w, mycell);
-    PHASE(g, KIND, 3);  // stage 2
-    PHASE_END(g, KIND);
-    ts_end(g, TS_P2G_E + KIND);
-}
-
 // ---- cloth elements: constitutive update + scatter in one kernel.  The element state arrives as coalesced float4
 // streams (lane = particle, one LDG.128 each; see mpm_device.cuh) -- no shared-memory staging, the tiles of stage 1
 // are the only shared-memory traffic.
@@ -799,16 +729,111 @@ __global__ void __launch_bounds__(128) k_mover_scatter(Grid g, MoverArgs ma) {
 // the tail of the vertex P2G; the wait before exit keeps completion transitive.  (Placing it between the two P2G
 // kernels was measured: its ~1.1 M vector atomics then collide with the element kernel's and slow that kernel by
 // more than the scatter's own exposed time.)  Thread triples [0, Mf) faces, then the movers.
-__global__ void __launch_bounds__(128) k_body_scatter(Grid g, ColliderArgs ca, MoverArgs ma) {
-    const int tt = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void body_scatter_thread(const Grid& g, const ColliderArgs& ca, const MoverArgs& ma, int tt) {
     const int t = tt / 3, i_only = tt - 3 * t;  // three threads per face / joint particle: one stencil plane each
-    pdl_trigger();
-    ts_begin(g, TS_SCATTER);
     if (t < ca.Mf) collider_scatter_face(g, ca, t, i_only);
     else if (t - ca.Mf < ma.njt + ma.njv + ma.njf) mover_scatter_one(g, ma, t - ca.Mf, i_only);
+}
+__global__ void __launch_bounds__(128) k_body_scatter(Grid g, ColliderArgs ca, MoverArgs ma) {
+    pdl_trigger();
+    ts_begin(g, TS_SCATTER);
+    body_scatter_thread(g, ca, ma, blockIdx.x * blockDim.x + threadIdx.x);
     ts_end(g, TS_SCATTER);  // before the wait: the stamp is the end of this kernel's own work
     pdl_wait();
 }
+// The same work as CTAs [first, first + n_ctas) of the vertex P2G grid (k_p2g<2>): placed in the MIDDLE of that grid they
+// start after the element kernel has drained (no collision of their ~1.1 M vector atomics with its own) and finish before
+// the vertex kernel does, so the scatter leaves the critical path and one launch disappears.
+struct BodyScatter {
+    ColliderArgs ca;
+    MoverArgs ma;
+    int first, n_ctas;
+};
+
+// KIND 1: traditional (stress*vol, :496), 2: cloth vertex.  PDL invariants of this file: (1) every kernel executes
+// griddepcontrol.wait before it exits, so completion is transitive along the stream; (2) a kernel whose successor
+// runs code in front of its own wait that READS what this kernel's predecessors wrote triggers only AFTER its
+// own wait, so "my grid has started" implies "my predecessor's predecessor has completed".
+template <int KIND>
+__global__ void __launch_bounds__(32 * (KIND == 2 ? P2G_V_NW : P2G_NW), KIND == 2 ? P2G_V_MINB : 1) k_p2g(Grid g, P2GIn in, int n, float dt, float rpic, BodyScatter bs) {
+    static_assert(KIND == 1 || KIND == 2, "elements have their own kernel");
+    constexpr int F0 = (KIND == 2) ? VP_F : KP_F;  // kinematics record
+    constexpr int NW = (KIND == 2) ? P2G_V_NW : P2G_NW;
+    int blk = blockIdx.x;
+    if (KIND == 2 && bs.n_ctas > 0) {  // the body scatter rides in this grid: CTAs [first, first + n_ctas)
+        const int rel = blk - bs.first;
+        if (rel >= 0 && rel < bs.n_ctas) {
+            // it depends on neither P2G kernel (different accumulators; the block table and the positions are those of the
+            // previous substep, complete since this grid could only start after the element kernel's wait): no wait here,
+            // the slab CTAs of this grid keep completion transitive
+            if (g.ts && threadIdx.x == 0 && rel < 256) atomicMin(&g.ts[2 * TS_SCATTER], globaltimer_ns());
+            body_scatter_thread(g, bs.ca, bs.ma, rel * (32 * NW) + (int)threadIdx.x);
+            if (g.ts && threadIdx.x == 0 && rel + 256 >= bs.n_ctas) atomicMax(&g.ts[2 * TS_SCATTER + 1], globaltimer_ns());
+            return;
+        }
+        if (rel >= bs.n_ctas) blk -= bs.n_ctas;
+    }
+    extern __shared__ __align__(128) unsigned char smem[];
+    Warp w;
+    if (!warp_begin<NW, P2G_WB>(w, n, smem, blk)) return;
+    ts_begin(g, TS_P2G_E + KIND);
+    PHASE_BEGIN();
+    float* buf = reinterpret_cast<float*>(w.buf);
+    // The vertex scatter only needs its predecessor (the element kernel) for the vertex forces: the VP slab is
+    // loaded and unpacked while the element kernel drains, griddepcontrol.wait sits in front of the VF read.
+    if (KIND != 2) {
+        pdl_wait();
+        pdl_trigger();  // let the successor's CTAs be scheduled into the slots this grid frees
+    }
+    float* raw1 = buf + 32 * F0;
+    if (KIND == 1) slab_load(w, {Slab{buf, in.KP, KP_F}, Slab{raw1, in.SF, S_F}});
+    if (KIND == 2) slab_load(w, {Slab{buf, in.KP, VP_F}});
+    PHASE(g, KIND, 0);  // slab load
+    const bool valid = w.lane < w.cnt;
+    P2GPart P;
+    P.m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { P.x[i] = 0.f; P.v[i] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 9; i++) { P.C[i] = 0.f; P.Sp[i] = 0.f; }
+    if (valid) {
+        const float* r = buf + w.lane * F0;
+        if (KIND == 2) {
+            const float4* r4 = reinterpret_cast<const float4*>(r);
+            const float4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
+            P.x[0] = a.x; P.x[1] = a.y; P.x[2] = a.z; P.m = a.w;
+            P.v[0] = b.x; P.v[1] = b.y; P.v[2] = b.z;
+            P.C[0] = b.w; P.C[1] = c.x; P.C[2] = c.y; P.C[3] = c.z; P.C[4] = c.w; P.C[5] = d.x; P.C[6] = d.y; P.C[7] = d.z; P.C[8] = d.w;
+        } else {
+            P.x[0] = r[0]; P.x[1] = r[1]; P.x[2] = r[2]; P.m = r[P_M];
+            P.v[0] = r[P_V]; P.v[1] = r[P_V + 1]; P.v[2] = r[P_V + 2];
+#pragma unroll
+            for (int i = 0; i < 9; i++) P.C[i] = r[P_C + i];
+            const float sc = -dt * g.inv_dx * r[P_VOL];
+            const float* s = raw1 + w.lane * S_F;
+#pragma unroll
+            for (int i = 0; i < 9; i++) P.Sp[i] = sc * s[i];
+        }
+    }
+    __syncwarp();  // the contributions overwrite the raw slabs
+    PHASE(g, KIND, 1);  // unpack
+    const int mycell = p2g_write_tiles<KIND == 1>(g, w, valid, P, dt, rpic, [&](float (&fv)[3]) {
+        if (KIND == 2) {  // the weights were computed while the element kernel drained
+            pdl_wait();
+            pdl_trigger();
+            if (valid) {
+                const float4 f4 = __ldcg(reinterpret_cast<const float4*>(in.SF) + w.p0 + w.lane);  // written by L2 atomics
+                fv[0] = f4.x; fv[1] = f4.y; fv[2] = f4.z;
+            }
+        }
+    });
+    PHASE(g, KIND, 2);  // stage 1
+    p2g_stage2(g, w, mycell);
+    PHASE(g, KIND, 3);  // stage 2
+    PHASE_END(g, KIND);
+    ts_end(g, TS_P2G_E + KIND);
+}
+
 
 // ============================================================ grid update
 // One pass over the nodes of the allocated blocks that fuses
