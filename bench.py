@@ -34,10 +34,11 @@ sys.path.insert(0, ROOT)
 
 SUBSTEPS_PER_STEP = 400
 # dram__bytes_read.sum + dram__bytes_write.sum of the P2G / G2P launches of one substep (ncu --set full, cold caches;
-# profiles/r2_v5_ncu_full_summary.txt): 58.55 + 17.88 + 16.15 + 33.68 MB for k_p2g_elements, k_p2g<2>, k_g2p_vertices,
-# k_g2p_elements.  A CONSTANT from that capture, not measured in the bench run (roofline.traffic_source says so).
-TRAFFIC_NCU = 126.25e6
-TRAFFIC_SOURCE = "constant: ncu --set full capture of one substep's P2G/G2P launches, cold caches (profiles/r2_v5_ncu_full_summary.txt), not measured in this run"
+# profiles/r2_v6_ncu_full_summary.txt): 58.1 + 20.4 + 16.1 + 34.3 MB for k_p2g_elements, k_p2g<2> (incl. the body scatter's
+# CTAs, 2.5 MB), k_g2p_vertices, k_g2p_elements.  A CONSTANT from that capture, not measured in the bench run
+# (roofline.traffic_source says so).
+TRAFFIC_NCU = 128.9e6
+TRAFFIC_SOURCE = "constant: ncu --set full capture of one substep's P2G/G2P launches, cold caches (profiles/r2_v6_ncu_full_summary.txt), not measured in this run"
 METRIC = "mpm_substeps_per_sec_500k_particles_256grid"
 
 
