@@ -1033,6 +1033,7 @@ __global__ void __launch_bounds__(256, PEER ? 4 : 5) k_grid_update(Grid g, Model
         g.vout[ni] = make_float4(vx, vy, vz, 0.0f);
     }
     }  // pass
+    if (PEER && g.ts) __syncthreads();  // probe only: the stamps are thread 0's, and other warps of the CTA may still be polling
     if (PEER) ts_end(g, TS_PULL);
     ts_end(g, TS_GRID);
     if (PEER) {  // the last CTA closes the exchange
